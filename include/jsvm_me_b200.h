@@ -1,0 +1,170 @@
+/*
+ * jsvm_me_b200.h -- C ABI of the B200-native JSVM motion-estimation hot path.
+ *
+ * This is the drop-in boundary: plain C, opaque handle, int status, caller-owned buffers,
+ * no torch / C++ types.  Every entry point names the reference interface it replaces
+ * (paths relative to /root/reference/JSVM/H264Extension):
+ *
+ *   ENC = src/lib/H264AVCEncoderLib, COM = src/lib/H264AVCCommonLib, INCC = include/H264AVCCommonLib
+ *
+ * The reference-side binding (replacement bodies for MotionEstimation.cpp /
+ * MotionEstimationQuarterPel.cpp / QuarterPelFilter::filterFrame that forward to these
+ * functions while the class headers stay byte-identical) is shown in INTEGRATION.md and
+ * implemented in jsvm-code-notes_b200/dropin/.
+ *
+ * Status convention = the reference's ErrVal (include/H264AVCCommonIf.h:26-38, Macros.h:23-43):
+ * 0 (Err::m_nOK) on success, -1 (Err::m_nERR) on failure; jsvm_me_last_error() gives the text.
+ * There is NO CPU fallback: every compute entry point fails if no sm_100 device is usable.
+ */
+#ifndef JSVM_ME_B200_H
+#define JSVM_ME_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JSVM_ME_OK   0
+#define JSVM_ME_ERR (-1)
+
+/* INCC/CommonDefs.h:169-190 (MbMode / BlkMode values accepted by estimateBlockWithStart) */
+#define JSVM_MODE_16x16 1
+#define JSVM_MODE_16x8  2
+#define JSVM_MODE_8x16  3
+#define JSVM_BLK_8x8    8
+#define JSVM_BLK_8x4    9
+#define JSVM_BLK_4x8   10
+#define JSVM_BLK_4x4   11
+
+/* INCC/CommonDefs.h:208-223 */
+#define JSVM_DF_SAD      0
+#define JSVM_DF_SSD      1
+#define JSVM_DF_HADAMARD 2
+#define JSVM_DF_YUV_SAD  3
+#define JSVM_SEARCH_BLOCK 0   /* SearchMode BLOCK_SEARCH = full search (xPelBlockSearch) */
+
+/* Luma plane geometry, INCC/CommonDefs.h:246-247 + COM/YuvBufferCtrl.cpp:134-157:
+ * stride = width + 2*32, 32 filled margin samples on every side. */
+#define JSVM_ME_MARGIN 32
+
+typedef struct jsvm_me_ctx jsvm_me_ctx;
+
+/* INCC/Mv.h: two Shorts, quarter-pel units, arithmetic >> on negatives. */
+typedef struct jsvm_mv { int16_t hor, ver; } jsvm_mv;
+
+/*
+ * One job == one call of
+ *   MotionEstimation::estimateBlockWithStart( rcMbDataAccess, rcRefFrame, rcMv, rcMvPred,
+ *                                             ruiBits, ruiCost, uiBlk, uiMode, uiSearchRange, pcPW, pcBSP )
+ * (ENC/MotionEstimation.cpp:129-340) for the un-weighted / fWeight==1 path, plus the MB state
+ * the reference keeps in members: the MB position that MotionCompensation::initMb
+ * (COM/MotionCompensation.cpp:152-167) turned into m_cMin/m_cMax, and the cost factor that
+ * xSetMEPars fetched from RateDistortionIf::getMotionCostShift (ENC/MotionEstimationCost.cpp:58-65).
+ * Jobs that share (cur_slot, ref_slot, mb_x, mb_y, org_index) and sit next to each other in the
+ * array are searched together from one SAD pass over the window (SAD reuse across partitions).
+ */
+typedef struct jsvm_me_job {
+  int16_t  cur_slot;       /* plane slot of the original picture (XDistortion::loadOrgMbPelData source) */
+  int16_t  ref_slot;       /* plane slot of rcRefFrame (full-pel + half-pel buffers) */
+  int16_t  mb_x, mb_y;     /* initMb( uiMbY, uiMbX ) */
+  uint8_t  blk;            /* uiBlk: 4x4 raster index 0..15 (B4x4Idx, INCC/CommonTypes.h:97-109) */
+  uint8_t  mode;           /* uiMode: JSVM_MODE_* / JSVM_BLK_* */
+  int16_t  search_range;   /* uiSearchRange; 0 = the value given to jsvm_me_set_params */
+  jsvm_mv  start;          /* rcMv on entry (search start, quarter-pel) */
+  jsvm_mv  pred;           /* rcMvPred (quarter-pel) */
+  uint32_t cost_factor;    /* m_uiCostFactor for SAD/HADAMARD = floor(65536*sqrt(lambda)), ENC/RateDistortion.cpp:59-70;
+                              computed on the host with the reference's own code (double, -ffloat-store) */
+  uint32_t bits_in;        /* ruiBits on entry */
+  int32_t  org_index;      /* -1: original block comes from cur_slot; >=0: index of a 16x16 int16 MB buffer in
+                              org_mbs (weighted / bi-pred "2*org - pred" originals prepared by the caller,
+                              ENC/MotionEstimation.cpp:163-247) */
+} jsvm_me_job;
+
+/* What one estimateBlockWithStart call returns (plus intermediate values for parity checks). */
+typedef struct jsvm_me_result {
+  jsvm_mv  mv;             /* rcMv on exit (quarter-pel) */
+  jsvm_mv  mv_fullpel;     /* result of xPelBlockSearch in integer pels (before cMv <<= 2) */
+  uint32_t sad_fullpel;    /* ruiSAD of xPelBlockSearch (rate already subtracted, :405) */
+  uint32_t min_sad;        /* uiMinSAD after xSubPelSearch: distortion INCLUDING the rate term (N9) */
+  uint32_t mv_bits;        /* uiMvBits = xGetBits( mv ) with the sub-pel table (shift 0) */
+  uint32_t bits;           /* ruiBits on exit = bits_in + mv_bits */
+  uint32_t cost;           /* ruiCost for fWeight == 1.0: (min_sad - cost(mv_bits)) + cost(bits)  (:335) */
+  uint32_t best_mode;      /* m_uiBestMode: n (half-pel stage winner) or n<<4 (quarter-pel winner) */
+} jsvm_me_result;
+
+/* ---- life cycle: MotionEstimationQuarterPel::create / destroy (ENC/MotionEstimationQuarterPel.cpp:54-66,
+ *      ENC/MotionEstimation.cpp:31-35) ---- */
+int jsvm_me_create (jsvm_me_ctx** ctx, int device);
+int jsvm_me_destroy(jsvm_me_ctx* ctx);
+const char* jsvm_me_last_error(void);
+
+/* MotionEstimation::init reading MotionVectorSearchParams (ENC/MotionEstimation.cpp:38-66,
+ * include/CodingParameter.h:41-89).  Only SearchMode 0 (BLOCK_SEARCH), full-pel DF_SAD and
+ * sub-pel DF_SAD / DF_HADAMARD are on the hot path; anything else returns JSVM_ME_ERR. */
+int jsvm_me_set_params(jsvm_me_ctx* ctx, int search_mode, int full_pel_dfunc, int sub_pel_dfunc, int search_range);
+
+/* Run every later call on this CUDA stream (a cudaStream_t / CUstream handle; NULL = default). */
+int jsvm_me_set_stream(jsvm_me_ctx* ctx, void* cuda_stream);
+
+/* Frame planes.  A slot holds the full-pel luma plane (with its 32-sample margin) and, after
+ * jsvm_me_interp_halfpel, the half-pel plane (YuvBufferCtrl with uiResolution = 1).
+ *
+ * upload_plane_xpel: `origin` points at sample (0,0) of a reference YuvPicBuffer luma plane
+ *   (XPel = int16, YuvPicBuffer::getMbLumAddr() after initMb(0,0)); the 32-sample margins around it
+ *   must already be filled (YuvPicBuffer::fillMargin, COM/YuvPicBuffer.cpp:1595-1641) and are copied
+ *   as they are.  Samples must be in [0,255] (reconstructed pictures are).
+ * upload_plane_u8: dense 8-bit picture without margins; the margin is generated on the device exactly
+ *   as fillMargin does (edge replication). `host` may be pinned memory. */
+int jsvm_me_upload_plane_xpel(jsvm_me_ctx* ctx, int slot, const int16_t* origin, int width, int height, int stride);
+int jsvm_me_upload_plane_u8  (jsvm_me_ctx* ctx, int slot, const uint8_t* host, int width, int height, int stride);
+/* Same as upload_plane_u8 but the source is already in device memory (bench "resident in HBM" leg). */
+int jsvm_me_set_plane_device_u8(jsvm_me_ctx* ctx, int slot, const uint8_t* dev, int width, int height, int stride);
+
+/* QuarterPelFilter::filterFrame( full, half ) (COM/QuarterPelFilter.cpp:61-149): builds the half-pel
+ * plane of the slot; it stays on the device (its only consumer is ME). */
+int jsvm_me_interp_halfpel(jsvm_me_ctx* ctx, int slot);
+/* Copy the half-pel plane back in YuvPicBuffer layout: `origin` = sample (0,0) of the half-pel buffer
+ * (stride 2*(width+64)); the region the reference writes, x in [-56, 2(W+28)), y in [-56, 2(H+28)), is stored. */
+int jsvm_me_download_halfpel_xpel(jsvm_me_ctx* ctx, int slot, int16_t* origin, int stride);
+/* Dense copy of that same region as bytes: rows 2*(H+56), cols 2*(W+56). */
+int jsvm_me_download_halfpel_u8(jsvm_me_ctx* ctx, int slot, uint8_t* dst, int dst_stride);
+
+/* estimateBlockWithStart for n jobs (host buffers; H2D of jobs, kernels, D2H of results, then sync).
+ * org_mbs: n_org_mbs dense 16x16 int16 blocks (or NULL).  preds (optional, may be NULL): n*256 bytes,
+ * the winning prediction block of every job as compensateBlock would return it
+ * (ENC/MotionEstimationQuarterPel.cpp:266-328), stride 16, top-left aligned. */
+int jsvm_me_search(jsvm_me_ctx* ctx, const jsvm_me_job* jobs, int n_jobs,
+                   const int16_t* org_mbs, int n_org_mbs,
+                   jsvm_me_result* results, uint8_t* preds);
+
+/* Same, everything already in device memory, asynchronous on the ctx stream (no sync).
+ * `groups`/`n_groups` come from jsvm_me_plan (host) copied to the device by the caller. */
+typedef struct jsvm_me_group jsvm_me_group;   /* opaque 64-byte records */
+size_t jsvm_me_group_size(void);
+/* Host-side planner: fuses neighbouring jobs of one macroblock into search groups.  groups_out must
+ * hold n_jobs records; returns the number of groups in *n_groups. */
+int jsvm_me_plan(jsvm_me_ctx* ctx, const jsvm_me_job* jobs, int n_jobs, void* groups_out, int* n_groups);
+int jsvm_me_search_device(jsvm_me_ctx* ctx, const jsvm_me_job* d_jobs, int n_jobs,
+                          const void* d_groups, int n_groups,
+                          const int16_t* d_org_mbs, int n_org_mbs,
+                          jsvm_me_result* d_results, uint8_t* d_preds);
+
+/* MotionEstimationQuarterPel::compensateBlock for job `job_idx` of the LAST jsvm_me_search call
+ * (the reference's stateful contract): writes w x h samples to dst (XPel, dst_stride). */
+int jsvm_me_fetch_pred(jsvm_me_ctx* ctx, int job_idx, int16_t* dst, int dst_stride);
+
+int jsvm_me_sync(jsvm_me_ctx* ctx);
+
+/* Measurement helpers (bench.py): kernel launches issued so far, and CUDA-event timing of the
+ * search / interpolation kernels on the ctx stream. */
+uint64_t jsvm_me_launch_count(jsvm_me_ctx* ctx);
+int jsvm_me_timing_begin(jsvm_me_ctx* ctx);                  /* start accumulating per-kernel event times */
+int jsvm_me_timing_end(jsvm_me_ctx* ctx, double* ms_interp, double* ms_search, double* ms_subpel,
+                       uint64_t* n_interp, uint64_t* n_search, uint64_t* n_subpel);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JSVM_ME_B200_H */

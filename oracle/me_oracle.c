@@ -1,0 +1,424 @@
+/*
+ * oracle/me_oracle.c -- TEST INFRASTRUCTURE ONLY (never part of the product path).
+ *
+ * CPU restatement, in plain C99, of the JSVM 9.19.8 motion-estimation hot path.  It is the
+ * checker the CUDA path is compared with; see me_oracle.h for how it is itself pinned against
+ * the compiled reference.  Scalar and single-threaded on purpose (as the reference is).
+ *
+ * Citations use R = /root/reference/JSVM/H264Extension, ENC = R/src/lib/H264AVCEncoderLib,
+ * COM = R/src/lib/H264AVCCommonLib, INCC = R/include/H264AVCCommonLib.
+ */
+#include "me_oracle.h"
+
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <limits.h>
+
+#define MARGIN   JSVM_ME_MARGIN          /* INCC/CommonDefs.h:246 YUV_X_MARGIN; y margin = 64/2 (COM/YuvBufferCtrl.cpp:134-135) */
+#define HP_ORG   (2 * MARGIN)            /* origin offset inside our half-pel plane (both axes) */
+
+typedef struct {
+  uint8_t* full;   /* (H+64) x (W+64), origin at (32,32) */
+  uint8_t* half;   /* 2(H+64) x 2(W+64), origin at (64,64); only [-56, 2(W+28)) x [-56, 2(H+28)) is written */
+  int      valid;
+} ora_plane;
+
+struct jsvm_ora_ctx {
+  int width, height, n_slots;
+  int search_mode, full_dfunc, sub_dfunc, search_range;
+  ora_plane* planes;
+};
+
+static inline int clip255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }   /* gClip, INCC/GlobalFunctions.h:37-44 */
+
+/* ---------------------------------------------------------------------------------------------
+ * a6  MotionEstimationCost::xGetComponentBits (ENC/MotionEstimationCost.cpp:75-87):
+ *     length of the signed Exp-Golomb code of one quarter-pel difference.
+ * ------------------------------------------------------------------------------------------- */
+uint32_t jsvm_ora_component_bits(int d) {
+  uint32_t len = 1;
+  uint32_t a = (uint32_t)(d < 0 ? -d : d);
+  uint32_t t = (a << 1) + 1;
+  while (t != 1) { t >>= 1; len += 2; }
+  return len;
+}
+
+/* xGetCost( bits ) = ( m_uiCostFactor * bits ) >> 16 in 32-bit unsigned arithmetic (ENC/MotionEstimationCost.h:27, N5). */
+static inline uint32_t rate_cost(uint32_t factor, uint32_t bits) { return (uint32_t)(factor * bits) >> 16; }
+
+/* a7  RateDistortion::setMbQpLambda (ENC/RateDistortion.cpp:59-70). The reference is built with
+ * -ffloat-store; on x86-64/SSE2 doubles are already IEEE binary64 so plain C gives the same value. */
+uint32_t jsvm_ora_cost_factor(double lambda, int sad) {
+  volatile double s = sqrt(lambda);
+  volatile double v = sad ? 65536.0 * s : 65536.0 * lambda;
+  return (uint32_t)floor(v);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Block geometry: XDistortion::init tables m_aiRows / m_aiCols (ENC/Distortion.cpp:50-74).
+ * ------------------------------------------------------------------------------------------- */
+static int mode_size(int mode, int* w, int* h) {
+  switch (mode) {
+    case JSVM_MODE_16x16: *w = 16; *h = 16; return 0;
+    case JSVM_MODE_16x8:  *w = 16; *h = 8;  return 0;
+    case JSVM_MODE_8x16:  *w = 8;  *h = 16; return 0;
+    case JSVM_BLK_8x8:    *w = 8;  *h = 8;  return 0;
+    case JSVM_BLK_8x4:    *w = 8;  *h = 4;  return 0;
+    case JSVM_BLK_4x8:    *w = 4;  *h = 8;  return 0;
+    case JSVM_BLK_4x4:    *w = 4;  *h = 4;  return 0;
+    default: return -1;
+  }
+}
+
+/* a4  XDistortion::xCalcHadamard4x4 (ENC/Distortion.cpp:291-340): vertical then horizontal 4-point
+ * butterflies on the difference block, sum of absolute coefficients, halved PER 4x4 (N8). */
+static uint32_t hadamard4x4(const int* d /* 4x4 diffs, row-major */) {
+  int m[16], t[4];
+  uint32_t sum = 0;
+  for (int n = 0; n < 4; ++n) {        /* columns */
+    t[0] = d[0 * 4 + n] + d[3 * 4 + n];
+    t[1] = d[1 * 4 + n] + d[2 * 4 + n];
+    t[2] = d[1 * 4 + n] - d[2 * 4 + n];
+    t[3] = d[0 * 4 + n] - d[3 * 4 + n];
+    m[0 * 4 + n] = t[0] + t[1];
+    m[2 * 4 + n] = t[0] - t[1];
+    m[1 * 4 + n] = t[3] + t[2];
+    m[3 * 4 + n] = t[3] - t[2];
+  }
+  for (int n = 0; n < 4; ++n) {        /* rows */
+    int a = m[n * 4 + 0] + m[n * 4 + 3];
+    int b = m[n * 4 + 1] + m[n * 4 + 2];
+    sum += (uint32_t)abs(a + b);
+    sum += (uint32_t)abs(a - b);
+    a = m[n * 4 + 1] - m[n * 4 + 2];
+    b = m[n * 4 + 0] - m[n * 4 + 3];
+    sum += (uint32_t)abs(a + b);
+    sum += (uint32_t)abs(a - b);
+  }
+  return sum / 2;
+}
+
+/* Generic "sample fetch" distortion so that the same code serves the full-pel plane, the
+ * half-pel candidates and the quarter-pel candidates.  get(user, x, y) returns the candidate
+ * prediction sample for block pixel (x, y).
+ * a3  xGetSAD16x/8x/4x (ENC/Distortion.cpp:397-429, 563-587, 691-711);
+ * a5  xGetSSE*       (:512-560, 653-686, 769-794);
+ * a4  xGetHAD16x/8x/4x (:798-855). */
+typedef int (*sample_fn)(const void* user, int x, int y);
+
+static uint32_t distortion(const int16_t* org /* stride 16 */, sample_fn get, const void* user, int w, int h, int dfunc) {
+  uint32_t sum = 0;
+  if (dfunc == JSVM_DF_HADAMARD) {
+    for (int by = 0; by < h; by += 4)
+      for (int bx = 0; bx < w; bx += 4) {
+        int d[16];
+        for (int y = 0; y < 4; ++y)
+          for (int x = 0; x < 4; ++x) d[y * 4 + x] = org[(by + y) * 16 + bx + x] - get(user, bx + x, by + y);
+        sum += hadamard4x4(d);
+      }
+    return sum;
+  }
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      int d = org[y * 16 + x] - get(user, x, y);
+      sum += (dfunc == JSVM_DF_SSD) ? (uint32_t)(d * d) : (uint32_t)abs(d);
+    }
+  return sum;
+}
+
+typedef struct { const int16_t* p; int stride; } raw16_src;
+static int get_raw16(const void* u, int x, int y) { const raw16_src* s = (const raw16_src*)u; return s->p[y * s->stride + x]; }
+
+uint32_t jsvm_ora_distortion(const int16_t* org16x16, const int16_t* ref, int ref_stride, int mode, int dfunc, int blk) {
+  int w, h;
+  if (mode_size(mode, &w, &h)) return 0xffffffffu;
+  raw16_src s = { ref, ref_stride };
+  return distortion(org16x16 + ((blk >> 2) * 4) * 16 + (blk & 3) * 4, get_raw16, &s, w, h, dfunc);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Planes
+ * ------------------------------------------------------------------------------------------- */
+jsvm_ora_ctx* jsvm_ora_create(int width, int height, int n_slots,
+                              int search_mode, int full_pel_dfunc, int sub_pel_dfunc, int search_range) {
+  if (width <= 0 || height <= 0 || (width & 15) || (height & 15) || n_slots <= 0) return NULL;
+  jsvm_ora_ctx* c = (jsvm_ora_ctx*)calloc(1, sizeof(*c));
+  c->width = width; c->height = height; c->n_slots = n_slots;
+  c->search_mode = search_mode; c->full_dfunc = full_pel_dfunc; c->sub_dfunc = sub_pel_dfunc; c->search_range = search_range;
+  c->planes = (ora_plane*)calloc((size_t)n_slots, sizeof(ora_plane));
+  for (int s = 0; s < n_slots; ++s) {
+    c->planes[s].full = (uint8_t*)calloc((size_t)(width + 2 * MARGIN) * (height + 2 * MARGIN), 1);
+    c->planes[s].half = (uint8_t*)calloc((size_t)4 * (width + 2 * MARGIN) * (height + 2 * MARGIN), 1);
+  }
+  return c;
+}
+
+void jsvm_ora_destroy(jsvm_ora_ctx* c) {
+  if (!c) return;
+  for (int s = 0; s < c->n_slots; ++s) { free(c->planes[s].full); free(c->planes[s].half); }
+  free(c->planes);
+  free(c);
+}
+
+/* YuvPicBuffer::xFillPlaneMargin (COM/YuvPicBuffer.cpp:1608-1641): left/right replicate per row,
+ * then whole padded rows are copied down / up. */
+static void fill_margin(uint8_t* full, int W, int H) {
+  const int S = W + 2 * MARGIN;
+  uint8_t* org = full + MARGIN * S + MARGIN;
+  for (int y = 0; y < H; ++y) {
+    uint8_t* r = org + y * S;
+    for (int m = -MARGIN; m < 0; ++m) r[m] = r[0];
+    for (int m = W; m < W + MARGIN; ++m) r[m] = r[W - 1];
+  }
+  for (int n = 0; n < MARGIN; ++n) {
+    memcpy(org - MARGIN + (H + n) * S, org - MARGIN + (H - 1) * S, (size_t)S);
+    memcpy(org - MARGIN - (n + 1) * S, org - MARGIN, (size_t)S);
+  }
+}
+
+/* a12 QuarterPelFilter::filterFrame (COM/QuarterPelFilter.cpp:61-149).
+ * Pass 1 (:83-102): per picture row, x in [-28, W+28): tmp[2x] = s[x] << 5,
+ *   tmp[2x+1] = s[x-2] - 5 s[x-1] + 20 s[x] + 20 s[x+1] - 5 s[x+2] + s[x+3]  (unrounded int).
+ *   The temp rows are zero outside that x range (memset :79) and replicated 32x below / above
+ *   from the LAST / FIRST picture row (:104-116) -- not from the plane's vertical margin.
+ * Pass 2 (:125-144): y in [-28, H+28), x in [-56, 2(W+28)):
+ *   out[2y][x]   = gClip( (tmp[y][x] + 16) / 32 )
+ *   out[2y+1][x] = gClip( (V6(tmp)[y][x] + 512) / 1024 ), V6 = the same taps over rows y-2..y+3.
+ *   '/' truncates toward zero; gClip then maps every negative quotient to 0. */
+static void filter_frame(const uint8_t* full, uint8_t* half, int W, int H) {
+  const int S = W + 2 * MARGIN;
+  const int TS = 2 * S;                 /* iTmpXSize */
+  const int TR = H + 2 * MARGIN;        /* iTmpYSize */
+  const int mn = MARGIN - 4;            /* iMarginNew = 28 */
+  int32_t* tmp = (int32_t*)calloc((size_t)TS * TR, sizeof(int32_t));
+  const uint8_t* src = full + MARGIN * S + MARGIN;
+  for (int y = 0; y < H; ++y) {
+    int32_t* ps = tmp + (size_t)(MARGIN + y) * TS + 2 * MARGIN;
+    const uint8_t* s = src + y * S;
+    for (int x = -mn; x < W + mn; ++x) {
+      int t = s[x] + s[x + 1];
+      t <<= 2;
+      t -= s[x - 1];
+      t -= s[x + 2];
+      t += t << 2;
+      t += s[x - 2];
+      t += s[x + 3];
+      ps[2 * x] = s[x] << 5;
+      ps[2 * x + 1] = t;
+    }
+  }
+  for (int n = 0; n < MARGIN; ++n) {
+    memcpy(tmp + (size_t)(MARGIN + H + n) * TS, tmp + (size_t)(MARGIN + H - 1) * TS, (size_t)TS * sizeof(int32_t));
+    memcpy(tmp + (size_t)(MARGIN - 1 - n) * TS, tmp + (size_t)MARGIN * TS, (size_t)TS * sizeof(int32_t));
+  }
+  const int HS = 2 * S;                 /* half-pel stride */
+  for (int y = -mn; y < H + mn; ++y) {
+    const int32_t* ps = tmp + (size_t)(MARGIN + y) * TS + 2 * MARGIN;
+    uint8_t* d0 = half + (size_t)(HP_ORG + 2 * y) * HS + HP_ORG;
+    uint8_t* d1 = d0 + HS;
+    for (int x = -2 * mn; x < 2 * (W + mn); ++x) {
+      int t = ps[x] + ps[x + TS];
+      t <<= 2;
+      t -= ps[x - TS];
+      t -= ps[x + 2 * TS];
+      t += t << 2;
+      t += ps[x - 2 * TS];
+      t += ps[x + 3 * TS];
+      d0[x] = (uint8_t)clip255((ps[x] + 16) / 32);
+      d1[x] = (uint8_t)clip255((t + 512) / 1024);
+    }
+  }
+  free(tmp);
+}
+
+int jsvm_ora_set_plane_u8(jsvm_ora_ctx* c, int slot, const uint8_t* luma, int stride) {
+  if (!c || slot < 0 || slot >= c->n_slots) return -1;
+  const int W = c->width, H = c->height, S = W + 2 * MARGIN;
+  ora_plane* p = &c->planes[slot];
+  for (int y = 0; y < H; ++y) memcpy(p->full + (size_t)(MARGIN + y) * S + MARGIN, luma + (size_t)y * stride, (size_t)W);
+  fill_margin(p->full, W, H);
+  memset(p->half, 0, (size_t)4 * S * (H + 2 * MARGIN));
+  filter_frame(p->full, p->half, W, H);
+  p->valid = 1;
+  return 0;
+}
+
+int jsvm_ora_get_fullpel_u8(jsvm_ora_ctx* c, int slot, uint8_t* dst, int dst_stride) {
+  if (!c || slot < 0 || slot >= c->n_slots) return -1;
+  const int S = c->width + 2 * MARGIN;
+  for (int y = 0; y < c->height + 2 * MARGIN; ++y) memcpy(dst + (size_t)y * dst_stride, c->planes[slot].full + (size_t)y * S, (size_t)S);
+  return 0;
+}
+
+int jsvm_ora_get_halfpel_u8(jsvm_ora_ctx* c, int slot, uint8_t* dst, int dst_stride) {
+  if (!c || slot < 0 || slot >= c->n_slots) return -1;
+  const int HS = 2 * (c->width + 2 * MARGIN);
+  const int m = 2 * (MARGIN - 4);
+  const int rows = 2 * c->height + 2 * m, cols = 2 * c->width + 2 * m;
+  for (int y = 0; y < rows; ++y)
+    memcpy(dst + (size_t)y * dst_stride, c->planes[slot].half + (size_t)(HP_ORG - m + y) * HS + (HP_ORG - m), (size_t)cols);
+  return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Search
+ * ------------------------------------------------------------------------------------------- */
+static inline int16_t sat16(int v) { return (int16_t)(v < SHRT_MIN ? SHRT_MIN : (v > SHRT_MAX ? SHRT_MAX : v)); }
+static inline int imin(int a, int b) { return a < b ? a : b; }
+static inline int imax(int a, int b) { return a > b ? a : b; }
+
+typedef struct { int neg_ver, pos_ver, neg_hor, pos_hor; } search_rect;
+
+/* a8 MotionCompensation::initMb (COM/MotionCompensation.cpp:152-167) -> m_cMin / m_cMax (quarter-pel, per MB);
+ * a2 limitComponents + '>>= 2' (ENC/MotionEstimation.cpp:373-374, INCC/Mv.h:80-85, 118-122);
+ *    SearchRect::init (ENC/MotionEstimation.h:44-56) with its Short casts (N2). */
+static void search_window(const jsvm_ora_ctx* c, const jsvm_me_job* j, int* cx, int* cy, search_rect* r) {
+  const int mbw = c->width >> 4, mbh = c->height >> 4;
+  int16_t min_h = sat16(((-(int)j->mb_x << 4) - 24) << 2), min_v = sat16(((-(int)j->mb_y << 4) - 24) << 2);
+  int16_t max_h = sat16((((mbw - j->mb_x) << 4) + 8) << 2), max_v = sat16((((mbh - j->mb_y) << 4) + 8) << 2);
+  int16_t h = (int16_t)imin(max_h, imax(min_h, j->start.hor));
+  int16_t v = (int16_t)imin(max_v, imax(min_v, j->start.ver));
+  h >>= 2; v >>= 2;
+  int16_t mnh = min_h >> 2, mnv = min_v >> 2, mxh = max_h >> 2, mxv = max_v >> 2;
+  int16_t lim = (int16_t)(j->search_range ? j->search_range : c->search_range);
+  int16_t pos_v = (int16_t)(mxv - v), neg_v = (int16_t)(v - mnv);
+  int16_t pos_h = (int16_t)(mxh - h), neg_h = (int16_t)(h - mnh);
+  r->neg_ver = imin(lim, neg_v) - v;
+  r->pos_ver = imin(lim, pos_v) + v;
+  r->neg_hor = imin(lim, neg_h) - h;
+  r->pos_hor = imin(lim, pos_h) + h;
+  *cx = h; *cy = v;
+}
+
+int jsvm_ora_window_positions(jsvm_ora_ctx* c, const jsvm_me_job* job) {
+  int cx, cy; search_rect r;
+  search_window(c, job, &cx, &cy, &r);
+  int nx = r.pos_hor + r.neg_hor + 1, ny = r.pos_ver + r.neg_ver + 1;
+  return (nx > 0 && ny > 0) ? nx * ny : 0;
+}
+
+typedef struct { const uint8_t* p; int stride; } u8_src;                 /* full-pel plane candidate */
+static int get_u8(const void* u, int x, int y) { const u8_src* s = (const u8_src*)u; return s->p[y * s->stride + x]; }
+
+typedef struct { const uint8_t* p; int stride; } hp_src;                 /* half-pel candidate: every 2nd sample */
+static int get_hp(const void* u, int x, int y) { const hp_src* s = (const hp_src*)u; return s->p[2 * y * s->stride + 2 * x]; }
+
+/* a11 QuarterPelFilter::xXFilter1..4 (COM/QuarterPelFilter.cpp:152-262) for one of the 8 neighbours
+ * (dx,dy) of the half-pel winner at c: filters 0 and 3 (winner on an integer or on the diagonal
+ * half sample) average the two AXIS neighbours for the diagonal quarter positions; filters 1 and 2
+ * average the centre with the neighbour itself. Rounding (p+q+1)>>1. */
+typedef struct { const uint8_t* c; int stride; int dx, dy; int axis_diag; } qp_src;
+static int get_qp(const void* u, int x, int y) {
+  const qp_src* s = (const qp_src*)u;
+  const uint8_t* o = s->c + 2 * y * s->stride + 2 * x;
+  if (s->axis_diag && s->dx && s->dy) return (o[s->dx] + o[s->dy * s->stride] + 1) >> 1;
+  return (o[0] + o[s->dy * s->stride + s->dx] + 1) >> 1;
+}
+
+/* candidate tables, ENC/MotionEstimationQuarterPel.cpp:11-41 */
+static const uint8_t kFilterOfHalf[9] = { 0, 2, 2, 1, 1, 3, 3, 3, 3 };
+static const int8_t kHalfMv[9][2] = { {0,0}, {0,-2}, {0,2}, {-2,0}, {2,0}, {-2,-2}, {2,-2}, {-2,2}, {2,2} };
+static const int8_t kQuarterMv[9][2] = { {0,0}, {0,-1}, {0,1}, {-1,-1}, {1,-1}, {-1,0}, {1,0}, {-1,1}, {1,1} };
+
+int jsvm_ora_search(jsvm_ora_ctx* c, const jsvm_me_job* jobs, int n_jobs,
+                    const int16_t* org_mbs, int n_org_mbs,
+                    jsvm_me_result* results, uint8_t* preds) {
+  if (!c) return -1;
+  if (c->search_mode != JSVM_SEARCH_BLOCK) return -1;     /* only xPelBlockSearch is on the hot path */
+  const int W = c->width, H = c->height, S = W + 2 * MARGIN, HS = 2 * S;
+  for (int i = 0; i < n_jobs; ++i) {
+    const jsvm_me_job* j = &jobs[i];
+    int w, h;
+    if (mode_size(j->mode, &w, &h)) return -1;
+    if (j->cur_slot < 0 || j->cur_slot >= c->n_slots || j->ref_slot < 0 || j->ref_slot >= c->n_slots) return -1;
+    if (j->mb_x < 0 || j->mb_x >= (W >> 4) || j->mb_y < 0 || j->mb_y >= (H >> 4) || j->blk > 15) return -1;
+    if (j->org_index >= n_org_mbs) return -1;
+    const ora_plane* cur = &c->planes[j->cur_slot];
+    const ora_plane* ref = &c->planes[j->ref_slot];
+    if (!ref->valid || (j->org_index < 0 && !cur->valid)) return -1;
+
+    /* ENC/MotionEstimation.cpp:142-152: position org / ref pointers on the 4x4 block uiBlk */
+    const int bx0 = 16 * j->mb_x + 4 * (j->blk & 3), by0 = 16 * j->mb_y + 4 * (j->blk >> 2);
+    int16_t org[256];                                       /* block-relative, stride 16 */
+    memset(org, 0, sizeof(org));
+    for (int y = 0; y < h; ++y)
+      for (int x = 0; x < w; ++x) {
+        if (j->org_index >= 0)
+          org[y * 16 + x] = org_mbs[(size_t)j->org_index * 256 + (4 * (j->blk >> 2) + y) * 16 + 4 * (j->blk & 3) + x];
+        else
+          org[y * 16 + x] = cur->full[(size_t)(MARGIN + by0 + y) * S + MARGIN + bx0 + x];
+      }
+    const uint32_t f = j->cost_factor;
+
+    /* ---- a2 xPelBlockSearch (ENC/MotionEstimation.cpp:351-412) ---- */
+    int cx, cy; search_rect r;
+    search_window(c, j, &cx, &cy, &r);
+    uint32_t best = 0xffffffffu;                            /* MSYS_UINT_MAX */
+    int best_x = cx, best_y = cy;                           /* rcMv keeps the clipped start if the window is empty */
+    const uint8_t* ref0 = ref->full + (size_t)(MARGIN + by0) * S + MARGIN + bx0;
+    for (int y = -r.neg_ver; y <= r.pos_ver; ++y)
+      for (int x = -r.neg_hor; x <= r.pos_hor; ++x) {
+        u8_src s = { ref0 + y * S + x, S };
+        uint32_t sad = distortion(org, get_u8, &s, w, h, c->full_dfunc);
+        /* xGetCost( x, y ) with m_uiMvScaleShift = 2 (N6): table index (x<<2) - pred */
+        sad += rate_cost(f, jsvm_ora_component_bits((x << 2) - j->pred.hor) + jsvm_ora_component_bits((y << 2) - j->pred.ver));
+        if (best > sad) { best = sad; best_x = x; best_y = y; }       /* first strict minimum in raster order (N1) */
+      }
+    best -= rate_cost(f, jsvm_ora_component_bits((best_x << 2) - j->pred.hor) + jsvm_ora_component_bits((best_y << 2) - j->pred.ver));
+    jsvm_me_result* out = &results[i];
+    out->mv_fullpel.hor = (int16_t)best_x; out->mv_fullpel.ver = (int16_t)best_y;
+    out->sad_fullpel = best;
+
+    /* ---- a9 xSubPelSearch (ENC/MotionEstimationQuarterPel.cpp:94-167) ---- */
+    int16_t mvh = (int16_t)(best_x << 2), mvv = (int16_t)(best_y << 2);           /* cMv <<= 2 (:313) */
+    /* a10 xCompensateBlocksHalf (:226-263): base = half-pel block origin + (mv>>1) */
+    const uint8_t* hp0 = ref->half + (size_t)(HP_ORG + 2 * by0) * HS + HP_ORG + 2 * bx0;
+    const uint8_t* hbase = hp0 + (mvh >> 1) + (mvv >> 1) * HS;
+    uint32_t best_sad = 0xffffffffu;
+    uint32_t best_mode = 0;
+    int16_t bh = mvh, bv = mvv;
+    for (int n = 0; n < 9; ++n) {
+      /* the 9 buffers of xInitBuffer (:69-79) are the half-pel plane sampled at offset (dx/2, dy/2) */
+      hp_src s = { hbase + (kHalfMv[n][0] / 2) + (kHalfMv[n][1] / 2) * HS, HS };
+      uint32_t sad = distortion(org, get_hp, &s, w, h, c->sub_dfunc);
+      int16_t th = (int16_t)(mvh + kHalfMv[n][0]), tv = (int16_t)(mvv + kHalfMv[n][1]);
+      sad += rate_cost(f, jsvm_ora_component_bits(th - j->pred.hor) + jsvm_ora_component_bits(tv - j->pred.ver));
+      if (sad < best_sad) { best_mode = (uint32_t)n; best_sad = sad; bh = th; bv = tv; }
+    }
+    mvh = bh; mvv = bv;
+    const uint8_t* qc = hp0 + (mvh >> 1) + (mvv >> 1) * HS;       /* :137-139 */
+    const int filt = kFilterOfHalf[best_mode];
+    const int axis_diag = (filt == 0 || filt == 3);
+    int q_winner = 0;
+    for (int n = 1; n < 9; ++n) {
+      qp_src s = { qc, HS, kQuarterMv[n][0], kQuarterMv[n][1], axis_diag };
+      uint32_t sad = distortion(org, get_qp, &s, w, h, c->sub_dfunc);
+      int16_t th = (int16_t)(mvh + kQuarterMv[n][0]), tv = (int16_t)(mvv + kQuarterMv[n][1]);
+      sad += rate_cost(f, jsvm_ora_component_bits(th - j->pred.hor) + jsvm_ora_component_bits(tv - j->pred.ver));
+      if (sad < best_sad) { best_mode = (uint32_t)n << 4; best_sad = sad; bh = th; bv = tv; q_winner = n; }
+    }
+    /* ---- ENC/MotionEstimation.cpp:331-337 (fWeight = 1.0) ---- */
+    uint32_t mv_bits = jsvm_ora_component_bits(bh - j->pred.hor) + jsvm_ora_component_bits(bv - j->pred.ver);
+    out->mv.hor = bh; out->mv.ver = bv;
+    out->min_sad = best_sad;
+    out->mv_bits = mv_bits;
+    out->bits = j->bits_in + mv_bits;
+    out->cost = (uint32_t)floor(1.0 * (double)(uint32_t)(best_sad - rate_cost(f, mv_bits))) + rate_cost(f, out->bits);
+    out->best_mode = best_mode;
+
+    /* ---- a13 compensateBlock (ENC/MotionEstimationQuarterPel.cpp:266-328), single-buffer branch ---- */
+    if (preds) {
+      uint8_t* dp = preds + (size_t)i * 256;
+      memset(dp, 0, 256);
+      if (best_mode < 0x10) {
+        hp_src s = { hbase + (kHalfMv[best_mode][0] / 2) + (kHalfMv[best_mode][1] / 2) * HS, HS };
+        for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) dp[y * 16 + x] = (uint8_t)get_hp(&s, x, y);
+      } else {
+        qp_src s = { qc, HS, kQuarterMv[q_winner][0], kQuarterMv[q_winner][1], axis_diag };
+        for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) dp[y * 16 + x] = (uint8_t)get_qp(&s, x, y);
+      }
+    }
+  }
+  return 0;
+}

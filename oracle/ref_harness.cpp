@@ -1,0 +1,338 @@
+// oracle/ref_harness.cpp -- TEST INFRASTRUCTURE ONLY (see ref_harness.h).
+//
+// Drives the UNMODIFIED reference classes.  Object graph and call order follow
+//   TEST/MCTFPreProcessor/MCTFPreProcessor.cpp:83-142 (create / init wiring),
+//   TEST/MCTFPreProcessor/MCTF.cpp:96-145, 248-277, 451-497 (SPS/PPS/SliceHeader, per-MB initMb loop),
+//   ENC/CreaterH264AVCEncoder.cpp:263-316.
+// Nothing from the reference is copied; this file only calls its public / protected interfaces.
+#include "H264AVCEncoderLib.h"
+#include "CodingParameter.h"
+#include "H264AVCCommonLib/Transform.h"
+#include "H264AVCCommonLib/YuvBufferCtrl.h"
+#include "H264AVCCommonLib/QuarterPelFilter.h"
+#include "H264AVCCommonLib/SampleWeighting.h"
+#include "H264AVCCommonLib/Frame.h"
+#include "H264AVCCommonLib/MbDataCtrl.h"
+#include "H264AVCCommonLib/SliceHeader.h"
+#include "H264AVCCommonLib/SequenceParameterSet.h"
+#include "H264AVCCommonLib/PictureParameterSet.h"
+#include "MotionEstimation.h"
+#include "MotionEstimationQuarterPel.h"
+#include "RateDistortion.h"
+#include "Distortion.h"
+
+#include <vector>
+#include <cstring>
+#include <cstdio>
+
+#include "ref_harness.h"
+
+using namespace h264;
+
+namespace {
+
+// RateDistortionIf whose motion cost factor is supplied per job (the job carries the value the
+// real RateDistortion::setMbQpLambda would have produced; jsvm_ref_cost_factor pins that mapping).
+class FixedRateDistortion : public RateDistortionIf {
+public:
+  FixedRateDistortion() : m_uiFactor(0) {}
+  virtual ~FixedRateDistortion() {}
+  ErrVal  setMbQpLambda(MbDataAccess&, UInt, Double) { return Err::m_nOK; }
+  Double  getCost (UInt, UInt) { return 0; }
+  Double  getFCost(UInt, UInt) { return 0; }
+  UInt    getMotionCostShift(Bool) { return m_uiFactor; }
+  ErrVal  fixMacroblockQP(MbDataAccess&) { return Err::m_nOK; }
+  UInt m_uiFactor;
+};
+
+// Probe subclass: records what xPelBlockSearch handed to xSubPelSearch and what came back.
+class ProbeME : public MotionEstimationQuarterPel {
+public:
+  ProbeME() { xInitBuffer(); }
+  virtual ~ProbeME() {}
+  Void xSubPelSearch(YuvPicBuffer* pcPelData, Mv& rcMv, UInt& ruiSAD, UInt uiBlk, UInt uiMode) {
+    m_cFullPelMv  = rcMv;     // already << 2
+    m_uiFullPelSad = ruiSAD;
+    MotionEstimationQuarterPel::xSubPelSearch(pcPelData, rcMv, ruiSAD, uiBlk, uiMode);
+    m_uiMinSad = ruiSAD;
+  }
+  UInt bestMode() const { return m_uiBestMode; }
+  Mv   m_cFullPelMv;
+  UInt m_uiFullPelSad;
+  UInt m_uiMinSad;
+};
+
+}  // namespace
+
+struct jsvm_ref_ctx {
+  int width, height, n_slots;
+  UInt mbw, mbh;
+  SequenceParameterSet* sps;
+  PictureParameterSet*  pps;
+  SliceHeader*          sh;
+  MbDataCtrl*           mbctrl;
+  YuvBufferCtrl*        full_ctrl;
+  YuvBufferCtrl*        half_ctrl;
+  QuarterPelFilter*     filter;
+  Transform*            transform;
+  SampleWeighting*      weighting;
+  XDistortion*          dist;
+  FixedRateDistortion*  rd;
+  ProbeME*              me;
+  CodingParameter*      cp;
+  std::vector<Frame*>   frames;
+  PredWeight            pw;
+};
+
+#define CHK(x) do { if ((x) != Err::m_nOK) { fprintf(stderr, "ref_harness: %s failed (%s:%d)\n", #x, __FILE__, __LINE__); return 0; } } while (0)
+#define CHKI(x) do { if ((x) != Err::m_nOK) { fprintf(stderr, "ref_harness: %s failed (%s:%d)\n", #x, __FILE__, __LINE__); return -1; } } while (0)
+
+extern "C" jsvm_ref_ctx* jsvm_ref_create(int width, int height, int n_slots,
+                                         int search_mode, int full_pel_dfunc, int sub_pel_dfunc, int search_range) {
+  if (width <= 0 || height <= 0 || (width & 15) || (height & 15) || n_slots <= 0) return 0;
+  jsvm_ref_ctx* c = new jsvm_ref_ctx();
+  c->width = width; c->height = height; c->n_slots = n_slots;
+  c->mbw = width >> 4; c->mbh = height >> 4;
+
+  CHK(SequenceParameterSet::create(c->sps));
+  CHK(PictureParameterSet ::create(c->pps));
+  c->sps->setFrameWidthInMbs (c->mbw);
+  c->sps->setFrameHeightInMbs(c->mbh);
+  c->sps->setDirect8x8InferenceFlag(true);
+  c->pps->setNumRefIdxActive(LIST_0, 1);
+  c->pps->setNumRefIdxActive(LIST_1, 1);
+  c->pps->setConstrainedIntraPredFlag(true);
+  c->pps->setNumSliceGroupsMinus1(0);
+
+  CHK(YuvBufferCtrl::create(c->full_ctrl));
+  CHK(YuvBufferCtrl::create(c->half_ctrl));
+  CHK(c->full_ctrl->initSPS(height, width, YUV_Y_MARGIN, YUV_X_MARGIN));
+  CHK(c->half_ctrl->initSPS(height, width, YUV_Y_MARGIN, YUV_X_MARGIN, 1));
+
+  c->sh = new SliceHeader(*c->sps, *c->pps);
+  c->sh->setNalUnitType(NAL_UNIT_CODED_SLICE_SCALABLE);
+  c->sh->setFirstMbInSlice(0);
+  c->sh->setLastMbInSlice(c->mbw * c->mbh - 1);
+  c->sh->setNumMbsInSlice(c->mbw * c->mbh);
+  c->sh->setSliceType(P_SLICE);
+  c->sh->setDirectSpatialMvPredFlag(true);
+  c->sh->setNumRefIdxActive(LIST_0, 1);
+  c->sh->setNumRefIdxActive(LIST_1, 0);
+  CHK(c->sh->getPredWeightTable(LIST_1).initDefaults(c->sh->getLumaLog2WeightDenom(), c->sh->getChromaLog2WeightDenom()));
+  CHK(c->sh->getPredWeightTable(LIST_0).initDefaults(c->sh->getLumaLog2WeightDenom(), c->sh->getChromaLog2WeightDenom()));
+  c->sh->setSliceGroupChangeCycle(1);
+  c->sh->FMOInit();
+
+  c->mbctrl = new MbDataCtrl();
+  CHK(c->mbctrl->init(*c->sps));
+  CHK(c->mbctrl->initSlice(*c->sh, PRE_PROCESS, false, NULL));
+
+  CHK(QuarterPelFilter::create(c->filter));
+  CHK(Transform       ::create(c->transform));
+  CHK(SampleWeighting ::create(c->weighting));
+  CHK(XDistortion     ::create(c->dist));
+  c->rd = new FixedRateDistortion();
+  c->me = new ProbeME();
+  CHK(c->dist     ->init());
+  CHK(c->weighting->init());
+  CHK(c->filter   ->init());
+
+  c->cp = new CodingParameter();
+  MotionVectorSearchParams& p = c->cp->getMotionVectorSearchParams();
+  p.setSearchMode  (search_mode);
+  p.setFullPelDFunc(full_pel_dfunc);
+  p.setSubPelDFunc (sub_pel_dfunc);
+  p.setSearchRange (search_range);
+  CHK(c->me->init(c->dist, c->cp, c->rd, c->filter, c->transform, c->weighting));
+  CHK(c->me->initSlice(*c->sh));
+
+  for (int s = 0; s < n_slots; ++s) {
+    Frame* f = new Frame(*c->full_ctrl, *c->half_ctrl, FRAME, 0);
+    CHK(f->init());
+    CHK(f->initHalfPel());
+    c->frames.push_back(f);
+  }
+  return c;
+}
+
+extern "C" void jsvm_ref_destroy(jsvm_ref_ctx* c) {
+  if (!c) return;
+  for (size_t i = 0; i < c->frames.size(); ++i) {
+    c->frames[i]->uninitHalfPel();
+    c->frames[i]->uninit();
+    delete c->frames[i];
+  }
+  c->me->uninit();
+  delete c->me;
+  delete c->rd;
+  delete c->cp;
+  c->dist->destroy();
+  c->weighting->uninit(); c->weighting->destroy();
+  c->filter->uninit();    c->filter->destroy();
+  c->transform->destroy();
+  c->mbctrl->uninit(); delete c->mbctrl;
+  delete c->sh;
+  c->full_ctrl->uninit(); c->full_ctrl->destroy();
+  c->half_ctrl->uninit(); c->half_ctrl->destroy();
+  c->sps->destroy();
+  c->pps->destroy();
+  delete c;
+}
+
+extern "C" int jsvm_ref_set_plane_u8(jsvm_ref_ctx* c, int slot, const uint8_t* luma, int stride) {
+  if (!c || slot < 0 || slot >= c->n_slots) return -1;
+  Frame* f = c->frames[slot];
+  CHKI(c->full_ctrl->initMb());
+  CHKI(c->half_ctrl->initMb());
+  YuvPicBuffer* pb = f->getFullPelYuvBuffer();
+  XPel* y = pb->getMbLumAddr();
+  const int ls = pb->getLStride();
+  for (int r = 0; r < c->height; ++r)
+    for (int x = 0; x < c->width; ++x) y[r * ls + x] = luma[r * stride + x];
+  XPel* cb = pb->getMbCbAddr();
+  XPel* cr = pb->getMbCrAddr();
+  const int cs = pb->getCStride();
+  for (int r = 0; r < c->height / 2; ++r)
+    for (int x = 0; x < c->width / 2; ++x) { cb[r * cs + x] = 128; cr[r * cs + x] = 128; }
+  CHKI(f->extendFrame(c->filter));
+  return 0;
+}
+
+extern "C" int jsvm_ref_get_fullpel_u8(jsvm_ref_ctx* c, int slot, uint8_t* dst, int dst_stride) {
+  if (!c || slot < 0 || slot >= c->n_slots) return -1;
+  CHKI(c->full_ctrl->initMb());
+  YuvPicBuffer* pb = c->frames[slot]->getFullPelYuvBuffer();
+  const XPel* y = pb->getMbLumAddr();
+  const int ls = pb->getLStride();
+  const int m = pb->getLXMargin();
+  int bad = 0;
+  for (int r = -m; r < c->height + m; ++r)
+    for (int x = -m; x < c->width + m; ++x) {
+      int v = y[r * ls + x];
+      if (v < 0 || v > 255) ++bad;
+      dst[(r + m) * dst_stride + (x + m)] = (uint8_t)v;
+    }
+  return bad;
+}
+
+extern "C" int jsvm_ref_get_halfpel_u8(jsvm_ref_ctx* c, int slot, uint8_t* dst, int dst_stride) {
+  if (!c || slot < 0 || slot >= c->n_slots) return -1;
+  CHKI(c->half_ctrl->initMb());
+  YuvPicBuffer* pb = c->frames[slot]->getHalfPelYuvBuffer();
+  const XPel* y = pb->getMbLumAddr();
+  const int ls = pb->getLStride();
+  const int m = 2 * (JSVM_ME_MARGIN - 4);   // filterFrame writes x in [-56, 2(W+28)), y in [-56, 2(H+28))
+  int bad = 0;
+  for (int r = -m; r < 2 * c->height + m; ++r)
+    for (int x = -m; x < 2 * c->width + m; ++x) {
+      int v = y[r * ls + x];
+      if (v < 0 || v > 255) ++bad;
+      dst[(r + m) * dst_stride + (x + m)] = (uint8_t)v;
+    }
+  return bad;
+}
+
+extern "C" int jsvm_ref_search(jsvm_ref_ctx* c, const jsvm_me_job* jobs, int n_jobs,
+                               const int16_t* org_mbs, int n_org_mbs,
+                               jsvm_me_result* results, uint8_t* preds) {
+  if (!c) return -1;
+  YuvMbBuffer rec;
+  for (int i = 0; i < n_jobs; ++i) {
+    const jsvm_me_job& j = jobs[i];
+    if (j.cur_slot < 0 || j.cur_slot >= c->n_slots || j.ref_slot < 0 || j.ref_slot >= c->n_slots) return -1;
+    if (j.mb_x < 0 || j.mb_x >= (int)c->mbw || j.mb_y < 0 || j.mb_y >= (int)c->mbh) return -1;
+    if (j.org_index >= n_org_mbs) return -1;
+
+    MbDataAccess* mba = 0;
+    CHKI(c->mbctrl   ->initMb(mba, j.mb_y, j.mb_x));
+    CHKI(c->full_ctrl->initMb(j.mb_y, j.mb_x, false));
+    CHKI(c->half_ctrl->initMb(j.mb_y, j.mb_x, false));
+    CHKI(c->me       ->initMb(j.mb_y, j.mb_x, *mba));
+
+    YuvMbBuffer* org = 0;
+    c->dist->loadOrgMbPelData(c->frames[j.cur_slot]->getFullPelYuvBuffer(), org);
+    if (j.org_index >= 0) {
+      const int16_t* src = org_mbs + (size_t)j.org_index * 256;
+      XPel* d = org->getMbLumAddr();
+      for (int r = 0; r < 16; ++r)
+        for (int x = 0; x < 16; ++x) d[r * org->getLStride() + x] = src[r * 16 + x];
+    }
+
+    c->rd->m_uiFactor = j.cost_factor;
+    Mv   mv(j.start.hor, j.start.ver);
+    Mv   pred(j.pred.hor, j.pred.ver);
+    UInt bits = j.bits_in, cost = 0;
+    CHKI(c->me->estimateBlockWithStart(*mba, *c->frames[j.ref_slot], mv, pred, bits, cost,
+                                       j.blk, j.mode, (UInt)j.search_range, &c->pw, 0));
+    jsvm_me_result& r = results[i];
+    r.mv.hor = mv.getHor(); r.mv.ver = mv.getVer();
+    r.mv_fullpel.hor = c->me->m_cFullPelMv.getHor() >> 2;
+    r.mv_fullpel.ver = c->me->m_cFullPelMv.getVer() >> 2;
+    r.sad_fullpel = c->me->m_uiFullPelSad;
+    r.min_sad     = c->me->m_uiMinSad;
+    r.mv_bits     = bits - j.bits_in;
+    r.bits        = bits;
+    r.cost        = cost;
+    r.best_mode   = c->me->bestMode();
+
+    if (preds) {
+      CHKI(c->me->compensateBlock(&rec, j.blk, j.mode, NULL));
+      rec.set4x4Block(B4x4Idx(j.blk));
+      const XPel* p = rec.getLumBlk();
+      const int w = c->dist->getBlockWidth(j.mode), h = c->dist->getBlockHeight(j.mode);
+      uint8_t* dp = preds + (size_t)i * 256;
+      memset(dp, 0, 256);
+      for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) dp[y * 16 + x] = (uint8_t)p[y * rec.getLStride() + x];
+    }
+  }
+  return 0;
+}
+
+extern "C" uint32_t jsvm_ref_cost_factor(double lambda, int sad) {
+  RateDistortion* rd = 0;
+  if (RateDistortion::create(rd) != Err::m_nOK) return 0;
+  // setMbQpLambda also stores the QP in the MbData of the access object, so give it a real one
+  // (1x1-MB picture).  Inner scope: SliceHeader / MbDataCtrl must die before the parameter sets.
+  SequenceParameterSet* sps = 0; PictureParameterSet* pps = 0;
+  SequenceParameterSet::create(sps); PictureParameterSet::create(pps);
+  sps->setFrameWidthInMbs(1); sps->setFrameHeightInMbs(1);
+  pps->setNumSliceGroupsMinus1(0);
+  uint32_t f = 0;
+  {
+    SliceHeader sh(*sps, *pps);
+    sh.setFirstMbInSlice(0); sh.setLastMbInSlice(0); sh.setNumMbsInSlice(1); sh.setSliceType(P_SLICE);
+    sh.setSliceGroupChangeCycle(1);
+    sh.FMOInit();
+    MbDataCtrl ctrl;
+    ctrl.init(*sps);
+    ctrl.initSlice(sh, PRE_PROCESS, false, NULL);
+    MbDataAccess* mba = 0;
+    ctrl.initMb(mba, 0, 0);
+    rd->setMbQpLambda(*mba, 30, lambda);
+    f = rd->getMotionCostShift(sad != 0);
+    ctrl.uninit();
+  }
+  rd->destroy();
+  sps->destroy(); pps->destroy();
+  return f;
+}
+
+extern "C" uint32_t jsvm_ref_distortion(const int16_t* org16x16, const int16_t* ref, int ref_stride, int mode, int dfunc, int blk) {
+  XDistortion* d = 0;
+  if (XDistortion::create(d) != Err::m_nOK) return 0xffffffffu;
+  d->init();
+  YuvMbBuffer* org = d->getYuvMbBuffer();
+  XPel* o = org->getMbLumAddr();
+  for (int r = 0; r < 16; ++r)
+    for (int x = 0; x < 16; ++x) o[r * org->getLStride() + x] = org16x16[r * 16 + x];
+  d->set4x4Block(B4x4Idx(blk));
+  XDistSearchStruct s;
+  d->getDistStruct(mode, (DFunc)dfunc, false, s);
+  s.pYSearch = const_cast<XPel*>(ref);
+  s.iYStride = ref_stride;
+  s.pUSearch = s.pVSearch = 0; s.iCStride = 0;
+  uint32_t v = s.Func(&s);
+  d->destroy();
+  return v;
+}
