@@ -100,6 +100,11 @@ int jsvm_me_create (jsvm_me_ctx** ctx, int device);
 int jsvm_me_destroy(jsvm_me_ctx* ctx);
 const char* jsvm_me_last_error(void);
 
+/* Picture geometry and frame store: YuvBufferCtrl::initSPS( height, width, YUV_Y_MARGIN, YUV_X_MARGIN [,1] )
+ * (ENC/ControlMngH264AVCEncoder.cpp:56-57) + allocation of n_slots Frames (full-pel and half-pel buffers).
+ * width and height must be multiples of 16.  One ctx serves one resolution (one spatial layer). */
+int jsvm_me_configure(jsvm_me_ctx* ctx, int width, int height, int n_slots);
+
 /* MotionEstimation::init reading MotionVectorSearchParams (ENC/MotionEstimation.cpp:38-66,
  * include/CodingParameter.h:41-89).  Only SearchMode 0 (BLOCK_SEARCH), full-pel DF_SAD and
  * sub-pel DF_SAD / DF_HADAMARD are on the hot path; anything else returns JSVM_ME_ERR. */
@@ -125,6 +130,8 @@ int jsvm_me_set_plane_device_u8(jsvm_me_ctx* ctx, int slot, const uint8_t* dev, 
 /* QuarterPelFilter::filterFrame( full, half ) (COM/QuarterPelFilter.cpp:61-149): builds the half-pel
  * plane of the slot; it stays on the device (its only consumer is ME). */
 int jsvm_me_interp_halfpel(jsvm_me_ctx* ctx, int slot);
+/* The same for several slots in ONE kernel launch (grid.z = slot), e.g. all reference pictures of a temporal level. */
+int jsvm_me_interp_halfpel_batch(jsvm_me_ctx* ctx, const int* slots, int n_slots);
 /* Copy the half-pel plane back in YuvPicBuffer layout: `origin` = sample (0,0) of the half-pel buffer
  * (stride 2*(width+64)); the region the reference writes, x in [-56, 2(W+28)), y in [-56, 2(H+28)), is stored. */
 int jsvm_me_download_halfpel_xpel(jsvm_me_ctx* ctx, int slot, int16_t* origin, int stride);
@@ -140,14 +147,21 @@ int jsvm_me_search(jsvm_me_ctx* ctx, const jsvm_me_job* jobs, int n_jobs,
                    jsvm_me_result* results, uint8_t* preds);
 
 /* Same, everything already in device memory, asynchronous on the ctx stream (no sync).
- * `groups`/`n_groups` come from jsvm_me_plan (host) copied to the device by the caller. */
-typedef struct jsvm_me_group jsvm_me_group;   /* opaque 64-byte records */
-size_t jsvm_me_group_size(void);
-/* Host-side planner: fuses neighbouring jobs of one macroblock into search groups.  groups_out must
- * hold n_jobs records; returns the number of groups in *n_groups. */
-int jsvm_me_plan(jsvm_me_ctx* ctx, const jsvm_me_job* jobs, int n_jobs, void* groups_out, int* n_groups);
+ * The search groups come from the host-side planner jsvm_me_plan: it fuses neighbouring jobs of one
+ * macroblock (same cur/ref slot, MB position and original) into one group that is evaluated from a
+ * single SAD pass; the caller copies the records to the device. */
+typedef struct jsvm_me_plan_info {
+  int32_t n_groups;          /* records written to groups_out */
+  int32_t n_groups_8x8;      /* the first n_groups_8x8 records need only 8x8-granular SADs (9-partition set) */
+  int32_t max_uh_8x8;        /* tallest union window among those / among the 4x4-granular groups (sizes shared memory) */
+  int32_t max_uh_4x4;
+  int64_t n_positions;       /* sum over jobs of the clipped window size (ALG_OPS accounting) */
+  int64_t n_group_positions; /* sum over groups of the union window size (positions actually evaluated) */
+} jsvm_me_plan_info;
+size_t jsvm_me_group_size(void);    /* bytes per group record */
+int jsvm_me_plan(jsvm_me_ctx* ctx, const jsvm_me_job* jobs, int n_jobs, void* groups_out, jsvm_me_plan_info* info);
 int jsvm_me_search_device(jsvm_me_ctx* ctx, const jsvm_me_job* d_jobs, int n_jobs,
-                          const void* d_groups, int n_groups,
+                          const void* d_groups, const jsvm_me_plan_info* info,
                           const int16_t* d_org_mbs, int n_org_mbs,
                           jsvm_me_result* d_results, uint8_t* d_preds);
 

@@ -1,0 +1,548 @@
+// jsvm_me_capi.cu -- the C ABI (include/jsvm_me_b200.h) over the sm_100a kernels K1 / K2 / K3.
+//
+// Host-side state mirrors what the reference keeps in its objects:
+//   * the frame store (full-pel + half-pel YuvPicBuffers of each Frame)      -> device plane pools
+//   * MotionVectorSearchParams (search range, sub-pel DFunc)                  -> jsvm_me_set_params
+//   * the buffers MotionEstimationQuarterPel keeps for compensateBlock       -> last-call preds
+// There is no CPU implementation behind any compute entry point: without a usable sm_100 device
+// jsvm_me_create fails and everything else refuses to run.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/jsvm_me_b200.h"
+#include "me_common.cuh"
+#include "k1_halfpel.cuh"
+#include "k2_fullsearch.cuh"
+#include "k3_subpel.cuh"
+
+using namespace jsvm;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return JSVM_ME_ERR;
+}
+
+#define CU_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+  return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+constexpr int kV8 = 8;        // strip height of the 8x8-granular search kernel
+constexpr int kV4 = 4;        // strip height of the 4x4-granular search kernel
+constexpr int kMaxUH = 176;   // tallest union window one CTA handles (by-table rows, shared memory)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr; size_t cap = 0;
+  int reserve(size_t n) {
+    if (n <= cap) return JSVM_ME_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = std::max(n, (size_t)1024);
+    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if (e != cudaSuccess) return fail("cudaMalloc(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(e));
+    cap = want;
+    return JSVM_ME_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct jsvm_me_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 0;
+  // geometry
+  int W = 0, H = 0, n_slots = 0;
+  int plane_stride = 0, plane_rows = 0; size_t plane_bytes = 0;
+  int half_stride = 0, half_rows = 0;   size_t half_bytes = 0;
+  uint8_t* d_planes = nullptr;
+  uint8_t* d_half = nullptr;
+  int* d_slot_ids = nullptr;            // scratch list of slots for batched launches (n_slots entries)
+  std::vector<char> slot_full, slot_half;
+  CUtensorMap map_k1{};
+  EncodeTiledFn encode = nullptr;
+  // params
+  int search_range = 0, sub_dfunc = JSVM_DF_SAD;
+  bool params_set = false;
+  // per-call device buffers (host-buffer API)
+  DevBuf<jsvm_me_job> d_jobs;
+  DevBuf<Group> d_groups;
+  DevBuf<uint32_t> d_keys;
+  DevBuf<JobAux> d_aux;
+  DevBuf<jsvm_me_result> d_results;
+  DevBuf<uint8_t> d_preds;
+  DevBuf<int16_t> d_org;
+  DevBuf<uint8_t> d_stage;              // staging for plane uploads
+  int* d_bad = nullptr;
+  std::vector<Group> h_groups;
+  // state of the last host-API search (compensateBlock contract)
+  std::vector<jsvm_me_job> last_jobs;
+  bool last_has_preds = false;
+  // measurement
+  uint64_t launches = 0;
+  bool timing = false;
+  struct Timed { cudaEvent_t e0, e1; int kind; };
+  std::vector<Timed> timed;
+};
+
+namespace {
+
+int make_map(jsvm_me_ctx* c, CUtensorMap* map, void* base, int box_w, int box_h) {
+  const cuuint64_t dims[3]    = { (cuuint64_t)c->plane_stride, (cuuint64_t)c->plane_rows, (cuuint64_t)c->n_slots };
+  const cuuint64_t strides[2] = { (cuuint64_t)c->plane_stride, (cuuint64_t)c->plane_bytes };   // bytes, dims 1 and 2
+  const cuuint32_t box[3]     = { (cuuint32_t)box_w, (cuuint32_t)box_h, 1 };
+  const cuuint32_t estr[3]    = { 1, 1, 1 };
+  CUresult r = c->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return JSVM_ME_OK;
+}
+
+void begin_timed(jsvm_me_ctx* c, int kind) {
+  if (!c->timing) return;
+  jsvm_me_ctx::Timed t; t.kind = kind;
+  cudaEventCreate(&t.e0); cudaEventCreate(&t.e1);
+  cudaEventRecord(t.e0, c->stream);
+  c->timed.push_back(t);
+}
+void end_timed(jsvm_me_ctx* c) {
+  if (!c->timing) return;
+  cudaEventRecord(c->timed.back().e1, c->stream);
+}
+
+int check_slot(jsvm_me_ctx* c, int slot) {
+  if (!c) return fail("null context");
+  if (!c->d_planes) return fail("jsvm_me_configure has not been called");
+  if (slot < 0 || slot >= c->n_slots) return fail("slot %d out of range [0,%d)", slot, c->n_slots);
+  return JSVM_ME_OK;
+}
+
+int launch_margin_fill(jsvm_me_ctx* c, const int* d_slots, int n) {
+  dim3 grid(2, c->plane_rows, n), block(256);
+  margin_fill_kernel<<<grid, block, 0, c->stream>>>(c->d_planes, c->plane_bytes, c->plane_stride, d_slots, c->W, c->H);
+  c->launches++;
+  CU_OK(cudaGetLastError());
+  return JSVM_ME_OK;
+}
+
+// The planner: restates nothing from the reference -- it only decides which estimateBlockWithStart
+// calls can share one SAD pass (same macroblock, planes and original; distinct partition slots;
+// union of the clipped windows small enough for one CTA).
+int plan_jobs(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, std::vector<Group>& out, jsvm_me_plan_info* info) {
+  const int mbw = c->W >> 4, mbh = c->H >> 4;
+  std::vector<Group> g8, g4;
+  Group cur; bool open = false; Window cw{};
+  int64_t npos = 0;
+  auto close = [&]() {
+    if (!open) return;
+    cur.ux0 = (int16_t)cw.xlo; cur.uy0 = (int16_t)cw.ylo;
+    cur.uw = (int16_t)(cw.xhi - cw.xlo + 1); cur.uh = (int16_t)(cw.yhi - cw.ylo + 1);
+    (cur.gran4 ? g4 : g8).push_back(cur);
+    open = false;
+  };
+  for (int i = 0; i < n_jobs; ++i) {
+    const jsvm_me_job& j = jobs[i];
+    int w, h;
+    if (!mode_size(j.mode, w, h)) return fail("job %d: unsupported mode %d", i, (int)j.mode);
+    if (j.blk > 15) return fail("job %d: blk %d out of range", i, (int)j.blk);
+    const int slot = partition_slot(j.mode, j.blk);
+    if (slot < 0) return fail("job %d: blk %d is not a legal origin for mode %d", i, (int)j.blk, (int)j.mode);
+    if (j.cur_slot < 0 || j.cur_slot >= c->n_slots || j.ref_slot < 0 || j.ref_slot >= c->n_slots)
+      return fail("job %d: plane slot out of range", i);
+    if (j.mb_x < 0 || j.mb_x >= mbw || j.mb_y < 0 || j.mb_y >= mbh) return fail("job %d: macroblock (%d,%d) outside the picture", i, j.mb_x, j.mb_y);
+    const Window w1 = job_window(j, mbw, mbh, c->search_range);
+    const int ww = w1.xhi - w1.xlo + 1, wh = w1.yhi - w1.ylo + 1;
+    if (ww < 1 || wh < 1) return fail("job %d: empty search window", i);
+    if (ww > kMaxUW || wh > kMaxUH || ww * wh > (1 << kIdxBits))
+      return fail("job %d: search window %dx%d exceeds the %dx%d limit of this build (search range <= 64)", i, ww, wh, kMaxUW, kMaxUH);
+    npos += (int64_t)ww * wh;
+    bool join = open && (i - cur.first_job) < 127 &&
+                j.cur_slot == cur.cur_slot && j.ref_slot == cur.ref_slot && j.mb_x == cur.mb_x && j.mb_y == cur.mb_y &&
+                j.org_index == cur.org_index && cur.slot_job[slot] < 0;
+    if (join) {
+      Window u = cw;
+      u.xlo = std::min(u.xlo, w1.xlo); u.xhi = std::max(u.xhi, w1.xhi);
+      u.ylo = std::min(u.ylo, w1.ylo); u.yhi = std::max(u.yhi, w1.yhi);
+      const int uw = u.xhi - u.xlo + 1, uh = u.yhi - u.ylo + 1;
+      if (uw > kMaxUW || uh > kMaxUH || uw * uh > (1 << kIdxBits)) join = false;
+      else cw = u;
+    }
+    if (!join) {
+      close();
+      memset(&cur, 0, sizeof(cur));
+      cur.first_job = i; cur.n_jobs = 0; cur.gran4 = 0;
+      cur.cur_slot = j.cur_slot; cur.ref_slot = j.ref_slot; cur.mb_x = j.mb_x; cur.mb_y = j.mb_y; cur.org_index = j.org_index;
+      memset(cur.slot_job, -1, sizeof(cur.slot_job));
+      cw = w1; open = true;
+    }
+    cur.slot_job[slot] = (int8_t)(i - cur.first_job);
+    cur.n_jobs = (int16_t)(i - cur.first_job + 1);
+    if (slot >= kSlotsGran8) cur.gran4 = 1;
+  }
+  close();
+  out.clear();
+  out.insert(out.end(), g8.begin(), g8.end());
+  out.insert(out.end(), g4.begin(), g4.end());
+  info->n_groups = (int32_t)out.size();
+  info->n_groups_8x8 = (int32_t)g8.size();
+  info->max_uh_8x8 = 0; info->max_uh_4x4 = 0;
+  info->n_positions = npos; info->n_group_positions = 0;
+  for (const Group& g : g8) { info->max_uh_8x8 = std::max<int>(info->max_uh_8x8, g.uh); info->n_group_positions += (int64_t)g.uw * g.uh; }
+  for (const Group& g : g4) { info->max_uh_4x4 = std::max<int>(info->max_uh_4x4, g.uh); info->n_group_positions += (int64_t)g.uw * g.uh; }
+  return JSVM_ME_OK;
+}
+
+template <int V, bool GRAN4>
+int launch_search(jsvm_me_ctx* c, const Group* d_groups, int first_group, int n_groups, int max_uh,
+                  const jsvm_me_job* d_jobs, const int16_t* d_org, uint32_t* d_keys, JobAux* d_aux) {
+  if (n_groups <= 0) return JSVM_ME_OK;
+  const size_t smem = k2_smem_bytes<V, GRAN4>(max_uh);
+  static size_t configured = 0;
+  if (smem > configured) {
+    CU_OK(cudaFuncSetAttribute(full_search_kernel<V, GRAN4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  begin_timed(c, 1);
+  full_search_kernel<V, GRAN4><<<n_groups, kK2Threads, smem, c->stream>>>(
+      c->d_planes, c->plane_bytes, c->plane_stride, d_groups + first_group, d_jobs, d_org,
+      c->W >> 4, c->H >> 4, c->search_range, d_keys, d_aux);
+  end_timed(c);
+  c->launches++;
+  CU_OK(cudaGetLastError());
+  return JSVM_ME_OK;
+}
+
+int run_search(jsvm_me_ctx* c, const jsvm_me_job* d_jobs, int n_jobs, const Group* d_groups, const jsvm_me_plan_info* info,
+               const int16_t* d_org, uint32_t* d_keys, JobAux* d_aux, jsvm_me_result* d_results, uint8_t* d_preds) {
+  if (!c->params_set) return fail("jsvm_me_set_params has not been called");
+  if (info->max_uh_8x8 > kMaxUH || info->max_uh_4x4 > kMaxUH) return fail("plan: union window taller than %d", kMaxUH);
+  if (launch_search<kV8, false>(c, d_groups, 0, info->n_groups_8x8, info->max_uh_8x8, d_jobs, d_org, d_keys, d_aux)) return JSVM_ME_ERR;
+  if (launch_search<kV4, true>(c, d_groups, info->n_groups_8x8, info->n_groups - info->n_groups_8x8, info->max_uh_4x4, d_jobs, d_org, d_keys, d_aux)) return JSVM_ME_ERR;
+  begin_timed(c, 2);
+  const int ctas = (n_jobs + kK3WarpsPerCta - 1) / kK3WarpsPerCta;
+  subpel_kernel<<<ctas, 32 * kK3WarpsPerCta, 0, c->stream>>>(
+      c->d_planes, c->plane_bytes, c->plane_stride, c->d_half, c->half_bytes, c->half_stride,
+      d_jobs, d_aux, n_jobs, d_org, d_keys, c->sub_dfunc, d_results, d_preds);
+  end_timed(c);
+  c->launches++;
+  CU_OK(cudaGetLastError());
+  return JSVM_ME_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* jsvm_me_last_error(void) { return g_err; }
+
+int jsvm_me_create(jsvm_me_ctx** out, int device) {
+  if (!out) return fail("null output pointer");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail("no CUDA device available (%s); this library has no CPU path", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail("device %d out of range [0,%d)", device, n);
+  cudaDeviceProp p;
+  CU_OK(cudaGetDeviceProperties(&p, device));
+  if (p.major != 10) return fail("device %d is sm_%d%d; the kernels are built for sm_100a only", device, p.major, p.minor);
+  CU_OK(cudaSetDevice(device));
+  jsvm_me_ctx* c = new jsvm_me_ctx();
+  c->device = device;
+  c->sm_count = p.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || !fn) { delete c; return fail("cuTensorMapEncodeTiled not available from the driver"); }
+  c->encode = (EncodeTiledFn)fn;
+  if (cudaMalloc((void**)&c->d_bad, sizeof(int)) != cudaSuccess) { delete c; return fail("cudaMalloc failed"); }
+  *out = c;
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_destroy(jsvm_me_ctx* c) {
+  if (!c) return JSVM_ME_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->d_planes) cudaFree(c->d_planes);
+  if (c->d_half) cudaFree(c->d_half);
+  if (c->d_slot_ids) cudaFree(c->d_slot_ids);
+  if (c->d_bad) cudaFree(c->d_bad);
+  c->d_jobs.release(); c->d_groups.release(); c->d_keys.release(); c->d_aux.release();
+  c->d_results.release(); c->d_preds.release(); c->d_org.release(); c->d_stage.release();
+  for (auto& t : c->timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+  delete c;
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_configure(jsvm_me_ctx* c, int width, int height, int n_slots) {
+  if (!c) return fail("null context");
+  if (width <= 0 || height <= 0 || (width & 15) || (height & 15)) return fail("picture size %dx%d must be a positive multiple of 16", width, height);
+  if (n_slots <= 0 || n_slots > 32767) return fail("n_slots %d out of range", n_slots);
+  CU_OK(cudaSetDevice(c->device));
+  CU_OK(cudaStreamSynchronize(c->stream));
+  if (c->d_planes) { cudaFree(c->d_planes); c->d_planes = nullptr; }
+  if (c->d_half) { cudaFree(c->d_half); c->d_half = nullptr; }
+  if (c->d_slot_ids) { cudaFree(c->d_slot_ids); c->d_slot_ids = nullptr; }
+  c->W = width; c->H = height; c->n_slots = n_slots;
+  c->plane_stride = width + 2 * kMargin; c->plane_rows = height + 2 * kMargin;
+  c->plane_bytes = (size_t)c->plane_stride * c->plane_rows;
+  c->half_stride = 2 * c->plane_stride; c->half_rows = 2 * c->plane_rows;
+  c->half_bytes = (size_t)c->half_stride * c->half_rows;
+  CU_OK(cudaMalloc((void**)&c->d_planes, c->plane_bytes * n_slots + 256));
+  CU_OK(cudaMalloc((void**)&c->d_half, c->half_bytes * n_slots));
+  CU_OK(cudaMalloc((void**)&c->d_slot_ids, sizeof(int) * n_slots));
+  CU_OK(cudaMemsetAsync(c->d_planes, 0, c->plane_bytes * n_slots + 256, c->stream));
+  CU_OK(cudaMemsetAsync(c->d_half, 0, c->half_bytes * n_slots, c->stream));     // samples outside the written region stay 0 (reference: memset at allocation)
+  c->slot_full.assign(n_slots, 0); c->slot_half.assign(n_slots, 0);
+  if (make_map(c, &c->map_k1, c->d_planes, kK1BoxW, kK1BoxH)) return JSVM_ME_ERR;
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_set_params(jsvm_me_ctx* c, int search_mode, int full_pel_dfunc, int sub_pel_dfunc, int search_range) {
+  if (!c) return fail("null context");
+  if (search_mode != JSVM_SEARCH_BLOCK) return fail("SearchMode %d: only BLOCK_SEARCH (0, full search) is implemented", search_mode);
+  if (full_pel_dfunc != JSVM_DF_SAD) return fail("SearchFuncFullPel %d: only SAD (0) is implemented", full_pel_dfunc);
+  if (sub_pel_dfunc != JSVM_DF_SAD && sub_pel_dfunc != JSVM_DF_HADAMARD) return fail("SearchFuncSubPel %d: only SAD (0) and HADAMARD (2) are implemented", sub_pel_dfunc);
+  if (search_range < 1 || search_range > 64) return fail("SearchRange %d outside [1,64]", search_range);
+  c->search_range = search_range; c->sub_dfunc = sub_pel_dfunc; c->params_set = true;
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_set_stream(jsvm_me_ctx* c, void* s) {
+  if (!c) return fail("null context");
+  c->stream = (cudaStream_t)s;
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_upload_plane_xpel(jsvm_me_ctx* c, int slot, const int16_t* origin, int width, int height, int stride) {
+  if (check_slot(c, slot)) return JSVM_ME_ERR;
+  if (!origin) return fail("null plane");
+  if (width != c->W || height != c->H) return fail("plane is %dx%d but the context is configured for %dx%d", width, height, c->W, c->H);
+  if (stride < c->plane_stride) return fail("stride %d smaller than width + 64", stride);
+  CU_OK(cudaSetDevice(c->device));
+  const size_t n16 = (size_t)c->plane_stride * c->plane_rows;
+  if (c->d_stage.reserve(n16 * 2)) return JSVM_ME_ERR;
+  const int16_t* top = origin - (ptrdiff_t)kMargin * stride - kMargin;
+  CU_OK(cudaMemcpy2DAsync(c->d_stage.p, (size_t)c->plane_stride * 2, top, (size_t)stride * 2, (size_t)c->plane_stride * 2, c->plane_rows, cudaMemcpyHostToDevice, c->stream));
+  CU_OK(cudaMemsetAsync(c->d_bad, 0, sizeof(int), c->stream));
+  dim3 grid((c->plane_stride + 255) / 256, c->plane_rows), block(256);
+  xpel_to_u8_kernel<<<grid, block, 0, c->stream>>>((const int16_t*)c->d_stage.p, c->plane_stride, c->d_planes + (size_t)slot * c->plane_bytes, c->plane_stride, c->plane_stride, c->plane_rows, c->d_bad);
+  c->launches++;
+  CU_OK(cudaGetLastError());
+  int bad = 0;
+  CU_OK(cudaMemcpyAsync(&bad, c->d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU_OK(cudaStreamSynchronize(c->stream));
+  if (bad) return fail("plane holds %d samples outside [0,255]; the 8-bit search path cannot represent them", bad);
+  c->slot_full[slot] = 1; c->slot_half[slot] = 0;
+  return JSVM_ME_OK;
+}
+
+static int set_plane_u8(jsvm_me_ctx* c, int slot, const uint8_t* src, int width, int height, int stride, cudaMemcpyKind kind) {
+  if (check_slot(c, slot)) return JSVM_ME_ERR;
+  if (!src) return fail("null plane");
+  if (width != c->W || height != c->H) return fail("plane is %dx%d but the context is configured for %dx%d", width, height, c->W, c->H);
+  if (stride < width) return fail("stride %d smaller than width", stride);
+  CU_OK(cudaSetDevice(c->device));
+  uint8_t* dst = c->d_planes + (size_t)slot * c->plane_bytes + (size_t)kMargin * c->plane_stride + kMargin;
+  CU_OK(cudaMemcpy2DAsync(dst, c->plane_stride, src, stride, width, height, kind, c->stream));
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_upload_plane_u8(jsvm_me_ctx* c, int slot, const uint8_t* host, int width, int height, int stride) {
+  if (set_plane_u8(c, slot, host, width, height, stride, cudaMemcpyHostToDevice)) return JSVM_ME_ERR;
+  int s = slot;
+  CU_OK(cudaMemcpyAsync(c->d_slot_ids, &s, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  if (launch_margin_fill(c, c->d_slot_ids, 1)) return JSVM_ME_ERR;   // (pageable H2D copies are staged before the call returns)
+  c->slot_full[slot] = 1; c->slot_half[slot] = 0;
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_set_plane_device_u8(jsvm_me_ctx* c, int slot, const uint8_t* dev, int width, int height, int stride) {
+  if (set_plane_u8(c, slot, dev, width, height, stride, cudaMemcpyDeviceToDevice)) return JSVM_ME_ERR;
+  int s = slot;
+  CU_OK(cudaMemcpyAsync(c->d_slot_ids, &s, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  if (launch_margin_fill(c, c->d_slot_ids, 1)) return JSVM_ME_ERR;
+  c->slot_full[slot] = 1; c->slot_half[slot] = 0;
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_interp_halfpel_batch(jsvm_me_ctx* c, const int* slots, int n) {
+  if (!c) return fail("null context");
+  if (n <= 0) return JSVM_ME_OK;
+  if (n > c->n_slots) return fail("batch of %d slots exceeds n_slots %d", n, c->n_slots);
+  for (int i = 0; i < n; ++i) {
+    if (check_slot(c, slots[i])) return JSVM_ME_ERR;
+    if (!c->slot_full[slots[i]]) return fail("slot %d holds no full-pel plane", slots[i]);
+  }
+  CU_OK(cudaSetDevice(c->device));
+  CU_OK(cudaMemcpyAsync(c->d_slot_ids, slots, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+  dim3 grid((c->W + 2 * kMargin + kK1TileX - 1) / kK1TileX, (c->H + 2 * (kMargin - 4) + kK1TileY - 1) / kK1TileY, n);
+  begin_timed(c, 0);
+  halfpel_kernel<<<grid, kK1Threads, 0, c->stream>>>(c->map_k1, c->d_half, c->half_bytes, c->half_stride, c->d_slot_ids, c->W, c->H);
+  end_timed(c);
+  c->launches++;
+  CU_OK(cudaGetLastError());
+  for (int i = 0; i < n; ++i) c->slot_half[slots[i]] = 1;
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_interp_halfpel(jsvm_me_ctx* c, int slot) { return jsvm_me_interp_halfpel_batch(c, &slot, 1); }
+
+int jsvm_me_download_halfpel_u8(jsvm_me_ctx* c, int slot, uint8_t* dst, int dst_stride) {
+  if (check_slot(c, slot)) return JSVM_ME_ERR;
+  if (!c->slot_half[slot]) return fail("slot %d holds no half-pel plane", slot);
+  const int m = 2 * (kMargin - 4);
+  const int rows = 2 * c->H + 2 * m, cols = 2 * c->W + 2 * m;
+  if (dst_stride < cols) return fail("dst_stride %d smaller than %d", dst_stride, cols);
+  CU_OK(cudaSetDevice(c->device));
+  const uint8_t* src = c->d_half + (size_t)slot * c->half_bytes + (size_t)(kHpOrigin - m) * c->half_stride + (kHpOrigin - m);
+  CU_OK(cudaMemcpy2DAsync(dst, dst_stride, src, c->half_stride, cols, rows, cudaMemcpyDeviceToHost, c->stream));
+  CU_OK(cudaStreamSynchronize(c->stream));
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_download_halfpel_xpel(jsvm_me_ctx* c, int slot, int16_t* origin, int stride) {
+  if (check_slot(c, slot)) return JSVM_ME_ERR;
+  if (!c->slot_half[slot]) return fail("slot %d holds no half-pel plane", slot);
+  const int m = 2 * (kMargin - 4);
+  const int rows = 2 * c->H + 2 * m, cols = 2 * c->W + 2 * m;
+  if (stride < cols) return fail("stride %d smaller than %d", stride, cols);
+  CU_OK(cudaSetDevice(c->device));
+  if (c->d_stage.reserve((size_t)rows * cols * 2)) return JSVM_ME_ERR;
+  const uint8_t* src = c->d_half + (size_t)slot * c->half_bytes + (size_t)(kHpOrigin - m) * c->half_stride + (kHpOrigin - m);
+  dim3 grid((cols + 255) / 256, rows), block(256);
+  u8_to_xpel_kernel<<<grid, block, 0, c->stream>>>(src, c->half_stride, (int16_t*)c->d_stage.p, cols, cols, rows);
+  c->launches++;
+  CU_OK(cudaGetLastError());
+  CU_OK(cudaMemcpy2DAsync(origin - (ptrdiff_t)m * stride - m, (size_t)stride * 2, c->d_stage.p, (size_t)cols * 2, (size_t)cols * 2, rows, cudaMemcpyDeviceToHost, c->stream));
+  CU_OK(cudaStreamSynchronize(c->stream));
+  return JSVM_ME_OK;
+}
+
+size_t jsvm_me_group_size(void) { return sizeof(Group); }
+
+int jsvm_me_plan(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, void* groups_out, jsvm_me_plan_info* info) {
+  if (!c || !jobs || !groups_out || !info) return fail("null argument");
+  if (!c->d_planes) return fail("jsvm_me_configure has not been called");
+  if (!c->params_set) return fail("jsvm_me_set_params has not been called");
+  std::vector<Group> g;
+  if (plan_jobs(c, jobs, n_jobs, g, info)) return JSVM_ME_ERR;
+  memcpy(groups_out, g.data(), g.size() * sizeof(Group));
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_search_device(jsvm_me_ctx* c, const jsvm_me_job* d_jobs, int n_jobs, const void* d_groups, const jsvm_me_plan_info* info,
+                          const int16_t* d_org_mbs, int n_org_mbs, jsvm_me_result* d_results, uint8_t* d_preds) {
+  (void)n_org_mbs;
+  if (!c || !d_jobs || !d_groups || !info || !d_results) return fail("null argument");
+  if (n_jobs <= 0) return JSVM_ME_OK;
+  CU_OK(cudaSetDevice(c->device));
+  if (c->d_keys.reserve(n_jobs) || c->d_aux.reserve(n_jobs)) return JSVM_ME_ERR;
+  return run_search(c, d_jobs, n_jobs, (const Group*)d_groups, info, d_org_mbs, c->d_keys.p, c->d_aux.p, d_results, d_preds);
+}
+
+int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const int16_t* org_mbs, int n_org_mbs,
+                   jsvm_me_result* results, uint8_t* preds) {
+  if (!c || !jobs || !results) return fail("null argument");
+  if (!c->d_planes) return fail("jsvm_me_configure has not been called");
+  if (!c->params_set) return fail("jsvm_me_set_params has not been called");
+  if (n_jobs <= 0) return JSVM_ME_OK;
+  for (int i = 0; i < n_jobs; ++i) {
+    if (jobs[i].org_index >= n_org_mbs) return fail("job %d: org_index %d >= n_org_mbs %d", i, jobs[i].org_index, n_org_mbs);
+    if (jobs[i].cur_slot >= 0 && jobs[i].cur_slot < c->n_slots && jobs[i].org_index < 0 && !c->slot_full[jobs[i].cur_slot]) return fail("job %d: cur_slot %d is empty", i, jobs[i].cur_slot);
+    if (jobs[i].ref_slot >= 0 && jobs[i].ref_slot < c->n_slots && !c->slot_half[jobs[i].ref_slot]) return fail("job %d: ref_slot %d has no half-pel plane", i, jobs[i].ref_slot);
+  }
+  if (n_org_mbs > 0) {
+    if (!org_mbs) return fail("org_mbs is null");
+    for (size_t i = 0; i < (size_t)n_org_mbs * 256; ++i)
+      if (org_mbs[i] < 0 || org_mbs[i] > 255)
+        return fail("org_mbs sample %zu = %d outside [0,255]: the signed 16-bit (residual-prediction) search variant is not implemented", i, (int)org_mbs[i]);
+  }
+  CU_OK(cudaSetDevice(c->device));
+  jsvm_me_plan_info info;
+  if (plan_jobs(c, jobs, n_jobs, c->h_groups, &info)) return JSVM_ME_ERR;
+  const bool want_preds = preds != nullptr || n_jobs <= 4096;
+  if (c->d_jobs.reserve(n_jobs) || c->d_groups.reserve(c->h_groups.size()) || c->d_keys.reserve(n_jobs) || c->d_aux.reserve(n_jobs) ||
+      c->d_results.reserve(n_jobs) || (want_preds && c->d_preds.reserve((size_t)n_jobs * 256)) ||
+      (n_org_mbs > 0 && c->d_org.reserve((size_t)n_org_mbs * 256))) return JSVM_ME_ERR;
+  CU_OK(cudaMemcpyAsync(c->d_jobs.p, jobs, sizeof(jsvm_me_job) * n_jobs, cudaMemcpyHostToDevice, c->stream));
+  CU_OK(cudaMemcpyAsync(c->d_groups.p, c->h_groups.data(), sizeof(Group) * c->h_groups.size(), cudaMemcpyHostToDevice, c->stream));
+  if (n_org_mbs > 0) CU_OK(cudaMemcpyAsync(c->d_org.p, org_mbs, sizeof(int16_t) * 256 * n_org_mbs, cudaMemcpyHostToDevice, c->stream));
+  if (run_search(c, c->d_jobs.p, n_jobs, c->d_groups.p, &info, c->d_org.p, c->d_keys.p, c->d_aux.p, c->d_results.p, want_preds ? c->d_preds.p : nullptr)) return JSVM_ME_ERR;
+  CU_OK(cudaMemcpyAsync(results, c->d_results.p, sizeof(jsvm_me_result) * n_jobs, cudaMemcpyDeviceToHost, c->stream));
+  if (preds) CU_OK(cudaMemcpyAsync(preds, c->d_preds.p, (size_t)n_jobs * 256, cudaMemcpyDeviceToHost, c->stream));
+  CU_OK(cudaStreamSynchronize(c->stream));
+  c->last_jobs.assign(jobs, jobs + n_jobs);
+  c->last_has_preds = want_preds;
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_fetch_pred(jsvm_me_ctx* c, int job_idx, int16_t* dst, int dst_stride) {
+  if (!c || !dst) return fail("null argument");
+  if (job_idx < 0 || job_idx >= (int)c->last_jobs.size()) return fail("job index %d is not part of the last jsvm_me_search call", job_idx);
+  if (!c->last_has_preds) return fail("the last jsvm_me_search call did not keep prediction blocks (more than 4096 jobs and preds == NULL)");
+  int w, h;
+  mode_size(c->last_jobs[job_idx].mode, w, h);
+  uint8_t blk[256];
+  CU_OK(cudaSetDevice(c->device));
+  CU_OK(cudaMemcpyAsync(blk, c->d_preds.p + (size_t)job_idx * 256, 256, cudaMemcpyDeviceToHost, c->stream));
+  CU_OK(cudaStreamSynchronize(c->stream));
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) dst[y * dst_stride + x] = blk[y * 16 + x];
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_sync(jsvm_me_ctx* c) {
+  if (!c) return fail("null context");
+  CU_OK(cudaSetDevice(c->device));
+  CU_OK(cudaStreamSynchronize(c->stream));
+  return JSVM_ME_OK;
+}
+
+uint64_t jsvm_me_launch_count(jsvm_me_ctx* c) { return c ? c->launches : 0; }
+
+int jsvm_me_timing_begin(jsvm_me_ctx* c) {
+  if (!c) return fail("null context");
+  for (auto& t : c->timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+  c->timed.clear();
+  c->timing = true;
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_timing_end(jsvm_me_ctx* c, double* ms_interp, double* ms_search, double* ms_subpel,
+                       uint64_t* n_interp, uint64_t* n_search, uint64_t* n_subpel) {
+  if (!c) return fail("null context");
+  CU_OK(cudaSetDevice(c->device));
+  CU_OK(cudaStreamSynchronize(c->stream));
+  double ms[3] = {0, 0, 0}; uint64_t n[3] = {0, 0, 0};
+  for (auto& t : c->timed) {
+    float f = 0;
+    CU_OK(cudaEventElapsedTime(&f, t.e0, t.e1));
+    ms[t.kind] += f; n[t.kind]++;
+    cudaEventDestroy(t.e0); cudaEventDestroy(t.e1);
+  }
+  c->timed.clear();
+  c->timing = false;
+  if (ms_interp) *ms_interp = ms[0]; if (ms_search) *ms_search = ms[1]; if (ms_subpel) *ms_subpel = ms[2];
+  if (n_interp) *n_interp = n[0]; if (n_search) *n_search = n[1]; if (n_subpel) *n_subpel = n[2];
+  return JSVM_ME_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,241 @@
+"""Host-side Python mirror of the reference's motion-search interface over the C ABI.
+
+Two layers:
+
+* ``MotionEstimator`` -- thin object wrapper over ``jsvm_me_*`` (bulk / batched use: bench, tests).
+* ``QuarterPelFilter`` / ``MotionEstimationQuarterPel`` -- the names, argument meaning and call order
+  of the reference classes (ENC/MotionEstimation.h:84-115, ENC/MotionEstimationQuarterPel.h,
+  INCC/QuarterPelFilter.h:24-35) so parity tests read like reference call sites:
+  ``initMb`` -> ``estimateBlockWithStart`` -> ``compensateBlock``.  Errors raise
+  ``MotionEstimationError`` where the reference returns ``Err::m_nERR``.
+
+The C++ drop-in that the unmodified H264AVCEncoderLib links against lives in ``dropin/`` and calls
+the same C ABI; nothing here or there computes motion search on the CPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .abi import JOB_DTYPE, RESULT_DTYPE, PlanInfo
+
+
+class MotionEstimationError(RuntimeError):
+    """A jsvm_me_* call returned Err::m_nERR."""
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class MotionEstimator:
+    """One device context = one picture resolution (one spatial layer) on one GPU."""
+
+    def __init__(self, device=0):
+        self._lib = abi.load_library()
+        self._ctx = C.c_void_p()
+        self._check(self._lib.jsvm_me_create(C.byref(self._ctx), int(device)))
+        self.width = self.height = self.n_slots = 0
+
+    def _check(self, rc):
+        if rc != 0:
+            raise MotionEstimationError(self._lib.jsvm_me_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._lib.jsvm_me_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- configuration -------------------------------------------------------------------
+    def configure(self, width, height, n_slots):
+        self._check(self._lib.jsvm_me_configure(self._ctx, width, height, n_slots))
+        self.width, self.height, self.n_slots = width, height, n_slots
+
+    def set_params(self, search_range, sub_pel_dfunc=abi.DF_SAD, full_pel_dfunc=abi.DF_SAD, search_mode=abi.SEARCH_BLOCK):
+        self._check(self._lib.jsvm_me_set_params(self._ctx, search_mode, full_pel_dfunc, sub_pel_dfunc, search_range))
+
+    def set_stream(self, cuda_stream):
+        self._check(self._lib.jsvm_me_set_stream(self._ctx, C.c_void_p(int(cuda_stream))))
+
+    # ---- planes --------------------------------------------------------------------------
+    def upload_plane(self, slot, luma):
+        """luma: (H, W) uint8 ndarray (no margins) -- or a raw host pointer via upload_plane_ptr."""
+        luma = np.ascontiguousarray(luma, dtype=np.uint8)
+        if luma.shape != (self.height, self.width):
+            raise MotionEstimationError(f"plane shape {luma.shape} != {(self.height, self.width)}")
+        self._check(self._lib.jsvm_me_upload_plane_u8(self._ctx, slot, _ptr(luma), self.width, self.height, self.width))
+
+    def upload_plane_ptr(self, slot, host_ptr, stride=None):
+        self._check(self._lib.jsvm_me_upload_plane_u8(self._ctx, slot, C.c_void_p(int(host_ptr)), self.width, self.height, stride or self.width))
+
+    def set_plane_device(self, slot, dev_ptr, stride=None):
+        self._check(self._lib.jsvm_me_set_plane_device_u8(self._ctx, slot, C.c_void_p(int(dev_ptr)), self.width, self.height, stride or self.width))
+
+    def upload_plane_xpel(self, slot, plane_with_margin):
+        """plane_with_margin: (H+64, W+64) int16 ndarray laid out like a YuvPicBuffer luma plane."""
+        p = np.ascontiguousarray(plane_with_margin, dtype=np.int16)
+        s = self.width + 2 * abi.MARGIN
+        if p.shape != (self.height + 2 * abi.MARGIN, s):
+            raise MotionEstimationError(f"plane shape {p.shape}")
+        origin = p.ctypes.data + 2 * (abi.MARGIN * s + abi.MARGIN)
+        self._check(self._lib.jsvm_me_upload_plane_xpel(self._ctx, slot, C.c_void_p(origin), self.width, self.height, s))
+
+    def interp_halfpel(self, slots):
+        """QuarterPelFilter::filterFrame for one slot or a list of slots (one launch)."""
+        slots = np.atleast_1d(np.asarray(slots, dtype=np.int32))
+        self._check(self._lib.jsvm_me_interp_halfpel_batch(self._ctx, _ptr(slots), len(slots)))
+
+    def halfpel_plane(self, slot):
+        """The region filterFrame writes, as (2(H+56), 2(W+56)) uint8."""
+        out = np.empty((2 * (self.height + 56), 2 * (self.width + 56)), np.uint8)
+        self._check(self._lib.jsvm_me_download_halfpel_u8(self._ctx, slot, _ptr(out), out.shape[1]))
+        return out
+
+    def halfpel_plane_xpel(self, slot):
+        """Half-pel YuvPicBuffer layout: (2(H+64), 2(W+64)) int16 with origin at (64, 64)."""
+        s = 2 * (self.width + 2 * abi.MARGIN)
+        out = np.zeros((2 * (self.height + 2 * abi.MARGIN), s), np.int16)
+        origin = out.ctypes.data + 2 * (2 * abi.MARGIN * s + 2 * abi.MARGIN)
+        self._check(self._lib.jsvm_me_download_halfpel_xpel(self._ctx, slot, C.c_void_p(origin), s))
+        return out
+
+    # ---- search --------------------------------------------------------------------------
+    def search(self, jobs, org_mbs=None, want_preds=False):
+        """estimateBlockWithStart for every record of `jobs` (JOB_DTYPE ndarray)."""
+        jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
+        n = len(jobs)
+        res = np.zeros(n, RESULT_DTYPE)
+        preds = np.zeros((n, 16, 16), np.uint8) if want_preds else None
+        n_org = 0
+        if org_mbs is not None:
+            org_mbs = np.ascontiguousarray(org_mbs, dtype=np.int16).reshape(-1, 16, 16)
+            n_org = len(org_mbs)
+        self._check(self._lib.jsvm_me_search(self._ctx, _ptr(jobs), n, _ptr(org_mbs), n_org, _ptr(res), _ptr(preds)))
+        return (res, preds) if want_preds else res
+
+    def plan(self, jobs):
+        jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
+        gsz = self._lib.jsvm_me_group_size()
+        groups = np.zeros(len(jobs) * gsz, np.uint8)
+        info = PlanInfo()
+        self._check(self._lib.jsvm_me_plan(self._ctx, _ptr(jobs), len(jobs), _ptr(groups), C.byref(info)))
+        return groups[: info.n_groups * gsz].copy(), info
+
+    def search_device(self, d_jobs, n_jobs, d_groups, info, d_results, d_org_mbs=0, n_org_mbs=0, d_preds=0):
+        """Asynchronous search on device-resident buffers (raw device pointers as ints)."""
+        self._check(self._lib.jsvm_me_search_device(
+            self._ctx, C.c_void_p(int(d_jobs)), n_jobs, C.c_void_p(int(d_groups)), C.byref(info),
+            C.c_void_p(int(d_org_mbs)) if d_org_mbs else None, n_org_mbs,
+            C.c_void_p(int(d_results)), C.c_void_p(int(d_preds)) if d_preds else None))
+
+    def fetch_pred(self, job_idx, w, h):
+        out = np.zeros((h, w), np.int16)
+        self._check(self._lib.jsvm_me_fetch_pred(self._ctx, job_idx, _ptr(out), w))
+        return out
+
+    def sync(self):
+        self._check(self._lib.jsvm_me_sync(self._ctx))
+
+    # ---- measurement ---------------------------------------------------------------------
+    def launch_count(self):
+        return int(self._lib.jsvm_me_launch_count(self._ctx))
+
+    def timing_begin(self):
+        self._check(self._lib.jsvm_me_timing_begin(self._ctx))
+
+    def timing_end(self):
+        ms = [C.c_double() for _ in range(3)]
+        n = [C.c_uint64() for _ in range(3)]
+        self._check(self._lib.jsvm_me_timing_end(self._ctx, *[C.byref(x) for x in ms], *[C.byref(x) for x in n]))
+        return {"interp_ms": ms[0].value, "search_ms": ms[1].value, "subpel_ms": ms[2].value,
+                "interp_launches": n[0].value, "search_launches": n[1].value, "subpel_launches": n[2].value}
+
+
+# ---------------------------------------------------------------------------------------------
+# Reference-named mirror
+# ---------------------------------------------------------------------------------------------
+BLOCK_SIZE = {abi.MODE_16x16: (16, 16), abi.MODE_16x8: (16, 8), abi.MODE_8x16: (8, 16),
+              abi.BLK_8x8: (8, 8), abi.BLK_8x4: (8, 4), abi.BLK_4x8: (4, 8), abi.BLK_4x4: (4, 4)}  # (w, h), ENC/Distortion.cpp:50-74
+
+
+def cost_factor_sad(lam):
+    """RateDistortion::setMbQpLambda: m_uiCostFactorMotionSAD = floor(65536 * sqrt(lambda)) (ENC/RateDistortion.cpp:59-70).
+    IEEE double on the host, exactly as the reference computes it (N11); never recomputed on the device."""
+    import math
+    return int(math.floor(65536.0 * math.sqrt(float(lam)))) & 0xFFFFFFFF
+
+
+class Frame:
+    """A frame-store slot: the stand-in for the reference's Frame (full-pel + half-pel YuvPicBuffer)."""
+
+    def __init__(self, slot):
+        self.slot = slot
+
+
+class QuarterPelFilter:
+    """INCC/QuarterPelFilter.h:24-35 -- only filterFrame is on the hot path."""
+
+    def __init__(self, estimator):
+        self._me = estimator
+
+    def filterFrame(self, frame):
+        self._me.interp_halfpel([frame.slot])
+
+
+class MotionEstimationQuarterPel:
+    """ENC/MotionEstimationQuarterPel.h + ENC/MotionEstimation.h:84-115, one call at a time."""
+
+    def __init__(self, estimator):
+        self._me = estimator
+        self._mb = None
+        self._cost_factor = 0
+        self._org_frame = None
+        self._last = None
+
+    @staticmethod
+    def create(estimator):
+        return MotionEstimationQuarterPel(estimator)
+
+    def init(self, search_range, sub_pel_dfunc=abi.DF_SAD, full_pel_dfunc=abi.DF_SAD, search_mode=abi.SEARCH_BLOCK):
+        self._me.set_params(search_range, sub_pel_dfunc, full_pel_dfunc, search_mode)
+
+    def setMbQpLambda(self, lam):
+        self._cost_factor = cost_factor_sad(lam)
+
+    def loadOrgMbPelData(self, org_frame):
+        """XDistortion::loadOrgMbPelData: the picture the original macroblock is taken from."""
+        self._org_frame = org_frame
+
+    def initMb(self, uiMbPosY, uiMbPosX):
+        self._mb = (uiMbPosY, uiMbPosX)
+
+    def estimateBlockWithStart(self, rcRefFrame, rcMv, rcMvPred, ruiBits, uiBlk, uiMode, uiSearchRange=0, org_mb=None):
+        """Returns (mv, bits, cost) = (rcMv, ruiBits, ruiCost) on exit."""
+        if self._mb is None:
+            raise MotionEstimationError("initMb has not been called")
+        job = np.zeros(1, JOB_DTYPE)
+        j = job[0]
+        j["cur_slot"] = self._org_frame.slot if self._org_frame is not None else rcRefFrame.slot
+        j["ref_slot"] = rcRefFrame.slot
+        j["mb_y"], j["mb_x"] = self._mb
+        j["blk"], j["mode"], j["search_range"] = uiBlk, uiMode, uiSearchRange
+        j["start_hor"], j["start_ver"] = rcMv
+        j["pred_hor"], j["pred_ver"] = rcMvPred
+        j["cost_factor"], j["bits_in"] = self._cost_factor, ruiBits
+        j["org_index"] = -1 if org_mb is None else 0
+        res = self._me.search(job, org_mbs=org_mb)
+        r = res[0]
+        self._last = (uiBlk, uiMode)
+        return (int(r["mv_hor"]), int(r["mv_ver"])), int(r["bits"]), int(r["cost"])
+
+    def compensateBlock(self, uiBlk, uiMode):
+        if self._last != (uiBlk, uiMode):
+            raise MotionEstimationError("compensateBlock must follow the matching estimateBlockWithStart")
+        w, h = BLOCK_SIZE[uiMode]
+        return self._me.fetch_pred(0, w, h)

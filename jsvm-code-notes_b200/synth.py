@@ -1,0 +1,142 @@
+"""Synthetic pictures and job lists for the five BASELINE.json configurations.
+
+Luma = box-blurred seeded uniform noise generated on a 4x finer grid and sampled with a per-frame
+global translation given in QUARTER pels (so true motion has half- and quarter-pel parts), contrast
+stretched, plus N(0, 2) noise.  Chroma is flat 128 and never enters this path.
+
+Jobs mirror what MbEncoder asks of estimateBlockWithStart for one (current, reference) pair: for every
+macroblock one call per partition of the configured partition set, with a start / predictor field that
+is either all-zero or seeded uniform in [-32, +32] quarter-pel per block (both are benchmarked).
+"""
+import math
+
+import numpy as np
+
+from .abi import (JOB_DTYPE, MODE_16x16, MODE_16x8, MODE_8x16, BLK_8x8, BLK_8x4, BLK_4x8, BLK_4x4, DF_SAD, DF_HADAMARD)
+
+# (mode, blk) of the 9-partition set {16x16, 2 x 16x8, 2 x 8x16, 4 x 8x8} and of all 41 partitions
+PARTS_9 = [(MODE_16x16, 0), (MODE_16x8, 0), (MODE_16x8, 8), (MODE_8x16, 0), (MODE_8x16, 2),
+           (BLK_8x8, 0), (BLK_8x8, 2), (BLK_8x8, 8), (BLK_8x8, 10)]
+PARTS_41 = list(PARTS_9)
+for _b8 in (0, 2, 8, 10):
+    PARTS_41 += [(BLK_8x4, _b8), (BLK_8x4, _b8 + 4), (BLK_4x8, _b8), (BLK_4x8, _b8 + 1),
+                 (BLK_4x4, _b8), (BLK_4x4, _b8 + 1), (BLK_4x4, _b8 + 4), (BLK_4x4, _b8 + 5)]
+
+# The five configurations of BASELINE.json (picture size of the layer whose ME is run, search range,
+# sub-pel distortion, partition set, pictures of one GOP / number of reference frames).
+CONFIGS = {
+    "C1": dict(name="QCIF 176x144 SR16 QPel", width=176, height=144, search_range=16, sub_dfunc=DF_HADAMARD, parts=PARTS_9, gop=8, refs=1),
+    "C2": dict(name="CIF 352x288 (EL of QCIF->CIF) SR32 SAD+SATD", width=352, height=288, search_range=32, sub_dfunc=DF_HADAMARD, parts=PARTS_9, gop=8, refs=1),
+    "C3": dict(name="720p 1280x720 SR32 all partitions", width=1280, height=720, search_range=32, sub_dfunc=DF_HADAMARD, parts=PARTS_41, gop=16, refs=1),
+    "C4": dict(name="1080p 1920x1088 SR64 QPel", width=1920, height=1088, search_range=64, sub_dfunc=DF_HADAMARD, parts=PARTS_9, gop=16, refs=1),
+    "C5": dict(name="1080p 1920x1088 (top layer of 540p->1080p) SR64 4 refs", width=1920, height=1088, search_range=64, sub_dfunc=DF_HADAMARD, parts=PARTS_9, gop=16, refs=4),
+}
+
+
+def lambda_for_qp(qp):
+    """lambda = 0.85 * 2^(QP/3 - 4) (ENC/GOPEncoder.cpp:2871-2875 with gamma = 1)."""
+    return 0.85 * 2.0 ** (qp / 3.0 - 4.0)
+
+
+def cost_factor_for_qp(qp):
+    return int(math.floor(65536.0 * math.sqrt(lambda_for_qp(qp)))) & 0xFFFFFFFF
+
+
+def _box_blur(a, k):
+    """k x k box mean with edge replication, via cumulative sums (fast for 4x-upsampled 1080p)."""
+    p = k // 2
+    a = np.pad(a, p, mode="edge").astype(np.float64)
+    c = np.cumsum(np.cumsum(a, 0), 1)
+    c = np.pad(c, ((1, 0), (1, 0)))
+    return (c[k:, k:] - c[:-k, k:] - c[k:, :-k] + c[:-k, :-k]) / (k * k)
+
+
+class Sequence:
+    """A seeded synthetic sequence; frame(n) is deterministic in (seed, n)."""
+
+    def __init__(self, width, height, seed, motion_qpel=(9, 5), blur=21, guard=96):
+        self.width, self.height, self.seed = width, height, seed
+        self.motion = motion_qpel
+        self.guard = guard
+        rng = np.random.default_rng(seed)
+        hh, ww = 4 * (height + 2 * guard), 4 * (width + 2 * guard)
+        # noise on a coarse grid (one value per 2x2 pixels), upsampled 8x, then blurred on the fine grid
+        coarse = rng.integers(0, 256, (hh // 8 + 1, ww // 8 + 1)).astype(np.float64)
+        fine = np.kron(coarse, np.ones((8, 8)))[:hh, :ww]
+        fine = _box_blur(fine, blur)
+        lo, hi = fine.min(), fine.max()
+        self.tex = ((fine - lo) / (hi - lo) * 255.0).astype(np.float32)
+
+    def frame(self, n):
+        """8-bit luma of picture n: texture translated by n * motion quarter-pels, + N(0,2)."""
+        g = 4 * self.guard
+        dx, dy = n * self.motion[0], n * self.motion[1]
+        if abs(dx) > g or abs(dy) > g:
+            raise ValueError("picture index outside the guard band of the synthetic texture")
+        y0, x0 = g + dy, g + dx
+        f = self.tex[y0:y0 + 4 * self.height:4, x0:x0 + 4 * self.width:4].astype(np.float64)
+        rng = np.random.default_rng(self.seed * 1000003 + n)
+        f = f + rng.normal(0.0, 2.0, f.shape)
+        return np.clip(np.rint(f), 0, 255).astype(np.uint8)
+
+
+def make_jobs(width, height, parts, cur_slot, ref_slot, qp=30, field="random", seed=0, mb_subset=None, bits_in=0):
+    """Job records for every macroblock x partition of one (current, reference) pair.
+
+    field: "zero"   -> start = pred = (0, 0) for every block
+           "random" -> start = pred = seeded uniform [-32, 32] quarter-pel per block
+           "split"  -> independent random start and predictor (inter-layer motion prediction: the start is
+                       the base-layer MV while the predictor is the spatial MVP, ENC/MbEncoder.cpp:4516-4529)
+    """
+    mbw, mbh = width // 16, height // 16
+    mbs = [(y, x) for y in range(mbh) for x in range(mbw)] if mb_subset is None else list(mb_subset)
+    n = len(mbs) * len(parts)
+    jobs = np.zeros(n, JOB_DTYPE)
+    mb = np.repeat(np.asarray(mbs, dtype=np.int16), len(parts), axis=0)
+    jobs["mb_y"], jobs["mb_x"] = mb[:, 0], mb[:, 1]
+    jobs["mode"] = np.tile(np.asarray([p[0] for p in parts], np.uint8), len(mbs))
+    jobs["blk"] = np.tile(np.asarray([p[1] for p in parts], np.uint8), len(mbs))
+    jobs["cur_slot"], jobs["ref_slot"] = cur_slot, ref_slot
+    jobs["search_range"] = 0
+    jobs["cost_factor"] = cost_factor_for_qp(qp)
+    jobs["bits_in"] = bits_in
+    jobs["org_index"] = -1
+    rng = np.random.default_rng(seed)
+    if field == "zero":
+        pass
+    elif field == "random":
+        v = rng.integers(-32, 33, (n, 2)).astype(np.int16)
+        jobs["start_hor"], jobs["start_ver"] = v[:, 0], v[:, 1]
+        jobs["pred_hor"], jobs["pred_ver"] = v[:, 0], v[:, 1]
+    elif field == "split":
+        v = rng.integers(-32, 33, (n, 4)).astype(np.int16)
+        jobs["start_hor"], jobs["start_ver"] = v[:, 0], v[:, 1]
+        jobs["pred_hor"], jobs["pred_ver"] = v[:, 2], v[:, 3]
+    else:
+        raise ValueError(field)
+    return jobs
+
+
+def hierarchical_b_pairs(gop, refs=1):
+    """(current, reference) picture pairs of one GOP, grouped by temporal level (coarsest first).
+
+    Hierarchical-B coding order of ENC/GOPEncoder.cpp:530-640: the key picture `gop` references picture 0;
+    level t >= 1 holds the pictures at odd multiples of gop / 2^t, each referencing its two neighbours at
+    distance gop / 2^t (list 0 = past, list 1 = future).  With refs > 1 further already-coded pictures of
+    lower levels are added, nearest first.  Pairs inside one level are independent of each other.
+    """
+    levels = []
+    coded = [0]
+    levels.append([(gop, 0)])
+    coded.append(gop)
+    step = gop // 2
+    while step >= 1:
+        lvl = []
+        for cur in range(step, gop, 2 * step):
+            past = sorted([p for p in coded if p < cur], key=lambda p: cur - p)[:refs]
+            fut = sorted([p for p in coded if p > cur], key=lambda p: p - cur)[:refs]
+            lvl += [(cur, r) for r in past] + [(cur, r) for r in fut]
+        levels.append(lvl)
+        coded += list(range(step, gop, 2 * step))
+        step //= 2
+    return levels

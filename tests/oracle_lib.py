@@ -1,0 +1,80 @@
+"""ctypes access to the two CPU checkers (TEST INFRASTRUCTURE ONLY -- never imported by the product).
+
+CpuBackend(path, prefix) wraps either oracle/libme_oracle.so (prefix jsvm_ora_, the C restatement)
+or oracle/_ref/libjsvm_ref.so (prefix jsvm_ref_, the unmodified reference behind our harness).
+Both take the product's job / result records (include/jsvm_me_b200.h).
+"""
+import ctypes as C
+import importlib
+
+import numpy as np
+
+abi = importlib.import_module("jsvm-code-notes_b200.abi")
+JOB_DTYPE, RESULT_DTYPE = abi.JOB_DTYPE, abi.RESULT_DTYPE
+
+
+class CpuSession:
+    def __init__(self, be, width, height, n_slots, search_range, sub_dfunc, full_dfunc=0, search_mode=0):
+        self.be, self.width, self.height = be, width, height
+        self.ctx = C.c_void_p(be.create(width, height, n_slots, search_mode, full_dfunc, sub_dfunc, search_range))
+        if not self.ctx:
+            raise RuntimeError("checker create() failed")
+
+    def close(self):
+        if self.ctx:
+            self.be.destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        self.close()
+
+    def set_plane(self, slot, luma):
+        luma = np.ascontiguousarray(luma, np.uint8)
+        assert luma.shape == (self.height, self.width)
+        assert self.be.set_plane_u8(self.ctx, slot, luma.ctypes.data, self.width) == 0
+
+    def fullpel(self, slot):
+        out = np.zeros((self.height + 64, self.width + 64), np.uint8)
+        assert self.be.get_fullpel_u8(self.ctx, slot, out.ctypes.data, out.shape[1]) == 0
+        return out
+
+    def halfpel(self, slot):
+        out = np.zeros((2 * (self.height + 56), 2 * (self.width + 56)), np.uint8)
+        assert self.be.get_halfpel_u8(self.ctx, slot, out.ctypes.data, out.shape[1]) == 0
+        return out
+
+    def search(self, jobs, org_mbs=None, want_preds=False):
+        jobs = np.ascontiguousarray(jobs, JOB_DTYPE)
+        n = len(jobs)
+        res = np.zeros(n, RESULT_DTYPE)
+        preds = np.zeros((n, 16, 16), np.uint8) if want_preds else None
+        n_org, org_ptr = 0, None
+        if org_mbs is not None:
+            org_mbs = np.ascontiguousarray(org_mbs, np.int16).reshape(-1, 16, 16)
+            n_org, org_ptr = len(org_mbs), org_mbs.ctypes.data
+        rc = self.be.search(self.ctx, jobs.ctypes.data, n, org_ptr, n_org, res.ctypes.data,
+                            preds.ctypes.data if want_preds else None)
+        assert rc == 0, "checker search() failed"
+        return (res, preds) if want_preds else res
+
+
+class CpuBackend:
+    def __init__(self, path, prefix):
+        self.path, self.prefix = path, prefix
+        lib = C.CDLL(path)
+        self.lib = lib
+        protos = [("create", C.c_void_p, [C.c_int] * 7),
+                  ("destroy", None, [C.c_void_p]),
+                  ("set_plane_u8", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+                  ("get_fullpel_u8", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+                  ("get_halfpel_u8", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+                  ("search", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+                  ("cost_factor", C.c_uint32, [C.c_double, C.c_int]),
+                  ("distortion", C.c_uint32, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int])]
+        for name, rt, at in protos:
+            fn = getattr(lib, prefix + name)
+            fn.restype, fn.argtypes = rt, at
+            setattr(self, name, fn)
+
+    def session(self, width, height, n_slots, search_range, sub_dfunc, full_dfunc=0):
+        return CpuSession(self, width, height, n_slots, search_range, sub_dfunc, full_dfunc)
