@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- 1080p full-search ME frame-pairs/s (SR+-64, QPel) on N B200s, with roofline and CPU baseline.
+
+One "step" = one pass of the hot path over one batch: the top temporal level of a GOP-16 hierarchical-B
+sequence at 1920x1088 (BASELINE.json configs[3]): 8 B pictures x 2 lists = 16 independent (current,
+reference) pairs per GPU -- K1 half-pel planes of the 9 reference pictures, K2 full search (SR +-64) and
+K3 quarter-pel refinement for all 8160 macroblocks x 9 partitions of every pair (1.17 M
+estimateBlockWithStart results per step per GPU).  Pairs shard across ranks (weak scaling, no data-path
+collective); for N > 1 the result field is gathered to rank 0 over NCCL inside the timed region.
+
+`value`   : pairs/s with planes, jobs and search groups already resident in HBM (CUDA events, max over ranks).
+`e2e`     : pairs/s through the host-buffer C ABI (jsvm_me_upload_plane_u8 / jsvm_me_search): pinned host
+            planes and jobs -> H2D, planning, kernels, results D2H, all inside the timed region.
+`roofline`: K2 (dominant kernel) algorithmic INT32 lane-ops / measured launch time vs the INT32 ALU-pipe peak
+            measured by tools/int32_peak on this pool; `roofline_k1` is the HBM roofline of the half-pel kernel.
+`cpu_baseline` / `--impl reference`: the unmodified reference (oracle/_ref) on the host cores, bounded sample.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "jsvm-code-notes_b200"
+METRIC = "1080p full-search ME frame-pairs/s (SR+-64, QPel)"
+UNIT = "frame-pairs/s"
+OPS_PER_POS_9 = 87       # 64 packed abs-diff-acc + 5 tree adds + 9 rate adds + 9 compare/selects
+OPS_PER_POS_41 = 171
+INT32_PEAK_FALLBACK = 1.855e13   # lane-ops/s, tools/int32_peak on this pool's B200 (profiles/int32_peak_r01.json)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="C4")
+    ap.add_argument("--field", default="random", choices=["zero", "random", "split"])
+    ap.add_argument("--pairs", type=int, default=16, help="(current, reference) pairs per GPU per step")
+    ap.add_argument("--cpu-sample-mbs", type=int, default=0, help="macroblocks in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def build_workload(synth, cfg, n_pairs, field, rank):
+    """Planes and jobs of the top temporal level: pictures 1,3,5,.. reference their even neighbours."""
+    W, H = cfg["width"], cfg["height"]
+    seq = synth.Sequence(W, H, 1234 + 4 + 1000 * rank)
+    n_cur = (n_pairs + 1) // 2
+    pics = list(range(0, 2 * n_cur + 1))                      # 0 .. 2*n_cur ; even = references, odd = current
+    frames = {p: seq.frame(p) for p in pics}
+    slot_of = {p: i for i, p in enumerate(pics)}
+    pairs = []
+    for c in range(1, 2 * n_cur, 2):
+        pairs += [(c, c - 1), (c, c + 1)]
+    pairs = pairs[:n_pairs]
+    qp = 35                                                   # top temporal level (DQP4TLevel), SURVEY 8d
+    jobs = [synth.make_jobs(W, H, cfg["parts"], slot_of[c], slot_of[r], qp=qp, field=field, seed=100 * rank + i)
+            for i, (c, r) in enumerate(pairs)]
+    jobs = np.concatenate(jobs)
+    ref_slots = sorted({slot_of[r] for _, r in pairs})
+    return frames, slot_of, pairs, jobs, ref_slots
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the unmodified reference (oracle/_ref) or, if it was not built, the C oracle
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    kind, path, prefix, W, H, sr, sub, cur, ref, jobs_bytes = args
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    abi = importlib.import_module(PKG + ".abi")
+    be = oracle_lib.CpuBackend(path, prefix)
+    ses = be.session(W, H, 2, sr, sub)
+    ses.set_plane(0, ref)
+    ses.set_plane(1, cur)
+    jobs = np.frombuffer(jobs_bytes, dtype=abi.JOB_DTYPE).copy()
+    jobs["ref_slot"], jobs["cur_slot"] = 0, 1
+    t0 = time.perf_counter()
+    ses.search(jobs)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(synth, cfg, field, sample_mbs, steps=1):
+    """Times estimateBlockWithStart of the reference on a bounded sample of the same workload."""
+    import multiprocessing as mp
+    ref_path = os.path.join(ROOT, "oracle", "_ref", "libjsvm_ref.so")
+    ora_path = os.path.join(ROOT, "oracle", "libme_oracle.so")
+    if os.path.exists(ref_path):
+        kind, path, prefix = "reference", ref_path, "jsvm_ref_"
+    else:
+        kind, path, prefix = "port", ora_path, "jsvm_ora_"
+        if not os.path.exists(ora_path):
+            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+    W, H = cfg["width"], cfg["height"]
+    cores = os.cpu_count() or 1
+    seq = synth.Sequence(W, H, 1234 + 4)
+    cur, ref = seq.frame(1), seq.frame(0)
+    mbw, mbh = W // 16, H // 16
+    if sample_mbs <= 0:
+        # the reference needs ~16 ms per 1080p SR64 macroblock (9 partitions) per core: ~15 s of work per core
+        sample_mbs = min(mbw * mbh, 900 * cores if kind == "reference" else 150 * cores)
+    rng = np.random.default_rng(99)
+    pick = rng.choice(mbw * mbh, size=sample_mbs, replace=False)
+    mbs = [(int(i) // mbw, int(i) % mbw) for i in sorted(pick)]
+    chunks = [mbs[i::cores] for i in range(cores)]
+    chunks = [c for c in chunks if c]
+    values = []
+    for _ in range(steps):
+        tasks = []
+        for i, c in enumerate(chunks):
+            jobs = synth.make_jobs(W, H, cfg["parts"], 1, 0, qp=35, field=field, seed=7 + i, mb_subset=c)
+            tasks.append((kind, path, prefix, W, H, cfg["search_range"], cfg["sub_dfunc"], cur, ref, jobs.tobytes()))
+        t0 = time.perf_counter()
+        with mp.get_context("fork").Pool(len(chunks)) as pool:
+            times = pool.map(_cpu_worker, tasks)
+        wall = max(times)                                   # search time only (plane set-up excluded), slowest worker
+        values.append((sample_mbs / (mbw * mbh)) / wall)
+        _ = time.perf_counter() - t0
+    v = float(np.mean(values))
+    return {"value": v, "unit": UNIT, "cores": len(chunks), "kind": kind,
+            "sample": f"{sample_mbs} of {mbw * mbh} macroblocks of one 1080p pair x {len(cfg['parts'])} partitions, SR+-{cfg['search_range']}, "
+                      f"{len(chunks)} processes x 1 thread, search time only"}, values
+
+
+# ------------------------------------------------------------------------------------------------
+def clocks_start():
+    try:
+        return subprocess.Popen(
+            ["nvidia-smi", "--query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+             "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except Exception:
+        return None
+
+
+def clocks_stop(proc, dev_index):
+    if proc is None:
+        return None
+    proc.terminate()
+    try:
+        out, _ = proc.communicate(timeout=5)
+    except Exception:
+        proc.kill()
+        return None
+    sm, mx, reasons = [], 0, set()
+    for line in out.splitlines():
+        f = [x.strip() for x in line.split(",")]
+        if len(f) < 9 or not f[0].isdigit() or int(f[0]) != dev_index:
+            continue
+        try:
+            sm.append(float(f[1])); mx = max(mx, float(f[2]))
+        except ValueError:
+            continue
+        for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+            if val.lower().startswith("active"):
+                reasons.add(name)
+    if not sm:
+        return None
+    busy = [s for s in sm if s > 0.5 * mx] or sm
+    return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def int32_peak():
+    """INT32 ALU-pipe peak (lane-ops/s): measured live with tools/int32_peak if present, else the recorded value."""
+    exe = os.path.join(ROOT, "tools", "int32_peak")
+    if os.path.exists(exe):
+        try:
+            out = subprocess.run([exe, "0.5"], capture_output=True, text=True, timeout=120).stdout
+            d = json.loads(out.strip().splitlines()[-1])
+            return float(d["burst"]["vabsdiff4_acc"]), "measured live (tools/int32_peak, VABSDIFF4.U8.ACC chains on all SMs)"
+        except Exception:
+            pass
+    return INT32_PEAK_FALLBACK, "recorded (profiles/int32_peak_r01.json)"
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    synth = importlib.import_module(PKG + ".synth")
+    cfg = synth.CONFIGS[args.config]
+    workload = f"{args.config}: {cfg['name']}, top temporal level of GOP 16, {args.pairs} (cur,ref) pairs/GPU/step, " \
+               f"{len(cfg['parts'])} partitions/MB, start=pred field '{args.field}'"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        base, values = cpu_baseline(synth, cfg, args.field, args.cpu_sample_mbs, steps=max(1, min(args.steps, 3)))
+        line = {"metric": METRIC, "value": base["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / base["value"] if base["value"] else None,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": workload}, "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module(PKG)      # fails loudly if the CUDA library is missing
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.current_stream()
+
+    W, H = cfg["width"], cfg["height"]
+    frames, slot_of, pairs, jobs, ref_slots = build_workload(synth, cfg, args.pairs, args.field, rank)
+    n_jobs = len(jobs)
+    me = pkg.MotionEstimator(local_rank)
+    me.configure(W, H, len(frames))
+    me.set_params(cfg["search_range"], cfg["sub_dfunc"])
+    me.set_stream(stream.cuda_stream)
+
+    # pinned host copies (e2e leg) and device-resident inputs (value leg)
+    host_planes = {p: torch.from_numpy(f).pin_memory() for p, f in frames.items()}
+    for p, t in host_planes.items():
+        me.upload_plane_ptr(slot_of[p], t.data_ptr())
+    groups, info = me.plan(jobs)
+    d_jobs = torch.from_numpy(jobs.view(np.uint8)).to(dev)
+    d_groups = torch.from_numpy(groups).to(dev)
+    d_results = torch.zeros(n_jobs * 32, dtype=torch.uint8, device=dev)
+    gathered = [torch.zeros_like(d_results) for _ in range(world)] if (world > 1 and rank == 0) else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def step_resident():
+        me.interp_halfpel(ref_slots)
+        me.search_device(d_jobs.data_ptr(), n_jobs, d_groups.data_ptr(), info, d_results.data_ptr())
+        if world > 1:
+            dist.gather(d_results, gathered, dst=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+
+    clk = clocks_start() if rank == 0 else None
+    launches0 = me.launch_count()
+    me.timing_begin()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for e0, e1 in ev:
+        flush.fill_(1)                         # L2 flush between timed iterations (outside the event pair)
+        e0.record(stream)
+        step_resident()
+        e1.record(stream)
+    barrier()
+    total_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    kt = me.timing_end()
+    launches = me.launch_count() - launches0
+    clocks = clocks_stop(clk, local_rank) if rank == 0 else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = args.pairs * world / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        host_jobs = torch.from_numpy(jobs.view(np.uint8).copy()).pin_memory()
+        hj = host_jobs.numpy().view(pkg.JOB_DTYPE)
+        def step_e2e():
+            for p, tns in host_planes.items():
+                me.upload_plane_ptr(slot_of[p], tns.data_ptr())
+            me.interp_halfpel(ref_slots)
+            return me.search(hj)
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_e2e()
+        barrier()
+        n_e2e = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            res = step_e2e()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        h2d = sum(int(tns.numel()) for tns in host_planes.values()) + n_jobs * 32 + len(groups)
+        e2e = {"value": args.pairs * world * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": n_jobs * 32, "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (K2) and of K1 ----
+    peak, peak_how = int32_peak()
+    per_pos = OPS_PER_POS_41 if len(cfg["parts"]) == 41 else OPS_PER_POS_9
+    alg_ops_per_launch = info.n_positions / len(cfg["parts"]) * per_pos
+    k2_ms = kt["search_ms"] / max(1, kt["search_launches"])
+    achieved = alg_ops_per_launch / (k2_ms * 1e-3)
+    roofline = {"bound": "int32", "kernel": "full_search_kernel<8,false>", "achieved": achieved / 1e12, "peak": peak / 1e12,
+                "unit": "Tlane-op/s", "frac": achieved / peak, "traffic": None,
+                "alg_ops_per_launch": alg_ops_per_launch, "ms_per_launch": k2_ms, "peak_source": peak_how,
+                "positions_evaluated_per_launch": int(info.n_group_positions),
+                "share_of_step": kt["search_ms"] / total_ms}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    k1_bytes = len(ref_slots) * (W * H + 4 * (W + 56) * (H + 56))
+    k1_ms = kt["interp_ms"] / max(1, kt["interp_launches"])
+    roofline_k1 = {"bound": "hbm", "kernel": "halfpel_kernel", "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                   "unit": "GB/s", "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                   "alg_bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
+                   "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                   "share_of_step": kt["interp_ms"] / total_ms}
+
+    base = None
+    if not args.no_cpu_baseline and world == 1:
+        base, _ = cpu_baseline(synth, cfg, args.field, args.cpu_sample_mbs)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload, "jobs_per_step_per_gpu": n_jobs, "l2": "256 MiB L2 flush between timed iterations",
+                       "timing": "CUDA events per step on the launching stream, summed; max over ranks"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "roofline_k1": roofline_k1, "cpu_baseline": base,
+            "kernel_ms_per_step": {"k1_halfpel": kt["interp_ms"] / args.steps, "k2_full_search": kt["search_ms"] / args.steps,
+                                   "k3_subpel": kt["subpel_ms"] / args.steps}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
