@@ -160,6 +160,9 @@ typedef struct jsvm_me_plan_info {
 } jsvm_me_plan_info;
 size_t jsvm_me_group_size(void);    /* bytes per group record */
 int jsvm_me_plan(jsvm_me_ctx* ctx, const jsvm_me_job* jobs, int n_jobs, void* groups_out, jsvm_me_plan_info* info);
+/* The same planner without a device context (pure host logic; groups_out must hold n_jobs records). */
+int jsvm_me_plan_host(int width, int height, int n_slots, int search_range, const jsvm_me_job* jobs, int n_jobs,
+                      void* groups_out, jsvm_me_plan_info* info);
 int jsvm_me_search_device(jsvm_me_ctx* ctx, const jsvm_me_job* d_jobs, int n_jobs,
                           const void* d_groups, const jsvm_me_plan_info* info,
                           const int16_t* d_org_mbs, int n_org_mbs,

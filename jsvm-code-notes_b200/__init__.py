@@ -7,6 +7,6 @@ from . import abi
 from .abi import (JOB_DTYPE, RESULT_DTYPE, MODE_16x16, MODE_16x8, MODE_8x16, BLK_8x8, BLK_8x4, BLK_4x8, BLK_4x4,
                   DF_SAD, DF_HADAMARD, load_library)
 from .me import (MotionEstimator, MotionEstimationError, MotionEstimationQuarterPel, QuarterPelFilter, Frame,
-                 cost_factor_sad, BLOCK_SIZE)
+                 cost_factor_sad, BLOCK_SIZE, plan_host, GROUP_DTYPE)
 
 load_library()

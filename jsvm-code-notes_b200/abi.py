@@ -71,6 +71,7 @@ PROTOTYPES = [
     ("jsvm_me_search", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     ("jsvm_me_group_size", C.c_size_t, []),
     ("jsvm_me_plan", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(PlanInfo)]),
+    ("jsvm_me_plan_host", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(PlanInfo)]),
     ("jsvm_me_search_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(PlanInfo),
                                         C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     ("jsvm_me_fetch_pred", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),

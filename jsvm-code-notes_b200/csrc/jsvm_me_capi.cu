@@ -144,8 +144,8 @@ int launch_margin_fill(jsvm_me_ctx* c, const int* d_slots, int n) {
 // The planner: restates nothing from the reference -- it only decides which estimateBlockWithStart
 // calls can share one SAD pass (same macroblock, planes and original; distinct partition slots;
 // union of the clipped windows small enough for one CTA).
-int plan_jobs(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, std::vector<Group>& out, jsvm_me_plan_info* info) {
-  const int mbw = c->W >> 4, mbh = c->H >> 4;
+int plan_jobs(int width, int height, int n_slots, int search_range, const jsvm_me_job* jobs, int n_jobs, std::vector<Group>& out, jsvm_me_plan_info* info) {
+  const int mbw = width >> 4, mbh = height >> 4;
   std::vector<Group> g8, g4;
   Group cur; bool open = false; Window cw{};
   int64_t npos = 0;
@@ -163,10 +163,10 @@ int plan_jobs(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, std::vector<G
     if (j.blk > 15) return fail("job %d: blk %d out of range", i, (int)j.blk);
     const int slot = partition_slot(j.mode, j.blk);
     if (slot < 0) return fail("job %d: blk %d is not a legal origin for mode %d", i, (int)j.blk, (int)j.mode);
-    if (j.cur_slot < 0 || j.cur_slot >= c->n_slots || j.ref_slot < 0 || j.ref_slot >= c->n_slots)
+    if (j.cur_slot < 0 || j.cur_slot >= n_slots || j.ref_slot < 0 || j.ref_slot >= n_slots)
       return fail("job %d: plane slot out of range", i);
     if (j.mb_x < 0 || j.mb_x >= mbw || j.mb_y < 0 || j.mb_y >= mbh) return fail("job %d: macroblock (%d,%d) outside the picture", i, j.mb_x, j.mb_y);
-    const Window w1 = job_window(j, mbw, mbh, c->search_range);
+    const Window w1 = job_window(j, mbw, mbh, search_range);
     const int ww = w1.xhi - w1.xlo + 1, wh = w1.yhi - w1.ylo + 1;
     if (ww < 1 || wh < 1) return fail("job %d: empty search window", i);
     if (ww > kMaxUW || wh > kMaxUH || ww * wh > (1 << kIdxBits))
@@ -442,8 +442,16 @@ int jsvm_me_plan(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, void* grou
   if (!c || !jobs || !groups_out || !info) return fail("null argument");
   if (!c->d_planes) return fail("jsvm_me_configure has not been called");
   if (!c->params_set) return fail("jsvm_me_set_params has not been called");
+  return jsvm_me_plan_host(c->W, c->H, c->n_slots, c->search_range, jobs, n_jobs, groups_out, info);
+}
+
+int jsvm_me_plan_host(int width, int height, int n_slots, int search_range, const jsvm_me_job* jobs, int n_jobs,
+                      void* groups_out, jsvm_me_plan_info* info) {
+  if (!jobs || !groups_out || !info) return fail("null argument");
+  if (width <= 0 || height <= 0 || (width & 15) || (height & 15)) return fail("picture size %dx%d must be a positive multiple of 16", width, height);
+  if (search_range < 1 || search_range > 64) return fail("SearchRange %d outside [1,64]", search_range);
   std::vector<Group> g;
-  if (plan_jobs(c, jobs, n_jobs, g, info)) return JSVM_ME_ERR;
+  if (plan_jobs(width, height, n_slots, search_range, jobs, n_jobs, g, info)) return JSVM_ME_ERR;
   memcpy(groups_out, g.data(), g.size() * sizeof(Group));
   return JSVM_ME_OK;
 }
@@ -477,7 +485,7 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
   }
   CU_OK(cudaSetDevice(c->device));
   jsvm_me_plan_info info;
-  if (plan_jobs(c, jobs, n_jobs, c->h_groups, &info)) return JSVM_ME_ERR;
+  if (plan_jobs(c->W, c->H, c->n_slots, c->search_range, jobs, n_jobs, c->h_groups, &info)) return JSVM_ME_ERR;
   const bool want_preds = preds != nullptr || n_jobs <= 4096;
   if (c->d_jobs.reserve(n_jobs) || c->d_groups.reserve(c->h_groups.size()) || c->d_keys.reserve(n_jobs) || c->d_aux.reserve(n_jobs) ||
       c->d_results.reserve(n_jobs) || (want_preds && c->d_preds.reserve((size_t)n_jobs * 256)) ||

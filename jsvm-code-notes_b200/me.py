@@ -28,6 +28,25 @@ def _ptr(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
 
 
+def plan_host(width, height, n_slots, search_range, jobs):
+    """jsvm_me_plan_host: group jobs into search groups without a device (host logic only)."""
+    lib = abi.load_library()
+    jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
+    gsz = lib.jsvm_me_group_size()
+    groups = np.zeros(max(1, len(jobs)) * gsz, np.uint8)
+    info = PlanInfo()
+    if lib.jsvm_me_plan_host(width, height, n_slots, search_range, _ptr(jobs), len(jobs), _ptr(groups), C.byref(info)) != 0:
+        raise MotionEstimationError(lib.jsvm_me_last_error().decode())
+    return groups[: info.n_groups * gsz].copy(), info
+
+
+# numpy view of the 80-byte search-group record (csrc/me_common.cuh: struct Group)
+GROUP_DTYPE = np.dtype([("first_job", "<i4"), ("n_jobs", "<i2"), ("gran4", "<i2"), ("cur_slot", "<i2"), ("ref_slot", "<i2"),
+                        ("mb_x", "<i2"), ("mb_y", "<i2"), ("org_index", "<i4"), ("ux0", "<i2"), ("uy0", "<i2"),
+                        ("uw", "<i2"), ("uh", "<i2"), ("slot_job", "i1", (41,)), ("pad", "i1", (11,))])
+assert GROUP_DTYPE.itemsize == 80
+
+
 class MotionEstimator:
     """One device context = one picture resolution (one spatial layer) on one GPU."""
 

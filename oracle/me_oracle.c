@@ -359,8 +359,16 @@ int jsvm_ora_search(jsvm_ora_ctx* c, const jsvm_me_job* jobs, int n_jobs,
     const uint8_t* ref0 = ref->full + (size_t)(MARGIN + by0) * S + MARGIN + bx0;
     for (int y = -r.neg_ver; y <= r.pos_ver; ++y)
       for (int x = -r.neg_hor; x <= r.pos_hor; ++x) {
-        u8_src s = { ref0 + y * S + x, S };
-        uint32_t sad = distortion(org, get_u8, &s, w, h, c->full_dfunc);
+        uint32_t sad;
+        if (c->full_dfunc == JSVM_DF_SAD) {                 /* same sums as distortion(); direct loops keep the checker fast */
+          const uint8_t* rp = ref0 + y * S + x;
+          sad = 0;
+          for (int yy = 0; yy < h; ++yy)
+            for (int xx = 0; xx < w; ++xx) sad += (uint32_t)abs(org[yy * 16 + xx] - rp[yy * S + xx]);
+        } else {
+          u8_src s = { ref0 + y * S + x, S };
+          sad = distortion(org, get_u8, &s, w, h, c->full_dfunc);
+        }
         /* xGetCost( x, y ) with m_uiMvScaleShift = 2 (N6): table index (x<<2) - pred */
         sad += rate_cost(f, jsvm_ora_component_bits((x << 2) - j->pred.hor) + jsvm_ora_component_bits((y << 2) - j->pred.ver));
         if (best > sad) { best = sad; best_x = x; best_y = y; }       /* first strict minimum in raster order (N1) */

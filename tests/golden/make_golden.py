@@ -1,0 +1,80 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/libjsvm_ref.so, built from
+/root/reference by `make -C oracle ref`).  Run in the build container only; the fixtures are committed so
+that the GPU box (which has no /root/reference) can pin the oracle and the CUDA path against them.
+
+    python tests/golden/make_golden.py
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle_lib  # noqa: E402
+
+synth = importlib.import_module("jsvm-code-notes_b200.synth")
+abi = importlib.import_module("jsvm-code-notes_b200.abi")
+
+CASES = {
+    # name: (W, H, search_range, sub_dfunc, parts, field, seed, mb_subset, qp)
+    "tiny_all41_had": (64, 48, 12, 2, "PARTS_41", "split", 21, None, 28),
+    "tiny_9_sad": (64, 48, 16, 0, "PARTS_9", "random", 22, None, 36),
+    "qcif_9_had": (176, 144, 16, 2, "PARTS_9", "random", 23, [(0, 0), (0, 10), (8, 0), (8, 10), (4, 5), (3, 7), (0, 5), (8, 4)], 30),
+    "qcif_9_zero_sr32": (176, 144, 32, 2, "PARTS_9", "zero", 24, [(0, 0), (8, 10), (4, 5), (2, 9)], 33),
+}
+
+
+def main():
+    ref = oracle_lib.CpuBackend(os.path.join(ROOT, "oracle", "_ref", "libjsvm_ref.so"), "jsvm_ref_")
+    for name, (W, H, sr, sub, parts, field, seed, subset, qp) in CASES.items():
+        seq = synth.Sequence(W, H, seed)
+        f0, f1 = seq.frame(0), seq.frame(1)
+        ses = ref.session(W, H, 2, sr, sub)
+        ses.set_plane(0, f0)
+        ses.set_plane(1, f1)
+        jobs = synth.make_jobs(W, H, getattr(synth, parts), 1, 0, qp=qp, field=field, seed=seed, mb_subset=subset, bits_in=2)
+        res, preds = ses.search(jobs, want_preds=True)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), width=W, height=H, search_range=sr, sub_dfunc=sub,
+                            frame0=f0, frame1=f1, jobs=jobs, results=res, preds=preds,
+                            halfpel0=ses.halfpel(0), fullpel0=ses.fullpel(0))
+        print(name, len(jobs), "jobs")
+    # weighted / bi-pred style originals handed in by the caller (8-bit range) and a signed 16-bit one
+    W, H, sr = 64, 48, 8
+    seq = synth.Sequence(W, H, 31)
+    f0, f1 = seq.frame(0), seq.frame(1)
+    rng = np.random.default_rng(31)
+    org8 = rng.integers(0, 256, (3, 16, 16)).astype(np.int16)
+    org16 = rng.integers(-255, 511, (3, 16, 16)).astype(np.int16)
+    for nm, org in (("org_override_8bit", org8), ("org_override_16bit", org16)):
+        ses = ref.session(W, H, 2, sr, 2)
+        ses.set_plane(0, f0); ses.set_plane(1, f1)
+        jobs = synth.make_jobs(W, H, synth.PARTS_9, 1, 0, qp=30, field="random", seed=5, mb_subset=[(0, 0), (1, 2), (2, 3)])
+        jobs["org_index"] = np.repeat(np.arange(3), 9)
+        res, preds = ses.search(jobs, org_mbs=org, want_preds=True)
+        np.savez_compressed(os.path.join(HERE, nm + ".npz"), width=W, height=H, search_range=sr, sub_dfunc=2,
+                            frame0=f0, frame1=f1, jobs=jobs, results=res, preds=preds, org_mbs=org)
+        print(nm, len(jobs), "jobs")
+    # distortion function table (XDistortion SAD / SSD / HADAMARD for all 7 block modes) and cost factors
+    orgs = rng.integers(0, 256, (8, 16, 16)).astype(np.int16)
+    refs = rng.integers(0, 256, (8, 20, 24)).astype(np.int16)
+    rows = []
+    for i in range(8):
+        for mode, blk in synth.PARTS_41[::3]:
+            for df in (0, 1, 2):
+                bx, by = 4 * (blk & 3), 4 * (blk >> 2)
+                sub = np.ascontiguousarray(refs[i])
+                v = ref.distortion(orgs[i].ctypes.data, sub[by:, bx:].ctypes.data if False else sub.ctypes.data + 2 * (by * 24 + bx), 24, mode, df, blk)
+                rows.append((i, mode, blk, df, v))
+    factors = np.array([[ref.cost_factor(synth.lambda_for_qp(q), 1), ref.cost_factor(synth.lambda_for_qp(q), 0)] for q in range(52)], np.uint32)
+    np.savez_compressed(os.path.join(HERE, "distortion_and_factors.npz"), orgs=orgs, refs=refs,
+                        rows=np.array(rows, np.int64), factors=factors)
+    print("distortion rows", len(rows))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,57 @@
+"""Pins the C oracle (oracle/me_oracle.c) against golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py ran oracle/_ref/libjsvm_ref.so in the build container).  Runs on CPU."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SEARCH_CASES = ["tiny_all41_had", "tiny_9_sad", "qcif_9_had", "qcif_9_zero_sr32", "org_override_8bit", "org_override_16bit"]
+
+
+def load(name):
+    return np.load(os.path.join(HERE, "golden", name + ".npz"))
+
+
+def test_fixtures_present():
+    assert len(glob.glob(os.path.join(HERE, "golden", "*.npz"))) >= 7
+
+
+@pytest.mark.parametrize("name", SEARCH_CASES)
+def test_oracle_search_matches_reference_golden(oracle, name):
+    g = load(name)
+    W, H = int(g["width"]), int(g["height"])
+    ses = oracle.session(W, H, 2, int(g["search_range"]), int(g["sub_dfunc"]))
+    ses.set_plane(0, g["frame0"])
+    ses.set_plane(1, g["frame1"])
+    org = g["org_mbs"] if "org_mbs" in g.files else None
+    res, preds = ses.search(g["jobs"], org_mbs=org, want_preds=True)
+    for f in res.dtype.names:
+        assert np.array_equal(res[f], g["results"][f]), f"{name}: field {f} differs from the reference golden"
+    assert np.array_equal(preds, g["preds"])
+    if "halfpel0" in g.files:
+        assert np.array_equal(ses.halfpel(0), g["halfpel0"])       # QuarterPelFilter::filterFrame
+        assert np.array_equal(ses.fullpel(0), g["fullpel0"])       # YuvPicBuffer::fillMargin
+
+
+def test_oracle_distortion_table_and_factors(oracle):
+    g = load("distortion_and_factors")
+    orgs, refs = g["orgs"], g["refs"]
+    for i, mode, blk, df, want in g["rows"]:
+        bx, by = 4 * (int(blk) & 3), 4 * (int(blk) >> 2)
+        r = np.ascontiguousarray(refs[i])
+        got = oracle.distortion(np.ascontiguousarray(orgs[i]).ctypes.data, r.ctypes.data + 2 * (by * 24 + bx), 24, int(mode), int(df), int(blk))
+        assert got == want, (i, mode, blk, df)
+    synth_lambda = lambda q: 0.85 * 2.0 ** (q / 3.0 - 4.0)
+    for q in range(52):
+        assert oracle.cost_factor(synth_lambda(q), 1) == g["factors"][q, 0]
+        assert oracle.cost_factor(synth_lambda(q), 0) == g["factors"][q, 1]
+
+
+def test_golden_results_exercise_subpel_and_edges():
+    """The fixtures are only useful if they hit half-pel and quarter-pel winners and clipped windows."""
+    modes = np.concatenate([load(n)["results"]["best_mode"] for n in SEARCH_CASES])
+    assert (modes == 0).any() and ((modes > 0) & (modes < 16)).any() and (modes >= 16).any()
+    g = load("qcif_9_had")
+    assert (g["jobs"]["mb_x"] == 0).any() and (g["jobs"]["mb_x"] == 10).any() and (g["jobs"]["mb_y"] == 8).any()

@@ -1,0 +1,51 @@
+"""world_size-2 gloo test of the multi-GPU layout: round-robin pair sharding + final result gather (CPU)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, n_pairs, jobs_per_pair, out_path):
+    sys.path.insert(0, ROOT)
+    sharding = importlib.import_module("jsvm-code-notes_b200.sharding")
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pairs = [(2 * i + 1, 2 * i) for i in range(n_pairs)]
+    mine = sharding.shard_pairs(pairs, rank, world)
+    # fake "results": one int32 record per job carrying (global pair index, job index)
+    local = torch.cat([torch.stack([torch.full((jobs_per_pair,), gi, dtype=torch.int32),
+                                    torch.arange(jobs_per_pair, dtype=torch.int32)], 1) for gi, _ in mine])
+    gathered = sharding.gather_results(local, dst=0)
+    if rank == 0:
+        full = sharding.assemble_level(gathered, len(mine), jobs_per_pair, world, n_pairs)
+        np.save(out_path, full.numpy())
+    else:
+        assert gathered is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_and_gather_two_ranks(tmp_path):
+    n_pairs, jobs_per_pair, world = 8, 5, 2
+    out = str(tmp_path / "full.npy")
+    mp.spawn(_worker, args=(world, 29531, n_pairs, jobs_per_pair, out), nprocs=world, join=True)
+    full = np.load(out)
+    assert full.shape == (n_pairs * jobs_per_pair, 2)
+    want_pair = np.repeat(np.arange(n_pairs), jobs_per_pair)
+    assert np.array_equal(full[:, 0], want_pair)
+    assert np.array_equal(full[:, 1], np.tile(np.arange(jobs_per_pair), n_pairs))
+
+
+def test_round_robin_owner():
+    sharding = importlib.import_module("jsvm-code-notes_b200.sharding")
+    pairs = list(range(10))
+    got = [sharding.shard_pairs(pairs, r, 4) for r in range(4)]
+    assert sorted(i for g in got for i, _ in g) == list(range(10))
+    assert all(sharding.pair_owner(i, 4) == r for r, g in enumerate(got) for i, _ in g)

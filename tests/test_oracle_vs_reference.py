@@ -1,0 +1,40 @@
+"""Oracle (C restatement) against the compiled, unmodified reference on fresh seeded inputs.
+Skipped where oracle/_ref was not built (the GPU box; the golden fixtures cover it there)."""
+import numpy as np
+import pytest
+
+
+@pytest.mark.parametrize("sub_dfunc,parts_name,field,sr", [(2, "PARTS_9", "random", 16), (0, "PARTS_41", "split", 12), (2, "PARTS_9", "zero", 32)])
+def test_search_and_planes_identical(oracle, reference, synth, sub_dfunc, parts_name, field, sr):
+    W, H = 96, 80
+    seq = synth.Sequence(W, H, 77 + sr)
+    f0, f1 = seq.frame(0), seq.frame(2)
+    a, b = oracle.session(W, H, 2, sr, sub_dfunc), reference.session(W, H, 2, sr, sub_dfunc)
+    for s in (a, b):
+        s.set_plane(0, f0); s.set_plane(1, f1)
+    assert np.array_equal(a.halfpel(0), b.halfpel(0)) and np.array_equal(a.halfpel(1), b.halfpel(1))
+    assert np.array_equal(a.fullpel(1), b.fullpel(1))
+    jobs = synth.make_jobs(W, H, getattr(synth, parts_name), 1, 0, qp=31, field=field, seed=sr, bits_in=1)
+    ra, pa = a.search(jobs, want_preds=True)
+    rb, pb = b.search(jobs, want_preds=True)
+    for f in ra.dtype.names:
+        assert np.array_equal(ra[f], rb[f]), f
+    assert np.array_equal(pa, pb)
+
+
+def test_extreme_content(oracle, reference, synth):
+    """Flat, saturated and checkerboard pictures: SAD ties everywhere, clipping in the 6-tap filter."""
+    W, H, sr = 64, 48, 8
+    yy, xx = np.mgrid[0:H, 0:W]
+    pics = [np.zeros((H, W), np.uint8), np.full((H, W), 255, np.uint8), (((xx + yy) & 1) * 255).astype(np.uint8),
+            (((xx // 4 + yy // 4) & 1) * 255).astype(np.uint8)]
+    for cur in pics:
+        for ref in pics:
+            a, b = oracle.session(W, H, 2, sr, 2), reference.session(W, H, 2, sr, 2)
+            for s in (a, b):
+                s.set_plane(0, ref); s.set_plane(1, cur)
+            assert np.array_equal(a.halfpel(0), b.halfpel(0))
+            jobs = synth.make_jobs(W, H, synth.PARTS_9, 1, 0, qp=26, field="random", seed=1)
+            ra, rb = a.search(jobs), b.search(jobs)
+            for f in ra.dtype.names:
+                assert np.array_equal(ra[f], rb[f]), f
