@@ -25,6 +25,7 @@
 #pragma once
 
 #include <cuda.h>
+#include <type_traits>
 #include "me_common.cuh"
 
 namespace jsvm {
@@ -34,7 +35,7 @@ constexpr int kWinRowBytes = 160;                 // bytes per staged window row
 constexpr int kWinRowWords = kWinRowBytes / 4;    // 40 words: 40 mod 32 = 8 keeps successive rows on different banks
 constexpr int kMaxUW       = 145;                 // widest union window handled by one CTA
 constexpr int kMaxM        = (kMaxUW + 3) / 4;    // 37
-constexpr int kMaxRows     = 192;                 // staged rows upper bound (uh <= 160 after strip rounding, + 15, rounded to 32)
+constexpr int kMaxRows     = 184;                 // window rows covered by the strips (uh <= 176, rounded up to a strip)
 
 __device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t d;
@@ -87,20 +88,51 @@ __host__ __device__ constexpr uint32_t slot_mask_gran4(int sl) {
   { int i = sl - 25, b = i >> 2, k = i & 3;    return 0x0001u << ((b >> 1) * 8 + (b & 1) * 2 + (k >> 1) * 4 + (k & 1)); }
 }
 
+// sad + ((factor * bits) >> 16), packed with the raster index: (cost << 15) + idx.
+//   t    = f * by + fbx          f * (bits_x + bits_y) in 32-bit wrap-around arithmetic (N5); FMA pipe (IMAD)
+//   cost = sad + (t >> 16)       xGetCost, ENC/MotionEstimationCost.h:27
+//   key  = cost * 32768 + idx    FMA pipe (IMAD); the min itself is the only ALU-pipe op besides the shift-add
+// Written as PTX so that the compiler cannot re-associate (cost << 15) into one multiply per SAD term.
+__device__ __forceinline__ uint32_t rate_key(uint32_t f, uint32_t by, uint32_t fbx, uint32_t sad, uint32_t idx) {
+  uint32_t key;
+  asm("{\n"
+      ".reg .u32 t, c;\n"
+      "mad.lo.u32 t, %1, %2, %3;\n"
+      "shr.u32 t, t, 16;\n"
+      "add.u32 c, t, %4;\n"
+      "mad.lo.u32 %0, c, 32768, %5;\n"
+      "}\n" : "=r"(key) : "r"(f), "r"(by), "r"(fbx), "r"(sad), "r"(idx));
+  return key;
+}
+
 template <int V, bool GRAN4>
 struct K2Smem {
   static constexpr int NS   = GRAN4 ? kSlots : kSlotsGran8;
   static constexpr int NACC = GRAN4 ? 16 : 4;
+  static constexpr int kMaxStrips = kMaxRows / V;
+  typedef typename std::conditional<GRAN4, unsigned long long, uint32_t>::type Mask;   // one bit per partition slot
   // dynamic shared memory layout (bytes); the four window copies come first
   uint32_t factor[NS];
-  int16_t  xlo[NS], xw[NS], ylo[NS], yhi[NS];     // relative to the union window origin; xw = xhi - xlo
+  int16_t  xlo[NS], xhi[NS], ylo[NS], yhi[NS];    // relative to the union window origin (empty slot: xhi < xlo)
   int32_t  job[NS];                               // absolute job index or -1
   uint32_t best[NS];
-  alignas(16) uint32_t by[NS][kMaxRows];          // bits of the vertical MV difference per window row
   uint8_t  bx[NS][4 * kMaxM + 12];                // bits of the horizontal difference, permuted [s][m]
+  Mask     xmask[4 * kMaxM];                      // slots whose window contains column x, permuted [s][m]
+  Mask     yfull[kMaxStrips];                     // slots whose window contains ALL rows of the strip
+  Mask     yany[kMaxStrips];                      // slots whose window contains SOME row of the strip
+  // followed by: uint32_t by[NS][nstrips * V]    bits of the vertical MV difference per window row (16-byte aligned)
 };
 
-__host__ __device__ inline int k2_rows(int uh, int V) { return ((uh + V - 1) / V) * V + 15; }   // reference rows the strips touch
+// Reference rows staged per copy: only the uh + 15 rows that valid displacements touch.  The last strip may reach up to
+// V-1 rows further; those reads belong to displacements outside every window (masked by yany / yfull), land in the
+// shared memory that follows the copies (tables) and are never used.
+__host__ __device__ inline int k2_rows(int uh) { return uh + 15; }
+// words between two window copies: padded so that (copy stride mod 32) == (M rounded up to even) mod 32 -- a warp whose
+// lanes run off the end of copy s (m = M-1) continues in copy s+1 (m = 0) on the NEXT bank: no shared-memory conflicts.
+__host__ __device__ inline int k2_copy_words(int rows, int m_units) {
+  const int base = rows * kWinRowWords;
+  return base + (((m_units - base) % 32) + 32) % 32;
+}
 
 template <int V, bool GRAN4>
 __global__ void __launch_bounds__(kK2Threads, GRAN4 ? 1 : 2)
@@ -114,6 +146,7 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
                    JobAux* __restrict__ aux)                      // per job: how K3 decodes the key
 {
   using SM = K2Smem<V, GRAN4>;
+  using Mask = typename SM::Mask;
   constexpr int NS = SM::NS, NACC = SM::NACC;
   extern __shared__ __align__(128) uint8_t smem_raw[];
 
@@ -121,12 +154,32 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
   const int tid = threadIdx.x;
   const int uw = g.uw, uh = g.uh;
   const int nstrips = (uh + V - 1) / V;
-  const int rows = nstrips * V + 15;
-  const int copy_words = rows * kWinRowWords;
+  const int rows = k2_rows(uh);
+  const int M = ((uw + 3) >> 2) + (((uw + 3) >> 2) & 1);          // column groups per copy, rounded up to even
+  const int copy_words = k2_copy_words(rows, M);
+  const int by_stride = nstrips * V;
   uint32_t* winw = reinterpret_cast<uint32_t*>(smem_raw);
-  SM& sm = *reinterpret_cast<SM*>(smem_raw + (((size_t)4 * copy_words * 4 + 15) & ~(size_t)15));
+  uint8_t* after = smem_raw + (((size_t)4 * copy_words * 4 + 15) & ~(size_t)15);
+  SM& sm = *reinterpret_cast<SM*>(after);
+  uint32_t* by_tab = reinterpret_cast<uint32_t*>(after + ((sizeof(SM) + 15) & ~(size_t)15));
 
-  // ---- prologue 1: the four byte-shifted copies of the reference window ----
+  // ---- prologue 1: per-slot job parameters ----
+  if (tid < NS) {
+    const int jo = g.slot_job[tid];
+    sm.job[tid] = jo < 0 ? -1 : g.first_job + jo;
+    sm.best[tid] = kKeyInvalid;
+    if (jo >= 0) {
+      const jsvm_me_job j = jobs[g.first_job + jo];
+      const Window w = job_window(j, mb_w, mb_h, default_range);
+      sm.factor[tid] = j.cost_factor;
+      sm.xlo[tid] = (int16_t)(w.xlo - g.ux0); sm.xhi[tid] = (int16_t)(w.xhi - g.ux0);
+      sm.ylo[tid] = (int16_t)(w.ylo - g.uy0); sm.yhi[tid] = (int16_t)(w.yhi - g.uy0);
+    } else {
+      sm.factor[tid] = 0; sm.xlo[tid] = 0; sm.xhi[tid] = -1; sm.ylo[tid] = 0; sm.yhi[tid] = -1;
+    }
+  }
+
+  // ---- prologue 2: the four byte-shifted copies of the reference window ----
   {
     const int px = kMargin + 16 * g.mb_x + g.ux0;               // window origin in plane coordinates
     const int py = kMargin + 16 * g.mb_y + g.uy0;
@@ -152,42 +205,6 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
     }
   }
 
-  // ---- prologue 2: per-slot job parameters and MV-rate tables ----
-  if (tid < NS) {
-    const int jo = g.slot_job[tid];
-    sm.job[tid] = jo < 0 ? -1 : g.first_job + jo;
-    sm.best[tid] = kKeyInvalid;
-    if (jo >= 0) {
-      const jsvm_me_job j = jobs[g.first_job + jo];
-      const Window w = job_window(j, mb_w, mb_h, default_range);
-      sm.factor[tid] = j.cost_factor;
-      sm.xlo[tid] = (int16_t)(w.xlo - g.ux0); sm.xw[tid] = (int16_t)(w.xhi - w.xlo);
-      sm.ylo[tid] = (int16_t)(w.ylo - g.uy0); sm.yhi[tid] = (int16_t)(w.yhi - g.uy0);
-    } else {
-      sm.factor[tid] = 0; sm.xlo[tid] = 0; sm.xw[tid] = -1; sm.ylo[tid] = 0; sm.yhi[tid] = -1;
-    }
-  }
-  const int M = (uw + 3) >> 2;
-  for (int i = tid; i < NS * kMaxRows; i += kK2Threads) {
-    const int sl = i / kMaxRows, y = i - sl * kMaxRows;
-    const int jo = g.slot_job[sl];
-    uint32_t b = 0;
-    if (jo >= 0 && y < uh) {
-      // xGetBits with m_uiMvScaleShift = 2: table index (y << 2) - pred (N6)
-      b = mv_component_bits(((g.uy0 + y) << 2) - jobs[g.first_job + jo].pred.ver);
-    }
-    sm.by[sl][y] = b;
-  }
-  for (int i = tid; i < NS * 4 * kMaxM; i += kK2Threads) {
-    const int sl = i / (4 * kMaxM), r = i - sl * 4 * kMaxM;
-    const int s = r / kMaxM, m = r - s * kMaxM;
-    const int x = 4 * m + s;
-    const int jo = g.slot_job[sl];
-    uint32_t b = 0;
-    if (jo >= 0 && x < uw) b = mv_component_bits(((g.ux0 + x) << 2) - jobs[g.first_job + jo].pred.hor);
-    sm.bx[sl][s * kMaxM + m] = (uint8_t)b;
-  }
-
   // ---- prologue 3: the current macroblock into registers (16 rows x 4 packed words) ----
   uint32_t cur[16][4];
   if (g.org_index < 0) {
@@ -208,6 +225,41 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
       }
     }
   }
+  __syncthreads();            // slot parameters visible
+
+  // ---- prologue 4: MV-rate tables and validity masks ----
+  for (int i = tid; i < NS * by_stride; i += kK2Threads) {
+    const int sl = i / by_stride, y = i - sl * by_stride;
+    uint32_t b = 0;
+    // xGetBits with m_uiMvScaleShift = 2: table index (y << 2) - pred (N6)
+    if (sm.job[sl] >= 0 && y < uh) b = mv_component_bits(((g.uy0 + y) << 2) - jobs[sm.job[sl]].pred.ver);
+    by_tab[sl * by_stride + y] = b;
+  }
+  for (int i = tid; i < NS * 4 * kMaxM; i += kK2Threads) {
+    const int sl = i / (4 * kMaxM), r = i - sl * 4 * kMaxM;
+    const int s = r / kMaxM, m = r - s * kMaxM;
+    const int x = 4 * m + s;
+    uint32_t b = 0;
+    if (sm.job[sl] >= 0 && x < uw) b = mv_component_bits(((g.ux0 + x) << 2) - jobs[sm.job[sl]].pred.hor);
+    sm.bx[sl][s * kMaxM + m] = (uint8_t)b;
+  }
+  for (int i = tid; i < 4 * kMaxM; i += kK2Threads) {
+    const int s = i / kMaxM, m = i - s * kMaxM;
+    const int x = 4 * m + s;
+    Mask mk = 0;
+    for (int sl = 0; sl < NS; ++sl) if (x >= sm.xlo[sl] && x <= sm.xhi[sl]) mk |= (Mask)1 << sl;
+    sm.xmask[i] = mk;
+  }
+  for (int i = tid; i < SM::kMaxStrips; i += kK2Threads) {
+    const int y0 = i * V, y1 = y0 + V - 1;
+    Mask full = 0, any = 0;
+    for (int sl = 0; sl < NS; ++sl) {
+      if (sm.xhi[sl] < sm.xlo[sl]) continue;
+      if (sm.ylo[sl] <= y0 && y1 <= sm.yhi[sl]) full |= (Mask)1 << sl;
+      if (sm.ylo[sl] <= y1 && y0 <= sm.yhi[sl]) any |= (Mask)1 << sl;
+    }
+    sm.yfull[i] = full; sm.yany[i] = any;
+  }
   __syncthreads();            // window copies and tables visible
 
   uint32_t best[NS];
@@ -223,6 +275,7 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
     const int s = rem / M, m = rem - s * M;
     const int x = 4 * m + s;
     const int ys = strip * V;
+    const int cidx = s * kMaxM + m;
 
     // ---- SAD pass over the strip ----
     uint32_t acc[V][NACC];
@@ -257,34 +310,72 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
     }
 
     // ---- per partition: SAD + rate, packed-key min ----
-    const uint32_t idx0 = (uint32_t)(ys * uw + x);
+    const Mask mx = sm.xmask[cidx];
+    const Mask mfull = mx & sm.yfull[strip], many = mx & sm.yany[strip];
+    if (many == 0) continue;                                      // dead lane (x >= uw) or outside every job's window
+    uint32_t idxv[V];
 #pragma unroll
-    for (int sl = 0; sl < NS; ++sl) {
-      const int xrel = x - sm.xlo[sl];
-      const int lo = sm.ylo[sl] - ys, hi = sm.yhi[sl] - ys;        // valid strip rows: lo <= v <= hi
-      if ((unsigned)xrel > (unsigned)(int)sm.xw[sl] || hi < 0 || lo >= V) continue;   // also skips empty slots (xw = -1)
+    for (int v = 0; v < V; ++v) idxv[v] = (uint32_t)((ys + v) * uw + x);
+
+    auto update = [&](const int sl, const uint32_t (&sadv)[V]) {
+      if (!((many >> sl) & 1)) return;
       const uint32_t f = sm.factor[sl];
-      const uint32_t fbx = f * (uint32_t)sm.bx[sl][s * kMaxM + m];
-      const uint32_t mask = GRAN4 ? slot_mask_gran4(sl) : slot_mask_gran8(sl);   // folds after unrolling
+      const uint32_t fbx = f * (uint32_t)sm.bx[sl][cidx];
       uint32_t byv[V];
 #pragma unroll
       for (int v4 = 0; v4 < V; v4 += 4) {
-        const uint4 q = *reinterpret_cast<const uint4*>(&sm.by[sl][ys + v4]);     // uniform address: one broadcast LDS.128
+        const uint4 q = *reinterpret_cast<const uint4*>(&by_tab[sl * by_stride + ys + v4]);   // warp-uniform address: broadcast LDS.128
         byv[v4] = q.x; byv[v4 + 1] = q.y; byv[v4 + 2] = q.z; byv[v4 + 3] = q.w;
       }
       uint32_t b = best[sl];
-      const bool all_rows = (lo <= 0) && (hi >= V - 1);
+      if ((mfull >> sl) & 1) {
 #pragma unroll
-      for (int v = 0; v < V; ++v) {
-        uint32_t sad = 0;
+        for (int v = 0; v < V; ++v) b = min(b, rate_key(f, byv[v], fbx, sadv[v], idxv[v]));
+      } else {
+        const int lo = sm.ylo[sl] - ys, hi = sm.yhi[sl] - ys;       // valid strip rows: lo <= v <= hi
 #pragma unroll
-        for (int a = 0; a < NACC; ++a) if (mask & (1u << a)) sad += acc[v][a];
-        const uint32_t t = f * byv[v] + fbx;                        // m_uiCostFactor * bits, 32-bit wrap (N5)
-        const uint32_t cost = sad + (t >> 16);
-        const uint32_t key = (cost << kIdxBits) + (idx0 + (uint32_t)(v * uw));
-        if (all_rows || (v >= lo && v <= hi)) b = min(b, key);
+        for (int v = 0; v < V; ++v) {
+          const uint32_t key = rate_key(f, byv[v], fbx, sadv[v], idxv[v]);
+          if (v >= lo && v <= hi) b = min(b, key);
+        }
       }
       best[sl] = b;
+    };
+
+    if (!GRAN4) {
+      uint32_t t0[V], t1[V];
+      // 8x8 partitions read the accumulators directly
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) t0[v] = acc[v][q];
+        update(5 + q, t0);
+      }
+      // 16x8 (upper, lower) and, from their sum, 16x16
+#pragma unroll
+      for (int v = 0; v < V; ++v) { t0[v] = acc[v][0] + acc[v][1]; t1[v] = acc[v][2] + acc[v][3]; }
+      update(1, t0); update(2, t1);
+#pragma unroll
+      for (int v = 0; v < V; ++v) t0[v] += t1[v];
+      update(0, t0);
+      // 8x16 (left, right)
+#pragma unroll
+      for (int v = 0; v < V; ++v) { t0[v] = acc[v][0] + acc[v][2]; t1[v] = acc[v][1] + acc[v][3]; }
+      update(3, t0); update(4, t1);
+    } else {
+#pragma unroll
+      for (int sl = 0; sl < NS; ++sl) {
+        const uint32_t mask = slot_mask_gran4(sl);                 // folds after unrolling
+        uint32_t t0[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          uint32_t sad = 0;
+#pragma unroll
+          for (int a = 0; a < NACC; ++a) if (mask & (1u << a)) sad += acc[v][a];
+          t0[v] = sad;
+        }
+        update(sl, t0);
+      }
     }
   }
 
@@ -304,8 +395,10 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
 
 template <int V, bool GRAN4>
 inline size_t k2_smem_bytes(int max_uh) {
-  const size_t win = (((size_t)4 * k2_rows(max_uh, V) * kWinRowBytes) + 15) & ~(size_t)15;
-  return win + sizeof(K2Smem<V, GRAN4>);
+  using SM = K2Smem<V, GRAN4>;
+  const size_t win = (((size_t)4 * (k2_rows(max_uh) * kWinRowWords + 31) * 4) + 15) & ~(size_t)15;
+  const size_t by = (size_t)SM::NS * (((max_uh + V - 1) / V) * V) * 4;
+  return win + ((sizeof(SM) + 15) & ~(size_t)15) + by;
 }
 
 }  // namespace jsvm
