@@ -8,12 +8,18 @@
 //   the tail of estimateBlockWithStart                 ENC/MotionEstimation.cpp:313-337
 //   MotionEstimationQuarterPel::compensateBlock        ENC/MotionEstimationQuarterPel.cpp:266-328
 //
-// One warp per job.  A lane task is (candidate, 4x4 sub-block): the 9 half-pel candidates are
-// the half-pel plane sampled at every second sample with an offset of (dx/2, dy/2); the 8
-// quarter-pel candidates are (p + q + 1) >> 1 of two half-pel-plane samples chosen by the
-// filter class of the half-pel winner.  Candidate order and strict '<' replicate the reference:
-// 64-bit keys (cost << 8 | n) are min-reduced, so ties go to the lowest n and the quarter-pel
-// stage can only strictly beat the half-pel winner (N1).  ~0.4 % of K2's work.
+// One warp per job.
+//   * The (2w+3) x (2h+3) patch of the half-pel plane around the full-pel winner is read ONCE with
+//     aligned 32-bit loads and de-interleaved into four phase planes in shared memory
+//     (phase = parity of the half-pel coordinates: integer / H-half / V-half / diagonal samples), so
+//     that the block a candidate predicts is 4 CONTIGUOUS bytes per 4x4 row -- exactly the four
+//     buffers xCompensateBlocksHalf gathers, kept for all 17 candidates.
+//   * A lane task is (candidate, 4x4 sub-block).  Half-pel candidates read one phase plane; quarter-pel
+//     candidates are the byte-wise rounded average (p + q + 1) >> 1 of two phase-plane reads chosen by the
+//     filter class of the half-pel winner (xXFilter1/4: axis neighbours for the diagonal positions).
+//   * SAD = VABSDIFF4 per row; SATD = the reference's 4x4 Hadamard with the per-4x4 halving (N8).
+//   * Candidate order and strict '<' are reproduced with 64-bit keys (cost << 8 | n): ties go to the lowest
+//     n, and the quarter-pel stage can only strictly beat the half-pel winner (N1).
 #pragma once
 
 #include "me_common.cuh"
@@ -21,7 +27,7 @@
 namespace jsvm {
 
 constexpr int kK3WarpsPerCta = 8;
-
+constexpr int kK3PlaneRows = 18, kK3PlanePitch = 24;       // phase plane: (2*16+3+1)/2 rows, 4-byte aligned pitch
 
 __constant__ int8_t c_half_mv[9][2]    = { {0,0}, {0,-2}, {0,2}, {-2,0}, {2,0}, {-2,-2}, {2,-2}, {-2,2}, {2,2} };   // g_acHPSearchMv
 __constant__ int8_t c_quarter_mv[9][2] = { {0,0}, {0,-1}, {0,1}, {-1,-1}, {1,-1}, {-1,0}, {1,0}, {-1,1}, {1,1} };   // g_acQPSearchMv
@@ -47,12 +53,22 @@ __device__ __forceinline__ uint32_t hadamard4x4(const int (&d)[16]) {
   return sum >> 1;
 }
 
-// one sample of sub-pel candidate: stage 0 = half-pel candidate n, stage 1 = quarter-pel candidate n
-__device__ __forceinline__ int subpel_sample(const uint8_t* base, int hs, int stage, int dx, int dy, bool axis_diag, int px, int py) {
-  const uint8_t* o = base + 2 * py * hs + 2 * px;
-  if (stage == 0) return o[(dy / 2) * hs + (dx / 2)];
-  if (axis_diag && dx != 0 && dy != 0) return (o[dx] + o[dy * hs] + 1) >> 1;
-  return (o[0] + o[dy * hs + dx] + 1) >> 1;
+struct K3Warp {
+  uint8_t  plane[4][kK3PlaneRows][kK3PlanePitch];   // [phase = (Y&1)*2 + (X&1)][(Y - Y0) >> 1][(X - X0) >> 1]
+  uint32_t org[16][4];                               // original block, 16 bytes per row
+};
+
+// Where the block predicted at half-pel offset (ox, oy) from the full-pel winner starts inside the phase planes:
+// half-pel coordinates X = BX + ox + 2x, Y = BY + oy + 2y; relx = BX - X0 (2..5), Y0 = BY - 2.  Returns the byte
+// offset of (block column x, block row y) inside K3Warp::plane; consecutive block rows are kK3PlanePitch bytes apart
+// and the pitch is a multiple of 4, so the alignment of a 4-sample read is the same for every row.
+__device__ __forceinline__ int cand_offset(int relx, int ox, int oy, int x, int y) {
+  const int hx = relx + ox, hy = 2 + oy;                       // >= 0 by construction
+  return (((hy & 1) * 2 + (hx & 1)) * kK3PlaneRows + (hy >> 1) + y) * kK3PlanePitch + (hx >> 1) + x;
+}
+__device__ __forceinline__ uint32_t fetch4(const uint8_t* planes, int off) {
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(planes + (off & ~3));
+  return __funnelshift_r(q[0], q[1], 8 * (off & 3));
 }
 
 __global__ void __launch_bounds__(32 * kK3WarpsPerCta)
@@ -63,14 +79,17 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
               const uint32_t* __restrict__ keys, int sub_dfunc,
               jsvm_me_result* __restrict__ results, uint8_t* __restrict__ preds)
 {
+  __shared__ __align__(16) K3Warp s_warp[kK3WarpsPerCta];
   const int job_idx = blockIdx.x * kK3WarpsPerCta + (threadIdx.x >> 5);
   if (job_idx >= n_jobs) return;
+  K3Warp& sw = s_warp[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const jsvm_me_job j = jobs[job_idx];
   const JobAux a = aux[job_idx];
   int w = 16, h = 16;
   mode_size(j.mode, w, h);
-  const int nbx = w >> 2, nb = nbx * (h >> 2);
+  const int nbx = w >> 2, nb = nbx * (h >> 2);               // 4x4 sub-blocks per row / per block: powers of two
+  const int lg_nbx = 31 - __clz(nbx), lg_nb = 31 - __clz(nb);
   const uint32_t f = j.cost_factor;
 
   // ---- decode the full-pel winner (xPelBlockSearch result) ----
@@ -81,65 +100,108 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
   const uint32_t full_rate = rate_cost(f, mv_component_bits((fx << 2) - j.pred.hor) + mv_component_bits((fy << 2) - j.pred.ver));
 
   const int bx0 = 16 * j.mb_x + 4 * (j.blk & 3), by0 = 16 * j.mb_y + 4 * (j.blk >> 2);
-  const uint8_t* hp0 = half_planes + (size_t)j.ref_slot * half_bytes + (size_t)(kHpOrigin + 2 * by0) * half_stride + kHpOrigin + 2 * bx0;
-  const uint8_t* cur0 = planes + (size_t)j.cur_slot * plane_bytes + (size_t)(kMargin + by0) * plane_stride + kMargin + bx0;
-  const int16_t* org0 = j.org_index >= 0 ? org_mbs + (size_t)j.org_index * 256 + (4 * (j.blk >> 2)) * 16 + 4 * (j.blk & 3) : nullptr;
 
-  int mvh = fx << 2, mvv = fy << 2;                       // cMv <<= 2
-  unsigned long long best = ~0ull;
+  // ---- stage the original block (16 bytes per row) ----
+  for (int i = lane; i < h * nbx; i += 32) {
+    const int r = i >> lg_nbx, k = i & (nbx - 1);
+    uint32_t v;
+    if (j.org_index >= 0) {
+      const short4 s4 = __ldg(reinterpret_cast<const short4*>(org_mbs + (size_t)j.org_index * 256 + (4 * (j.blk >> 2) + r) * 16 + 4 * (j.blk & 3) + 4 * k));
+      v = (uint32_t)(s4.x & 0xff) | ((uint32_t)(s4.y & 0xff) << 8) | ((uint32_t)(s4.z & 0xff) << 16) | ((uint32_t)(s4.w & 0xff) << 24);
+    } else {
+      v = __ldg(reinterpret_cast<const uint32_t*>(planes + (size_t)j.cur_slot * plane_bytes + (size_t)(kMargin + by0 + r) * plane_stride + kMargin + bx0 + 4 * k));
+    }
+    sw.org[r][k] = v;
+  }
+
+  // ---- stage the half-pel patch, de-interleaved into phase planes ----
+  const int BX = 2 * (bx0 + fx), BY = 2 * (by0 + fy);         // half-pel coordinates of the block at the full-pel winner
+  const int X0 = (BX - 2) & ~3, Y0 = BY - 2;                  // patch origin: 4-byte aligned column, even row
+  const int relx = BX - X0;                                   // 2..5
+  {
+    const int nwords = ((BX + 2 * w) - X0) / 4 + 1;           // <= 10
+    const int nrows = 2 * h + 3;
+    const uint8_t* src = half_planes + (size_t)j.ref_slot * half_bytes + (size_t)(kHpOrigin + Y0) * half_stride + kHpOrigin + X0;
+    const int lr = lane / nwords, lk = lane - lr * nwords;     // one division per lane, then whole rows per pass
+    const int rows_per_pass = 32 / nwords;
+    if (lr < rows_per_pass) {
+      for (int r = lr; r < nrows; r += rows_per_pass) {
+        const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)r * half_stride + 4 * lk));
+        const int py = r & 1, pr = r >> 1;
+        *reinterpret_cast<uint16_t*>(&sw.plane[py * 2 + 0][pr][2 * lk]) = (uint16_t)__byte_perm(v, 0, 0x4420);   // bytes 0, 2: even X
+        *reinterpret_cast<uint16_t*>(&sw.plane[py * 2 + 1][pr][2 * lk]) = (uint16_t)__byte_perm(v, 0, 0x4431);   // bytes 1, 3: odd X
+      }
+    }
+  }
+  __syncwarp();
+
+  // each lane always works on the same 4x4 sub-block (32 % nb == 0): keep its original rows in registers
+  const int blk_b = lane & (nb - 1);
+  const int px0 = (blk_b & (nbx - 1)) * 4, py0 = (blk_b >> lg_nbx) * 4;
+  const uint8_t* pl = &sw.plane[0][0][0];
+  uint32_t orow[4];
+#pragma unroll
+  for (int y = 0; y < 4; ++y) orow[y] = sw.org[py0 + y][px0 >> 2];
+
+  int mvh = fx << 2, mvv = fy << 2;                           // cMv <<= 2
+  uint32_t best = 0xffffffffu;
   uint32_t best_mode = 0;
-  const uint8_t* base = hp0 + (mvh >> 1) + (mvv >> 1) * half_stride;
+  int cx = 0, cy = 0;                                         // half-pel winner, in half-pel units from the full-pel position
   bool axis_diag = false;
 
   for (int stage = 0; stage < 2; ++stage) {
     const int n0 = stage, ncand = 9 - stage;
-    unsigned long long stage_best = ~0ull;
+    uint32_t stage_best = 0xffffffffu;
     for (int t0 = 0; t0 < ncand * nb; t0 += 32) {
       const int t = t0 + lane;
       const bool active = t < ncand * nb;
-      const int n = n0 + (active ? t / nb : 0);
-      const int b = active ? t % nb : 0;
-      const int px0 = (b % nbx) * 4, py0 = (b / nbx) * 4;
+      const int n = n0 + (active ? (t >> lg_nb) : 0);
       const int dx = stage == 0 ? c_half_mv[n][0] : c_quarter_mv[n][0];
       const int dy = stage == 0 ? c_half_mv[n][1] : c_quarter_mv[n][1];
       uint32_t dist = 0;
       if (active) {
-        int d[16];
+        // stage 0: the half-pel plane at (dx/2, dy/2); stage 1: rounded average of two half-pel samples, chosen by the
+        // filter class of the half-pel winner (xXFilter1/4 average the two AXIS neighbours for diagonal positions)
+        int offa, offb;
+        if (stage == 0) { offa = offb = cand_offset(relx, dx / 2, dy / 2, px0, py0); }
+        else if (axis_diag && dx != 0 && dy != 0) { offa = cand_offset(relx, cx + dx, cy, px0, py0); offb = cand_offset(relx, cx, cy + dy, px0, py0); }
+        else { offa = cand_offset(relx, cx, cy, px0, py0); offb = cand_offset(relx, cx + dx, cy + dy, px0, py0); }
+        uint32_t crow[4];
 #pragma unroll
-        for (int y = 0; y < 4; ++y)
+        for (int y = 0; y < 4; ++y) {
+          const uint32_t pa = fetch4(pl, offa + y * kK3PlanePitch);
+          crow[y] = stage == 0 ? pa : __vavgu4(pa, fetch4(pl, offb + y * kK3PlanePitch));   // per byte (p + q + 1) >> 1
+        }
+        if (sub_dfunc == JSVM_DF_HADAMARD) {
+          int d[16];
 #pragma unroll
-          for (int x = 0; x < 4; ++x) {
-            const int o = org0 ? (int)org0[(py0 + y) * 16 + px0 + x] : (int)cur0[(py0 + y) * plane_stride + px0 + x];
-            d[y * 4 + x] = o - subpel_sample(base, half_stride, stage, dx, dy, axis_diag, px0 + x, py0 + y);
-          }
-        if (sub_dfunc == JSVM_DF_HADAMARD) dist = hadamard4x4(d);
-        else {
+          for (int y = 0; y < 4; ++y)
 #pragma unroll
-          for (int i = 0; i < 16; ++i) dist += (uint32_t)abs(d[i]);
+            for (int x = 0; x < 4; ++x) d[y * 4 + x] = (int)((orow[y] >> (8 * x)) & 0xff) - (int)((crow[y] >> (8 * x)) & 0xff);
+          dist = hadamard4x4(d);
+        } else {
+#pragma unroll
+          for (int y = 0; y < 4; ++y) dist = __vsadu4(orow[y], crow[y]) + dist;
         }
       }
       // sum the 4x4 blocks of one candidate (nb is a power of two, groups are lane-aligned)
       for (int off = 1; off < nb; off <<= 1) dist += __shfl_xor_sync(0xffffffffu, dist, off);
-      unsigned long long k = ~0ull;
-      if (active && b == 0) {
+      uint32_t k = 0xffffffffu;                           // (cost << 8) | n : cost < 2^17 in the 8-bit domain (N12)
+      if (active && blk_b == 0) {
         const int th = mvh + dx, tv = mvv + dy;
         const uint32_t c = dist + rate_cost(f, mv_component_bits(th - j.pred.hor) + mv_component_bits(tv - j.pred.ver));
-        k = ((unsigned long long)c << 8) | (unsigned)n;
+        k = (c << 8) | (uint32_t)n;
       }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const unsigned long long o = __shfl_xor_sync(0xffffffffu, k, off);
-        k = o < k ? o : k;
-      }
+      k = __reduce_min_sync(0xffffffffu, k);
       stage_best = k < stage_best ? k : stage_best;
     }
     if (stage == 0) {
-      best = stage_best & ~0xffull;                       // incumbent for the quarter-pel stage (n field 0 wins ties)
+      best = stage_best & ~0xffu;                         // incumbent for the quarter-pel stage (n field 0 wins ties)
       best_mode = (uint32_t)(stage_best & 0xff);
       mvh += c_half_mv[best_mode][0]; mvv += c_half_mv[best_mode][1];
+      cx = c_half_mv[best_mode][0] / 2; cy = c_half_mv[best_mode][1] / 2;   // ENC/MotionEstimationQuarterPel.cpp:137-139
       const int filt = c_filter_of_half[best_mode];
       axis_diag = (filt == 0 || filt == 3);
-      base = hp0 + (mvh >> 1) + (mvv >> 1) * half_stride;   // ENC/MotionEstimationQuarterPel.cpp:137-139
     } else if (stage_best < best) {
       const uint32_t n = (uint32_t)(stage_best & 0xff);
       best = stage_best;
@@ -148,7 +210,7 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
     }
   }
 
-  const uint32_t min_sad = (uint32_t)(best >> 8);
+  const uint32_t min_sad = best >> 8;
   if (lane == 0) {
     // ENC/MotionEstimation.cpp:331-337 with fWeight = 1.0
     const uint32_t mv_bits = mv_component_bits(mvh - j.pred.hor) + mv_component_bits(mvv - j.pred.ver);
@@ -161,21 +223,29 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
     r.bits = j.bits_in + mv_bits;
     r.cost = (min_sad - rate_cost(f, mv_bits)) + rate_cost(f, j.bits_in + mv_bits);
     r.best_mode = best_mode;
-    results[job_idx] = r;
+    *reinterpret_cast<uint4*>(&results[job_idx]) = *reinterpret_cast<const uint4*>(&r);
+    *(reinterpret_cast<uint4*>(&results[job_idx]) + 1) = *(reinterpret_cast<const uint4*>(&r) + 1);
   }
 
   // ---- compensateBlock: the winner's prediction block (stride 16, zero padded) ----
   if (preds) {
-    uint8_t* dp = preds + (size_t)job_idx * 256;
+    uint32_t* dp = reinterpret_cast<uint32_t*>(preds + (size_t)job_idx * 256);
     const int stage = best_mode < 0x10 ? 0 : 1;
     const int n = stage ? (int)(best_mode >> 4) : (int)best_mode;
     const int dx = stage ? c_quarter_mv[n][0] : c_half_mv[n][0];
     const int dy = stage ? c_quarter_mv[n][1] : c_half_mv[n][1];
-    // the half-pel buffers were filled around the FULL-PEL mv, the quarter-pel ones around the half-pel winner
-    const uint8_t* pbase = stage ? base : hp0 + ((fx << 2) >> 1) + ((fy << 2) >> 1) * half_stride;
-    for (int i = lane; i < 256; i += 32) {
-      const int x = i & 15, y = i >> 4;
-      dp[i] = (x < w && y < h) ? (uint8_t)subpel_sample(pbase, half_stride, stage, dx, dy, axis_diag, x, y) : 0;
+    int offa, offb;
+    if (stage == 0) { offa = offb = cand_offset(relx, dx / 2, dy / 2, 0, 0); }
+    else if (axis_diag && dx != 0 && dy != 0) { offa = cand_offset(relx, cx + dx, cy, 0, 0); offb = cand_offset(relx, cx, cy + dy, 0, 0); }
+    else { offa = cand_offset(relx, cx, cy, 0, 0); offb = cand_offset(relx, cx + dx, cy + dy, 0, 0); }
+    for (int i = lane; i < 64; i += 32) {
+      const int y = i >> 2, k = i & 3;
+      uint32_t v = 0;
+      if (4 * k < w && y < h) {
+        const uint32_t pa = fetch4(pl, offa + y * kK3PlanePitch + 4 * k);
+        v = stage == 0 ? pa : __vavgu4(pa, fetch4(pl, offb + y * kK3PlanePitch + 4 * k));
+      }
+      dp[i] = v;
     }
   }
 }
