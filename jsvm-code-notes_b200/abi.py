@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjsvm_me_b200.so")
+LIB_PATH = os.environ.get("JSVM_ME_LIB", os.path.join(_HERE, "libjsvm_me_b200.so"))   # override only for A/B kernel experiments
 
 # INCC/CommonDefs.h:169-190, 208-223
 MODE_16x16, MODE_16x8, MODE_8x16 = 1, 2, 3

@@ -30,11 +30,20 @@
 
 namespace jsvm {
 
-constexpr int kK2Threads   = 256;
+#ifndef K2_COST_IMADHI
+#define K2_COST_IMADHI 0
+#endif
+#ifndef K2_FASTPATH
+#define K2_FASTPATH 0
+#endif
+#ifndef K2_THREADS
+#define K2_THREADS 256
+#endif
+constexpr int kK2Threads   = K2_THREADS;
 constexpr int kWinRowBytes = 160;                 // bytes per staged window row (max 145 positions + 15)
 constexpr int kWinRowWords = kWinRowBytes / 4;    // 40 words: 40 mod 32 = 8 keeps successive rows on different banks
 constexpr int kMaxUW       = 145;                 // widest union window handled by one CTA
-constexpr int kMaxM        = (kMaxUW + 3) / 4;    // 37
+constexpr int kMaxM        = 38;                  // column groups per copy: (145 + 3 alignment columns + 3) / 4 = 37, rounded up to even
 constexpr int kMaxRows     = 184;                 // window rows covered by the strips (uh <= 176, rounded up to a strip)
 
 __device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t c) {
@@ -98,8 +107,12 @@ __device__ __forceinline__ uint32_t rate_key(uint32_t f, uint32_t by, uint32_t f
   asm("{\n"
       ".reg .u32 t, c;\n"
       "mad.lo.u32 t, %1, %2, %3;\n"
+#if K2_COST_IMADHI
+      "mad.hi.u32 c, t, 65536, %4;\n"         // (t * 2^16) >> 32 + sad == (t >> 16) + sad, on the FMA pipe
+#else
       "shr.u32 t, t, 16;\n"
       "add.u32 c, t, %4;\n"
+#endif
       "mad.lo.u32 %0, c, 32768, %5;\n"
       "}\n" : "=r"(key) : "r"(f), "r"(by), "r"(fbx), "r"(sad), "r"(idx));
   return key;
@@ -115,6 +128,8 @@ struct K2Smem {
   uint32_t factor[NS];
   int16_t  xlo[NS], xhi[NS], ylo[NS], yhi[NS];    // relative to the union window origin (empty slot: xhi < xlo)
   int32_t  job[NS];                               // absolute job index or -1
+  int16_t  pred_h[NS], pred_v[NS];                // rcMvPred of the slot's job
+  int32_t  next_unit;                             // work counter: warps pull batches of 32 units
   uint32_t best[NS];
   uint8_t  bx[NS][4 * kMaxM + 12];                // bits of the horizontal difference, permuted [s][m]
   Mask     xmask[4 * kMaxM];                      // slots whose window contains column x, permuted [s][m]
@@ -152,10 +167,15 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
 
   const Group& g = groups[blockIdx.x];
   const int tid = threadIdx.x;
-  const int uw = g.uw, uh = g.uh;
+  // The staged window starts on a 4-byte boundary of the reference plane: `xa` (0..3) extra columns on the left.
+  // Column x' of the staged window is displacement ux0 - xa + x'; the extra columns belong to no job's window.
+  const int px = kMargin + 16 * g.mb_x + g.ux0;                 // union window origin in plane coordinates
+  const int py = kMargin + 16 * g.mb_y + g.uy0;
+  const int xa = px & 3;
+  const int uw = g.uw, uh = g.uh, uwx = uw + xa;
   const int nstrips = (uh + V - 1) / V;
   const int rows = k2_rows(uh);
-  const int M = ((uw + 3) >> 2) + (((uw + 3) >> 2) & 1);          // column groups per copy, rounded up to even
+  const int M = ((uwx + 3) >> 2) + (((uwx + 3) >> 2) & 1);        // column groups per copy, rounded up to even
   const int copy_words = k2_copy_words(rows, M);
   const int by_stride = nstrips * V;
   uint32_t* winw = reinterpret_cast<uint32_t*>(smem_raw);
@@ -163,7 +183,7 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
   SM& sm = *reinterpret_cast<SM*>(after);
   uint32_t* by_tab = reinterpret_cast<uint32_t*>(after + ((sizeof(SM) + 15) & ~(size_t)15));
 
-  // ---- prologue 1: per-slot job parameters ----
+  // ---- prologue 1: per-slot job parameters (window relative to the staged origin, predictor, factor) ----
   if (tid < NS) {
     const int jo = g.slot_job[tid];
     sm.job[tid] = jo < 0 ? -1 : g.first_job + jo;
@@ -172,35 +192,35 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
       const jsvm_me_job j = jobs[g.first_job + jo];
       const Window w = job_window(j, mb_w, mb_h, default_range);
       sm.factor[tid] = j.cost_factor;
-      sm.xlo[tid] = (int16_t)(w.xlo - g.ux0); sm.xhi[tid] = (int16_t)(w.xhi - g.ux0);
-      sm.ylo[tid] = (int16_t)(w.ylo - g.uy0); sm.yhi[tid] = (int16_t)(w.yhi - g.uy0);
+      sm.xlo[tid] = (int16_t)(w.xlo - g.ux0 + xa); sm.xhi[tid] = (int16_t)(w.xhi - g.ux0 + xa);
+      sm.ylo[tid] = (int16_t)(w.ylo - g.uy0);      sm.yhi[tid] = (int16_t)(w.yhi - g.uy0);
+      sm.pred_h[tid] = j.pred.hor; sm.pred_v[tid] = j.pred.ver;
     } else {
       sm.factor[tid] = 0; sm.xlo[tid] = 0; sm.xhi[tid] = -1; sm.ylo[tid] = 0; sm.yhi[tid] = -1;
+      sm.pred_h[tid] = 0; sm.pred_v[tid] = 0;
     }
   }
+  if (tid == 0) sm.next_unit = 0;
 
   // ---- prologue 2: the four byte-shifted copies of the reference window ----
+  // item = (row, 4 destination words): 5 aligned source words -> 4 x 4 funnel-shifted words -> two 8-byte stores per copy
   {
-    const int px = kMargin + 16 * g.mb_x + g.ux0;               // window origin in plane coordinates
-    const int py = kMargin + 16 * g.mb_y + g.uy0;
-    const int a16 = px & 15;
-    const uint8_t* src0 = planes + (size_t)g.ref_slot * plane_bytes + (size_t)py * plane_stride + (px - a16);   // 16-byte aligned
-    constexpr int kGroups = (kWinRowWords + 4 + 3) / 4;         // 11 groups of 4 source words cover every destination word
+    const uint32_t* src0 = reinterpret_cast<const uint32_t*>(
+        planes + (size_t)g.ref_slot * plane_bytes + (size_t)py * plane_stride + (px - xa));
+    const int stride_w = plane_stride >> 2;
+    constexpr int kGroups = kWinRowWords / 4;                   // 10
     for (int i = tid; i < rows * kGroups; i += kK2Threads) {
       const int r = i / kGroups, gq = i - r * kGroups;
-      const uint8_t* sp = src0 + (size_t)r * plane_stride + 16 * gq;
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(sp));
-      const uint32_t w4 = __ldg(reinterpret_cast<const uint32_t*>(sp + 16));
-      const uint32_t w[5] = { v.x, v.y, v.z, v.w, w4 };
+      const uint32_t* sp = src0 + (size_t)r * stride_w + 4 * gq;
+      uint32_t w[5];
 #pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        const int sh = a16 + s, q = sh >> 2, rb = (sh & 3) * 8;
-        uint32_t* dst = winw + s * copy_words + r * kWinRowWords;
+      for (int k = 0; k < 5; ++k) w[k] = __ldg(sp + k);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int m = 4 * gq + k - q;                         // destination word of copy s
-          if (m >= 0 && m < kWinRowWords) dst[m] = __funnelshift_r(w[k], w[k + 1], rb);
-        }
+      for (int sft = 0; sft < 4; ++sft) {
+        // copy_words is even (M is), not a multiple of 4: 8-byte stores
+        uint2* dst = reinterpret_cast<uint2*>(winw + sft * copy_words + r * kWinRowWords + 4 * gq);
+        dst[0] = make_uint2(__funnelshift_r(w[0], w[1], 8 * sft), __funnelshift_r(w[1], w[2], 8 * sft));
+        dst[1] = make_uint2(__funnelshift_r(w[2], w[3], 8 * sft), __funnelshift_r(w[3], w[4], 8 * sft));
       }
     }
   }
@@ -227,30 +247,27 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
   }
   __syncthreads();            // slot parameters visible
 
-  // ---- prologue 4: MV-rate tables and validity masks ----
-  for (int i = tid; i < NS * by_stride; i += kK2Threads) {
-    const int sl = i / by_stride, y = i - sl * by_stride;
-    uint32_t b = 0;
+  // ---- prologue 4: MV-rate tables and validity masks (no runtime divisions: slot loops outside, strided loops inside) ----
+  for (int sl = 0; sl < NS; ++sl) {
+    const bool present = sm.job[sl] >= 0;
+    const int pv = sm.pred_v[sl], ph = sm.pred_h[sl];
     // xGetBits with m_uiMvScaleShift = 2: table index (y << 2) - pred (N6)
-    if (sm.job[sl] >= 0 && y < uh) b = mv_component_bits(((g.uy0 + y) << 2) - jobs[sm.job[sl]].pred.ver);
-    by_tab[sl * by_stride + y] = b;
+    for (int y = tid; y < by_stride; y += kK2Threads)
+      by_tab[sl * by_stride + y] = (present && y < uh) ? mv_component_bits(((g.uy0 + y) << 2) - pv) : 0u;
+    for (int ci = tid; ci < 4 * kMaxM; ci += kK2Threads) {
+      const int sft = ci / kMaxM, m = ci - sft * kMaxM;         // division by a compile-time constant
+      const int x = 4 * m + sft;                                // staged column
+      sm.bx[sl][ci] = (present && x < uwx) ? (uint8_t)mv_component_bits(((g.ux0 - xa + x) << 2) - ph) : (uint8_t)0;
+    }
   }
-  for (int i = tid; i < NS * 4 * kMaxM; i += kK2Threads) {
-    const int sl = i / (4 * kMaxM), r = i - sl * 4 * kMaxM;
-    const int s = r / kMaxM, m = r - s * kMaxM;
-    const int x = 4 * m + s;
-    uint32_t b = 0;
-    if (sm.job[sl] >= 0 && x < uw) b = mv_component_bits(((g.ux0 + x) << 2) - jobs[sm.job[sl]].pred.hor);
-    sm.bx[sl][s * kMaxM + m] = (uint8_t)b;
-  }
-  for (int i = tid; i < 4 * kMaxM; i += kK2Threads) {
-    const int s = i / kMaxM, m = i - s * kMaxM;
-    const int x = 4 * m + s;
+  for (int ci = tid; ci < 4 * kMaxM; ci += kK2Threads) {
+    const int sft = ci / kMaxM, m = ci - sft * kMaxM;
+    const int x = 4 * m + sft;
     Mask mk = 0;
     for (int sl = 0; sl < NS; ++sl) if (x >= sm.xlo[sl] && x <= sm.xhi[sl]) mk |= (Mask)1 << sl;
-    sm.xmask[i] = mk;
+    sm.xmask[ci] = mk;
   }
-  for (int i = tid; i < SM::kMaxStrips; i += kK2Threads) {
+  for (int i = tid; i < nstrips; i += kK2Threads) {
     const int y0 = i * V, y1 = y0 + V - 1;
     Mask full = 0, any = 0;
     for (int sl = 0; sl < NS; ++sl) {
@@ -268,12 +285,20 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
 
   const int units_per_strip = 4 * M;
   const int nunits = nstrips * units_per_strip;
+  const int lane = tid & 31;
 
-  for (int u = tid; u < nunits; u += kK2Threads) {
+  // warps pull batches of 32 units from a shared counter: they all finish within one batch of each other
+  for (;;) {
+    int u0 = 0;
+    if (lane == 0) u0 = atomicAdd(&sm.next_unit, 32);
+    u0 = __shfl_sync(0xffffffffu, u0, 0);
+    if (u0 >= nunits) break;
+    const bool live = u0 + lane < nunits;
+    const int u = live ? u0 + lane : nunits - 1;                  // idle lanes redo the last unit with every slot masked off
     const int strip = u / units_per_strip;
     const int rem = u - strip * units_per_strip;
     const int s = rem / M, m = rem - s * M;
-    const int x = 4 * m + s;
+    const int x = 4 * m + s - xa;                                 // column inside the union window (negative: alignment columns)
     const int ys = strip * V;
     const int cidx = s * kMaxM + m;
 
@@ -287,38 +312,35 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
     const uint32_t* rp = winw + s * copy_words + ys * kWinRowWords + m;
 #pragma unroll
     for (int r = 0; r < 15 + V; ++r) {
-      const uint32_t w0 = rp[r * kWinRowWords + 0], w1 = rp[r * kWinRowWords + 1];
-      const uint32_t w2 = rp[r * kWinRowWords + 2], w3 = rp[r * kWinRowWords + 3];
+      const uint32_t w[4] = { rp[r * kWinRowWords + 0], rp[r * kWinRowWords + 1], rp[r * kWinRowWords + 2], rp[r * kWinRowWords + 3] };
+      // word-major order: the two updates of one accumulator (words 0/1 or 2/3 of a row) end up V instructions apart
+      // instead of back to back, so a warp does not wait out the ALU latency between them
 #pragma unroll
-      for (int v = 0; v < V; ++v) {
-        const int c = r - v;                    // current-MB row matched by this reference row at displacement ys+v
-        if (c < 0 || c > 15) continue;
-        if (GRAN4) {
-          const int a = (c >> 2) * 4;
-          acc[v][a + 0] = sad4(cur[c][0], w0, acc[v][a + 0]);
-          acc[v][a + 1] = sad4(cur[c][1], w1, acc[v][a + 1]);
-          acc[v][a + 2] = sad4(cur[c][2], w2, acc[v][a + 2]);
-          acc[v][a + 3] = sad4(cur[c][3], w3, acc[v][a + 3]);
-        } else {
-          const int q = (c >> 3) * 2;
-          acc[v][q + 0] = sad4(cur[c][0], w0, acc[v][q + 0]);
-          acc[v][q + 0] = sad4(cur[c][1], w1, acc[v][q + 0]);
-          acc[v][q + 1] = sad4(cur[c][2], w2, acc[v][q + 1]);
-          acc[v][q + 1] = sad4(cur[c][3], w3, acc[v][q + 1]);
+      for (int kk = 0; kk < 4; ++kk) {
+        const int k = GRAN4 ? kk : ((kk & 1) * 2 + (kk >> 1));      // 8x8 granularity: 0, 2, 1, 3
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const int c = r - v;                  // current-MB row matched by this reference row at displacement ys+v
+          if (c < 0 || c > 15) continue;
+          const int a = GRAN4 ? (c >> 2) * 4 + k : (c >> 3) * 2 + (k >> 1);
+          acc[v][a] = sad4(cur[c][k], w[k], acc[v][a]);
         }
       }
     }
 
     // ---- per partition: SAD + rate, packed-key min ----
-    const Mask mx = sm.xmask[cidx];
+    const Mask mx = live ? sm.xmask[cidx] : (Mask)0;
     const Mask mfull = mx & sm.yfull[strip], many = mx & sm.yany[strip];
-    if (many == 0) continue;                                      // dead lane (x >= uw) or outside every job's window
+    constexpr Mask kAllSlots = (Mask)(~(Mask)0) >> (8 * sizeof(Mask) - NS);
+    // warp-uniform fast path: every slot is searched and every row of the strip is inside every window for all lanes
+    const bool fast = K2_FASTPATH && __all_sync(0xffffffffu, mfull == kAllSlots);
+    if (!fast && many == 0) continue;                             // dead lane (x >= uw) or outside every job's window
     uint32_t idxv[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) idxv[v] = (uint32_t)((ys + v) * uw + x);
 
     auto update = [&](const int sl, const uint32_t (&sadv)[V]) {
-      if (!((many >> sl) & 1)) return;
+      if (!fast && !((many >> sl) & 1)) return;
       const uint32_t f = sm.factor[sl];
       const uint32_t fbx = f * (uint32_t)sm.bx[sl][cidx];
       uint32_t byv[V];
@@ -328,7 +350,7 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
         byv[v4] = q.x; byv[v4 + 1] = q.y; byv[v4 + 2] = q.z; byv[v4 + 3] = q.w;
       }
       uint32_t b = best[sl];
-      if ((mfull >> sl) & 1) {
+      if (fast || ((mfull >> sl) & 1)) {
 #pragma unroll
         for (int v = 0; v < V; ++v) b = min(b, rate_key(f, byv[v], fbx, sadv[v], idxv[v]));
       } else {
