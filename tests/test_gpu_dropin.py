@@ -1,0 +1,26 @@
+"""System-level drop-in parity: the unmodified reference encoder CLI linked with the B200 drop-in must write the same
+bitstream and the same reconstruction as the stock build (the check of R/data/runAndCheckSVC.bat:45-50).
+Both binaries are built in the container that has /root/reference and travel to the GPU box."""
+import os
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+@pytest.mark.parametrize("args", [
+    ["--frames", "9", "--gop", "8", "--sr", "16", "--subpel", "2"],                                   # C1: QCIF, SR 16, hier-B, SATD sub-pel
+    ["--frames", "5", "--gop", "4", "--sr", "32", "--subpel", "0", "--all-partitions", "--refs", "2"],  # all 41 partitions, 2 refs, SAD sub-pel
+])
+def test_encoder_with_dropin_is_bit_identical(args):
+    import system_parity
+    if not (os.path.exists(system_parity.STOCK) and os.path.exists(system_parity.B200)):
+        pytest.skip("reference encoder binaries not built (need /root/reference at build time)")
+    res = system_parity.compare(args + ["--timeout", "600"])
+    assert res["stock"]["bitstream_md5"] == res["b200"]["bitstream_md5"], res
+    assert res["stock"]["recon_md5"] == res["b200"]["recon_md5"], res
+    assert res["stock"]["bytes"] > 1000
