@@ -278,11 +278,13 @@ def main():
     if not args.no_e2e:
         host_jobs = torch.from_numpy(jobs.view(np.uint8).copy()).pin_memory()
         hj = host_jobs.numpy().view(pkg.JOB_DTYPE)
+        host_res = torch.empty(n_jobs * 32, dtype=torch.uint8).pin_memory()
+        hr = host_res.numpy().view(pkg.RESULT_DTYPE)
         def step_e2e():
             for p, tns in host_planes.items():
                 me.upload_plane_ptr(slot_of[p], tns.data_ptr())
             me.interp_halfpel(ref_slots)
-            return me.search(hj)
+            return me.search(hj, out=hr)
         for _ in range(max(1, min(args.warmup, 2))):
             step_e2e()
         barrier()

@@ -13,6 +13,8 @@
 #include <cstring>
 #include <vector>
 #include <algorithm>
+#include <thread>
+#include <functional>
 
 #include "../../include/jsvm_me_b200.h"
 #include "me_common.cuh"
@@ -143,38 +145,50 @@ int launch_margin_fill(jsvm_me_ctx* c, const int* d_slots, int n) {
 
 // The planner: restates nothing from the reference -- it only decides which estimateBlockWithStart
 // calls can share one SAD pass (same macroblock, planes and original; distinct partition slots;
-// union of the clipped windows small enough for one CTA).
-int plan_jobs(int width, int height, int n_slots, int search_range, const jsvm_me_job* jobs, int n_jobs, std::vector<Group>& out, jsvm_me_plan_info* info) {
-  const int mbw = width >> 4, mbh = height >> 4;
+// union of the clipped windows small enough for one CTA).  Pure host logic; large job lists are cut at
+// macroblock boundaries and planned by several threads (the result equals the serial plan).
+struct PlanChunk {
   std::vector<Group> g8, g4;
-  Group cur; bool open = false; Window cw{};
   int64_t npos = 0;
+  int err_job = -1;
+  char err[160] = "";
+};
+
+inline bool same_mb(const jsvm_me_job& a, const jsvm_me_job& b) {
+  return a.cur_slot == b.cur_slot && a.ref_slot == b.ref_slot && a.mb_x == b.mb_x && a.mb_y == b.mb_y && a.org_index == b.org_index;
+}
+
+void plan_range(int width, int height, int n_slots, int search_range, const jsvm_me_job* jobs, int begin, int end, PlanChunk& out) {
+  const int mbw = width >> 4, mbh = height >> 4;
+  Group cur; bool open = false; Window cw{};
   auto close = [&]() {
     if (!open) return;
     cur.ux0 = (int16_t)cw.xlo; cur.uy0 = (int16_t)cw.ylo;
     cur.uw = (int16_t)(cw.xhi - cw.xlo + 1); cur.uh = (int16_t)(cw.yhi - cw.ylo + 1);
-    (cur.gran4 ? g4 : g8).push_back(cur);
+    (cur.gran4 ? out.g4 : out.g8).push_back(cur);
     open = false;
   };
-  for (int i = 0; i < n_jobs; ++i) {
+  auto bad = [&](int i, const char* fmt, int a = 0, int b = 0, int c = 0, int d = 0) {
+    out.err_job = i;
+    snprintf(out.err, sizeof(out.err), fmt, a, b, c, d);
+  };
+  out.g8.reserve((size_t)(end - begin) / 8 + 16);
+  for (int i = begin; i < end; ++i) {
     const jsvm_me_job& j = jobs[i];
     int w, h;
-    if (!mode_size(j.mode, w, h)) return fail("job %d: unsupported mode %d", i, (int)j.mode);
-    if (j.blk > 15) return fail("job %d: blk %d out of range", i, (int)j.blk);
+    if (!mode_size(j.mode, w, h)) return bad(i, "unsupported mode %d", (int)j.mode);
+    if (j.blk > 15) return bad(i, "blk %d out of range", (int)j.blk);
     const int slot = partition_slot(j.mode, j.blk);
-    if (slot < 0) return fail("job %d: blk %d is not a legal origin for mode %d", i, (int)j.blk, (int)j.mode);
-    if (j.cur_slot < 0 || j.cur_slot >= n_slots || j.ref_slot < 0 || j.ref_slot >= n_slots)
-      return fail("job %d: plane slot out of range", i);
-    if (j.mb_x < 0 || j.mb_x >= mbw || j.mb_y < 0 || j.mb_y >= mbh) return fail("job %d: macroblock (%d,%d) outside the picture", i, j.mb_x, j.mb_y);
+    if (slot < 0) return bad(i, "blk %d is not a legal origin for mode %d", (int)j.blk, (int)j.mode);
+    if (j.cur_slot < 0 || j.cur_slot >= n_slots || j.ref_slot < 0 || j.ref_slot >= n_slots) return bad(i, "plane slot out of range");
+    if (j.mb_x < 0 || j.mb_x >= mbw || j.mb_y < 0 || j.mb_y >= mbh) return bad(i, "macroblock (%d,%d) outside the picture", j.mb_x, j.mb_y);
     const Window w1 = job_window(j, mbw, mbh, search_range);
     const int ww = w1.xhi - w1.xlo + 1, wh = w1.yhi - w1.ylo + 1;
-    if (ww < 1 || wh < 1) return fail("job %d: empty search window", i);
+    if (ww < 1 || wh < 1) return bad(i, "empty search window");
     if (ww > kMaxUW || wh > kMaxUH || ww * wh > (1 << kIdxBits))
-      return fail("job %d: search window %dx%d exceeds the %dx%d limit of this build (search range <= 64)", i, ww, wh, kMaxUW, kMaxUH);
-    npos += (int64_t)ww * wh;
-    bool join = open && (i - cur.first_job) < 127 &&
-                j.cur_slot == cur.cur_slot && j.ref_slot == cur.ref_slot && j.mb_x == cur.mb_x && j.mb_y == cur.mb_y &&
-                j.org_index == cur.org_index && cur.slot_job[slot] < 0;
+      return bad(i, "search window %dx%d exceeds the %dx%d limit of this build (search range <= 64)", ww, wh, kMaxUW, kMaxUH);
+    out.npos += (int64_t)ww * wh;
+    bool join = open && (i - cur.first_job) < 127 && same_mb(j, jobs[cur.first_job]) && cur.slot_job[slot] < 0;
     if (join) {
       Window u = cw;
       u.xlo = std::min(u.xlo, w1.xlo); u.xhi = std::max(u.xhi, w1.xhi);
@@ -196,15 +210,49 @@ int plan_jobs(int width, int height, int n_slots, int search_range, const jsvm_m
     if (slot >= kSlotsGran8) cur.gran4 = 1;
   }
   close();
-  out.clear();
-  out.insert(out.end(), g8.begin(), g8.end());
-  out.insert(out.end(), g4.begin(), g4.end());
+}
+
+int plan_jobs(int width, int height, int n_slots, int search_range, const jsvm_me_job* jobs, int n_jobs, std::vector<Group>& out, jsvm_me_plan_info* info) {
+  int n_thr = 1;
+  if (n_jobs >= 65536) n_thr = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+  // chunk boundaries only where the macroblock changes: the serial planner starts a new group there anyway
+  std::vector<int> cut(n_thr + 1, n_jobs);
+  cut[0] = 0;
+  for (int t = 1; t < n_thr; ++t) {
+    int i = std::max(cut[t - 1], (int)((int64_t)n_jobs * t / n_thr));
+    while (i < n_jobs && i > 0 && same_mb(jobs[i], jobs[i - 1])) ++i;
+    cut[t] = i;
+  }
+  std::vector<PlanChunk> chunks(n_thr);
+  if (n_thr == 1) plan_range(width, height, n_slots, search_range, jobs, 0, n_jobs, chunks[0]);
+  else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_thr; ++t)
+      th.emplace_back(plan_range, width, height, n_slots, search_range, jobs, cut[t], cut[t + 1], std::ref(chunks[t]));
+    for (auto& x : th) x.join();
+  }
+  size_t n8 = 0, n4 = 0;
+  for (auto& c : chunks) {
+    if (c.err_job >= 0) return fail("job %d: %s", c.err_job, c.err);
+    n8 += c.g8.size(); n4 += c.g4.size();
+  }
+  out.resize(n8 + n4);
+  size_t o8 = 0, o4 = n8;
+  info->max_uh_8x8 = 0; info->max_uh_4x4 = 0; info->n_positions = 0; info->n_group_positions = 0;
+  for (auto& c : chunks) {
+    if (!c.g8.empty()) memcpy(&out[o8], c.g8.data(), c.g8.size() * sizeof(Group));
+    if (!c.g4.empty()) memcpy(&out[o4], c.g4.data(), c.g4.size() * sizeof(Group));
+    o8 += c.g8.size(); o4 += c.g4.size();
+    info->n_positions += c.npos;
+  }
+  for (size_t i = 0; i < out.size(); ++i) {
+    const Group& g = out[i];
+    int32_t& mx = g.gran4 ? info->max_uh_4x4 : info->max_uh_8x8;
+    mx = std::max<int32_t>(mx, g.uh);
+    info->n_group_positions += (int64_t)g.uw * g.uh;
+  }
   info->n_groups = (int32_t)out.size();
-  info->n_groups_8x8 = (int32_t)g8.size();
-  info->max_uh_8x8 = 0; info->max_uh_4x4 = 0;
-  info->n_positions = npos; info->n_group_positions = 0;
-  for (const Group& g : g8) { info->max_uh_8x8 = std::max<int>(info->max_uh_8x8, g.uh); info->n_group_positions += (int64_t)g.uw * g.uh; }
-  for (const Group& g : g4) { info->max_uh_4x4 = std::max<int>(info->max_uh_4x4, g.uh); info->n_group_positions += (int64_t)g.uw * g.uh; }
+  info->n_groups_8x8 = (int32_t)n8;
   return JSVM_ME_OK;
 }
 
@@ -472,11 +520,6 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
   if (!c->d_planes) return fail("jsvm_me_configure has not been called");
   if (!c->params_set) return fail("jsvm_me_set_params has not been called");
   if (n_jobs <= 0) return JSVM_ME_OK;
-  for (int i = 0; i < n_jobs; ++i) {
-    if (jobs[i].org_index >= n_org_mbs) return fail("job %d: org_index %d >= n_org_mbs %d", i, jobs[i].org_index, n_org_mbs);
-    if (jobs[i].cur_slot >= 0 && jobs[i].cur_slot < c->n_slots && jobs[i].org_index < 0 && !c->slot_full[jobs[i].cur_slot]) return fail("job %d: cur_slot %d is empty", i, jobs[i].cur_slot);
-    if (jobs[i].ref_slot >= 0 && jobs[i].ref_slot < c->n_slots && !c->slot_half[jobs[i].ref_slot]) return fail("job %d: ref_slot %d has no half-pel plane", i, jobs[i].ref_slot);
-  }
   if (n_org_mbs > 0) {
     if (!org_mbs) return fail("org_mbs is null");
     for (size_t i = 0; i < (size_t)n_org_mbs * 256; ++i)
@@ -484,28 +527,35 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
         return fail("org_mbs sample %zu = %d outside [0,255]: the signed 16-bit (residual-prediction) search variant is not implemented", i, (int)org_mbs[i]);
   }
   CU_OK(cudaSetDevice(c->device));
-  jsvm_me_plan_info info;
-  if (plan_jobs(c->W, c->H, c->n_slots, c->search_range, jobs, n_jobs, c->h_groups, &info)) return JSVM_ME_ERR;
   const bool want_preds = preds != nullptr || n_jobs <= 4096;
-  if (c->d_jobs.reserve(n_jobs) || c->d_groups.reserve(c->h_groups.size()) || c->d_keys.reserve(n_jobs) || c->d_aux.reserve(n_jobs) ||
+  if (c->d_jobs.reserve(n_jobs) || c->d_keys.reserve(n_jobs) || c->d_aux.reserve(n_jobs) ||
       c->d_results.reserve(n_jobs) || (want_preds && c->d_preds.reserve((size_t)n_jobs * 256)) ||
       (n_org_mbs > 0 && c->d_org.reserve((size_t)n_org_mbs * 256))) return JSVM_ME_ERR;
+  // the job upload runs while the host plans the search groups
   CU_OK(cudaMemcpyAsync(c->d_jobs.p, jobs, sizeof(jsvm_me_job) * n_jobs, cudaMemcpyHostToDevice, c->stream));
-  CU_OK(cudaMemcpyAsync(c->d_groups.p, c->h_groups.data(), sizeof(Group) * c->h_groups.size(), cudaMemcpyHostToDevice, c->stream));
   if (n_org_mbs > 0) CU_OK(cudaMemcpyAsync(c->d_org.p, org_mbs, sizeof(int16_t) * 256 * n_org_mbs, cudaMemcpyHostToDevice, c->stream));
+  jsvm_me_plan_info info;
+  if (plan_jobs(c->W, c->H, c->n_slots, c->search_range, jobs, n_jobs, c->h_groups, &info)) return JSVM_ME_ERR;
+  for (const Group& g : c->h_groups) {                     // one check per group: planes present, originals in range
+    if (g.org_index >= n_org_mbs) return fail("job %d: org_index %d >= n_org_mbs %d", g.first_job, g.org_index, n_org_mbs);
+    if (g.org_index < 0 && !c->slot_full[g.cur_slot]) return fail("job %d: cur_slot %d is empty", g.first_job, g.cur_slot);
+    if (!c->slot_half[g.ref_slot]) return fail("job %d: ref_slot %d has no half-pel plane", g.first_job, g.ref_slot);
+  }
+  if (c->d_groups.reserve(c->h_groups.size())) return JSVM_ME_ERR;
+  CU_OK(cudaMemcpyAsync(c->d_groups.p, c->h_groups.data(), sizeof(Group) * c->h_groups.size(), cudaMemcpyHostToDevice, c->stream));
   if (run_search(c, c->d_jobs.p, n_jobs, c->d_groups.p, &info, c->d_org.p, c->d_keys.p, c->d_aux.p, c->d_results.p, want_preds ? c->d_preds.p : nullptr)) return JSVM_ME_ERR;
   CU_OK(cudaMemcpyAsync(results, c->d_results.p, sizeof(jsvm_me_result) * n_jobs, cudaMemcpyDeviceToHost, c->stream));
   if (preds) CU_OK(cudaMemcpyAsync(preds, c->d_preds.p, (size_t)n_jobs * 256, cudaMemcpyDeviceToHost, c->stream));
   CU_OK(cudaStreamSynchronize(c->stream));
-  c->last_jobs.assign(jobs, jobs + n_jobs);
-  c->last_has_preds = want_preds;
+  if (want_preds && n_jobs <= 4096) c->last_jobs.assign(jobs, jobs + n_jobs); else c->last_jobs.clear();
+  c->last_has_preds = want_preds && n_jobs <= 4096;
   return JSVM_ME_OK;
 }
 
 int jsvm_me_fetch_pred(jsvm_me_ctx* c, int job_idx, int16_t* dst, int dst_stride) {
   if (!c || !dst) return fail("null argument");
-  if (job_idx < 0 || job_idx >= (int)c->last_jobs.size()) return fail("job index %d is not part of the last jsvm_me_search call", job_idx);
-  if (!c->last_has_preds) return fail("the last jsvm_me_search call did not keep prediction blocks (more than 4096 jobs and preds == NULL)");
+  if (job_idx < 0 || job_idx >= (int)c->last_jobs.size() || !c->last_has_preds)
+    return fail("job index %d: no prediction block kept from the last jsvm_me_search call (kept for calls of up to 4096 jobs)", job_idx);
   int w, h;
   mode_size(c->last_jobs[job_idx].mode, w, h);
   uint8_t blk[256];

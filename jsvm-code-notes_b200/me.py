@@ -33,7 +33,7 @@ def plan_host(width, height, n_slots, search_range, jobs):
     lib = abi.load_library()
     jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
     gsz = lib.jsvm_me_group_size()
-    groups = np.zeros(max(1, len(jobs)) * gsz, np.uint8)
+    groups = np.empty(max(1, len(jobs)) * gsz, np.uint8)
     info = PlanInfo()
     if lib.jsvm_me_plan_host(width, height, n_slots, search_range, _ptr(jobs), len(jobs), _ptr(groups), C.byref(info)) != 0:
         raise MotionEstimationError(lib.jsvm_me_last_error().decode())
@@ -125,11 +125,14 @@ class MotionEstimator:
         return out
 
     # ---- search --------------------------------------------------------------------------
-    def search(self, jobs, org_mbs=None, want_preds=False):
-        """estimateBlockWithStart for every record of `jobs` (JOB_DTYPE ndarray)."""
+    def search(self, jobs, org_mbs=None, want_preds=False, out=None):
+        """estimateBlockWithStart for every record of `jobs` (JOB_DTYPE ndarray).
+        `out`: optional preallocated RESULT_DTYPE array (e.g. a view of pinned memory) that receives the results."""
         jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
         n = len(jobs)
-        res = np.zeros(n, RESULT_DTYPE)
+        res = np.empty(n, RESULT_DTYPE) if out is None else out
+        if res.dtype != RESULT_DTYPE or len(res) != n or not res.flags.c_contiguous:
+            raise MotionEstimationError("out must be a contiguous RESULT_DTYPE array with one record per job")
         preds = np.zeros((n, 16, 16), np.uint8) if want_preds else None
         n_org = 0
         if org_mbs is not None:
@@ -141,7 +144,7 @@ class MotionEstimator:
     def plan(self, jobs):
         jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
         gsz = self._lib.jsvm_me_group_size()
-        groups = np.zeros(len(jobs) * gsz, np.uint8)
+        groups = np.empty(len(jobs) * gsz, np.uint8)
         info = PlanInfo()
         self._check(self._lib.jsvm_me_plan(self._ctx, _ptr(jobs), len(jobs), _ptr(groups), C.byref(info)))
         return groups[: info.n_groups * gsz].copy(), info

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """System-level parity: the UNMODIFIED reference encoder CLI (oracle/_ref/H264AVCEncoderLibTestStatic) against the
-same CLI linked with the B200 drop-in (jsvm-code-notes_b200/dropin/_build/H264AVCEncoderLibTestB200) on a synthetic
+same CLI linked with the B200 drop-in (oracle/_ref/H264AVCEncoderLibTestB200, recipe in oracle/Makefile) on a synthetic
 sequence: bitstream and reconstruction must be byte-identical (the check of R/data/runAndCheckSVC.bat:45-50, applied
 across the two builds).  Needs a GPU for the drop-in leg.
 
@@ -20,7 +20,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 STOCK = os.path.join(ROOT, "oracle", "_ref", "H264AVCEncoderLibTestStatic")
-B200 = os.path.join(ROOT, "jsvm-code-notes_b200", "dropin", "_build", "H264AVCEncoderLibTestB200")
+B200 = os.path.join(ROOT, "oracle", "_ref", "H264AVCEncoderLibTestB200")
 
 MAIN_CFG = """OutputFile {out}
 FrameRate 30.0
