@@ -15,6 +15,9 @@
 #include <algorithm>
 #include <thread>
 #include <functional>
+#include <mutex>
+#include <condition_variable>
+#include <string>
 
 #include "../../include/jsvm_me_b200.h"
 #include "me_common.cuh"
@@ -92,6 +95,9 @@ struct jsvm_me_ctx {
   DevBuf<uint8_t> d_stage;              // staging for plane uploads
   int* d_bad = nullptr;
   std::vector<Group> h_groups;
+  Group* pinned_groups[4] = {nullptr, nullptr, nullptr, nullptr};   // pinned ring: truly asynchronous group uploads
+  size_t pinned_cap = 0;
+  cudaEvent_t chunk_done[4] = {nullptr, nullptr, nullptr, nullptr};
   // state of the last host-API search (compensateBlock contract)
   std::vector<jsvm_me_job> last_jobs;
   bool last_has_preds = false;
@@ -214,7 +220,7 @@ void plan_range(int width, int height, int n_slots, int search_range, const jsvm
 
 int plan_jobs(int width, int height, int n_slots, int search_range, const jsvm_me_job* jobs, int n_jobs, std::vector<Group>& out, jsvm_me_plan_info* info) {
   int n_thr = 1;
-  if (n_jobs >= 65536) n_thr = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+  if (n_jobs >= 32768) n_thr = (int)std::min<unsigned>(std::min<unsigned>(16u, (unsigned)(n_jobs / 16384)), std::max(1u, std::thread::hardware_concurrency()));
   // chunk boundaries only where the macroblock changes: the serial planner starts a new group there anyway
   std::vector<int> cut(n_thr + 1, n_jobs);
   cut[0] = 0;
@@ -276,17 +282,22 @@ int launch_search(jsvm_me_ctx* c, const Group* d_groups, int first_group, int n_
   return JSVM_ME_OK;
 }
 
-int run_search(jsvm_me_ctx* c, const jsvm_me_job* d_jobs, int n_jobs, const Group* d_groups, const jsvm_me_plan_info* info,
+// K2 for the groups of a plan, then K3 for the jobs [job_begin, job_end) they cover (K2 reaches jobs through the groups'
+// absolute first_job; all per-job arrays are indexed by the absolute job number).
+int run_search(jsvm_me_ctx* c, const jsvm_me_job* d_jobs, int job_begin, int job_end, const Group* d_groups, const jsvm_me_plan_info* info,
                const int16_t* d_org, uint32_t* d_keys, JobAux* d_aux, jsvm_me_result* d_results, uint8_t* d_preds) {
   if (!c->params_set) return fail("jsvm_me_set_params has not been called");
   if (info->max_uh_8x8 > kMaxUH || info->max_uh_4x4 > kMaxUH) return fail("plan: union window taller than %d", kMaxUH);
   if (launch_search<kV8, false>(c, d_groups, 0, info->n_groups_8x8, info->max_uh_8x8, d_jobs, d_org, d_keys, d_aux)) return JSVM_ME_ERR;
   if (launch_search<kV4, true>(c, d_groups, info->n_groups_8x8, info->n_groups - info->n_groups_8x8, info->max_uh_4x4, d_jobs, d_org, d_keys, d_aux)) return JSVM_ME_ERR;
+  const int n = job_end - job_begin;
+  if (n <= 0) return JSVM_ME_OK;
   begin_timed(c, 2);
-  const int ctas = (n_jobs + kK3WarpsPerCta - 1) / kK3WarpsPerCta;
+  const int ctas = (n + kK3WarpsPerCta - 1) / kK3WarpsPerCta;
   subpel_kernel<<<ctas, 32 * kK3WarpsPerCta, 0, c->stream>>>(
       c->d_planes, c->plane_bytes, c->plane_stride, c->d_half, c->half_bytes, c->half_stride,
-      d_jobs, d_aux, n_jobs, d_org, d_keys, c->sub_dfunc, d_results, d_preds);
+      d_jobs + job_begin, d_aux + job_begin, n, d_org, d_keys + job_begin, c->sub_dfunc, d_results + job_begin,
+      d_preds ? d_preds + (size_t)job_begin * 256 : nullptr);
   end_timed(c);
   c->launches++;
   CU_OK(cudaGetLastError());
@@ -335,6 +346,8 @@ int jsvm_me_destroy(jsvm_me_ctx* c) {
   c->d_jobs.release(); c->d_groups.release(); c->d_keys.release(); c->d_aux.release();
   c->d_results.release(); c->d_preds.release(); c->d_org.release(); c->d_stage.release();
   for (auto& t : c->timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+  for (auto& e : c->chunk_done) if (e) cudaEventDestroy(e);
+  for (auto& pg : c->pinned_groups) if (pg) cudaFreeHost(pg);
   delete c;
   return JSVM_ME_OK;
 }
@@ -511,7 +524,7 @@ int jsvm_me_search_device(jsvm_me_ctx* c, const jsvm_me_job* d_jobs, int n_jobs,
   if (n_jobs <= 0) return JSVM_ME_OK;
   CU_OK(cudaSetDevice(c->device));
   if (c->d_keys.reserve(n_jobs) || c->d_aux.reserve(n_jobs)) return JSVM_ME_ERR;
-  return run_search(c, d_jobs, n_jobs, (const Group*)d_groups, info, d_org_mbs, c->d_keys.p, c->d_aux.p, d_results, d_preds);
+  return run_search(c, d_jobs, 0, n_jobs, (const Group*)d_groups, info, d_org_mbs, c->d_keys.p, c->d_aux.p, d_results, d_preds);
 }
 
 int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const int16_t* org_mbs, int n_org_mbs,
@@ -531,20 +544,80 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
   if (c->d_jobs.reserve(n_jobs) || c->d_keys.reserve(n_jobs) || c->d_aux.reserve(n_jobs) ||
       c->d_results.reserve(n_jobs) || (want_preds && c->d_preds.reserve((size_t)n_jobs * 256)) ||
       (n_org_mbs > 0 && c->d_org.reserve((size_t)n_org_mbs * 256))) return JSVM_ME_ERR;
-  // the job upload runs while the host plans the search groups
-  CU_OK(cudaMemcpyAsync(c->d_jobs.p, jobs, sizeof(jsvm_me_job) * n_jobs, cudaMemcpyHostToDevice, c->stream));
   if (n_org_mbs > 0) CU_OK(cudaMemcpyAsync(c->d_org.p, org_mbs, sizeof(int16_t) * 256 * n_org_mbs, cudaMemcpyHostToDevice, c->stream));
-  jsvm_me_plan_info info;
-  if (plan_jobs(c->W, c->H, c->n_slots, c->search_range, jobs, n_jobs, c->h_groups, &info)) return JSVM_ME_ERR;
-  for (const Group& g : c->h_groups) {                     // one check per group: planes present, originals in range
-    if (g.org_index >= n_org_mbs) return fail("job %d: org_index %d >= n_org_mbs %d", g.first_job, g.org_index, n_org_mbs);
-    if (g.org_index < 0 && !c->slot_full[g.cur_slot]) return fail("job %d: cur_slot %d is empty", g.first_job, g.cur_slot);
-    if (!c->slot_half[g.ref_slot]) return fail("job %d: ref_slot %d has no half-pel plane", g.first_job, g.ref_slot);
+  // Pipeline over chunks of ~32 K jobs cut at macroblock boundaries.  Worker threads plan different chunks
+  // concurrently (chunk k is ready long before the GPU has finished chunk k-1); the calling thread uploads each
+  // chunk's jobs and groups right before its kernels and queues the copy-back of its results right after them.
+  const int kChunk = 32768;
+  std::vector<int> cut(1, 0);
+  while (cut.back() < n_jobs) {
+    int end = std::min(n_jobs, cut.back() + kChunk);
+    while (end < n_jobs && same_mb(jobs[end], jobs[end - 1])) ++end;
+    cut.push_back(end);
   }
-  if (c->d_groups.reserve(c->h_groups.size())) return JSVM_ME_ERR;
-  CU_OK(cudaMemcpyAsync(c->d_groups.p, c->h_groups.data(), sizeof(Group) * c->h_groups.size(), cudaMemcpyHostToDevice, c->stream));
-  if (run_search(c, c->d_jobs.p, n_jobs, c->d_groups.p, &info, c->d_org.p, c->d_keys.p, c->d_aux.p, c->d_results.p, want_preds ? c->d_preds.p : nullptr)) return JSVM_ME_ERR;
-  CU_OK(cudaMemcpyAsync(results, c->d_results.p, sizeof(jsvm_me_result) * n_jobs, cudaMemcpyDeviceToHost, c->stream));
+  const int n_chunks = (int)cut.size() - 1;
+  if (c->d_groups.reserve((size_t)n_jobs)) return JSVM_ME_ERR;                      // upper bound: one group per job
+  const size_t ring_cap = (size_t)kChunk + 256;             // a chunk never holds more groups than jobs (+ the MB it finishes)
+  if (c->pinned_cap < ring_cap) {
+    for (auto& pg : c->pinned_groups) { if (pg) cudaFreeHost(pg); pg = nullptr; }
+    for (auto& pg : c->pinned_groups) CU_OK(cudaMallocHost((void**)&pg, ring_cap * sizeof(Group)));
+    c->pinned_cap = ring_cap;
+  }
+  std::vector<std::vector<Group>> plans(n_chunks);
+  std::vector<jsvm_me_plan_info> infos(n_chunks);
+  std::vector<int> status(n_chunks, 0);                     // 0 = pending, 1 = planned, -1 = failed (g_err of the worker copied below)
+  std::vector<std::string> errs(n_chunks);
+  std::mutex mu; std::condition_variable cv;
+  const int n_workers = n_chunks <= 1 ? 0 : (int)std::min<unsigned>((unsigned)n_chunks, std::min(8u, std::max(1u, std::thread::hardware_concurrency())));
+  auto plan_chunk = [&](int k) {
+    PlanChunk pc;
+    plan_range(c->W, c->H, c->n_slots, c->search_range, jobs, cut[k], cut[k + 1], pc);
+    int st = 1;
+    if (pc.err_job >= 0) { st = -1; char b[256]; snprintf(b, sizeof(b), "job %d: %s", pc.err_job, pc.err); errs[k] = b; }
+    else {
+      std::vector<Group>& g = plans[k];
+      g.resize(pc.g8.size() + pc.g4.size());
+      if (!pc.g8.empty()) memcpy(g.data(), pc.g8.data(), pc.g8.size() * sizeof(Group));
+      if (!pc.g4.empty()) memcpy(g.data() + pc.g8.size(), pc.g4.data(), pc.g4.size() * sizeof(Group));
+      jsvm_me_plan_info& in = infos[k];
+      in.n_groups = (int32_t)g.size(); in.n_groups_8x8 = (int32_t)pc.g8.size();
+      in.max_uh_8x8 = in.max_uh_4x4 = 0; in.n_positions = pc.npos; in.n_group_positions = 0;
+      for (const Group& gg : g) { int32_t& mx = gg.gran4 ? in.max_uh_4x4 : in.max_uh_8x8; mx = std::max<int32_t>(mx, gg.uh); }
+    }
+    { std::lock_guard<std::mutex> lk(mu); status[k] = st; }
+    cv.notify_all();
+  };
+  std::vector<std::thread> workers;
+  for (int t = 0; t < n_workers; ++t)
+    workers.emplace_back([&, t]() { for (int k = t; k < n_chunks; k += n_workers) plan_chunk(k); });
+  struct Joiner { std::vector<std::thread>& w; ~Joiner() { for (auto& x : w) if (x.joinable()) x.join(); } } joiner{workers};
+
+  size_t groups_done = 0;
+  for (int k = 0; k < n_chunks; ++k) {
+    if (n_workers == 0) plan_chunk(k);
+    { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return status[k] != 0; }); }
+    if (status[k] < 0) return fail("%s", errs[k].c_str());
+    const int begin = cut[k], end = cut[k + 1];
+    std::vector<Group>& hg = plans[k];
+    for (const Group& g : hg) {                             // one check per group: planes present, originals in range
+      if (g.org_index >= n_org_mbs) return fail("job %d: org_index %d >= n_org_mbs %d", g.first_job, g.org_index, n_org_mbs);
+      if (g.org_index < 0 && !c->slot_full[g.cur_slot]) return fail("job %d: cur_slot %d is empty", g.first_job, g.cur_slot);
+      if (!c->slot_half[g.ref_slot]) return fail("job %d: ref_slot %d has no half-pel plane", g.first_job, g.ref_slot);
+    }
+    if (hg.size() > ring_cap) return fail("internal: chunk plan larger than its ring slot");
+    Group* pg = c->pinned_groups[k & 3];
+    if (k >= 4) CU_OK(cudaEventSynchronize(c->chunk_done[k & 3]));                  // the slot's previous upload has been consumed
+    memcpy(pg, hg.data(), sizeof(Group) * hg.size());
+    CU_OK(cudaMemcpyAsync(c->d_jobs.p + begin, jobs + begin, sizeof(jsvm_me_job) * (end - begin), cudaMemcpyHostToDevice, c->stream));
+    CU_OK(cudaMemcpyAsync(c->d_groups.p + groups_done, pg, sizeof(Group) * hg.size(), cudaMemcpyHostToDevice, c->stream));
+    if (!c->chunk_done[k & 3]) CU_OK(cudaEventCreateWithFlags(&c->chunk_done[k & 3], cudaEventDisableTiming));
+    CU_OK(cudaEventRecord(c->chunk_done[k & 3], c->stream));
+    if (run_search(c, c->d_jobs.p, begin, end, c->d_groups.p + groups_done, &infos[k], c->d_org.p, c->d_keys.p, c->d_aux.p, c->d_results.p,
+                   want_preds ? c->d_preds.p : nullptr)) return JSVM_ME_ERR;
+    CU_OK(cudaMemcpyAsync(results + begin, c->d_results.p + begin, sizeof(jsvm_me_result) * (end - begin), cudaMemcpyDeviceToHost, c->stream));
+    groups_done += hg.size();
+    std::vector<Group>().swap(hg);
+  }
   if (preds) CU_OK(cudaMemcpyAsync(preds, c->d_preds.p, (size_t)n_jobs * 256, cudaMemcpyDeviceToHost, c->stream));
   CU_OK(cudaStreamSynchronize(c->stream));
   if (want_preds && n_jobs <= 4096) c->last_jobs.assign(jobs, jobs + n_jobs); else c->last_jobs.clear();
