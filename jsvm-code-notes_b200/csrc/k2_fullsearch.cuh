@@ -128,7 +128,6 @@ struct K2Smem {
   uint32_t factor[NS];
   int16_t  xlo[NS], xhi[NS], ylo[NS], yhi[NS];    // relative to the union window origin (empty slot: xhi < xlo)
   int32_t  job[NS];                               // absolute job index or -1
-  int16_t  pred_h[NS], pred_v[NS];                // rcMvPred of the slot's job
   int32_t  next_unit;                             // work counter: warps pull batches of 32 units
   uint32_t best[NS];
   uint8_t  bx[NS][4 * kMaxM + 12];                // bits of the horizontal difference, permuted [s][m]
@@ -183,24 +182,35 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
   SM& sm = *reinterpret_cast<SM*>(after);
   uint32_t* by_tab = reinterpret_cast<uint32_t*>(after + ((sizeof(SM) + 15) & ~(size_t)15));
 
-  // ---- prologue 1: per-slot job parameters (window relative to the staged origin, predictor, factor) ----
-  if (tid < NS) {
-    const int jo = g.slot_job[tid];
-    sm.job[tid] = jo < 0 ? -1 : g.first_job + jo;
-    sm.best[tid] = kKeyInvalid;
+  // ---- prologue 1: per-slot job parameters, computed by EVERY warp in its lanes (lane l owns slots l and l + 32) and
+  //      read back with shuffles while the tables are built, so that no barrier is needed before them; warp 0 also
+  //      stores them to shared memory for the main loop ----
+  const int lane = tid & 31;
+  constexpr int kSlotRegs = (NS + 31) / 32;
+  int p_present[kSlotRegs], p_xlo[kSlotRegs], p_xhi[kSlotRegs], p_ylo[kSlotRegs], p_yhi[kSlotRegs], p_ph[kSlotRegs], p_pv[kSlotRegs];
+#pragma unroll
+  for (int q = 0; q < kSlotRegs; ++q) {
+    const int sl = lane + 32 * q;
+    const int jo = sl < NS ? (int)g.slot_job[sl] : -1;
+    p_present[q] = jo >= 0; p_xlo[q] = 0; p_xhi[q] = -1; p_ylo[q] = 0; p_yhi[q] = -1; p_ph[q] = 0; p_pv[q] = 0;
+    uint32_t fac = 0;
     if (jo >= 0) {
       const jsvm_me_job j = jobs[g.first_job + jo];
       const Window w = job_window(j, mb_w, mb_h, default_range);
-      sm.factor[tid] = j.cost_factor;
-      sm.xlo[tid] = (int16_t)(w.xlo - g.ux0 + xa); sm.xhi[tid] = (int16_t)(w.xhi - g.ux0 + xa);
-      sm.ylo[tid] = (int16_t)(w.ylo - g.uy0);      sm.yhi[tid] = (int16_t)(w.yhi - g.uy0);
-      sm.pred_h[tid] = j.pred.hor; sm.pred_v[tid] = j.pred.ver;
-    } else {
-      sm.factor[tid] = 0; sm.xlo[tid] = 0; sm.xhi[tid] = -1; sm.ylo[tid] = 0; sm.yhi[tid] = -1;
-      sm.pred_h[tid] = 0; sm.pred_v[tid] = 0;
+      fac = j.cost_factor;
+      p_xlo[q] = w.xlo - g.ux0 + xa; p_xhi[q] = w.xhi - g.ux0 + xa;    // relative to the staged window origin
+      p_ylo[q] = w.ylo - g.uy0;      p_yhi[q] = w.yhi - g.uy0;
+      p_ph[q] = j.pred.hor; p_pv[q] = j.pred.ver;
+    }
+    if (tid < 32 && sl < NS) {
+      sm.job[sl] = jo < 0 ? -1 : g.first_job + jo;
+      sm.best[sl] = kKeyInvalid;
+      sm.factor[sl] = fac;
+      sm.xlo[sl] = (int16_t)p_xlo[q]; sm.xhi[sl] = (int16_t)p_xhi[q];
+      sm.ylo[sl] = (int16_t)p_ylo[q]; sm.yhi[sl] = (int16_t)p_yhi[q];
     }
   }
-  if (tid == 0) sm.next_unit = 0;
+  if (tid == 0) sm.next_unit = kK2Threads;                        // the first batch of every warp is static (u0 = 32 * warp)
 
   // ---- prologue 2: the four byte-shifted copies of the reference window ----
   // item = (row, 4 destination words): 5 aligned source words -> 4 x 4 funnel-shifted words -> two 8-byte stores per copy
@@ -245,12 +255,16 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
       }
     }
   }
-  __syncthreads();            // slot parameters visible
-
   // ---- prologue 4: MV-rate tables and validity masks (no runtime divisions: slot loops outside, strided loops inside) ----
+#pragma unroll 1
   for (int sl = 0; sl < NS; ++sl) {
-    const bool present = sm.job[sl] >= 0;
-    const int pv = sm.pred_v[sl], ph = sm.pred_h[sl];
+    const int q = sl >> 5, src = sl & 31;
+    int present = 0, pv = 0, ph = 0;
+#pragma unroll
+    for (int qq = 0; qq < kSlotRegs; ++qq) {
+      const int a = __shfl_sync(0xffffffffu, p_present[qq], src), b = __shfl_sync(0xffffffffu, p_pv[qq], src), c2 = __shfl_sync(0xffffffffu, p_ph[qq], src);
+      if (qq == q) { present = a; pv = b; ph = c2; }
+    }
     // xGetBits with m_uiMvScaleShift = 2: table index (y << 2) - pred (N6)
     for (int y = tid; y < by_stride; y += kK2Threads)
       by_tab[sl * by_stride + y] = (present && y < uh) ? mv_component_bits(((g.uy0 + y) << 2) - pv) : 0u;
@@ -260,22 +274,29 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
       sm.bx[sl][ci] = (present && x < uwx) ? (uint8_t)mv_component_bits(((g.ux0 - xa + x) << 2) - ph) : (uint8_t)0;
     }
   }
-  for (int ci = tid; ci < 4 * kMaxM; ci += kK2Threads) {
-    const int sft = ci / kMaxM, m = ci - sft * kMaxM;
-    const int x = 4 * m + sft;
-    Mask mk = 0;
-    for (int sl = 0; sl < NS; ++sl) if (x >= sm.xlo[sl] && x <= sm.xhi[sl]) mk |= (Mask)1 << sl;
-    sm.xmask[ci] = mk;
-  }
-  for (int i = tid; i < nstrips; i += kK2Threads) {
-    const int y0 = i * V, y1 = y0 + V - 1;
-    Mask full = 0, any = 0;
+  {
+    // column / strip validity masks: every thread evaluates its entry against all slots (ballots over the slot lanes)
+    const int ci = tid, sft = ci / kMaxM, m = ci - sft * kMaxM, x = 4 * m + sft;
+    const int y0 = tid * V, y1 = y0 + V - 1;
+    Mask mk = 0, full = 0, any = 0;
+#pragma unroll 1
     for (int sl = 0; sl < NS; ++sl) {
-      if (sm.xhi[sl] < sm.xlo[sl]) continue;
-      if (sm.ylo[sl] <= y0 && y1 <= sm.yhi[sl]) full |= (Mask)1 << sl;
-      if (sm.ylo[sl] <= y1 && y0 <= sm.yhi[sl]) any |= (Mask)1 << sl;
+      const int q = sl >> 5, src = sl & 31;
+      int xlo = 0, xhi = -1, ylo = 0, yhi = -1;
+#pragma unroll
+      for (int qq = 0; qq < kSlotRegs; ++qq) {
+        const int a = __shfl_sync(0xffffffffu, p_xlo[qq], src), b = __shfl_sync(0xffffffffu, p_xhi[qq], src);
+        const int c2 = __shfl_sync(0xffffffffu, p_ylo[qq], src), d = __shfl_sync(0xffffffffu, p_yhi[qq], src);
+        if (qq == q) { xlo = a; xhi = b; ylo = c2; yhi = d; }
+      }
+      if (x >= xlo && x <= xhi) mk |= (Mask)1 << sl;
+      if (xhi >= xlo) {
+        if (ylo <= y0 && y1 <= yhi) full |= (Mask)1 << sl;
+        if (ylo <= y1 && y0 <= yhi) any |= (Mask)1 << sl;
+      }
     }
-    sm.yfull[i] = full; sm.yany[i] = any;
+    if (ci < 4 * kMaxM) sm.xmask[ci] = mk;
+    if (tid < nstrips) { sm.yfull[tid] = full; sm.yany[tid] = any; }
   }
   __syncthreads();            // window copies and tables visible
 
@@ -285,19 +306,25 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
 
   const int units_per_strip = 4 * M;
   const int nunits = nstrips * units_per_strip;
-  const int lane = tid & 31;
+  // exact division of u < 2^16 by d < 2^16: (u * ceil(2^32 / d)) >> 32
+  const uint32_t inv_ups = (uint32_t)((0x100000000ull + units_per_strip - 1) / units_per_strip);
+  const uint32_t inv_m = (uint32_t)((0x100000000ull + M - 1) / M);
 
-  // warps pull batches of 32 units from a shared counter: they all finish within one batch of each other
+  // warps pull batches of 32 units from a shared counter (the first batch is static), always one batch ahead of
+  // the one they work on: they all finish within one batch of each other and never wait for the counter
+  int u0 = (tid >> 5) * 32;
+  int u0_next = 0;
+  if (lane == 0) u0_next = atomicAdd(&sm.next_unit, 32);
   for (;;) {
-    int u0 = 0;
-    if (lane == 0) u0 = atomicAdd(&sm.next_unit, 32);
-    u0 = __shfl_sync(0xffffffffu, u0, 0);
     if (u0 >= nunits) break;
+    const int fetched = __shfl_sync(0xffffffffu, u0_next, 0);
+    if (lane == 0) u0_next = atomicAdd(&sm.next_unit, 32);        // prefetch the batch after the next one
     const bool live = u0 + lane < nunits;
     const int u = live ? u0 + lane : nunits - 1;                  // idle lanes redo the last unit with every slot masked off
-    const int strip = u / units_per_strip;
+    u0 = fetched;
+    const int strip = (int)__umulhi((uint32_t)u, inv_ups);
     const int rem = u - strip * units_per_strip;
-    const int s = rem / M, m = rem - s * M;
+    const int s = (int)__umulhi((uint32_t)rem, inv_m), m = rem - s * M;
     const int x = 4 * m + s - xa;                                 // column inside the union window (negative: alignment columns)
     const int ys = strip * V;
     const int cidx = s * kMaxM + m;
