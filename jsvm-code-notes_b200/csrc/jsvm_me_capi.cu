@@ -536,8 +536,8 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
   if (n_org_mbs > 0) {
     if (!org_mbs) return fail("org_mbs is null");
     for (size_t i = 0; i < (size_t)n_org_mbs * 256; ++i)
-      if (org_mbs[i] < 0 || org_mbs[i] > 255)
-        return fail("org_mbs sample %zu = %d outside [0,255]: the signed 16-bit (residual-prediction) search variant is not implemented", i, (int)org_mbs[i]);
+      if (org_mbs[i] < -1024 || org_mbs[i] > 1023)      // residual-prediction originals span [-255, 510] (N3); the key widths assume |v| < 1024
+        return fail("org_mbs sample %zu = %d outside [-1024,1023]", i, (int)org_mbs[i]);
   }
   CU_OK(cudaSetDevice(c->device));
   const bool want_preds = preds != nullptr || n_jobs <= 4096;

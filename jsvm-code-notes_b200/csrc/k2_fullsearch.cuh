@@ -251,7 +251,10 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const short4 v = __ldg(reinterpret_cast<const short4*>(op + r * 16 + 4 * k));
-        cur[r][k] = (uint32_t)(v.x & 0xff) | ((uint32_t)(v.y & 0xff) << 8) | ((uint32_t)(v.z & 0xff) << 16) | ((uint32_t)(v.w & 0xff) << 24);
+        // signed 16-bit originals (residual-prediction passes, N3) are searched as their [0,255] clip: the reference
+        // samples lie in [0,255], so |org - ref| = |clip(org) - ref| + |org - clip(org)| and the second term does not
+        // depend on the displacement -- same argmin, same tie-break; K3 adds the constant back to the SAD it reports
+        cur[r][k] = pack_clip8(v);
       }
     }
   }

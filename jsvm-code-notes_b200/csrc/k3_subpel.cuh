@@ -55,7 +55,6 @@ __device__ __forceinline__ uint32_t hadamard4x4(const int (&d)[16]) {
 
 struct K3Warp {
   uint8_t  plane[4][kK3PlaneRows][kK3PlanePitch];   // [phase = (Y&1)*2 + (X&1)][(Y - Y0) >> 1][(X - X0) >> 1]
-  uint32_t org[16][4];                               // original block, 16 bytes per row
 };
 
 // Where the block predicted at half-pel offset (ox, oy) from the full-pel winner starts inside the phase planes:
@@ -101,18 +100,37 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
 
   const int bx0 = 16 * j.mb_x + 4 * (j.blk & 3), by0 = 16 * j.mb_y + 4 * (j.blk >> 2);
 
-  // ---- stage the original block (16 bytes per row) ----
-  for (int i = lane; i < h * nbx; i += 32) {
-    const int r = i >> lg_nbx, k = i & (nbx - 1);
-    uint32_t v;
-    if (j.org_index >= 0) {
-      const short4 s4 = __ldg(reinterpret_cast<const short4*>(org_mbs + (size_t)j.org_index * 256 + (4 * (j.blk >> 2) + r) * 16 + 4 * (j.blk & 3) + 4 * k));
-      v = (uint32_t)(s4.x & 0xff) | ((uint32_t)(s4.y & 0xff) << 8) | ((uint32_t)(s4.z & 0xff) << 16) | ((uint32_t)(s4.w & 0xff) << 24);
-    } else {
-      v = __ldg(reinterpret_cast<const uint32_t*>(planes + (size_t)j.cur_slot * plane_bytes + (size_t)(kMargin + by0 + r) * plane_stride + kMargin + bx0 + 4 * k));
+  // each lane always works on the same 4x4 sub-block (32 % nb == 0): keep its original rows in registers
+  const int blk_b = lane & (nb - 1);
+  const int px0 = (blk_b & (nbx - 1)) * 4, py0 = (blk_b >> lg_nbx) * 4;
+  // The lane's 4x4 of the original: packed bytes for the SAD, plain ints for the Hadamard.  Originals supplied by the
+  // caller (org_mbs) may be signed 16-bit (residual-prediction passes, N3): every prediction sample p lies in [0,255], so
+  // |o - p| = |clip(o) - p| + |o - clip(o)|; the SAD runs on the clipped bytes and `excess` (a per-4x4 constant) is added.
+  uint32_t orow[4];
+  int o16[16];
+  uint32_t excess = 0;
+  if (j.org_index >= 0) {
+    const int16_t* op = org_mbs + (size_t)j.org_index * 256 + (4 * (j.blk >> 2) + py0) * 16 + 4 * (j.blk & 3) + px0;
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+      const short4 s4 = __ldg(reinterpret_cast<const short4*>(op + y * 16));
+      o16[4 * y] = s4.x; o16[4 * y + 1] = s4.y; o16[4 * y + 2] = s4.z; o16[4 * y + 3] = s4.w;
+      orow[y] = pack_clip8(s4);
+#pragma unroll
+      for (int x = 0; x < 4; ++x) excess += (uint32_t)abs(o16[4 * y + x] - (int)((orow[y] >> (8 * x)) & 0xff));
     }
-    sw.org[r][k] = v;
+  } else {
+    const uint8_t* cp = planes + (size_t)j.cur_slot * plane_bytes + (size_t)(kMargin + by0 + py0) * plane_stride + kMargin + bx0 + px0;
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+      orow[y] = __ldg(reinterpret_cast<const uint32_t*>(cp + (size_t)y * plane_stride));
+#pragma unroll
+      for (int x = 0; x < 4; ++x) o16[4 * y + x] = (int)((orow[y] >> (8 * x)) & 0xff);
+    }
   }
+  uint32_t excess_block = excess;                            // the whole partition's constant (full-pel SAD)
+  for (int off = 1; off < nb; off <<= 1) excess_block += __shfl_xor_sync(0xffffffffu, excess_block, off);
+
 
   // ---- stage the half-pel patch, de-interleaved into phase planes ----
   const int BX = 2 * (bx0 + fx), BY = 2 * (by0 + fy);         // half-pel coordinates of the block at the full-pel winner
@@ -135,14 +153,7 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
   }
   __syncwarp();
 
-  // each lane always works on the same 4x4 sub-block (32 % nb == 0): keep its original rows in registers
-  const int blk_b = lane & (nb - 1);
-  const int px0 = (blk_b & (nbx - 1)) * 4, py0 = (blk_b >> lg_nbx) * 4;
   const uint8_t* pl = &sw.plane[0][0][0];
-  uint32_t orow[4];
-#pragma unroll
-  for (int y = 0; y < 4; ++y) orow[y] = sw.org[py0 + y][px0 >> 2];
-
   int mvh = fx << 2, mvv = fy << 2;                           // cMv <<= 2
   uint32_t best = 0xffffffffu;
   uint32_t best_mode = 0;
@@ -177,16 +188,18 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
 #pragma unroll
           for (int y = 0; y < 4; ++y)
 #pragma unroll
-            for (int x = 0; x < 4; ++x) d[y * 4 + x] = (int)((orow[y] >> (8 * x)) & 0xff) - (int)((crow[y] >> (8 * x)) & 0xff);
+            for (int x = 0; x < 4; ++x) d[y * 4 + x] = o16[y * 4 + x] - (int)((crow[y] >> (8 * x)) & 0xff);
           dist = hadamard4x4(d);
         } else {
 #pragma unroll
           for (int y = 0; y < 4; ++y) dist = __vsadu4(orow[y], crow[y]) + dist;
+          dist += excess;
         }
       }
       // sum the 4x4 blocks of one candidate (nb is a power of two, groups are lane-aligned)
       for (int off = 1; off < nb; off <<= 1) dist += __shfl_xor_sync(0xffffffffu, dist, off);
-      uint32_t k = 0xffffffffu;                           // (cost << 8) | n : cost < 2^17 in the 8-bit domain (N12)
+      uint32_t k = 0xffffffffu;                           // (cost << 8) | n : cost < 2^17 in the 8-bit domain (N12), < 2^23 for
+                                                          // originals in [-1024, 1023] (enforced by jsvm_me_search)
       if (active && blk_b == 0) {
         const int th = mvh + dx, tv = mvv + dy;
         const uint32_t c = dist + rate_cost(f, mv_component_bits(th - j.pred.hor) + mv_component_bits(tv - j.pred.ver));
@@ -217,7 +230,7 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
     jsvm_me_result r;
     r.mv.hor = (int16_t)mvh; r.mv.ver = (int16_t)mvv;
     r.mv_fullpel.hor = (int16_t)fx; r.mv_fullpel.ver = (int16_t)fy;
-    r.sad_fullpel = full_cost - full_rate;
+    r.sad_fullpel = full_cost - full_rate + excess_block;
     r.min_sad = min_sad;
     r.mv_bits = mv_bits;
     r.bits = j.bits_in + mv_bits;

@@ -119,6 +119,14 @@ __host__ __device__ inline int partition_slot(int mode, int blk) {
   }
 }
 
+#if defined(__CUDACC__)
+// four int16 samples -> four bytes, each clipped to [0,255] (gClip, INCC/GlobalFunctions.h:37-44)
+__device__ __forceinline__ uint32_t pack_clip8(const short4 v) {
+  const int a = min(max((int)v.x, 0), 255), b = min(max((int)v.y, 0), 255), c = min(max((int)v.z, 0), 255), d = min(max((int)v.w, 0), 255);
+  return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24);
+}
+#endif
+
 // packed argmin key: cost in the high 17 bits, raster index inside the union window in the low 15
 // (N12: SAD16x16 <= 65280 and rate << 2^16 in the 8-bit domain; uw*uh <= 32768 is enforced by the planner).
 constexpr int kIdxBits = 15;

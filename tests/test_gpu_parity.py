@@ -85,7 +85,8 @@ import os
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("name", ["tiny_all41_had", "tiny_9_sad", "qcif_9_had", "qcif_9_zero_sr32", "org_override_8bit"])
+@pytest.mark.parametrize("name", ["tiny_all41_had", "tiny_9_sad", "qcif_9_had", "qcif_9_zero_sr32", "org_override_8bit",
+                                  "org_override_16bit"])
 def test_cuda_matches_reference_golden(me, name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     W, H = int(g["width"]), int(g["height"])
@@ -101,15 +102,45 @@ def test_cuda_matches_reference_golden(me, name):
         assert np.array_equal(me.halfpel_plane(0), g["halfpel0"])
 
 
-def test_signed_16bit_originals_are_refused(me, pkg):
-    """Residual-prediction originals (N3) need the 16-bit-lane kernel, which is not built yet: loud error, no fallback."""
+@pytest.mark.parametrize("sub_dfunc", [0, 2])
+@pytest.mark.parametrize("parts_name", ["PARTS_9", "PARTS_41"])
+def test_signed_16bit_originals_bit_exact(me, oracle, synth, sub_dfunc, parts_name):
+    """Residual-prediction originals (org - base-layer residual, un-clipped, N3): samples in [-255, 510].
+    The SAD stages run on the clipped bytes plus the displacement-independent excess; the Hadamard uses the true
+    16-bit differences.  Every field and the prediction blocks must equal the checker's."""
+    cfg = synth.CONFIGS["C1"]
+    W, H = cfg["width"], cfg["height"]
+    ses, frames = _setup(me, oracle, synth, cfg, seed=1250, sub_dfunc=sub_dfunc)
+    parts = getattr(synth, parts_name)
+    mbs = [(0, 0), (0, 10), (8, 0), (8, 10), (4, 5), (3, 7), (5, 2), (7, 9)]
+    rng = np.random.default_rng(77)
+    cur = frames[1]
+    org = np.zeros((len(mbs), 16, 16), np.int16)
+    for i, (mby, mbx) in enumerate(mbs):
+        blk = cur[16 * mby:16 * mby + 16, 16 * mbx:16 * mbx + 16].astype(np.int16)
+        resid = rng.integers(-255, 256, (16, 16)).astype(np.int16)
+        resid[rng.random((16, 16)) < 0.5] = 0                               # a mix of in-range and out-of-range samples
+        org[i] = blk - resid
+    assert org.min() < 0 and org.max() > 255
+    jobs = synth.make_jobs(W, H, parts, cur_slot=1, ref_slot=0, qp=31, field="random", seed=13, mb_subset=mbs, bits_in=1)
+    jobs["org_index"] = np.repeat(np.arange(len(mbs)), len(parts))
+    got, gp = me.search(jobs, org_mbs=org, want_preds=True)
+    want, wp = ses.search(jobs, org_mbs=org, want_preds=True)
+    assert_results_equal(got, want, jobs)
+    assert np.array_equal(gp, wp)
+
+
+def test_originals_outside_the_supported_range_are_refused(me, pkg):
+    """|sample| >= 1024 cannot come from a residual-prediction pass; loud error, no fallback."""
     g = np.load(os.path.join(GOLDEN, "org_override_16bit.npz"))
     me.configure(int(g["width"]), int(g["height"]), 2)
     me.set_params(int(g["search_range"]), int(g["sub_dfunc"]))
     me.upload_plane(0, g["frame0"]); me.upload_plane(1, g["frame1"])
     me.interp_halfpel([0, 1])
+    org = g["org_mbs"].copy()
+    org[0, 0, 0] = 2000
     with pytest.raises(pkg.MotionEstimationError):
-        me.search(g["jobs"], org_mbs=g["org_mbs"])
+        me.search(g["jobs"], org_mbs=org)
 
 
 def test_reference_named_interface(me, pkg, oracle, synth):

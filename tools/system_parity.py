@@ -49,9 +49,8 @@ LoopFilterBetaOffset 0
 InterLayerLoopFilterDisable 2
 InterLayerLoopFilterAlphaC0Offset 0
 InterLayerLoopFilterBetaOffset 0
-NumLayers 1
-LayerCfg {layer}
-WeightedPrediction 0
+NumLayers {nlayers}
+{layercfgs}WeightedPrediction 0
 WeightedBiprediction 0
 LARDO 0
 MultiLayerLambdaSel 0
@@ -71,7 +70,7 @@ MbAff 0
 PAff 0
 BottomFieldFirst 0
 LowComplexityMbMode 0
-ProfileIdc 100
+ProfileIdc {profile}
 MinLevelIdc 13
 UseLongTerm 0
 MMCOEnable 0
@@ -88,10 +87,10 @@ DisableBSlices 0
 MaxDeltaQP 0
 QP {qp}
 ForceReOrdering 0
-InterLayerPred 0
-ILModePred 0
-ILMotionPred 0
-ILResidualPred 0
+InterLayerPred {ilpred}
+ILModePred {ilpred}
+ILMotionPred {ilpred}
+ILResidualPred {ilpred}
 SliceSkip 0
 UseESS 0
 """
@@ -105,31 +104,66 @@ def md5(path):
     return h.hexdigest()
 
 
-def write_yuv(path, width, height, frames, seed):
-    synth = importlib.import_module("jsvm-code-notes_b200.synth")
-    seq = synth.Sequence(width, height, seed)
-    chroma = np.full((height // 2) * (width // 2) * 2, 128, np.uint8).tobytes()
+def write_yuv(path, frames_u8):
+    h, w = frames_u8[0].shape
+    chroma = np.full((h // 2) * (w // 2) * 2, 128, np.uint8).tobytes()
     with open(path, "wb") as f:
-        for n in range(frames):
-            f.write(seq.frame(n).tobytes())
+        for fr in frames_u8:
+            f.write(np.ascontiguousarray(fr).tobytes())
             f.write(chroma)
+
+
+def layer_plan(a):
+    """Spatial layers from the top resolution down: --layers 2 --quality-layers 1 at 352x288 gives QCIF -> CIF -> CIF(CGS).
+    Each dyadic layer halves the picture (sizes stay multiples of 16 at the layers used here)."""
+    sizes = [(a.width >> (a.layers - 1 - i), a.height >> (a.layers - 1 - i)) for i in range(a.layers)]
+    plan = [{"w": w, "h": h, "qp": a.qp + 2.0 * (a.layers - 1 - i), "spatial": i} for i, (w, h) in enumerate(sizes)]
+    for q in range(a.quality_layers):
+        plan.append({"w": a.width, "h": a.height, "qp": a.qp - 4.0 * (q + 1), "spatial": a.layers - 1})
+    for l in plan:
+        if l["w"] % 16 or l["h"] % 16:
+            raise ValueError(f"layer size {l['w']}x{l['h']} is not a multiple of 16")
+    return plan
+
+
+def write_inputs(workdir, a):
+    synth = importlib.import_module("jsvm-code-notes_b200.synth")
+    seq = synth.Sequence(a.width, a.height, a.seed)
+    top = [seq.frame(n) for n in range(a.frames)]
+    by_spatial = {a.layers - 1: top}
+    cur = top
+    for s in range(a.layers - 2, -1, -1):                    # 2x2 box down-sampling for the lower spatial layers
+        cur = [((f[0::2, 0::2].astype(np.uint16) + f[0::2, 1::2] + f[1::2, 0::2] + f[1::2, 1::2] + 2) >> 2).astype(np.uint8) for f in cur]
+        by_spatial[s] = cur
+    for s, frs in by_spatial.items():
+        write_yuv(os.path.join(workdir, f"in_s{s}.yuv"), frs)
 
 
 def run(exe, workdir, tag, a):
     out = os.path.join(workdir, f"{tag}.264")
-    rec = os.path.join(workdir, f"{tag}_rec.yuv")
-    layer = os.path.join(workdir, f"{tag}_layer0.cfg")
     main_cfg = os.path.join(workdir, f"{tag}_encoder.cfg")
-    open(layer, "w").write(LAYER_CFG.format(w=a.width, h=a.height, yuv=os.path.join(workdir, "in.yuv"), rec=rec, qp=a.qp,
-                                            lt8=0 if a.all_partitions else 1))
-    open(main_cfg, "w").write(MAIN_CFG.format(out=out, frames=a.frames, gop=a.gop, refs=a.refs, sr=a.sr, subpel=a.subpel, layer=layer))
+    plan = layer_plan(a)
+    lines, recs = "", []
+    for i, l in enumerate(plan):
+        layer = os.path.join(workdir, f"{tag}_layer{i}.cfg")
+        rec = os.path.join(workdir, f"{tag}_rec{i}.yuv")
+        recs.append(rec)
+        open(layer, "w").write(LAYER_CFG.format(w=l["w"], h=l["h"], yuv=os.path.join(workdir, f"in_s{l['spatial']}.yuv"), rec=rec, qp=l["qp"],
+                                                lt8=0 if a.all_partitions else 1, ilpred=0 if i == 0 else a.ilpred,
+                                                profile=100 if i == 0 else 86))
+        lines += f"LayerCfg {layer}\n"
+    open(main_cfg, "w").write(MAIN_CFG.format(out=out, frames=a.frames, gop=a.gop, refs=a.refs, sr=a.sr, subpel=a.subpel,
+                                              nlayers=len(plan), layercfgs=lines))
     t0 = time.perf_counter()
     p = subprocess.run([exe, "-pf", main_cfg], cwd=workdir, capture_output=True, text=True, timeout=a.timeout)
     dt = time.perf_counter() - t0
     if p.returncode != 0 or not os.path.exists(out):
         sys.stderr.write(p.stdout[-3000:] + "\n" + p.stderr[-3000:] + "\n")
         raise RuntimeError(f"{os.path.basename(exe)} failed with code {p.returncode}")
-    return {"bitstream_md5": md5(out), "recon_md5": md5(rec), "bytes": os.path.getsize(out), "seconds": round(dt, 2)}
+    h = hashlib.md5()
+    for r in recs:
+        h.update(md5(r).encode())
+    return {"bitstream_md5": md5(out), "recon_md5": h.hexdigest(), "bytes": os.path.getsize(out), "seconds": round(dt, 2), "layers": len(plan)}
 
 
 def compare(argv=None):
@@ -144,12 +178,15 @@ def compare(argv=None):
     ap.add_argument("--qp", type=float, default=32.0)
     ap.add_argument("--all-partitions", action="store_true")
     ap.add_argument("--seed", type=int, default=1235)
+    ap.add_argument("--layers", type=int, default=1, help="dyadic spatial layers; --width/--height name the TOP layer")
+    ap.add_argument("--quality-layers", type=int, default=0, help="extra CGS quality layers at the top resolution")
+    ap.add_argument("--ilpred", type=int, default=2, help="InterLayerPred / ILModePred / ILMotionPred / ILResidualPred of enhancement layers")
     ap.add_argument("--only", choices=["stock", "b200"], default=None)
     ap.add_argument("--timeout", type=int, default=1500)
     a = ap.parse_args(argv)
     res = {}
     with tempfile.TemporaryDirectory() as wd:
-        write_yuv(os.path.join(wd, "in.yuv"), a.width, a.height, a.frames, a.seed)
+        write_inputs(wd, a)
         if a.only != "b200":
             res["stock"] = run(STOCK, wd, "stock", a)
         if a.only != "stock":
