@@ -98,6 +98,9 @@ struct jsvm_me_ctx {
   Group* pinned_groups[4] = {nullptr, nullptr, nullptr, nullptr};   // pinned ring: truly asynchronous group uploads
   size_t pinned_cap = 0;
   cudaEvent_t chunk_done[4] = {nullptr, nullptr, nullptr, nullptr};
+  // host-buffer search: uploads and result copy-backs run on their own streams so that they overlap the kernels
+  cudaStream_t up_stream = nullptr, down_stream = nullptr;
+  cudaEvent_t ev_entry = nullptr, ev_kernels = nullptr;
   // state of the last host-API search (compensateBlock contract)
   std::vector<jsvm_me_job> last_jobs;
   bool last_has_preds = false;
@@ -347,6 +350,9 @@ int jsvm_me_destroy(jsvm_me_ctx* c) {
   c->d_results.release(); c->d_preds.release(); c->d_org.release(); c->d_stage.release();
   for (auto& t : c->timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
   for (auto& e : c->chunk_done) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {c->ev_entry, c->ev_kernels}) if (e) cudaEventDestroy(e);
+  if (c->up_stream) cudaStreamDestroy(c->up_stream);
+  if (c->down_stream) cudaStreamDestroy(c->down_stream);
   for (auto& pg : c->pinned_groups) if (pg) cudaFreeHost(pg);
   delete c;
   return JSVM_ME_OK;
@@ -545,6 +551,15 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
       c->d_results.reserve(n_jobs) || (want_preds && c->d_preds.reserve((size_t)n_jobs * 256)) ||
       (n_org_mbs > 0 && c->d_org.reserve((size_t)n_org_mbs * 256))) return JSVM_ME_ERR;
   if (n_org_mbs > 0) CU_OK(cudaMemcpyAsync(c->d_org.p, org_mbs, sizeof(int16_t) * 256 * n_org_mbs, cudaMemcpyHostToDevice, c->stream));
+  if (!c->up_stream) {
+    CU_OK(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+    CU_OK(cudaStreamCreateWithFlags(&c->down_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&c->ev_entry, &c->ev_kernels}) CU_OK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  }
+  // the side streams start after whatever the caller queued on the ctx stream before this call (plane uploads, K1)
+  CU_OK(cudaEventRecord(c->ev_entry, c->stream));
+  CU_OK(cudaStreamWaitEvent(c->up_stream, c->ev_entry, 0));
+  CU_OK(cudaStreamWaitEvent(c->down_stream, c->ev_entry, 0));
   // Pipeline over chunks of ~32 K jobs cut at macroblock boundaries.  Worker threads plan different chunks
   // concurrently (chunk k is ready long before the GPU has finished chunk k-1); the calling thread uploads each
   // chunk's jobs and groups right before its kernels and queues the copy-back of its results right after them.
@@ -608,18 +623,22 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
     Group* pg = c->pinned_groups[k & 3];
     if (k >= 4) CU_OK(cudaEventSynchronize(c->chunk_done[k & 3]));                  // the slot's previous upload has been consumed
     memcpy(pg, hg.data(), sizeof(Group) * hg.size());
-    CU_OK(cudaMemcpyAsync(c->d_jobs.p + begin, jobs + begin, sizeof(jsvm_me_job) * (end - begin), cudaMemcpyHostToDevice, c->stream));
-    CU_OK(cudaMemcpyAsync(c->d_groups.p + groups_done, pg, sizeof(Group) * hg.size(), cudaMemcpyHostToDevice, c->stream));
+    CU_OK(cudaMemcpyAsync(c->d_jobs.p + begin, jobs + begin, sizeof(jsvm_me_job) * (end - begin), cudaMemcpyHostToDevice, c->up_stream));
+    CU_OK(cudaMemcpyAsync(c->d_groups.p + groups_done, pg, sizeof(Group) * hg.size(), cudaMemcpyHostToDevice, c->up_stream));
     if (!c->chunk_done[k & 3]) CU_OK(cudaEventCreateWithFlags(&c->chunk_done[k & 3], cudaEventDisableTiming));
-    CU_OK(cudaEventRecord(c->chunk_done[k & 3], c->stream));
+    CU_OK(cudaEventRecord(c->chunk_done[k & 3], c->up_stream));                     // ring slot consumed; chunk k is on the device
+    CU_OK(cudaStreamWaitEvent(c->stream, c->chunk_done[k & 3], 0));
     if (run_search(c, c->d_jobs.p, begin, end, c->d_groups.p + groups_done, &infos[k], c->d_org.p, c->d_keys.p, c->d_aux.p, c->d_results.p,
                    want_preds ? c->d_preds.p : nullptr)) return JSVM_ME_ERR;
-    CU_OK(cudaMemcpyAsync(results + begin, c->d_results.p + begin, sizeof(jsvm_me_result) * (end - begin), cudaMemcpyDeviceToHost, c->stream));
+    CU_OK(cudaEventRecord(c->ev_kernels, c->stream));
+    CU_OK(cudaStreamWaitEvent(c->down_stream, c->ev_kernels, 0));
+    CU_OK(cudaMemcpyAsync(results + begin, c->d_results.p + begin, sizeof(jsvm_me_result) * (end - begin), cudaMemcpyDeviceToHost, c->down_stream));
     groups_done += hg.size();
     std::vector<Group>().swap(hg);
   }
   if (preds) CU_OK(cudaMemcpyAsync(preds, c->d_preds.p, (size_t)n_jobs * 256, cudaMemcpyDeviceToHost, c->stream));
   CU_OK(cudaStreamSynchronize(c->stream));
+  CU_OK(cudaStreamSynchronize(c->down_stream));
   if (want_preds && n_jobs <= 4096) c->last_jobs.assign(jobs, jobs + n_jobs); else c->last_jobs.clear();
   c->last_has_preds = want_preds && n_jobs <= 4096;
   return JSVM_ME_OK;

@@ -39,6 +39,19 @@ namespace jsvm {
 #ifndef K2_THREADS
 #define K2_THREADS 256
 #endif
+// Warps w and w + 4 of a CTA share an SM sub-partition.  After the prologue barrier all warps would run their
+// SAD pass (ALU pipe) and their rate / argmin pass (FMA pipe) in lockstep, leaving each pipe idle half of the time;
+// the upper half of the CTA therefore starts its first batch K2_STAGGER_NS later (the offset persists).
+#ifndef K2_STAGGER_NS
+#define K2_STAGGER_NS 0
+#endif
+#ifndef K2_MINTREE
+#define K2_MINTREE 0
+#endif
+// timing experiments only (results are wrong): 1 = no rate/argmin update, 2 = no SAD pass, 3 = no rate tables / masks
+#ifndef K2_ABLATE
+#define K2_ABLATE 0
+#endif
 constexpr int kK2Threads   = K2_THREADS;
 constexpr int kWinRowBytes = 160;                 // bytes per staged window row (max 145 positions + 15)
 constexpr int kWinRowWords = kWinRowBytes / 4;    // 40 words: 40 mod 32 = 8 keeps successive rows on different banks
@@ -125,6 +138,7 @@ struct K2Smem {
   static constexpr int kMaxStrips = kMaxRows / V;
   typedef typename std::conditional<GRAN4, unsigned long long, uint32_t>::type Mask;   // one bit per partition slot
   // dynamic shared memory layout (bytes); the four window copies come first
+  uint32_t cur[16][4];                            // the current macroblock, 16 packed bytes per row (16-byte aligned)
   uint32_t factor[NS];
   int16_t  xlo[NS], xhi[NS], ylo[NS], yhi[NS];    // relative to the union window origin (empty slot: xhi < xlo)
   int32_t  job[NS];                               // absolute job index or -1
@@ -235,32 +249,25 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
     }
   }
 
-  // ---- prologue 3: the current macroblock into registers (16 rows x 4 packed words) ----
-  uint32_t cur[16][4];
-  if (g.org_index < 0) {
-    const uint8_t* cp = planes + (size_t)g.cur_slot * plane_bytes + (size_t)(kMargin + 16 * g.mb_y) * plane_stride + kMargin + 16 * g.mb_x;
-#pragma unroll
-    for (int r = 0; r < 16; ++r) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(cp + (size_t)r * plane_stride));
-      cur[r][0] = v.x; cur[r][1] = v.y; cur[r][2] = v.z; cur[r][3] = v.w;
+  // ---- prologue 3: the current macroblock into shared memory (16 rows x 4 packed words); every unit re-reads it with 16
+  //      broadcast LDS.128 so that its 64 registers are free during the rate / argmin pass ----
+  if (tid < 64) {
+    const int r = tid >> 2, k = tid & 3;
+    uint32_t v;
+    if (g.org_index < 0) {
+      v = __ldg(reinterpret_cast<const uint32_t*>(planes + (size_t)g.cur_slot * plane_bytes + (size_t)(kMargin + 16 * g.mb_y + r) * plane_stride +
+                                                  kMargin + 16 * g.mb_x + 4 * k));
+    } else {
+      // signed 16-bit originals (residual-prediction passes, N3) are searched as their [0,255] clip: the reference
+      // samples lie in [0,255], so |org - ref| = |clip(org) - ref| + |org - clip(org)| and the second term does not
+      // depend on the displacement -- same argmin, same tie-break; K3 adds the constant back to the SAD it reports
+      v = pack_clip8(__ldg(reinterpret_cast<const short4*>(org_mbs + (size_t)g.org_index * 256 + r * 16 + 4 * k)));
     }
-  } else {
-    const int16_t* op = org_mbs + (size_t)g.org_index * 256;
-#pragma unroll
-    for (int r = 0; r < 16; ++r) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const short4 v = __ldg(reinterpret_cast<const short4*>(op + r * 16 + 4 * k));
-        // signed 16-bit originals (residual-prediction passes, N3) are searched as their [0,255] clip: the reference
-        // samples lie in [0,255], so |org - ref| = |clip(org) - ref| + |org - clip(org)| and the second term does not
-        // depend on the displacement -- same argmin, same tie-break; K3 adds the constant back to the SAD it reports
-        cur[r][k] = pack_clip8(v);
-      }
-    }
+    sm.cur[r][k] = v;
   }
   // ---- prologue 4: MV-rate tables and validity masks (no runtime divisions: slot loops outside, strided loops inside) ----
 #pragma unroll 1
-  for (int sl = 0; sl < NS; ++sl) {
+  for (int sl = 0; sl < (K2_ABLATE == 3 ? 0 : NS); ++sl) {
     const int q = sl >> 5, src = sl & 31;
     int present = 0, pv = 0, ph = 0;
 #pragma unroll
@@ -283,7 +290,7 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
     const int y0 = tid * V, y1 = y0 + V - 1;
     Mask mk = 0, full = 0, any = 0;
 #pragma unroll 1
-    for (int sl = 0; sl < NS; ++sl) {
+    for (int sl = 0; sl < (K2_ABLATE == 3 ? 0 : NS); ++sl) {
       const int q = sl >> 5, src = sl & 31;
       int xlo = 0, xhi = -1, ylo = 0, yhi = -1;
 #pragma unroll
@@ -298,6 +305,7 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
         if (ylo <= y1 && y0 <= yhi) any |= (Mask)1 << sl;
       }
     }
+    if (K2_ABLATE == 3) { mk = full = any = (Mask)(~(Mask)0) >> (8 * sizeof(Mask) - NS); }
     if (ci < 4 * kMaxM) sm.xmask[ci] = mk;
     if (tid < nstrips) { sm.yfull[tid] = full; sm.yany[tid] = any; }
   }
@@ -315,6 +323,7 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
 
   // warps pull batches of 32 units from a shared counter (the first batch is static), always one batch ahead of
   // the one they work on: they all finish within one batch of each other and never wait for the counter
+  if (K2_STAGGER_NS > 0 && tid >= kK2Threads / 2) __nanosleep(K2_STAGGER_NS);
   int u0 = (tid >> 5) * 32;
   int u0_next = 0;
   if (lane == 0) u0_next = atomicAdd(&sm.next_unit, 32);
@@ -333,6 +342,12 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
     const int cidx = s * kMaxM + m;
 
     // ---- SAD pass over the strip ----
+    uint32_t cur[16][4];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const uint4 v = *reinterpret_cast<const uint4*>(&sm.cur[r][0]);
+      cur[r][0] = v.x; cur[r][1] = v.y; cur[r][2] = v.z; cur[r][3] = v.w;
+    }
     uint32_t acc[V][NACC];
 #pragma unroll
     for (int v = 0; v < V; ++v)
@@ -340,8 +355,14 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
       for (int a = 0; a < NACC; ++a) acc[v][a] = 0;
 
     const uint32_t* rp = winw + s * copy_words + ys * kWinRowWords + m;
+#if K2_ABLATE == 2
 #pragma unroll
-    for (int r = 0; r < 15 + V; ++r) {
+    for (int v = 0; v < V; ++v)
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) acc[v][a] = rp[0] + (uint32_t)(v * NACC + a);
+#endif
+#pragma unroll
+    for (int r = 0; r < (K2_ABLATE == 2 ? 0 : 15 + V); ++r) {
       const uint32_t w[4] = { rp[r * kWinRowWords + 0], rp[r * kWinRowWords + 1], rp[r * kWinRowWords + 2], rp[r * kWinRowWords + 3] };
       // word-major order: the two updates of one accumulator (words 0/1 or 2/3 of a row) end up V instructions apart
       // instead of back to back, so a warp does not wait out the ALU latency between them
@@ -358,19 +379,30 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
       }
     }
 
+#if K2_ABLATE == 1
+    {
+      uint32_t t = 0;
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) t += acc[v][a];
+      best[0] = min(best[0], t);
+      continue;
+    }
+#endif
     // ---- per partition: SAD + rate, packed-key min ----
+    // Pass 1 is straight-line code over all partition slots (no branches, so the loads of the next slot and the 8 x NS
+    // independent rate / key chains overlap): every strip row is evaluated and the result is committed only for slots
+    // whose window holds this column and ALL rows of the strip.  Pass 2 (rare: the strips that straddle the top or
+    // bottom edge of some job's window) re-evaluates those slots row by row.
     const Mask mx = live ? sm.xmask[cidx] : (Mask)0;
     const Mask mfull = mx & sm.yfull[strip], many = mx & sm.yany[strip];
-    constexpr Mask kAllSlots = (Mask)(~(Mask)0) >> (8 * sizeof(Mask) - NS);
-    // warp-uniform fast path: every slot is searched and every row of the strip is inside every window for all lanes
-    const bool fast = K2_FASTPATH && __all_sync(0xffffffffu, mfull == kAllSlots);
-    if (!fast && many == 0) continue;                             // dead lane (x >= uw) or outside every job's window
+    if (__all_sync(0xffffffffu, many == 0)) continue;               // outside every job's window (alignment columns, x >= uw)
     uint32_t idxv[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) idxv[v] = (uint32_t)((ys + v) * uw + x);
 
-    auto update = [&](const int sl, const uint32_t (&sadv)[V]) {
-      if (!fast && !((many >> sl) & 1)) return;
+    auto slot_keys = [&](const int sl, const uint32_t (&sadv)[V], uint32_t (&kv)[V]) {
       const uint32_t f = sm.factor[sl];
       const uint32_t fbx = f * (uint32_t)sm.bx[sl][cidx];
       uint32_t byv[V];
@@ -379,55 +411,79 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
         const uint4 q = *reinterpret_cast<const uint4*>(&by_tab[sl * by_stride + ys + v4]);   // warp-uniform address: broadcast LDS.128
         byv[v4] = q.x; byv[v4 + 1] = q.y; byv[v4 + 2] = q.z; byv[v4 + 3] = q.w;
       }
+#pragma unroll
+      for (int v = 0; v < V; ++v) kv[v] = rate_key(f, byv[v], fbx, sadv[v], idxv[v]);
+    };
+    auto update_full = [&](const int sl, const uint32_t (&sadv)[V]) {
+      uint32_t kv[V];
+      slot_keys(sl, sadv, kv);
+      // two levels of three-input minima (VIMNMX3) instead of a serial chain through best[sl]
+#pragma unroll
+      for (int v = 0; v + 2 < V; v += 3) kv[v] = min(min(kv[v], kv[v + 1]), kv[v + 2]);
+      uint32_t m;
+      if (V == 8) m = min(min(kv[0], kv[3]), min(kv[6], kv[7]));
+      else        m = min(min(kv[0], kv[3]), kv[V - 1]);
+      if ((mfull >> sl) & 1) best[sl] = min(best[sl], m);
+    };
+    auto update_partial = [&](const int sl, const uint32_t (&sadv)[V]) {
+      uint32_t kv[V];
+      slot_keys(sl, sadv, kv);
+      const int lo = sm.ylo[sl] - ys, hi = sm.yhi[sl] - ys;         // valid strip rows: lo <= v <= hi
       uint32_t b = best[sl];
-      if (fast || ((mfull >> sl) & 1)) {
 #pragma unroll
-        for (int v = 0; v < V; ++v) b = min(b, rate_key(f, byv[v], fbx, sadv[v], idxv[v]));
-      } else {
-        const int lo = sm.ylo[sl] - ys, hi = sm.yhi[sl] - ys;       // valid strip rows: lo <= v <= hi
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          const uint32_t key = rate_key(f, byv[v], fbx, sadv[v], idxv[v]);
-          if (v >= lo && v <= hi) b = min(b, key);
-        }
-      }
+      for (int v = 0; v < V; ++v)
+        if (v >= lo && v <= hi) b = min(b, kv[v]);
       best[sl] = b;
     };
 
-    if (!GRAN4) {
-      uint32_t t0[V], t1[V];
-      // 8x8 partitions read the accumulators directly
+    // partition SADs from the accumulators (8x8 granularity: 5 adds per displacement for the 9-partition set)
+    auto for_each_slot = [&](auto&& fn) {
+      if (!GRAN4) {
+        uint32_t t0[V], t1[V];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 4; ++q) {
 #pragma unroll
-        for (int v = 0; v < V; ++v) t0[v] = acc[v][q];
-        update(5 + q, t0);
-      }
-      // 16x8 (upper, lower) and, from their sum, 16x16
-#pragma unroll
-      for (int v = 0; v < V; ++v) { t0[v] = acc[v][0] + acc[v][1]; t1[v] = acc[v][2] + acc[v][3]; }
-      update(1, t0); update(2, t1);
-#pragma unroll
-      for (int v = 0; v < V; ++v) t0[v] += t1[v];
-      update(0, t0);
-      // 8x16 (left, right)
-#pragma unroll
-      for (int v = 0; v < V; ++v) { t0[v] = acc[v][0] + acc[v][2]; t1[v] = acc[v][1] + acc[v][3]; }
-      update(3, t0); update(4, t1);
-    } else {
-#pragma unroll
-      for (int sl = 0; sl < NS; ++sl) {
-        const uint32_t mask = slot_mask_gran4(sl);                 // folds after unrolling
-        uint32_t t0[V];
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          uint32_t sad = 0;
-#pragma unroll
-          for (int a = 0; a < NACC; ++a) if (mask & (1u << a)) sad += acc[v][a];
-          t0[v] = sad;
+          for (int v = 0; v < V; ++v) t0[v] = acc[v][q];
+          fn(5 + q, t0);
         }
-        update(sl, t0);
+#pragma unroll
+        for (int v = 0; v < V; ++v) { t0[v] = acc[v][0] + acc[v][1]; t1[v] = acc[v][2] + acc[v][3]; }
+        fn(1, t0); fn(2, t1);                                       // 16x8 upper, lower
+#pragma unroll
+        for (int v = 0; v < V; ++v) t0[v] += t1[v];
+        fn(0, t0);                                                  // 16x16
+#pragma unroll
+        for (int v = 0; v < V; ++v) { t0[v] = acc[v][0] + acc[v][2]; t1[v] = acc[v][1] + acc[v][3]; }
+        fn(3, t0); fn(4, t1);                                       // 8x16 left, right
+      } else {
+#pragma unroll
+        for (int sl = 0; sl < NS; ++sl) {
+          const uint32_t mask = slot_mask_gran4(sl);                // folds after unrolling
+          uint32_t t0[V];
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            uint32_t sad = 0;
+#pragma unroll
+            for (int a = 0; a < NACC; ++a) if (mask & (1u << a)) sad += acc[v][a];
+            t0[v] = sad;
+          }
+          fn(sl, t0);
+        }
       }
+    };
+
+    for_each_slot(update_full);
+    const Mask part = many & ~mfull;
+    if (__any_sync(0xffffffffu, part != 0)) {
+      // the keys are recomputed from an opaque copy of the column: keeping the 8 x NS keys of pass 1 alive for this rare
+      // pass would spill them in the hot path
+      int x2 = x;
+      asm volatile("mov.b32 %0, %0;" : "+r"(x2));
+#pragma unroll
+      for (int v = 0; v < V; ++v) idxv[v] = (uint32_t)((ys + v) * uw + x2);
+      for_each_slot([&](const int sl, const uint32_t (&sadv)[V]) {
+        if ((part >> sl) & 1) update_partial(sl, sadv);
+      });
     }
   }
 

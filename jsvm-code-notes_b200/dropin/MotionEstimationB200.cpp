@@ -53,10 +53,17 @@ struct B200State {
   // the buffers compensateBlock serves from (the reference keeps m_aXHPelSearch / m_aXQPelSearch)
   unsigned char last_pred[256];
   bool last_valid;
-  unsigned long long n_calls;
-  B200State() : search_range(0), sub_dfunc(0), params_valid(false), device(0), last_valid(false), n_calls(0) {
+  unsigned long long n_calls, n_calls_16bit, n_calls_bipred, n_frames;
+  B200State() : search_range(0), sub_dfunc(0), params_valid(false), device(0), last_valid(false), n_calls(0), n_calls_16bit(0),
+                n_calls_bipred(0), n_frames(0) {
     const char* d = getenv("JSVM_ME_DEVICE");
     if (d) device = atoi(d);
+  }
+  ~B200State() {
+    // JSVM_ME_STATS=1: what went through the device (evidence for the system parity runs)
+    if (getenv("JSVM_ME_STATS"))
+      fprintf(stderr, "jsvm_me_b200 stats: filterFrame %llu, estimateBlockWithStart %llu (signed 16-bit originals %llu, bi-pred %llu), layers %zu\n",
+              n_frames, n_calls, n_calls_16bit, n_calls_bipred, layers.size());
   }
 };
 
@@ -117,6 +124,7 @@ ErrVal QuarterPelFilter::filterFrame( YuvPicBuffer* pcPelBuffer, YuvPicBuffer* p
   LayerStore* ls = layerFor( iWidth, iHeight );
   ROF( ls );
   const int slot = slotForFill( ls, pcHalfPelBuffer );
+  state().n_frames++;
   if( jsvm_me_upload_plane_xpel( ls->ctx, slot, pcPelBuffer->getMbLumAddr(), iWidth, iHeight, pcPelBuffer->getLStride() ) != JSVM_ME_OK )
     return reportFailure( "jsvm_me_upload_plane_xpel" );
   if( jsvm_me_interp_halfpel( ls->ctx, slot ) != JSVM_ME_OK )
@@ -309,6 +317,14 @@ MotionEstimation::estimateBlockWithStart( const MbDataAccess&          rcMbDataA
   const Int   iOrgStride = pcOrg->getLStride();
   for( Int y = 0; y < 16; y++ )
     for( Int x = 0; x < 16; x++ ) asOrg[y * 16 + x] = pOrgMb[y * iOrgStride + x];
+  {
+    const Int bx = 4 * ( uiBlk & 3 ), by = 4 * ( uiBlk >> 2 );
+    bool bWide = false;
+    for( Int y = by; y < by + iYSize; y++ )
+      for( Int x = bx; x < bx + iXSize; x++ ) bWide |= ( asOrg[y * 16 + x] < 0 || asOrg[y * 16 + x] > 255 );
+    if( bWide ) st.n_calls_16bit++;
+    if( pcBSP ) st.n_calls_bipred++;
+  }
   // samples of the MB outside the searched partition may be stale in a prepared buffer: only the partition matters,
   // keep them in range so that the 8-bit check of the library looks at the partition alone
   if( pcOrg == &cPrepared )

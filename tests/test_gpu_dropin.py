@@ -15,7 +15,12 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 @pytest.mark.parametrize("args", [
     ["--frames", "9", "--gop", "8", "--sr", "16", "--subpel", "2"],                                   # C1: QCIF, SR 16, hier-B, SATD sub-pel
     ["--frames", "5", "--gop", "4", "--sr", "32", "--subpel", "0", "--all-partitions", "--refs", "2"],  # all 41 partitions, 2 refs, SAD sub-pel
-])
+    # C2: two spatial layers QCIF -> CIF, adaptive inter-layer mode / motion / residual prediction (signed 16-bit originals, N3)
+    ["--width", "352", "--height", "288", "--layers", "2", "--frames", "5", "--gop", "4", "--sr", "32", "--subpel", "2", "--saturate"],
+    # C5 in small: spatial + quality (CGS) layers, 2 reference frames, inter-layer motion prediction
+    ["--width", "352", "--height", "288", "--layers", "2", "--quality-layers", "1", "--refs", "2", "--frames", "5", "--gop", "4",
+     "--sr", "16", "--subpel", "2"],
+], ids=["C1-qcif-hierB-satd", "all41-2refs-sad", "C2-two-spatial-layers", "C5-spatial+quality-2refs"])
 def test_encoder_with_dropin_is_bit_identical(args):
     import system_parity
     if not (os.path.exists(system_parity.STOCK) and os.path.exists(system_parity.B200)):
@@ -24,3 +29,7 @@ def test_encoder_with_dropin_is_bit_identical(args):
     assert res["stock"]["bitstream_md5"] == res["b200"]["bitstream_md5"], res
     assert res["stock"]["recon_md5"] == res["b200"]["recon_md5"], res
     assert res["stock"]["bytes"] > 1000
+    assert res["b200"]["device_path"] and "estimateBlockWithStart 0 " not in res["b200"]["device_path"]     # the search really ran on the device
+    if "--saturate" in args:                                   # residual prediction reached the search with signed 16-bit originals (N3)
+        assert "signed 16-bit originals 0," not in res["b200"]["device_path"], res["b200"]["device_path"]
+    print(res["b200"]["device_path"])

@@ -130,6 +130,10 @@ def write_inputs(workdir, a):
     synth = importlib.import_module("jsvm-code-notes_b200.synth")
     seq = synth.Sequence(a.width, a.height, a.seed)
     top = [seq.frame(n) for n in range(a.frames)]
+    if a.saturate:
+        # contrast x3 around mid-grey with hard clipping: large areas at 0 and 255, so that "original minus base-layer
+        # residual" leaves [0,255] in the residual-prediction passes (N3)
+        top = [np.clip((f.astype(np.int32) - 128) * 3 + 128, 0, 255).astype(np.uint8) for f in top]
     by_spatial = {a.layers - 1: top}
     cur = top
     for s in range(a.layers - 2, -1, -1):                    # 2x2 box down-sampling for the lower spatial layers
@@ -155,7 +159,8 @@ def run(exe, workdir, tag, a):
     open(main_cfg, "w").write(MAIN_CFG.format(out=out, frames=a.frames, gop=a.gop, refs=a.refs, sr=a.sr, subpel=a.subpel,
                                               nlayers=len(plan), layercfgs=lines))
     t0 = time.perf_counter()
-    p = subprocess.run([exe, "-pf", main_cfg], cwd=workdir, capture_output=True, text=True, timeout=a.timeout)
+    p = subprocess.run([exe, "-pf", main_cfg], cwd=workdir, capture_output=True, text=True, timeout=a.timeout,
+                       env=dict(os.environ, JSVM_ME_STATS="1"))
     dt = time.perf_counter() - t0
     if p.returncode != 0 or not os.path.exists(out):
         sys.stderr.write(p.stdout[-3000:] + "\n" + p.stderr[-3000:] + "\n")
@@ -163,7 +168,9 @@ def run(exe, workdir, tag, a):
     h = hashlib.md5()
     for r in recs:
         h.update(md5(r).encode())
-    return {"bitstream_md5": md5(out), "recon_md5": h.hexdigest(), "bytes": os.path.getsize(out), "seconds": round(dt, 2), "layers": len(plan)}
+    stats = [ln for ln in p.stderr.splitlines() if ln.startswith("jsvm_me_b200 stats:")]
+    return {"bitstream_md5": md5(out), "recon_md5": h.hexdigest(), "bytes": os.path.getsize(out), "seconds": round(dt, 2), "layers": len(plan),
+            "device_path": stats[-1][len("jsvm_me_b200 stats: "):] if stats else None}
 
 
 def compare(argv=None):
@@ -178,6 +185,7 @@ def compare(argv=None):
     ap.add_argument("--qp", type=float, default=32.0)
     ap.add_argument("--all-partitions", action="store_true")
     ap.add_argument("--seed", type=int, default=1235)
+    ap.add_argument("--saturate", action="store_true", help="clip the synthetic luma hard at 0 / 255")
     ap.add_argument("--layers", type=int, default=1, help="dyadic spatial layers; --width/--height name the TOP layer")
     ap.add_argument("--quality-layers", type=int, default=0, help="extra CGS quality layers at the top resolution")
     ap.add_argument("--ilpred", type=int, default=2, help="InterLayerPred / ILModePred / ILMotionPred / ILResidualPred of enhancement layers")
