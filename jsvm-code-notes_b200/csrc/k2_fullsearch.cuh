@@ -30,9 +30,6 @@
 
 namespace jsvm {
 
-#ifndef K2_COST_IMADHI
-#define K2_COST_IMADHI 0
-#endif
 #ifndef K2_FASTPATH
 #define K2_FASTPATH 0
 #endif
@@ -44,9 +41,6 @@ namespace jsvm {
 // the upper half of the CTA therefore starts its first batch K2_STAGGER_NS later (the offset persists).
 #ifndef K2_STAGGER_NS
 #define K2_STAGGER_NS 0
-#endif
-#ifndef K2_MINTREE
-#define K2_MINTREE 0
 #endif
 // timing experiments only (results are wrong): 1 = no rate/argmin update, 2 = no SAD pass, 3 = no rate tables / masks
 #ifndef K2_ABLATE
@@ -84,6 +78,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   } while (!done);
 }
+// the same with a pause between polls: for waiters that have nothing urgent to do (they must not steal issue slots)
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(200);
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -112,20 +120,18 @@ __host__ __device__ constexpr uint32_t slot_mask_gran4(int sl) {
 
 // sad + ((factor * bits) >> 16), packed with the raster index: (cost << 15) + idx.
 //   t    = f * by + fbx          f * (bits_x + bits_y) in 32-bit wrap-around arithmetic (N5); FMA pipe (IMAD)
-//   cost = sad + (t >> 16)       xGetCost, ENC/MotionEstimationCost.h:27
-//   key  = cost * 32768 + idx    FMA pipe (IMAD); the min itself is the only ALU-pipe op besides the shift-add
+//   cost = sad + (t >> 16)       xGetCost, ENC/MotionEstimationCost.h:27; one LEA.HI on the ALU pipe
+//   key  = cost * 32768 + idx    FMA pipe (IMAD)
 // Written as PTX so that the compiler cannot re-associate (cost << 15) into one multiply per SAD term.
+// (Measured on B200: the shift-add as hi32(t * 65536) + sad -- IMAD.HI with the constant hidden in a kernel argument, which
+// keeps it on the FMA pipe -- is 16 % slower: IMAD.HI wants a 64-bit addend pair and runs at a fraction of the IMAD rate.)
 __device__ __forceinline__ uint32_t rate_key(uint32_t f, uint32_t by, uint32_t fbx, uint32_t sad, uint32_t idx) {
   uint32_t key;
   asm("{\n"
       ".reg .u32 t, c;\n"
       "mad.lo.u32 t, %1, %2, %3;\n"
-#if K2_COST_IMADHI
-      "mad.hi.u32 c, t, 65536, %4;\n"         // (t * 2^16) >> 32 + sad == (t >> 16) + sad, on the FMA pipe
-#else
       "shr.u32 t, t, 16;\n"
       "add.u32 c, t, %4;\n"
-#endif
       "mad.lo.u32 %0, c, 32768, %5;\n"
       "}\n" : "=r"(key) : "r"(f), "r"(by), "r"(fbx), "r"(sad), "r"(idx));
   return key;
@@ -137,12 +143,13 @@ struct K2Smem {
   static constexpr int NACC = GRAN4 ? 16 : 4;
   static constexpr int kMaxStrips = kMaxRows / V;
   typedef typename std::conditional<GRAN4, unsigned long long, uint32_t>::type Mask;   // one bit per partition slot
-  // dynamic shared memory layout (bytes); the four window copies come first
+  // one stage of dynamic shared memory: the four window copies come first, then this record, then the by table
   uint32_t cur[16][4];                            // the current macroblock, 16 packed bytes per row (16-byte aligned)
   uint32_t factor[NS];
   int16_t  xlo[NS], xhi[NS], ylo[NS], yhi[NS];    // relative to the union window origin (empty slot: xhi < xlo)
   int32_t  job[NS];                               // absolute job index or -1
   int32_t  next_unit;                             // work counter: warps pull batches of 32 units
+  int16_t  ux0, uy0, uw, uh, xa, pad;             // geometry of the staged group (persistent kernel: consumers read it here)
   uint32_t best[NS];
   uint8_t  bx[NS][4 * kMaxM + 12];                // bits of the horizontal difference, permuted [s][m]
   Mask     xmask[4 * kMaxM];                      // slots whose window contains column x, permuted [s][m]
@@ -153,7 +160,7 @@ struct K2Smem {
 
 // Reference rows staged per copy: only the uh + 15 rows that valid displacements touch.  The last strip may reach up to
 // V-1 rows further; those reads belong to displacements outside every window (masked by yany / yfull), land in the
-// shared memory that follows the copies (tables) and are never used.
+// shared memory that follows the copies (by table, slack) and are never used.
 __host__ __device__ inline int k2_rows(int uh) { return uh + 15; }
 // words between two window copies: padded so that (copy stride mod 32) == (M rounded up to even) mod 32 -- a warp whose
 // lanes run off the end of copy s (m = M-1) continues in copy s+1 (m = 0) on the NEXT bank: no shared-memory conflicts.
@@ -162,44 +169,58 @@ __host__ __device__ inline int k2_copy_words(int rows, int m_units) {
   return base + (((m_units - base) % 32) + 32) % 32;
 }
 
+// Geometry of one staged group.  The staged window starts on a 4-byte boundary of the reference plane: `xa` (0..3) extra
+// columns on the left; column x' of the staged window is displacement ux0 - xa + x' (the extra columns belong to no window).
+template <int V>
+struct K2Geo {
+  int xa, uw, uh, uwx, nstrips, rows, M, copy_words, by_stride;
+  __device__ __forceinline__ K2Geo(int xa_, int uw_, int uh_) {
+    xa = xa_; uw = uw_; uh = uh_; uwx = uw + xa;
+    nstrips = (uh + V - 1) / V;
+    rows = k2_rows(uh);
+    M = ((uwx + 3) >> 2) + (((uwx + 3) >> 2) & 1);                // column groups per copy, rounded up to even
+    copy_words = k2_copy_words(rows, M);
+    by_stride = nstrips * V;
+  }
+};
+
+// One stage of dynamic shared memory: [K2Smem record][four window copies][by table][slack].  The record sits at a fixed
+// offset so that its position does not move with the size of the staged group (the persistent kernel writes a finished
+// group's keys out of the record while the next group's window is already being staged behind it).
 template <int V, bool GRAN4>
-__global__ void __launch_bounds__(kK2Threads, GRAN4 ? 1 : 2)
-full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel plane pool [slot][H+64][W+64]
-                   size_t plane_bytes, int plane_stride,
-                   const Group* __restrict__ groups,
-                   const jsvm_me_job* __restrict__ jobs,
-                   const int16_t* __restrict__ org_mbs,
-                   int mb_w, int mb_h, int default_range,
-                   uint32_t* __restrict__ keys,                   // per job: packed (cost << 15 | idx)
-                   JobAux* __restrict__ aux)                      // per job: how K3 decodes the key
+struct K2Stage {
+  using SM = K2Smem<V, GRAN4>;
+  static constexpr size_t kRecBytes = (sizeof(SM) + 127) & ~(size_t)127;
+  uint32_t* winw; SM* sm; uint32_t* by_tab;
+  __device__ __forceinline__ K2Stage(uint8_t* base, const K2Geo<V>& geo) {
+    sm = reinterpret_cast<SM*>(base);
+    winw = reinterpret_cast<uint32_t*>(base + kRecBytes);
+    by_tab = reinterpret_cast<uint32_t*>(base + kRecBytes + (((size_t)4 * geo.copy_words * 4 + 15) & ~(size_t)15));
+  }
+};
+
+// ---- staging of one group: job parameters, the four window copies, the current macroblock, rate tables, masks ----
+// Executed by `pthreads` threads (whole warps; ptid = index among them); no barrier inside: every warp derives the
+// per-slot job parameters in its own lanes (lane l owns slots l and l + 32) and reads them back with shuffles.
+template <int V, bool GRAN4>
+__device__ __forceinline__ void k2_build_stage(const Group& g, const K2Geo<V>& geo, const K2Stage<V, GRAN4>& st,
+                                               const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_stride,
+                                               const jsvm_me_job* __restrict__ jobs, const int16_t* __restrict__ org_mbs,
+                                               int mb_w, int mb_h, int default_range,
+                                               const int ptid, const int pthreads, const int first_unit)
 {
   using SM = K2Smem<V, GRAN4>;
   using Mask = typename SM::Mask;
-  constexpr int NS = SM::NS, NACC = SM::NACC;
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-
-  const Group& g = groups[blockIdx.x];
-  const int tid = threadIdx.x;
-  // The staged window starts on a 4-byte boundary of the reference plane: `xa` (0..3) extra columns on the left.
-  // Column x' of the staged window is displacement ux0 - xa + x'; the extra columns belong to no job's window.
+  constexpr int NS = SM::NS;
+  SM& sm = *st.sm;
+  uint32_t* winw = st.winw;
+  uint32_t* by_tab = st.by_tab;
+  const int xa = geo.xa, uh = geo.uh, uwx = geo.uwx, rows = geo.rows, copy_words = geo.copy_words, by_stride = geo.by_stride, nstrips = geo.nstrips;
   const int px = kMargin + 16 * g.mb_x + g.ux0;                 // union window origin in plane coordinates
   const int py = kMargin + 16 * g.mb_y + g.uy0;
-  const int xa = px & 3;
-  const int uw = g.uw, uh = g.uh, uwx = uw + xa;
-  const int nstrips = (uh + V - 1) / V;
-  const int rows = k2_rows(uh);
-  const int M = ((uwx + 3) >> 2) + (((uwx + 3) >> 2) & 1);        // column groups per copy, rounded up to even
-  const int copy_words = k2_copy_words(rows, M);
-  const int by_stride = nstrips * V;
-  uint32_t* winw = reinterpret_cast<uint32_t*>(smem_raw);
-  uint8_t* after = smem_raw + (((size_t)4 * copy_words * 4 + 15) & ~(size_t)15);
-  SM& sm = *reinterpret_cast<SM*>(after);
-  uint32_t* by_tab = reinterpret_cast<uint32_t*>(after + ((sizeof(SM) + 15) & ~(size_t)15));
+  const int lane = ptid & 31;
 
-  // ---- prologue 1: per-slot job parameters, computed by EVERY warp in its lanes (lane l owns slots l and l + 32) and
-  //      read back with shuffles while the tables are built, so that no barrier is needed before them; warp 0 also
-  //      stores them to shared memory for the main loop ----
-  const int lane = tid & 31;
+  // ---- 1: per-slot job parameters; the first warp also stores them for the search loop ----
   constexpr int kSlotRegs = (NS + 31) / 32;
   int p_present[kSlotRegs], p_xlo[kSlotRegs], p_xhi[kSlotRegs], p_ylo[kSlotRegs], p_yhi[kSlotRegs], p_ph[kSlotRegs], p_pv[kSlotRegs];
 #pragma unroll
@@ -216,7 +237,7 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
       p_ylo[q] = w.ylo - g.uy0;      p_yhi[q] = w.yhi - g.uy0;
       p_ph[q] = j.pred.hor; p_pv[q] = j.pred.ver;
     }
-    if (tid < 32 && sl < NS) {
+    if (ptid < 32 && sl < NS) {
       sm.job[sl] = jo < 0 ? -1 : g.first_job + jo;
       sm.best[sl] = kKeyInvalid;
       sm.factor[sl] = fac;
@@ -224,16 +245,19 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
       sm.ylo[sl] = (int16_t)p_ylo[q]; sm.yhi[sl] = (int16_t)p_yhi[q];
     }
   }
-  if (tid == 0) sm.next_unit = kK2Threads;                        // the first batch of every warp is static (u0 = 32 * warp)
+  if (ptid == 0) {
+    sm.next_unit = first_unit;
+    sm.ux0 = g.ux0; sm.uy0 = g.uy0; sm.uw = g.uw; sm.uh = g.uh; sm.xa = (int16_t)xa;
+  }
 
-  // ---- prologue 2: the four byte-shifted copies of the reference window ----
+  // ---- 2: the four byte-shifted copies of the reference window ----
   // item = (row, 4 destination words): 5 aligned source words -> 4 x 4 funnel-shifted words -> two 8-byte stores per copy
   {
     const uint32_t* src0 = reinterpret_cast<const uint32_t*>(
         planes + (size_t)g.ref_slot * plane_bytes + (size_t)py * plane_stride + (px - xa));
     const int stride_w = plane_stride >> 2;
     constexpr int kGroups = kWinRowWords / 4;                   // 10
-    for (int i = tid; i < rows * kGroups; i += kK2Threads) {
+    for (int i = ptid; i < rows * kGroups; i += pthreads) {
       const int r = i / kGroups, gq = i - r * kGroups;
       const uint32_t* sp = src0 + (size_t)r * stride_w + 4 * gq;
       uint32_t w[5];
@@ -249,10 +273,10 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
     }
   }
 
-  // ---- prologue 3: the current macroblock into shared memory (16 rows x 4 packed words); every unit re-reads it with 16
-  //      broadcast LDS.128 so that its 64 registers are free during the rate / argmin pass ----
-  if (tid < 64) {
-    const int r = tid >> 2, k = tid & 3;
+  // ---- 3: the current macroblock (16 rows x 4 packed words); every unit re-reads it with 16 broadcast LDS.128 so that its
+  //      64 registers are free during the rate / argmin pass ----
+  if (ptid < 64) {
+    const int r = ptid >> 2, k = ptid & 3;
     uint32_t v;
     if (g.org_index < 0) {
       v = __ldg(reinterpret_cast<const uint32_t*>(planes + (size_t)g.cur_slot * plane_bytes + (size_t)(kMargin + 16 * g.mb_y + r) * plane_stride +
@@ -265,7 +289,8 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
     }
     sm.cur[r][k] = v;
   }
-  // ---- prologue 4: MV-rate tables and validity masks (no runtime divisions: slot loops outside, strided loops inside) ----
+
+  // ---- 4: MV-rate tables and validity masks (no runtime divisions: slot loops outside, strided loops inside) ----
 #pragma unroll 1
   for (int sl = 0; sl < (K2_ABLATE == 3 ? 0 : NS); ++sl) {
     const int q = sl >> 5, src = sl & 31;
@@ -276,18 +301,18 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
       if (qq == q) { present = a; pv = b; ph = c2; }
     }
     // xGetBits with m_uiMvScaleShift = 2: table index (y << 2) - pred (N6)
-    for (int y = tid; y < by_stride; y += kK2Threads)
+    for (int y = ptid; y < by_stride; y += pthreads)
       by_tab[sl * by_stride + y] = (present && y < uh) ? mv_component_bits(((g.uy0 + y) << 2) - pv) : 0u;
-    for (int ci = tid; ci < 4 * kMaxM; ci += kK2Threads) {
+    for (int ci = ptid; ci < 4 * kMaxM; ci += pthreads) {
       const int sft = ci / kMaxM, m = ci - sft * kMaxM;         // division by a compile-time constant
       const int x = 4 * m + sft;                                // staged column
       sm.bx[sl][ci] = (present && x < uwx) ? (uint8_t)mv_component_bits(((g.ux0 - xa + x) << 2) - ph) : (uint8_t)0;
     }
   }
-  {
-    // column / strip validity masks: every thread evaluates its entry against all slots (ballots over the slot lanes)
-    const int ci = tid, sft = ci / kMaxM, m = ci - sft * kMaxM, x = 4 * m + sft;
-    const int y0 = tid * V, y1 = y0 + V - 1;
+  // column / strip validity masks: a thread evaluates its entries against all slots
+  for (int e0 = 0; e0 < 4 * kMaxM; e0 += pthreads) {              // warp-uniform trip count: the shuffles below need whole warps
+    const int ci = e0 + ptid, sft = ci / kMaxM, m = ci - sft * kMaxM, x = 4 * m + sft;
+    const int y0 = ci * V, y1 = y0 + V - 1;                        // entry ci doubles as strip index for the row masks
     Mask mk = 0, full = 0, any = 0;
 #pragma unroll 1
     for (int sl = 0; sl < (K2_ABLATE == 3 ? 0 : NS); ++sl) {
@@ -307,25 +332,35 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
     }
     if (K2_ABLATE == 3) { mk = full = any = (Mask)(~(Mask)0) >> (8 * sizeof(Mask) - NS); }
     if (ci < 4 * kMaxM) sm.xmask[ci] = mk;
-    if (tid < nstrips) { sm.yfull[tid] = full; sm.yany[tid] = any; }
+    if (ci < nstrips) { sm.yfull[ci] = full; sm.yany[ci] = any; }
   }
-  __syncthreads();            // window copies and tables visible
+}
 
-  uint32_t best[NS];
-#pragma unroll
-  for (int sl = 0; sl < NS; ++sl) best[sl] = kKeyInvalid;
+// ---- the search loop of one warp over one staged group: batches of 32 units (unit = column x strip of V displacements)
+//      pulled from the stage's counter, always one batch ahead of the one being worked on ----
+template <int V, bool GRAN4>
+__device__ __forceinline__ void k2_search_units(const K2Geo<V>& geo, const K2Stage<V, GRAN4>& st, const int lane, const int first_u0,
+                                                uint32_t (&best)[K2Smem<V, GRAN4>::NS])
+{
+  using SM = K2Smem<V, GRAN4>;
+  using Mask = typename SM::Mask;
+  constexpr int NS = SM::NS, NACC = SM::NACC;
+  SM& sm = *st.sm;
+  const uint32_t* winw = st.winw;
+  const uint32_t* by_tab = st.by_tab;
+  const int xa = geo.xa, uw = geo.uw, M = geo.M, copy_words = geo.copy_words, by_stride = geo.by_stride;
 
   const int units_per_strip = 4 * M;
-  const int nunits = nstrips * units_per_strip;
+  const int nunits = geo.nstrips * units_per_strip;
   // exact division of u < 2^16 by d < 2^16: (u * ceil(2^32 / d)) >> 32
   const uint32_t inv_ups = (uint32_t)((0x100000000ull + units_per_strip - 1) / units_per_strip);
   const uint32_t inv_m = (uint32_t)((0x100000000ull + M - 1) / M);
 
-  // warps pull batches of 32 units from a shared counter (the first batch is static), always one batch ahead of
-  // the one they work on: they all finish within one batch of each other and never wait for the counter
-  if (K2_STAGGER_NS > 0 && tid >= kK2Threads / 2) __nanosleep(K2_STAGGER_NS);
-  int u0 = (tid >> 5) * 32;
-  int u0_next = 0;
+  int u0 = first_u0, u0_next = 0;
+  if (first_u0 < 0) {                                             // no static first batch: fetch it
+    if (lane == 0) u0 = atomicAdd(&sm.next_unit, 32);
+    u0 = __shfl_sync(0xffffffffu, u0, 0);
+  }
   if (lane == 0) u0_next = atomicAdd(&sm.next_unit, 32);
   for (;;) {
     if (u0 >= nunits) break;
@@ -342,12 +377,9 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
     const int cidx = s * kMaxM + m;
 
     // ---- SAD pass over the strip ----
-    uint32_t cur[16][4];
-#pragma unroll
-    for (int r = 0; r < 16; ++r) {
-      const uint4 v = *reinterpret_cast<const uint4*>(&sm.cur[r][0]);
-      cur[r][0] = v.x; cur[r][1] = v.y; cur[r][2] = v.z; cur[r][3] = v.w;
-    }
+    // Row c of the current macroblock (one broadcast LDS.128) meets the V reference rows c .. c+V-1, which sit in a sliding
+    // register window (one new row = 4 LDS.32 per step): 16 x 4 x V VABSDIFF4.U8.ACC, 36 live data registers besides the
+    // accumulators.  Word order 0, 2, 1, 3: the two updates of one accumulator are 2V instructions apart.
     uint32_t acc[V][NACC];
 #pragma unroll
     for (int v = 0; v < V; ++v)
@@ -360,24 +392,29 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
     for (int v = 0; v < V; ++v)
 #pragma unroll
       for (int a = 0; a < NACC; ++a) acc[v][a] = rp[0] + (uint32_t)(v * NACC + a);
-#endif
+#else
+    {
+      uint32_t ref[V][4];
 #pragma unroll
-    for (int r = 0; r < (K2_ABLATE == 2 ? 0 : 15 + V); ++r) {
-      const uint32_t w[4] = { rp[r * kWinRowWords + 0], rp[r * kWinRowWords + 1], rp[r * kWinRowWords + 2], rp[r * kWinRowWords + 3] };
-      // word-major order: the two updates of one accumulator (words 0/1 or 2/3 of a row) end up V instructions apart
-      // instead of back to back, so a warp does not wait out the ALU latency between them
+      for (int r = 0; r < V - 1; ++r)
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const int k = GRAN4 ? kk : ((kk & 1) * 2 + (kk >> 1));      // 8x8 granularity: 0, 2, 1, 3
+        for (int k = 0; k < 4; ++k) ref[r][k] = rp[r * kWinRowWords + k];
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-          const int c = r - v;                  // current-MB row matched by this reference row at displacement ys+v
-          if (c < 0 || c > 15) continue;
+      for (int c = 0; c < 16; ++c) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ref[(c + V - 1) % V][k] = rp[(c + V - 1) * kWinRowWords + k];
+        const uint4 cq = *reinterpret_cast<const uint4*>(&sm.cur[c][0]);
+        const uint32_t cw[4] = { cq.x, cq.y, cq.z, cq.w };
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = GRAN4 ? kk : ((kk & 1) * 2 + (kk >> 1));      // 8x8 granularity: 0, 2, 1, 3
           const int a = GRAN4 ? (c >> 2) * 4 + k : (c >> 3) * 2 + (k >> 1);
-          acc[v][a] = sad4(cur[c][k], w[k], acc[v][a]);
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[v][a] = sad4(cw[k], ref[(c + v) % V][k], acc[v][a]);
         }
       }
     }
+#endif
 
 #if K2_ABLATE == 1
     {
@@ -417,7 +454,8 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
     auto update_full = [&](const int sl, const uint32_t (&sadv)[V]) {
       uint32_t kv[V];
       slot_keys(sl, sadv, kv);
-      // two levels of three-input minima (VIMNMX3) instead of a serial chain through best[sl]
+      // two levels of three-input minima (VIMNMX3) instead of a serial chain through best[sl].  (A 4-instruction tree that
+      // folds best[sl] into the last VIMNMX3 measured 2 % slower than this 5-instruction one.)
 #pragma unroll
       for (int v = 0; v + 2 < V; v += 3) kv[v] = min(min(kv[v], kv[v + 1]), kv[v + 2]);
       uint32_t m;
@@ -486,27 +524,171 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
       });
     }
   }
+}
 
-  // ---- CTA reduction: warp min, then shared atomicMin, then one store per job ----
+// warp minimum of every slot, then shared atomicMin
+template <int V, bool GRAN4>
+__device__ __forceinline__ void k2_warp_reduce(K2Smem<V, GRAN4>& sm, const int lane, const uint32_t (&best)[K2Smem<V, GRAN4>::NS]) {
 #pragma unroll
-  for (int sl = 0; sl < NS; ++sl) {
+  for (int sl = 0; sl < K2Smem<V, GRAN4>::NS; ++sl) {
     const uint32_t w = __reduce_min_sync(0xffffffffu, best[sl]);
-    if ((tid & 31) == 0 && w != kKeyInvalid) atomicMin(&sm.best[sl], w);
+    if (lane == 0 && w != kKeyInvalid) atomicMin(&sm.best[sl], w);
+  }
+}
+
+// one key per job to HBM; K3 decodes it with the group's window geometry
+template <int V, bool GRAN4>
+__device__ __forceinline__ void k2_flush(const K2Smem<V, GRAN4>& sm, const int ptid, const int pthreads,
+                                         uint32_t* __restrict__ keys, JobAux* __restrict__ aux) {
+  for (int sl = ptid; sl < K2Smem<V, GRAN4>::NS; sl += pthreads) {
+    const int job = sm.job[sl];
+    if (job >= 0) {
+      keys[job] = sm.best[sl];
+      JobAux a; a.ux0 = sm.ux0; a.uy0 = sm.uy0; a.uw = sm.uw; a.pad = 0;
+      aux[job] = a;
+    }
+  }
+}
+
+// ---- kernel A: one CTA per search group (small launches, 4x4-granular groups, very tall union windows) ----
+template <int V, bool GRAN4>
+__global__ void __launch_bounds__(kK2Threads, GRAN4 ? 1 : 2)
+full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel plane pool [slot][H+64][W+64]
+                   size_t plane_bytes, int plane_stride,
+                   const Group* __restrict__ groups,
+                   const jsvm_me_job* __restrict__ jobs,
+                   const int16_t* __restrict__ org_mbs,
+                   int mb_w, int mb_h, int default_range,
+                   uint32_t* __restrict__ keys,                   // per job: packed (cost << 15 | idx)
+                   JobAux* __restrict__ aux)                      // per job: how K3 decodes the key
+{
+  using SM = K2Smem<V, GRAN4>;
+  constexpr int NS = SM::NS;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const Group& g = groups[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const K2Geo<V> geo((kMargin + 16 * g.mb_x + g.ux0) & 3, g.uw, g.uh);
+  const K2Stage<V, GRAN4> st(smem_raw, geo);
+
+  // the first batch of every warp is static (u0 = 32 * warp), the counter starts behind them
+  k2_build_stage<V, GRAN4>(g, geo, st, planes, plane_bytes, plane_stride, jobs, org_mbs, mb_w, mb_h, default_range, tid, kK2Threads, kK2Threads);
+  __syncthreads();            // window copies and tables visible
+
+  uint32_t best[NS];
+#pragma unroll
+  for (int sl = 0; sl < NS; ++sl) best[sl] = kKeyInvalid;
+  k2_search_units<V, GRAN4>(geo, st, lane, (tid >> 5) * 32, best);
+  k2_warp_reduce<V, GRAN4>(*st.sm, lane, best);
+  __syncthreads();
+  k2_flush<V, GRAN4>(*st.sm, tid, kK2Threads, keys, aux);
+}
+
+// ---- kernel B: persistent, one CTA per SM, producer / consumer warps over two shared-memory stages ----
+// kK2PConsumers warps run the search loop on stage s while kK2PProducers warps stage the next group into stage s ^ 1
+// (and write the finished group's keys to HBM), handing stages over with mbarriers.  The search warps never execute
+// staging code and never wait at a CTA-wide barrier, so the ALU pipe always has SAD work queued.
+#ifndef K2P_CONSUMERS
+#define K2P_CONSUMERS 13
+#endif
+#ifndef K2P_PRODUCERS
+#define K2P_PRODUCERS 3
+#endif
+constexpr int kK2PConsumers = K2P_CONSUMERS, kK2PProducers = K2P_PRODUCERS;
+constexpr int kK2PThreads = 32 * (kK2PConsumers + kK2PProducers);
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+template <int V>
+__global__ void __launch_bounds__(kK2PThreads, 1)
+full_search_persistent_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_stride,
+                              const Group* __restrict__ groups, int n_groups,
+                              const jsvm_me_job* __restrict__ jobs,
+                              const int16_t* __restrict__ org_mbs,
+                              int mb_w, int mb_h, int default_range,
+                              uint32_t* __restrict__ keys, JobAux* __restrict__ aux,
+                              int stage_bytes)
+{
+  using SM = K2Smem<V, false>;
+  constexpr int NS = SM::NS;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  // [0, 64): mbarriers full[2], done[2]; stages follow at 128
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* done = full + 2;
+  // (stage addresses are computed from smem_raw at each use: an indexed pointer array makes the compiler fall back to
+  //  generic loads instead of LDS)
+#define K2P_STAGE(s_) (smem_raw + 128 + (size_t)(s_) * (size_t)stage_bytes)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_mine = ((int)blockIdx.x < n_groups) ? (n_groups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // groups b, b + G, ...
+  if (tid == 0) {
+    mbar_init(&full[0], 32 * kK2PProducers); mbar_init(&full[1], 32 * kK2PProducers);
+    mbar_init(&done[0], kK2PConsumers);      mbar_init(&done[1], kK2PConsumers);
+    fence_barrier_init();
   }
   __syncthreads();
-  if (tid < NS && sm.job[tid] >= 0) {
-    keys[sm.job[tid]] = sm.best[tid];
-    JobAux a; a.ux0 = g.ux0; a.uy0 = g.uy0; a.uw = g.uw; a.pad = 0;
-    aux[sm.job[tid]] = a;
+
+  if (warp >= kK2PConsumers) {
+    // ================= producers =================
+    const int ptid = tid - 32 * kK2PConsumers;
+    constexpr int pthreads = 32 * kK2PProducers;
+    for (int k = 0; k < n_mine + 2; ++k) {
+      const int s = k & 1, use = k >> 1;
+      if (k >= 2) {
+        // stage s was used by group k - 2: wait until every search warp has folded its minima in, then write the keys out
+        mbar_wait_relaxed(&done[s], (uint32_t)((use - 1) & 1));
+        const Group& gp = groups[blockIdx.x + (size_t)(k - 2) * gridDim.x];
+        const K2Geo<V> geop((kMargin + 16 * gp.mb_x + gp.ux0) & 3, gp.uw, gp.uh);
+        const K2Stage<V, false> stp(K2P_STAGE(s), geop);
+        if (ptid < 32) {                                      // the warp that re-initialises best[] in k2_build_stage
+          k2_flush<V, false>(*stp.sm, ptid, 32, keys, aux);
+          __syncwarp();
+        }
+      }
+      if (k < n_mine) {
+        const Group& g = groups[blockIdx.x + (size_t)k * gridDim.x];
+        const K2Geo<V> geo((kMargin + 16 * g.mb_x + g.ux0) & 3, g.uw, g.uh);
+        const K2Stage<V, false> st(K2P_STAGE(s), geo);
+        k2_build_stage<V, false>(g, geo, st, planes, plane_bytes, plane_stride, jobs, org_mbs, mb_w, mb_h, default_range, ptid, pthreads, 0);
+        mbar_arrive(&full[s]);                                // release: this thread's stage writes are visible to waiters
+      }
+    }
+  } else {
+    // ================= search warps =================
+    for (int k = 0; k < n_mine; ++k) {
+      const int s = k & 1, use = k >> 1;
+      mbar_wait(&full[s], (uint32_t)(use & 1));
+      // the stage record sits behind the group's window copies: recover the geometry from the group itself
+      const Group& g = groups[blockIdx.x + (size_t)k * gridDim.x];
+      const K2Geo<V> geo((kMargin + 16 * g.mb_x + g.ux0) & 3, g.uw, g.uh);
+      const K2Stage<V, false> st(K2P_STAGE(s), geo);
+      uint32_t best[NS];
+#pragma unroll
+      for (int sl = 0; sl < NS; ++sl) best[sl] = kKeyInvalid;
+      k2_search_units<V, false>(geo, st, lane, -1, best);
+      k2_warp_reduce<V, false>(*st.sm, lane, best);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&done[s]);                   // release: the atomicMin results are visible to the producer
+    }
   }
+#undef K2P_STAGE
 }
 
 template <int V, bool GRAN4>
 inline size_t k2_smem_bytes(int max_uh) {
   using SM = K2Smem<V, GRAN4>;
+  const size_t rec = (sizeof(SM) + 127) & ~(size_t)127;
   const size_t win = (((size_t)4 * (k2_rows(max_uh) * kWinRowWords + 31) * 4) + 15) & ~(size_t)15;
   const size_t by = (size_t)SM::NS * (((max_uh + V - 1) / V) * V) * 4;
-  return win + ((sizeof(SM) + 15) & ~(size_t)15) + by;
+  const size_t slack = (size_t)V * kWinRowBytes;            // rows the last strip reads past the staged ones (never used)
+  return rec + win + by + slack;
 }
+
+// persistent kernel: barriers + two stages
+template <int V>
+inline size_t k2p_stage_bytes(int max_uh) { return (k2_smem_bytes<V, false>(max_uh) + 127) & ~(size_t)127; }
+template <int V>
+inline size_t k2p_smem_bytes(int max_uh) { return 128 + 2 * k2p_stage_bytes<V>(max_uh); }
 
 }  // namespace jsvm

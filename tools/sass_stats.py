@@ -31,6 +31,6 @@ for b in blocks[1:]:
         spill_all = sum(1 for o in ops if o.startswith(("LDL", "STL")))
         print(f"  VABSDIFF4 {len(v)} span [{lo},{hi}]  spills in SAD span {spill_in}, total {spill_all}")
         tail = collections.Counter(o.split(".")[0] for o in ops[hi:])
-        print("  after SAD span:", dict(tail.most_common(14)), "total", len(ops) - hi)
+        import signal; signal.signal(signal.SIGPIPE, signal.SIG_DFL); print("  after SAD span:", dict(tail.most_common(14)), "total", len(ops) - hi)
         head = collections.Counter(o.split(".")[0] for o in ops[:lo])
         print("  before SAD span:", dict(head.most_common(10)), "total", lo)
