@@ -173,6 +173,16 @@ def clocks_stop(proc, dev_index):
     return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(pairs):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+    (profiles/r01_traffic.json, written by tools/summarize_profile.py); only valid for the batch size that was profiled."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        return d["dram_bytes_per_launch"] if int(d.get("pairs", -1)) == int(pairs) else {}
+    except Exception:
+        return {}
+
+
 def int32_peak():
     """INT32 ALU-pipe peak (lane-ops/s): measured live with tools/int32_peak if present, else the recorded value."""
     exe = os.path.join(ROOT, "tools", "int32_peak")
@@ -313,8 +323,9 @@ def main():
     alg_ops_per_launch = info.n_positions / len(cfg["parts"]) * per_pos
     k2_ms = kt["search_ms"] / max(1, kt["search_launches"])
     achieved = alg_ops_per_launch / (k2_ms * 1e-3)
-    roofline = {"bound": "int32", "kernel": "full_search_kernel<8,false>", "achieved": achieved / 1e12, "peak": peak / 1e12,
-                "unit": "Tlane-op/s", "frac": achieved / peak, "traffic": None,
+    traffic = ncu_traffic(args.pairs)
+    roofline = {"bound": "int32", "kernel": me.last_search_kernel(), "achieved": achieved / 1e12, "peak": peak / 1e12,
+                "unit": "Tlane-op/s", "frac": achieved / peak, "traffic": traffic.get("k2_full_search"),
                 "alg_ops_per_launch": alg_ops_per_launch, "ms_per_launch": k2_ms, "peak_source": peak_how,
                 "positions_evaluated_per_launch": int(info.n_group_positions),
                 "share_of_step": kt["search_ms"] / total_ms}
@@ -327,7 +338,7 @@ def main():
     k1_bytes = len(ref_slots) * (W * H + 4 * (W + 56) * (H + 56))
     k1_ms = kt["interp_ms"] / max(1, kt["interp_launches"])
     roofline_k1 = {"bound": "hbm", "kernel": "halfpel_kernel", "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                   "unit": "GB/s", "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                   "unit": "GB/s", "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic.get("k1_halfpel"),
                    "alg_bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                    "share_of_step": kt["interp_ms"] / total_ms}

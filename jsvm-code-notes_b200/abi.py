@@ -77,6 +77,7 @@ PROTOTYPES = [
     ("jsvm_me_fetch_pred", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     ("jsvm_me_sync", C.c_int, [C.c_void_p]),
     ("jsvm_me_launch_count", C.c_uint64, [C.c_void_p]),
+    ("jsvm_me_last_search_kernel", C.c_char_p, [C.c_void_p]),
     ("jsvm_me_timing_begin", C.c_int, [C.c_void_p]),
     ("jsvm_me_timing_end", C.c_int, [C.c_void_p] + [C.POINTER(C.c_double)] * 3 + [C.POINTER(C.c_uint64)] * 3),
 ]

@@ -107,6 +107,7 @@ struct jsvm_me_ctx {
   bool last_has_preds = false;
   // measurement
   uint64_t launches = 0;
+  const char* last_k2 = "";
   bool timing = false;
   struct Timed { cudaEvent_t e0, e1; int kind; };
   std::vector<Timed> timed;
@@ -321,6 +322,7 @@ int run_search(jsvm_me_ctx* c, const jsvm_me_job* d_jobs, int job_begin, int job
     if (k2p_smem_bytes<kV8>(info->max_uh_8x8) > kMaxDynSmem) return fail("JSVM_ME_K2=persistent: union windows of %d rows do not fit two stages", info->max_uh_8x8);
     persistent = info->n_groups_8x8 > 0;
   }
+  if (info->n_groups_8x8 > 0) c->last_k2 = persistent ? "full_search_persistent_kernel<8>" : "full_search_kernel<8,false>";
   if (persistent) {
     if (launch_search_persistent(c, d_groups, info->n_groups_8x8, info->max_uh_8x8, d_jobs, d_org, d_keys, d_aux)) return JSVM_ME_ERR;
   } else if (launch_search<kV8, false>(c, d_groups, 0, info->n_groups_8x8, info->max_uh_8x8, d_jobs, d_org, d_keys, d_aux)) return JSVM_ME_ERR;
@@ -699,6 +701,7 @@ int jsvm_me_sync(jsvm_me_ctx* c) {
 }
 
 uint64_t jsvm_me_launch_count(jsvm_me_ctx* c) { return c ? c->launches : 0; }
+const char* jsvm_me_last_search_kernel(jsvm_me_ctx* c) { return c ? c->last_k2 : ""; }
 
 int jsvm_me_timing_begin(jsvm_me_ctx* c) {
   if (!c) return fail("null context");

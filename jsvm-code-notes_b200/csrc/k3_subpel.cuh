@@ -26,6 +26,9 @@
 
 namespace jsvm {
 
+#ifndef K3_MIN_CTAS
+#define K3_MIN_CTAS 5
+#endif
 constexpr int kK3WarpsPerCta = 8;
 constexpr int kK3PlaneRows = 18, kK3PlanePitch = 24;       // phase plane: (2*16+3+1)/2 rows, 4-byte aligned pitch
 
@@ -33,7 +36,10 @@ __constant__ int8_t c_half_mv[9][2]    = { {0,0}, {0,-2}, {0,2}, {-2,0}, {2,0}, 
 __constant__ int8_t c_quarter_mv[9][2] = { {0,0}, {0,-1}, {0,1}, {-1,-1}, {1,-1}, {-1,0}, {1,0}, {-1,1}, {1,1} };   // g_acQPSearchMv
 __constant__ uint8_t c_filter_of_half[9] = { 0, 2, 2, 1, 1, 3, 3, 3, 3 };                                          // g_aucFilter
 
-// XDistortion::xCalcHadamard4x4 on a 4x4 difference block (per-4x4 halving, N8)
+// XDistortion::xCalcHadamard4x4 on a 4x4 difference block (per-4x4 halving, N8).
+// The reference ends every row with the butterflies (a + b, a - b) and sums the absolute values; since
+// |a + b| + |a - b| = 2 max(|a|, |b|) the block sum is even, the reference's "/ 2" is exact, and the SATD is the sum of
+// max(|a|, |b|) over the 8 final pairs -- one butterfly stage and the halving disappear.
 __device__ __forceinline__ uint32_t hadamard4x4(const int (&d)[16]) {
   int m[16];
 #pragma unroll
@@ -46,11 +52,11 @@ __device__ __forceinline__ uint32_t hadamard4x4(const int (&d)[16]) {
 #pragma unroll
   for (int n = 0; n < 4; ++n) {
     int a = m[4 * n] + m[4 * n + 3], b = m[4 * n + 1] + m[4 * n + 2];
-    sum += (uint32_t)abs(a + b) + (uint32_t)abs(a - b);
+    sum += (uint32_t)max(abs(a), abs(b));
     a = m[4 * n + 1] - m[4 * n + 2]; b = m[4 * n] - m[4 * n + 3];
-    sum += (uint32_t)abs(a + b) + (uint32_t)abs(a - b);
+    sum += (uint32_t)max(abs(a), abs(b));
   }
-  return sum >> 1;
+  return sum;
 }
 
 struct K3Warp {
@@ -70,7 +76,7 @@ __device__ __forceinline__ uint32_t fetch4(const uint8_t* planes, int off) {
   return __funnelshift_r(q[0], q[1], 8 * (off & 3));
 }
 
-__global__ void __launch_bounds__(32 * kK3WarpsPerCta)
+__global__ void __launch_bounds__(32 * kK3WarpsPerCta, K3_MIN_CTAS)
 subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_stride,
               const uint8_t* __restrict__ half_planes, size_t half_bytes, int half_stride,
               const jsvm_me_job* __restrict__ jobs, const JobAux* __restrict__ aux, int n_jobs,
@@ -188,7 +194,7 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
 #pragma unroll
           for (int y = 0; y < 4; ++y)
 #pragma unroll
-            for (int x = 0; x < 4; ++x) d[y * 4 + x] = o16[y * 4 + x] - (int)((crow[y] >> (8 * x)) & 0xff);
+            for (int x = 0; x < 4; ++x) d[y * 4 + x] = o16[y * 4 + x] - (int)__byte_perm(crow[y], 0, 0x4440 + x);   // byte x, zero-extended
           dist = hadamard4x4(d);
         } else {
 #pragma unroll

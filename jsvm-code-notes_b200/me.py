@@ -168,6 +168,9 @@ class MotionEstimator:
     def launch_count(self):
         return int(self._lib.jsvm_me_launch_count(self._ctx))
 
+    def last_search_kernel(self):
+        return self._lib.jsvm_me_last_search_kernel(self._ctx).decode()
+
     def timing_begin(self):
         self._check(self._lib.jsvm_me_timing_begin(self._ctx))
 
