@@ -597,10 +597,13 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
   // Pipeline over chunks of ~32 K jobs cut at macroblock boundaries.  Worker threads plan different chunks
   // concurrently (chunk k is ready long before the GPU has finished chunk k-1); the calling thread uploads each
   // chunk's jobs and groups right before its kernels and queues the copy-back of its results right after them.
-  const int kChunk = 32768;
+  // The first chunks are small so that the GPU starts early; later ones are large: a persistent K2 launch loses its pipeline
+  // fill and its last-wave imbalance once per launch (~1 group of ~25 per SM at 32 K jobs, of ~100 at 128 K jobs).
+  const int kChunk = 131072;
   std::vector<int> cut(1, 0);
   while (cut.back() < n_jobs) {
-    int end = std::min(n_jobs, cut.back() + kChunk);
+    const int size = cut.size() == 1 ? kChunk / 4 : cut.size() == 2 ? kChunk / 2 : kChunk;
+    int end = std::min(n_jobs, cut.back() + size);
     while (end < n_jobs && same_mb(jobs[end], jobs[end - 1])) ++end;
     cut.push_back(end);
   }
