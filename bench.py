@@ -323,7 +323,7 @@ def main():
     alg_ops_per_launch = info.n_positions / len(cfg["parts"]) * per_pos
     k2_ms = kt["search_ms"] / max(1, kt["search_launches"])
     achieved = alg_ops_per_launch / (k2_ms * 1e-3)
-    traffic = ncu_traffic(args.pairs)
+    traffic = ncu_traffic(args.pairs) if args.config == "C4" else {}
     roofline = {"bound": "int32", "kernel": me.last_search_kernel(), "achieved": achieved / 1e12, "peak": peak / 1e12,
                 "unit": "Tlane-op/s", "frac": achieved / peak, "traffic": traffic.get("k2_full_search"),
                 "alg_ops_per_launch": alg_ops_per_launch, "ms_per_launch": k2_ms, "peak_source": peak_how,

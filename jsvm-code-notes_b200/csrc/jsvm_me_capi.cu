@@ -287,24 +287,42 @@ int launch_search(jsvm_me_ctx* c, const Group* d_groups, int first_group, int n_
   return JSVM_ME_OK;
 }
 
-// The persistent producer / consumer kernel (one CTA per SM, two shared-memory stages) for 8x8-granular groups: used when
-// the launch is large enough to keep every SM busy for many groups and two stages of the tallest union window fit.
+// The persistent producer / consumer kernel (one CTA per SM, two shared-memory stages): used when the launch is large
+// enough to keep every SM busy for many groups and two stages of the tallest union window fit.
 constexpr size_t kMaxDynSmem = 232448;     // 227 KB per CTA on sm_100
+template <int V, bool GRAN4>
 int launch_search_persistent(jsvm_me_ctx* c, const Group* d_groups, int n_groups, int max_uh,
                              const jsvm_me_job* d_jobs, const int16_t* d_org, uint32_t* d_keys, JobAux* d_aux) {
-  const size_t smem = k2p_smem_bytes<kV8>(max_uh);
+  const size_t smem = k2p_smem_bytes<V, GRAN4>(max_uh);
   static size_t configured = 0;
   if (smem > configured) {
-    CU_OK(cudaFuncSetAttribute(full_search_persistent_kernel<kV8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_OK(cudaFuncSetAttribute(full_search_persistent_kernel<V, GRAN4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   begin_timed(c, 1);
-  full_search_persistent_kernel<kV8><<<std::min(n_groups, c->sm_count), kK2PThreads, smem, c->stream>>>(
+  full_search_persistent_kernel<V, GRAN4><<<std::min(n_groups, c->sm_count), kK2PThreads, smem, c->stream>>>(
       c->d_planes, c->plane_bytes, c->plane_stride, d_groups, n_groups, d_jobs, d_org,
-      c->W >> 4, c->H >> 4, c->search_range, d_keys, d_aux, (int)k2p_stage_bytes<kV8>(max_uh));
+      c->W >> 4, c->H >> 4, c->search_range, d_keys, d_aux, (int)k2p_stage_bytes<V, GRAN4>(max_uh));
   end_timed(c);
   c->launches++;
   CU_OK(cudaGetLastError());
+  return JSVM_ME_OK;
+}
+
+// which of the two kernels serves n_groups groups whose tallest union window has max_uh rows
+template <int V, bool GRAN4>
+int choose_persistent(jsvm_me_ctx* c, int n_groups, int max_uh, bool* persistent) {
+  // JSVM_ME_K2 = group | persistent forces one of the two kernels (A/B measurements)
+  static const char* force = getenv("JSVM_ME_K2");
+  const bool fits = k2p_smem_bytes<V, GRAN4>(max_uh) <= kMaxDynSmem;
+  // 4x4-granular groups (41 slots): staging 41 rate tables keeps 3 producer warps busier than 13 search warps; measured
+  // 19 % slower than one CTA per group on C3, so the persistent kernel is only chosen for them when forced
+  *persistent = n_groups >= 4 * c->sm_count && fits && !GRAN4;
+  if (force && !strcmp(force, "group")) *persistent = false;
+  if (force && !strcmp(force, "persistent")) {
+    if (!fits) return fail("JSVM_ME_K2=persistent: union windows of %d rows do not fit two stages", max_uh);
+    *persistent = n_groups > 0;
+  }
   return JSVM_ME_OK;
 }
 
@@ -314,19 +332,15 @@ int run_search(jsvm_me_ctx* c, const jsvm_me_job* d_jobs, int job_begin, int job
                const int16_t* d_org, uint32_t* d_keys, JobAux* d_aux, jsvm_me_result* d_results, uint8_t* d_preds) {
   if (!c->params_set) return fail("jsvm_me_set_params has not been called");
   if (info->max_uh_8x8 > kMaxUH || info->max_uh_4x4 > kMaxUH) return fail("plan: union window taller than %d", kMaxUH);
-  // JSVM_ME_K2 = group | persistent forces one of the two 8x8-granular kernels (A/B measurements)
-  static const char* force = getenv("JSVM_ME_K2");
-  bool persistent = info->n_groups_8x8 >= 4 * c->sm_count && k2p_smem_bytes<kV8>(info->max_uh_8x8) <= kMaxDynSmem;
-  if (force && !strcmp(force, "group")) persistent = false;
-  if (force && !strcmp(force, "persistent")) {
-    if (k2p_smem_bytes<kV8>(info->max_uh_8x8) > kMaxDynSmem) return fail("JSVM_ME_K2=persistent: union windows of %d rows do not fit two stages", info->max_uh_8x8);
-    persistent = info->n_groups_8x8 > 0;
-  }
-  if (info->n_groups_8x8 > 0) c->last_k2 = persistent ? "full_search_persistent_kernel<8>" : "full_search_kernel<8,false>";
-  if (persistent) {
-    if (launch_search_persistent(c, d_groups, info->n_groups_8x8, info->max_uh_8x8, d_jobs, d_org, d_keys, d_aux)) return JSVM_ME_ERR;
-  } else if (launch_search<kV8, false>(c, d_groups, 0, info->n_groups_8x8, info->max_uh_8x8, d_jobs, d_org, d_keys, d_aux)) return JSVM_ME_ERR;
-  if (launch_search<kV4, true>(c, d_groups, info->n_groups_8x8, info->n_groups - info->n_groups_8x8, info->max_uh_4x4, d_jobs, d_org, d_keys, d_aux)) return JSVM_ME_ERR;
+  const int n8 = info->n_groups_8x8, n4 = info->n_groups - info->n_groups_8x8;
+  bool p8 = false, p4 = false;
+  if (choose_persistent<kV8, false>(c, n8, info->max_uh_8x8, &p8) || choose_persistent<kV4, true>(c, n4, info->max_uh_4x4, &p4)) return JSVM_ME_ERR;
+  if (n8 > 0) c->last_k2 = p8 ? "full_search_persistent_kernel<8,false>" : "full_search_kernel<8,false>";
+  else if (n4 > 0) c->last_k2 = p4 ? "full_search_persistent_kernel<4,true>" : "full_search_kernel<4,true>";
+  if (n8 > 0 && (p8 ? launch_search_persistent<kV8, false>(c, d_groups, n8, info->max_uh_8x8, d_jobs, d_org, d_keys, d_aux)
+                    : launch_search<kV8, false>(c, d_groups, 0, n8, info->max_uh_8x8, d_jobs, d_org, d_keys, d_aux))) return JSVM_ME_ERR;
+  if (n4 > 0 && (p4 ? launch_search_persistent<kV4, true>(c, d_groups + n8, n4, info->max_uh_4x4, d_jobs, d_org, d_keys, d_aux)
+                    : launch_search<kV4, true>(c, d_groups, n8, n4, info->max_uh_4x4, d_jobs, d_org, d_keys, d_aux))) return JSVM_ME_ERR;
   const int n = job_end - job_begin;
   if (n <= 0) return JSVM_ME_OK;
   begin_timed(c, 2);

@@ -142,6 +142,10 @@ struct K2Smem {
   static constexpr int NS   = GRAN4 ? kSlots : kSlotsGran8;
   static constexpr int NACC = GRAN4 ? 16 : 4;
   static constexpr int kMaxStrips = kMaxRows / V;
+  // Running minima a thread carries through a group.  8x8 granularity: one register per slot (per-thread minima, reduced
+  // over the warp once per group).  4x4 granularity (41 slots): the minimum of every unit is reduced over the warp at once
+  // (REDUX) and lane l keeps the warp's minima of slots l and l + 32 -- 2 registers instead of 41.
+  static constexpr int NBEST = GRAN4 ? (NS + 31) / 32 : NS;
   typedef typename std::conditional<GRAN4, unsigned long long, uint32_t>::type Mask;   // one bit per partition slot
   // one stage of dynamic shared memory: the four window copies come first, then this record, then the by table
   uint32_t cur[16][4];                            // the current macroblock, 16 packed bytes per row (16-byte aligned)
@@ -340,7 +344,7 @@ __device__ __forceinline__ void k2_build_stage(const Group& g, const K2Geo<V>& g
 //      pulled from the stage's counter, always one batch ahead of the one being worked on ----
 template <int V, bool GRAN4>
 __device__ __forceinline__ void k2_search_units(const K2Geo<V>& geo, const K2Stage<V, GRAN4>& st, const int lane, const int first_u0,
-                                                uint32_t (&best)[K2Smem<V, GRAN4>::NS])
+                                                uint32_t (&best)[K2Smem<V, GRAN4>::NBEST])
 {
   using SM = K2Smem<V, GRAN4>;
   using Mask = typename SM::Mask;
@@ -435,6 +439,7 @@ __device__ __forceinline__ void k2_search_units(const K2Geo<V>& geo, const K2Sta
     const Mask mx = live ? sm.xmask[cidx] : (Mask)0;
     const Mask mfull = mx & sm.yfull[strip], many = mx & sm.yany[strip];
     if (__all_sync(0xffffffffu, many == 0)) continue;               // outside every job's window (alignment columns, x >= uw)
+    const Mask part = many & ~mfull;                                // slots with only SOME valid rows in this strip
     uint32_t idxv[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) idxv[v] = (uint32_t)((ys + v) * uw + x);
@@ -461,17 +466,26 @@ __device__ __forceinline__ void k2_search_units(const K2Geo<V>& geo, const K2Sta
       uint32_t m;
       if (V == 8) m = min(min(kv[0], kv[3]), min(kv[6], kv[7]));
       else        m = min(min(kv[0], kv[3]), kv[V - 1]);
-      if ((mfull >> sl) & 1) best[sl] = min(best[sl], m);
+      if (!GRAN4) {
+        if ((mfull >> sl) & 1) best[sl] = min(best[sl], m);
+      } else {
+        const uint32_t w = __reduce_min_sync(0xffffffffu, ((mfull >> sl) & 1) ? m : kKeyInvalid);
+        if (lane == (sl & 31)) best[sl >> 5] = min(best[sl >> 5], w);
+      }
     };
     auto update_partial = [&](const int sl, const uint32_t (&sadv)[V]) {
       uint32_t kv[V];
       slot_keys(sl, sadv, kv);
       const int lo = sm.ylo[sl] - ys, hi = sm.yhi[sl] - ys;         // valid strip rows: lo <= v <= hi
-      uint32_t b = best[sl];
+      uint32_t b = GRAN4 ? kKeyInvalid : best[GRAN4 ? 0 : sl];
 #pragma unroll
       for (int v = 0; v < V; ++v)
         if (v >= lo && v <= hi) b = min(b, kv[v]);
-      best[sl] = b;
+      if (!GRAN4) best[GRAN4 ? 0 : sl] = b;
+      else {
+        const uint32_t w = __reduce_min_sync(0xffffffffu, ((part >> sl) & 1) ? b : kKeyInvalid);
+        if (lane == (sl & 31)) best[sl >> 5] = min(best[sl >> 5], w);
+      }
     };
 
     // partition SADs from the accumulators (8x8 granularity: 5 adds per displacement for the 9-partition set)
@@ -494,45 +508,75 @@ __device__ __forceinline__ void k2_search_units(const K2Geo<V>& geo, const K2Sta
         for (int v = 0; v < V; ++v) { t0[v] = acc[v][0] + acc[v][2]; t1[v] = acc[v][1] + acc[v][3]; }
         fn(3, t0); fn(4, t1);                                       // 8x16 left, right
       } else {
+        // 4x4 granularity: the 41 partition SADs are built hierarchically, one 8x8 quadrant at a time (25 adds per
+        // displacement; few sums alive at once).  acc index of 4x4 block k of quadrant b: see slot_mask_gran4.
+        uint32_t s88[4][V];
 #pragma unroll
-        for (int sl = 0; sl < NS; ++sl) {
-          const uint32_t mask = slot_mask_gran4(sl);                // folds after unrolling
-          uint32_t t0[V];
+        for (int b = 0; b < 4; ++b) {
+          const int a0 = (b >> 1) * 8 + (b & 1) * 2;                 // accumulators a0, a0+1 (upper), a0+4, a0+5 (lower)
+          uint32_t t[V], up[V], lo[V];
 #pragma unroll
-          for (int v = 0; v < V; ++v) {
-            uint32_t sad = 0;
+          for (int k = 0; k < 4; ++k) {
 #pragma unroll
-            for (int a = 0; a < NACC; ++a) if (mask & (1u << a)) sad += acc[v][a];
-            t0[v] = sad;
+            for (int v = 0; v < V; ++v) t[v] = acc[v][a0 + (k >> 1) * 4 + (k & 1)];
+            fn(25 + b * 4 + k, t);                                   // 4x4
           }
-          fn(sl, t0);
+#pragma unroll
+          for (int v = 0; v < V; ++v) { up[v] = acc[v][a0] + acc[v][a0 + 1]; lo[v] = acc[v][a0 + 4] + acc[v][a0 + 5]; }
+          fn(9 + b * 2, up); fn(9 + b * 2 + 1, lo);                  // 8x4 upper, lower
+#pragma unroll
+          for (int v = 0; v < V; ++v) s88[b][v] = up[v] + lo[v];
+          fn(5 + b, s88[b]);                                         // 8x8
+#pragma unroll
+          for (int v = 0; v < V; ++v) { up[v] = acc[v][a0] + acc[v][a0 + 4]; lo[v] = acc[v][a0 + 1] + acc[v][a0 + 5]; }
+          fn(17 + b * 2, up); fn(17 + b * 2 + 1, lo);                // 4x8 left, right
         }
+        uint32_t t0[V], t1[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) { t0[v] = s88[0][v] + s88[1][v]; t1[v] = s88[2][v] + s88[3][v]; }
+        fn(1, t0); fn(2, t1);                                        // 16x8 upper, lower
+#pragma unroll
+        for (int v = 0; v < V; ++v) t0[v] += t1[v];
+        fn(0, t0);                                                   // 16x16
+#pragma unroll
+        for (int v = 0; v < V; ++v) { t0[v] = s88[0][v] + s88[2][v]; t1[v] = s88[1][v] + s88[3][v]; }
+        fn(3, t0); fn(4, t1);                                        // 8x16 left, right
       }
     };
 
     for_each_slot(update_full);
-    const Mask part = many & ~mfull;
     if (__any_sync(0xffffffffu, part != 0)) {
       // the keys are recomputed from an opaque copy of the column: keeping the 8 x NS keys of pass 1 alive for this rare
       // pass would spill them in the hot path
       int x2 = x;
       asm volatile("mov.b32 %0, %0;" : "+r"(x2));
+
 #pragma unroll
       for (int v = 0; v < V; ++v) idxv[v] = (uint32_t)((ys + v) * uw + x2);
       for_each_slot([&](const int sl, const uint32_t (&sadv)[V]) {
-        if ((part >> sl) & 1) update_partial(sl, sadv);
+        if (!GRAN4) { if ((part >> sl) & 1) update_partial(sl, sadv); }
+        else if (__any_sync(0xffffffffu, (part >> sl) & 1)) update_partial(sl, sadv);     // warp-uniform: REDUX inside
       });
     }
   }
 }
 
-// warp minimum of every slot, then shared atomicMin
+// fold a warp's minima into the stage: warp minimum of every slot (8x8 granularity) or the lane-distributed minima (4x4)
 template <int V, bool GRAN4>
-__device__ __forceinline__ void k2_warp_reduce(K2Smem<V, GRAN4>& sm, const int lane, const uint32_t (&best)[K2Smem<V, GRAN4>::NS]) {
+__device__ __forceinline__ void k2_warp_reduce(K2Smem<V, GRAN4>& sm, const int lane, const uint32_t (&best)[K2Smem<V, GRAN4>::NBEST]) {
+  using SM = K2Smem<V, GRAN4>;
+  if (!GRAN4) {
 #pragma unroll
-  for (int sl = 0; sl < K2Smem<V, GRAN4>::NS; ++sl) {
-    const uint32_t w = __reduce_min_sync(0xffffffffu, best[sl]);
-    if (lane == 0 && w != kKeyInvalid) atomicMin(&sm.best[sl], w);
+    for (int sl = 0; sl < SM::NBEST; ++sl) {
+      const uint32_t w = __reduce_min_sync(0xffffffffu, best[sl]);
+      if (lane == 0 && w != kKeyInvalid) atomicMin(&sm.best[sl], w);
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < SM::NBEST; ++q) {
+      const int sl = lane + 32 * q;
+      if (sl < SM::NS && best[q] != kKeyInvalid) atomicMin(&sm.best[sl], best[q]);
+    }
   }
 }
 
@@ -552,7 +596,7 @@ __device__ __forceinline__ void k2_flush(const K2Smem<V, GRAN4>& sm, const int p
 
 // ---- kernel A: one CTA per search group (small launches, 4x4-granular groups, very tall union windows) ----
 template <int V, bool GRAN4>
-__global__ void __launch_bounds__(kK2Threads, GRAN4 ? 1 : 2)
+__global__ void __launch_bounds__(kK2Threads, 2)
 full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel plane pool [slot][H+64][W+64]
                    size_t plane_bytes, int plane_stride,
                    const Group* __restrict__ groups,
@@ -574,9 +618,9 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
   k2_build_stage<V, GRAN4>(g, geo, st, planes, plane_bytes, plane_stride, jobs, org_mbs, mb_w, mb_h, default_range, tid, kK2Threads, kK2Threads);
   __syncthreads();            // window copies and tables visible
 
-  uint32_t best[NS];
+  uint32_t best[SM::NBEST];
 #pragma unroll
-  for (int sl = 0; sl < NS; ++sl) best[sl] = kKeyInvalid;
+  for (int sl = 0; sl < SM::NBEST; ++sl) best[sl] = kKeyInvalid;
   k2_search_units<V, GRAN4>(geo, st, lane, (tid >> 5) * 32, best);
   k2_warp_reduce<V, GRAN4>(*st.sm, lane, best);
   __syncthreads();
@@ -600,7 +644,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
-template <int V>
+template <int V, bool GRAN4>
 __global__ void __launch_bounds__(kK2PThreads, 1)
 full_search_persistent_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_stride,
                               const Group* __restrict__ groups, int n_groups,
@@ -610,9 +654,8 @@ full_search_persistent_kernel(const uint8_t* __restrict__ planes, size_t plane_b
                               uint32_t* __restrict__ keys, JobAux* __restrict__ aux,
                               int stage_bytes)
 {
-  using SM = K2Smem<V, false>;
-  constexpr int NS = SM::NS;
-  extern __shared__ __align__(128) uint8_t smem_raw[];
+  using SM = K2Smem<V, GRAN4>;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
   // [0, 64): mbarriers full[2], done[2]; stages follow at 128
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* done = full + 2;
@@ -640,17 +683,17 @@ full_search_persistent_kernel(const uint8_t* __restrict__ planes, size_t plane_b
         mbar_wait_relaxed(&done[s], (uint32_t)((use - 1) & 1));
         const Group& gp = groups[blockIdx.x + (size_t)(k - 2) * gridDim.x];
         const K2Geo<V> geop((kMargin + 16 * gp.mb_x + gp.ux0) & 3, gp.uw, gp.uh);
-        const K2Stage<V, false> stp(K2P_STAGE(s), geop);
+        const K2Stage<V, GRAN4> stp(K2P_STAGE(s), geop);
         if (ptid < 32) {                                      // the warp that re-initialises best[] in k2_build_stage
-          k2_flush<V, false>(*stp.sm, ptid, 32, keys, aux);
+          k2_flush<V, GRAN4>(*stp.sm, ptid, 32, keys, aux);
           __syncwarp();
         }
       }
       if (k < n_mine) {
         const Group& g = groups[blockIdx.x + (size_t)k * gridDim.x];
         const K2Geo<V> geo((kMargin + 16 * g.mb_x + g.ux0) & 3, g.uw, g.uh);
-        const K2Stage<V, false> st(K2P_STAGE(s), geo);
-        k2_build_stage<V, false>(g, geo, st, planes, plane_bytes, plane_stride, jobs, org_mbs, mb_w, mb_h, default_range, ptid, pthreads, 0);
+        const K2Stage<V, GRAN4> st(K2P_STAGE(s), geo);
+        k2_build_stage<V, GRAN4>(g, geo, st, planes, plane_bytes, plane_stride, jobs, org_mbs, mb_w, mb_h, default_range, ptid, pthreads, 0);
         mbar_arrive(&full[s]);                                // release: this thread's stage writes are visible to waiters
       }
     }
@@ -662,12 +705,12 @@ full_search_persistent_kernel(const uint8_t* __restrict__ planes, size_t plane_b
       // the stage record sits behind the group's window copies: recover the geometry from the group itself
       const Group& g = groups[blockIdx.x + (size_t)k * gridDim.x];
       const K2Geo<V> geo((kMargin + 16 * g.mb_x + g.ux0) & 3, g.uw, g.uh);
-      const K2Stage<V, false> st(K2P_STAGE(s), geo);
-      uint32_t best[NS];
+      const K2Stage<V, GRAN4> st(K2P_STAGE(s), geo);
+      uint32_t best[SM::NBEST];
 #pragma unroll
-      for (int sl = 0; sl < NS; ++sl) best[sl] = kKeyInvalid;
-      k2_search_units<V, false>(geo, st, lane, -1, best);
-      k2_warp_reduce<V, false>(*st.sm, lane, best);
+      for (int sl = 0; sl < SM::NBEST; ++sl) best[sl] = kKeyInvalid;
+      k2_search_units<V, GRAN4>(geo, st, lane, -1, best);
+      k2_warp_reduce<V, GRAN4>(*st.sm, lane, best);
       __syncwarp();
       if (lane == 0) mbar_arrive(&done[s]);                   // release: the atomicMin results are visible to the producer
     }
@@ -686,9 +729,9 @@ inline size_t k2_smem_bytes(int max_uh) {
 }
 
 // persistent kernel: barriers + two stages
-template <int V>
-inline size_t k2p_stage_bytes(int max_uh) { return (k2_smem_bytes<V, false>(max_uh) + 127) & ~(size_t)127; }
-template <int V>
-inline size_t k2p_smem_bytes(int max_uh) { return 128 + 2 * k2p_stage_bytes<V>(max_uh); }
+template <int V, bool GRAN4>
+inline size_t k2p_stage_bytes(int max_uh) { return (k2_smem_bytes<V, GRAN4>(max_uh) + 127) & ~(size_t)127; }
+template <int V, bool GRAN4>
+inline size_t k2p_smem_bytes(int max_uh) { return 128 + 2 * k2p_stage_bytes<V, GRAN4>(max_uh); }
 
 }  // namespace jsvm
