@@ -18,8 +18,14 @@
 // picture row and the reference's row replication of `tmp` is reproduced by reading them.
 //
 // One CTA = 64 x 32 integer positions = 128 x 64 output bytes.  The (64+32) x (32+5) input tile
-// with its apron is staged by ONE 3D TMA box load (UTMALDG), pass 1 goes to shared memory as
-// int16, pass 2 writes 16-byte vectors (8-byte at the two region edges, which sit at 8 mod 16).
+// with its apron is staged by ONE 3D TMA box load (UTMALDG).  The arithmetic is packed:
+//   * the 2-D filter is separable and exact in integers, so the diagonal samples are computed as H6( V6( s ) ) instead of
+//     the reference's V6( H6( s ) ) -- same integers, and V6 on BYTES fits 16-bit lanes;
+//   * phase A: V6(s) for 72 columns x 32 rows with two samples per register (VIADD.16x2, IMAD on packed non-negative
+//     lanes), stored as int16 pairs in shared memory;
+//   * phase B (thread = 8 integer columns of one row = 2 x 16 output bytes): horizontal half samples with IDP.4A (u8 x s8
+//     dot products) straight from the staged bytes, diagonal samples with IDP.2A (s16 x s8) from phase A's pairs, rounding
+//     and clamping two samples at a time (VIADDMNMX.S16x2.RELU), bytes interleaved with PRMT, one 16-byte store per row.
 #pragma once
 
 #include <cuda.h>
@@ -33,15 +39,31 @@ constexpr int kK1BoxW = 96, kK1BoxH = kK1TileY + 5;     // 37 rows: y-2 .. y+34;
 // (TMA tiled loads need a 16-byte aligned innermost start coordinate -- measured on B200: an unaligned one
 //  raises 'illegal instruction' -- so the box starts 16 columns left of the tile instead of 2.)
 constexpr int kK1Threads = 256;
-constexpr int kK1TmpStride = 2 * kK1TileX + 8;          // int16 elements per tmp row (+8: 16-byte aligned rows, spreads banks)
+constexpr int kK1VCols = 72;                             // phase A columns x0-4 .. x0+67 (taps of x0 .. x0+63 need x0-2 .. x0+66)
+constexpr int kK1VPitch = kK1VCols / 2 + 2;              // 32-bit words (int16 pairs) per row of s_v: 38 (even: 8-byte aligned rows)
 
+__device__ __forceinline__ int dp4a_u8s8(uint32_t a, uint32_t b, int c) { int d; asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int dp2a_lo_s16s8(uint32_t a, uint32_t b, int c) { int d; asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int dp2a_hi_s16s8(uint32_t a, uint32_t b, int c) { int d; asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+
+// two int16 lanes t -> two bytes clip255( (t + 16) >> 5 ), each in the HIGH byte of its lane:
+// clamp t + 16 to [0, 8191] first (negative results clip to 0 anyway), then the shift is a plain logical one per lane
+// (the shift is done as a multiplication by 8 on the FMA pipe: the result byte is then byte 1 of its lane and the
+//  PRMT that interleaves the output bytes picks it from there)
+__device__ __forceinline__ uint32_t round5_clip_x2_hi(uint32_t t) {
+  return __viaddmin_s16x2_relu(t, 0x00100010u, 0x1fff1fffu) * 8u;        // lanes <= 65528: bytes 1 and 3 hold the results
+}
+__device__ __forceinline__ uint32_t pack_lo16(int lo, int hi) { return __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410); }
+
+// (A persistent variant that keeps the TMA load of the next tile in flight measured 10-30 % slower: the kernel is bound by
+//  instruction issue, 82 % of peak, not by load latency.)
 __global__ void __launch_bounds__(kK1Threads)
-halfpel_kernel(const __grid_constant__ CUtensorMap plane_map,  // [slot][H+64][W+64] u8, box {80, 37, 1}
+halfpel_kernel(const __grid_constant__ CUtensorMap plane_map,  // [slot][H+64][W+64] u8, box {96, 37, 1}
                uint8_t* __restrict__ half_planes, size_t half_bytes, int half_stride,
                const int* __restrict__ slots, int W, int H)
 {
   __shared__ __align__(128) uint8_t  s_in[kK1BoxH * kK1BoxW];
-  __shared__ __align__(16)  int16_t  s_tmp[kK1BoxH * kK1TmpStride];
+  __shared__ __align__(16)  uint32_t s_v[kK1TileY * kK1VPitch];     // V6(s) as int16 pairs (col 2i, col 2i+1), col 0 = x0 - 4
   __shared__ uint64_t s_bar;
 
   const int tid = threadIdx.x;
@@ -57,70 +79,98 @@ halfpel_kernel(const __grid_constant__ CUtensorMap plane_map,  // [slot][H+64][W
   }
   mbar_wait(&s_bar, 0);
 
-  // ---- pass 1: horizontal 6-tap on the 37 staged rows ----
-  for (int i = tid; i < kK1BoxH * (kK1TileX / 4); i += kK1Threads) {
-    const int r = i / (kK1TileX / 4), xc = (i - r * (kK1TileX / 4)) * 4;     // 4 integer columns xc .. xc+3
-    // tile byte 0 = column x0-16, so s[x0+xc-2] sits at byte xc+14; load the aligned words from byte xc+12
-    const uint32_t* rw = reinterpret_cast<const uint32_t*>(s_in + r * kK1BoxW + xc + 12);
-    const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
-    int b[12];
+  // ---- phase A: vertical 6-tap on bytes.  item = 4 columns x 4 rows; tile byte 12 = column x0 - 4 ----
+  if (tid < (kK1VCols / 4) * (kK1TileY / 4)) {
+    const int cg = tid % (kK1VCols / 4), rb = tid / (kK1VCols / 4);                 // column group 0..17, row block 0..7
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(s_in + (4 * rb) * kK1BoxW + 12 + 4 * cg);   // staged row r = picture row y0 - 2 + r
+    uint32_t ev[9], od[9];                                                          // bytes (0, 2) and (1, 3) of each input row as 16-bit lanes
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { b[k] = (w0 >> (8 * k)) & 0xff; b[4 + k] = (w1 >> (8 * k)) & 0xff; b[8 + k] = (w2 >> (8 * k)) & 0xff; }
-    int16_t o[8];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      // s[x] = b[k+4]
-      int t = b[k + 4] + b[k + 5];
-      t <<= 2;
-      t -= b[k + 3] + b[k + 6];
-      t += t << 2;
-      t += b[k + 2] + b[k + 7];
-      o[2 * k] = (int16_t)(b[k + 4] << 5);
-      o[2 * k + 1] = (int16_t)t;
+    for (int r = 0; r < 9; ++r) {
+      const uint32_t w = src[r * (kK1BoxW / 4)];
+      ev[r] = __byte_perm(w, 0, 0x4240);
+      od[r] = __byte_perm(w, 0, 0x4341);
     }
-    *reinterpret_cast<uint4*>(&s_tmp[r * kK1TmpStride + 2 * xc]) = *reinterpret_cast<const uint4*>(o);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {                                                   // output row 4 rb + o: taps at staged rows o .. o+5
+      // t = 20 (s2 + s3) - 5 (s1 + s4) + (s0 + s5): the products of the non-negative packed sums stay inside their lanes
+      const uint32_t te = __vsub2(__vadd2(__vadd2(ev[o + 2], ev[o + 3]) * 20u, __vadd2(ev[o], ev[o + 5])), __vadd2(ev[o + 1], ev[o + 4]) * 5u);
+      const uint32_t to = __vsub2(__vadd2(__vadd2(od[o + 2], od[o + 3]) * 20u, __vadd2(od[o], od[o + 5])), __vadd2(od[o + 1], od[o + 4]) * 5u);
+      // (c0, c2), (c1, c3) -> (c0, c1), (c2, c3)
+      uint2 pr;
+      pr.x = __byte_perm(te, to, 0x5410);
+      pr.y = __byte_perm(te, to, 0x7632);
+      *reinterpret_cast<uint2*>(&s_v[(4 * rb + o) * kK1VPitch + 2 * cg]) = pr;
+    }
   }
   __syncthreads();
 
-  // ---- pass 2: vertical 6-tap, rounding, clamp, 16 output bytes per row per thread ----
-  const int tx = tid & 7, ty = tid >> 3;                      // 8 x 32 threads; thread = 16 half-pel columns x 1 integer row
+  // ---- phase B: thread = row y0 + ty, integer columns x0 + 8 tx .. + 7 ----
+  const int tx = tid & 7, ty = tid >> 3;
   const int y = y0 + ty;
-  if (y >= H + kMargin - 4) return;
-  const int c0 = 16 * tx;                                      // first half-pel column inside the tile
-  const int16_t* tp = &s_tmp[(ty + 2) * kK1TmpStride + c0];
-  uint32_t row0[4], row1[4];
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    // 6 rows x 8 int16 columns as 128-bit shared loads
-    uint4 rv[6];
-#pragma unroll
-    for (int r = 0; r < 6; ++r) rv[r] = *reinterpret_cast<const uint4*>(tp + 8 * half + (r - 2) * kK1TmpStride);
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      uint32_t p0 = 0, p1 = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int c = 4 * q + k;                       // 0..7 inside this half
-        int e[6];
-#pragma unroll
-        for (int r = 0; r < 6; ++r) {
-          const uint32_t wv = (c >> 1) == 0 ? rv[r].x : (c >> 1) == 1 ? rv[r].y : (c >> 1) == 2 ? rv[r].z : rv[r].w;
-          e[r] = (c & 1) ? ((int)wv >> 16) : (int)(int16_t)(wv & 0xffff);
-        }
-        int t = e[2] + e[3];
-        t <<= 2;
-        t -= e[1] + e[4];
-        t += t << 2;
-        t += e[0] + e[5];
-        int v0 = (e[2] + 16) >> 5, v1 = (t + 512) >> 10;
-        v0 = min(max(v0, 0), 255); v1 = min(max(v1, 0), 255);
-        p0 |= (uint32_t)v0 << (8 * k);
-        p1 |= (uint32_t)v1 << (8 * k);
-      }
-      row0[2 * half + q] = p0; row1[2 * half + q] = p1;
-    }
+  if (y < H + kMargin - 4) {
+  const int X = 8 * tx;
+  // staged bytes of row y: columns X-4 .. X+11 (tile byte 16 = column x0)
+  const uint32_t* rw = reinterpret_cast<const uint32_t*>(s_in + (ty + 2) * kK1BoxW + 12 + X);
+  const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2], w3 = rw[3];
+
+  // horizontal half samples: H(x) = s[x-2] - 5 s[x-1] + 20 s[x] + 20 s[x+1] - 5 s[x+2] + s[x+3]
+  constexpr uint32_t kCoefA = 0x1414fb01u;     // bytes ( 1, -5, 20, 20 )
+  constexpr uint32_t kCoefB = 0x000001fbu;     // bytes ( -5, 1, 0, 0 )
+  int hh[8];
+  {
+    // column X+k reads bytes (k+2 .. k+7) of the 16 staged bytes
+    const uint32_t a0 = __funnelshift_r(w0, w1, 16), b0 = __funnelshift_r(w1, w2, 16);
+    const uint32_t a1 = __funnelshift_r(w0, w1, 24), b1 = __funnelshift_r(w1, w2, 24);
+    const uint32_t a3 = __funnelshift_r(w1, w2, 8),  b3 = __funnelshift_r(w2, w3, 8);
+    const uint32_t a4 = b0,                          b4 = __funnelshift_r(w2, w3, 16);
+    const uint32_t a5 = b1,                          b5 = __funnelshift_r(w2, w3, 24);
+    const uint32_t a7 = b3,                          b7 = w3 >> 8;
+    hh[0] = dp4a_u8s8(b0, kCoefB, dp4a_u8s8(a0, kCoefA, 0));
+    hh[1] = dp4a_u8s8(b1, kCoefB, dp4a_u8s8(a1, kCoefA, 0));
+    hh[2] = dp4a_u8s8(w2, kCoefB, dp4a_u8s8(w1, kCoefA, 0));
+    hh[3] = dp4a_u8s8(b3, kCoefB, dp4a_u8s8(a3, kCoefA, 0));
+    hh[4] = dp4a_u8s8(b4, kCoefB, dp4a_u8s8(a4, kCoefA, 0));
+    hh[5] = dp4a_u8s8(b5, kCoefB, dp4a_u8s8(a5, kCoefA, 0));
+    hh[6] = dp4a_u8s8(w3, kCoefB, dp4a_u8s8(w2, kCoefA, 0));
+    hh[7] = dp4a_u8s8(b7, kCoefB, dp4a_u8s8(a7, kCoefA, 0));
   }
-  // half-pel coordinates of this thread's 16 bytes: hx = 2*x0 + c0 .. +15, rows 2y and 2y+1
+  // even output row: ( s[x], clip255( (H(x) + 16) >> 5 ) ) interleaved
+  uint32_t row0[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t hq = round5_clip_x2_hi(pack_lo16(hh[2 * j], hh[2 * j + 1]));               // bytes 1 and 3
+    const uint32_t sw = (j < 2) ? w1 : w2;                                                    // s[X .. X+3] / s[X+4 .. X+7]
+    row0[j] = __byte_perm(sw, hq, (j & 1) ? 0x7352 : 0x7150);
+  }
+
+  // vertical and diagonal half samples from V6(s) pairs: columns X-2 .. X+11 are s_v pairs (X+2)/2 .. (X+2)/2 + 6
+  const uint32_t* vp = &s_v[ty * kK1VPitch + (X + 2) / 2];
+  uint32_t E[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) E[i] = vp[i];
+  uint32_t O[6];                                                   // ( col 2i+1, col 2i+2 )
+#pragma unroll
+  for (int i = 0; i < 6; ++i) O[i] = __byte_perm(E[i], E[i + 1], 0x5432);
+  constexpr uint32_t kCoefC = 0x1414fb01u;     // lo: ( 1, -5 )  hi: ( 20, 20 )
+  constexpr uint32_t kCoefD = 0x000001fbu;     // lo: ( -5, 1 )
+  int hv[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    // HV(x) = H6 over V6(s)[x-2 .. x+3], + 512 for the rounding of ( . + 512 ) >> 10
+    hv[2 * i]     = dp2a_lo_s16s8(E[i + 2], kCoefD, dp2a_hi_s16s8(E[i + 1], kCoefC, dp2a_lo_s16s8(E[i], kCoefC, 512)));
+    hv[2 * i + 1] = dp2a_lo_s16s8(O[i + 2], kCoefD, dp2a_hi_s16s8(O[i + 1], kCoefC, dp2a_lo_s16s8(O[i], kCoefC, 512)));
+  }
+  uint32_t row1[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t vq = round5_clip_x2_hi(E[j + 1]);                                  // clip255( (V6(s) + 16) >> 5 ), columns X+2j, X+2j+1: bytes 1, 3
+    // ( hv >> 10 ) clipped: bits 8..23 of each sum as int16 lanes (|hv| < 2^23), clamp to [0, 1023], x 64 -> bytes 1, 3
+    const uint32_t dq = __viaddmin_s16x2_relu(__byte_perm((uint32_t)hv[2 * j], (uint32_t)hv[2 * j + 1], 0x6521), 0u, 0x03ff03ffu) * 64u;
+    row1[j] = __byte_perm(vq, dq, 0x7351);
+  }
+
+  // half-pel coordinates of this thread's 16 bytes: hx = 2*x0 + 16 tx .. +15, rows 2y and 2y+1
+  const int c0 = 16 * tx;
   const int hx = 2 * x0 + c0;
   const int hx_lo = -2 * (kMargin - 4), hx_hi = 2 * (W + kMargin - 4);          // written region [-56, 2(W+28))
   uint8_t* d0 = half_planes + (size_t)slot * half_bytes + (size_t)(kHpOrigin + 2 * y) * half_stride + kHpOrigin + hx;
@@ -137,6 +187,7 @@ halfpel_kernel(const __grid_constant__ CUtensorMap plane_map,  // [slot][H+64][W
       *reinterpret_cast<uint2*>(d0 + 8) = make_uint2(row0[2], row0[3]);
       *reinterpret_cast<uint2*>(d1 + 8) = make_uint2(row1[2], row1[3]);
     }
+  }
   }
 }
 
