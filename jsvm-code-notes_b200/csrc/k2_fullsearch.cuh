@@ -227,11 +227,12 @@ __device__ __forceinline__ void k2_build_stage(const Group& g, const K2Geo<V>& g
   // ---- 1: per-slot job parameters; the first warp also stores them for the search loop ----
   constexpr int kSlotRegs = (NS + 31) / 32;
   int p_present[kSlotRegs], p_xlo[kSlotRegs], p_xhi[kSlotRegs], p_ylo[kSlotRegs], p_yhi[kSlotRegs], p_ph[kSlotRegs], p_pv[kSlotRegs];
+  uint32_t p_inv[kSlotRegs];
 #pragma unroll
   for (int q = 0; q < kSlotRegs; ++q) {
     const int sl = lane + 32 * q;
     const int jo = sl < NS ? (int)g.slot_job[sl] : -1;
-    p_present[q] = jo >= 0; p_xlo[q] = 0; p_xhi[q] = -1; p_ylo[q] = 0; p_yhi[q] = -1; p_ph[q] = 0; p_pv[q] = 0;
+    p_present[q] = jo >= 0; p_xlo[q] = 0; p_xhi[q] = -1; p_ylo[q] = 0; p_yhi[q] = -1; p_ph[q] = 0; p_pv[q] = 0; p_inv[q] = 0;
     uint32_t fac = 0;
     if (jo >= 0) {
       const jsvm_me_job j = jobs[g.first_job + jo];
@@ -240,6 +241,12 @@ __device__ __forceinline__ void k2_build_stage(const Group& g, const K2Geo<V>& g
       p_xlo[q] = w.xlo - g.ux0 + xa; p_xhi[q] = w.xhi - g.ux0 + xa;    // relative to the staged window origin
       p_ylo[q] = w.ylo - g.uy0;      p_yhi[q] = w.yhi - g.uy0;
       p_ph[q] = j.pred.hor; p_pv[q] = j.pred.ver;
+      // Rows of the union window outside this job's own window are neutralised through the rate table: their "bits" entry
+      // makes (f * bits) >> 16 >= kRowOutCost, more than any valid cost of a partition of at most 128 samples
+      // (SAD <= 32640, rate <= 62 bits * 2^22.5 / 65536 < 6000) and small enough for the 17-bit cost field
+      // (65280 + 40001 + 6000 < 2^17) and for f * bits + f * bits_x to stay below 2^32.  Not for the 16x16 partition
+      // (its valid costs reach 71000) and not for f == 0: those slots keep the exact row-by-row pass.
+      if (sl != 0 && fac != 0) p_inv[q] = (kRowOutCost * 65536u + fac - 1u) / fac;
     }
     if (ptid < 32 && sl < NS) {
       sm.job[sl] = jo < 0 ? -1 : g.first_job + jo;
@@ -298,15 +305,21 @@ __device__ __forceinline__ void k2_build_stage(const Group& g, const K2Geo<V>& g
 #pragma unroll 1
   for (int sl = 0; sl < (K2_ABLATE == 3 ? 0 : NS); ++sl) {
     const int q = sl >> 5, src = sl & 31;
-    int present = 0, pv = 0, ph = 0;
+    int present = 0, pv = 0, ph = 0, ylo = 0, yhi = -1;
+    uint32_t inv = 0;
 #pragma unroll
     for (int qq = 0; qq < kSlotRegs; ++qq) {
       const int a = __shfl_sync(0xffffffffu, p_present[qq], src), b = __shfl_sync(0xffffffffu, p_pv[qq], src), c2 = __shfl_sync(0xffffffffu, p_ph[qq], src);
-      if (qq == q) { present = a; pv = b; ph = c2; }
+      const int d = __shfl_sync(0xffffffffu, (p_ylo[qq] & 0xffff) | (p_yhi[qq] << 16), src);
+      const uint32_t e = __shfl_sync(0xffffffffu, p_inv[qq], src);
+      if (qq == q) { present = a; pv = b; ph = c2; ylo = (int)(int16_t)(d & 0xffff); yhi = d >> 16; inv = e; }
     }
-    // xGetBits with m_uiMvScaleShift = 2: table index (y << 2) - pred (N6)
-    for (int y = ptid; y < by_stride; y += pthreads)
-      by_tab[sl * by_stride + y] = (present && y < uh) ? mv_component_bits(((g.uy0 + y) << 2) - pv) : 0u;
+    // xGetBits with m_uiMvScaleShift = 2: table index (y << 2) - pred (N6); rows outside the job's window: see p_inv
+    for (int y = ptid; y < by_stride; y += pthreads) {
+      uint32_t b = 0u;
+      if (present) b = (y >= ylo && y <= yhi) ? mv_component_bits(((g.uy0 + y) << 2) - pv) : inv;
+      by_tab[sl * by_stride + y] = b;
+    }
     for (int ci = ptid; ci < 4 * kMaxM; ci += pthreads) {
       const int sft = ci / kMaxM, m = ci - sft * kMaxM;         // division by a compile-time constant
       const int x = 4 * m + sft;                                // staged column
@@ -322,16 +335,21 @@ __device__ __forceinline__ void k2_build_stage(const Group& g, const K2Geo<V>& g
     for (int sl = 0; sl < (K2_ABLATE == 3 ? 0 : NS); ++sl) {
       const int q = sl >> 5, src = sl & 31;
       int xlo = 0, xhi = -1, ylo = 0, yhi = -1;
+      uint32_t inv = 0;
 #pragma unroll
       for (int qq = 0; qq < kSlotRegs; ++qq) {
         const int a = __shfl_sync(0xffffffffu, p_xlo[qq], src), b = __shfl_sync(0xffffffffu, p_xhi[qq], src);
         const int c2 = __shfl_sync(0xffffffffu, p_ylo[qq], src), d = __shfl_sync(0xffffffffu, p_yhi[qq], src);
-        if (qq == q) { xlo = a; xhi = b; ylo = c2; yhi = d; }
+        const uint32_t e = __shfl_sync(0xffffffffu, p_inv[qq], src);
+        if (qq == q) { xlo = a; xhi = b; ylo = c2; yhi = d; inv = e; }
       }
       if (x >= xlo && x <= xhi) mk |= (Mask)1 << sl;
       if (xhi >= xlo) {
-        if (ylo <= y0 && y1 <= yhi) full |= (Mask)1 << sl;
-        if (ylo <= y1 && y0 <= yhi) any |= (Mask)1 << sl;
+        const bool some = ylo <= y1 && y0 <= yhi;
+        // "full": the straight-line pass may commit all V rows of the strip -- every row is inside the job's window, or
+        // the rows outside are neutralised through the rate table
+        if ((ylo <= y0 && y1 <= yhi) || (some && inv != 0)) full |= (Mask)1 << sl;
+        if (some) any |= (Mask)1 << sl;
       }
     }
     if (K2_ABLATE == 3) { mk = full = any = (Mask)(~(Mask)0) >> (8 * sizeof(Mask) - NS); }

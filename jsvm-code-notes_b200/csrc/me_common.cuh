@@ -131,5 +131,8 @@ __device__ __forceinline__ uint32_t pack_clip8(const short4 v) {
 // (N12: SAD16x16 <= 65280 and rate << 2^16 in the 8-bit domain; uw*uh <= 32768 is enforced by the planner).
 constexpr int kIdxBits = 15;
 constexpr uint32_t kKeyInvalid = 0xffffffffu;
+// rate term of a union-window row that lies outside a job's own window (see k2_build_stage): above every valid cost of a
+// partition of at most 128 samples, and 65280 + kRowOutCost + rate still fits the 17-bit cost field
+constexpr uint32_t kRowOutCost = 40000u;
 
 }  // namespace jsvm
