@@ -245,8 +245,9 @@ __device__ __forceinline__ void k2_build_stage(const Group& g, const K2Geo<V>& g
       // makes (f * bits) >> 16 >= kRowOutCost, more than any valid cost of a partition of at most 128 samples
       // (SAD <= 32640, rate <= 62 bits * 2^22.5 / 65536 < 6000) and small enough for the 17-bit cost field
       // (65280 + 40001 + 6000 < 2^17) and for f * bits + f * bits_x to stay below 2^32.  Not for the 16x16 partition
-      // (its valid costs reach 71000) and not for f == 0: those slots keep the exact row-by-row pass.
-      if (sl != 0 && fac != 0) p_inv[q] = (kRowOutCost * 65536u + fac - 1u) / fac;
+      // (its valid costs reach 71000), not for f == 0 and not for factors beyond the SAD range (f > 7e6: QP 51 gives 5.5e6; an
+      // SSE-style factor could make the rate itself wrap, N5): those slots keep the exact row-by-row pass.
+      if (sl != 0 && fac != 0 && fac <= 7000000u) p_inv[q] = (kRowOutCost * 65536u + fac - 1u) / fac;
     }
     if (ptid < 32 && sl < NS) {
       sm.job[sl] = jo < 0 ? -1 : g.first_job + jo;
