@@ -130,6 +130,25 @@ def test_signed_16bit_originals_bit_exact(me, oracle, synth, sub_dfunc, parts_na
     assert np.array_equal(gp, wp)
 
 
+@pytest.mark.parametrize("parts_name", ["PARTS_9", "PARTS_41"])
+def test_extreme_cost_factors_bit_exact(me, oracle, synth, parts_name):
+    """Cost factors from 0 (lambda = 0) over QP 51 to values whose rate term wraps in 32 bits (N5), with per-partition starts so
+    that every macroblock has strips straddling the edge of some job's window: the rate-table neutralisation of out-of-window
+    rows (K2) must stay exact or step aside."""
+    cfg = synth.CONFIGS["C1"]
+    W, H = cfg["width"], cfg["height"]
+    ses, _ = _setup(me, oracle, synth, cfg, seed=1260, sub_dfunc=0)
+    parts = getattr(synth, parts_name)
+    jobs = synth.make_jobs(W, H, parts, cur_slot=1, ref_slot=0, qp=30, field="random", seed=21, bits_in=2)
+    factors = np.array([0, 1, 77, synth.cost_factor_for_qp(51), 7000000, 7000001, 123456789, 0x80000000, 0xFFFFFFFF], np.uint32)
+    rng = np.random.default_rng(5)
+    jobs["cost_factor"] = factors[rng.integers(0, len(factors), len(jobs))]
+    got, gp = me.search(jobs, want_preds=True)
+    want, wp = ses.search(jobs, want_preds=True)
+    assert_results_equal(got, want, jobs)
+    assert np.array_equal(gp, wp)
+
+
 def test_originals_outside_the_supported_range_are_refused(me, pkg):
     """|sample| >= 1024 cannot come from a residual-prediction pass; loud error, no fallback."""
     g = np.load(os.path.join(GOLDEN, "org_override_16bit.npz"))
