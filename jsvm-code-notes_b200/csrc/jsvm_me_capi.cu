@@ -102,6 +102,14 @@ struct jsvm_me_ctx {
   // host-buffer search: uploads and result copy-backs run on their own streams so that they overlap the kernels
   cudaStream_t up_stream = nullptr, down_stream = nullptr;
   cudaEvent_t ev_entry = nullptr, ev_kernels = nullptr;
+  // small calls (the drop-in's one-job searches): one pinned, device-mapped arena that the kernels read and write directly --
+  // no staging copies, two launches and one synchronisation per call
+  struct SmallArena {
+    jsvm_me_job job[64]; Group group[64]; jsvm_me_result result[64];
+    int16_t org[64 * 256]; uint8_t pred[64 * 256];
+  };
+  SmallArena* small = nullptr;
+  bool last_small = false;
   // state of the last host-API search (compensateBlock contract)
   std::vector<jsvm_me_job> last_jobs;
   bool last_has_preds = false;
@@ -355,6 +363,39 @@ int run_search(jsvm_me_ctx* c, const jsvm_me_job* d_jobs, int job_begin, int job
   return JSVM_ME_OK;
 }
 
+// jsvm_me_search for up to 64 jobs: what MbEncoder's one-call-at-a-time use of estimateBlockWithStart turns into.
+int search_small(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const int16_t* org_mbs, int n_org_mbs,
+                 jsvm_me_result* results, uint8_t* preds) {
+  CU_OK(cudaSetDevice(c->device));
+  if (!c->small) CU_OK(cudaHostAlloc((void**)&c->small, sizeof(jsvm_me_ctx::SmallArena), cudaHostAllocMapped));
+  jsvm_me_ctx::SmallArena* a = c->small;                     // unified addressing: the same pointer is valid on the device
+  PlanChunk pc;
+  plan_range(c->W, c->H, c->n_slots, c->search_range, jobs, 0, n_jobs, pc);
+  if (pc.err_job >= 0) return fail("job %d: %s", pc.err_job, pc.err);
+  jsvm_me_plan_info info{};
+  info.n_groups_8x8 = (int32_t)pc.g8.size(); info.n_groups = (int32_t)(pc.g8.size() + pc.g4.size()); info.n_positions = pc.npos;
+  int ng = 0;
+  for (const std::vector<Group>* v : {&pc.g8, &pc.g4})
+    for (const Group& g : *v) {
+      if (g.org_index >= n_org_mbs) return fail("job %d: org_index %d >= n_org_mbs %d", g.first_job, g.org_index, n_org_mbs);
+      if (g.org_index < 0 && !c->slot_full[g.cur_slot]) return fail("job %d: cur_slot %d is empty", g.first_job, g.cur_slot);
+      if (!c->slot_half[g.ref_slot]) return fail("job %d: ref_slot %d has no half-pel plane", g.first_job, g.ref_slot);
+      int32_t& mx = g.gran4 ? info.max_uh_4x4 : info.max_uh_8x8;
+      mx = std::max<int32_t>(mx, g.uh);
+      a->group[ng++] = g;
+    }
+  memcpy(a->job, jobs, sizeof(jsvm_me_job) * n_jobs);
+  if (n_org_mbs > 0) memcpy(a->org, org_mbs, sizeof(int16_t) * 256 * n_org_mbs);
+  if (c->d_keys.reserve(64) || c->d_aux.reserve(64)) return JSVM_ME_ERR;
+  if (run_search(c, a->job, 0, n_jobs, a->group, &info, a->org, c->d_keys.p, c->d_aux.p, a->result, a->pred)) return JSVM_ME_ERR;
+  CU_OK(cudaStreamSynchronize(c->stream));
+  memcpy(results, a->result, sizeof(jsvm_me_result) * n_jobs);
+  if (preds) memcpy(preds, a->pred, (size_t)n_jobs * 256);
+  c->last_jobs.assign(jobs, jobs + n_jobs);
+  c->last_has_preds = true; c->last_small = true;
+  return JSVM_ME_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -402,6 +443,7 @@ int jsvm_me_destroy(jsvm_me_ctx* c) {
   if (c->up_stream) cudaStreamDestroy(c->up_stream);
   if (c->down_stream) cudaStreamDestroy(c->down_stream);
   for (auto& pg : c->pinned_groups) if (pg) cudaFreeHost(pg);
+  if (c->small) cudaFreeHost(c->small);
   delete c;
   return JSVM_ME_OK;
 }
@@ -593,6 +635,8 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
       if (org_mbs[i] < -1024 || org_mbs[i] > 1023)      // residual-prediction originals span [-255, 510] (N3); the key widths assume |v| < 1024
         return fail("org_mbs sample %zu = %d outside [-1024,1023]", i, (int)org_mbs[i]);
   }
+  if (n_jobs <= 64 && n_org_mbs <= 64) return search_small(c, jobs, n_jobs, org_mbs, n_org_mbs, results, preds);
+  c->last_small = false;
   CU_OK(cudaSetDevice(c->device));
   const bool want_preds = preds != nullptr || n_jobs <= 4096;
   if (c->d_jobs.reserve(n_jobs) || c->d_keys.reserve(n_jobs) || c->d_aux.reserve(n_jobs) ||
@@ -702,9 +746,12 @@ int jsvm_me_fetch_pred(jsvm_me_ctx* c, int job_idx, int16_t* dst, int dst_stride
   int w, h;
   mode_size(c->last_jobs[job_idx].mode, w, h);
   uint8_t blk[256];
-  CU_OK(cudaSetDevice(c->device));
-  CU_OK(cudaMemcpyAsync(blk, c->d_preds.p + (size_t)job_idx * 256, 256, cudaMemcpyDeviceToHost, c->stream));
-  CU_OK(cudaStreamSynchronize(c->stream));
+  if (c->last_small) memcpy(blk, c->small->pred + (size_t)job_idx * 256, 256);
+  else {
+    CU_OK(cudaSetDevice(c->device));
+    CU_OK(cudaMemcpyAsync(blk, c->d_preds.p + (size_t)job_idx * 256, 256, cudaMemcpyDeviceToHost, c->stream));
+    CU_OK(cudaStreamSynchronize(c->stream));
+  }
   for (int y = 0; y < h; ++y)
     for (int x = 0; x < w; ++x) dst[y * dst_stride + x] = blk[y * 16 + x];
   return JSVM_ME_OK;

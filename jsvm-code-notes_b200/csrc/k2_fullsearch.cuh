@@ -367,7 +367,7 @@ __device__ __forceinline__ void k2_search_units(const K2Geo<V>& geo, const K2Sta
 {
   using SM = K2Smem<V, GRAN4>;
   using Mask = typename SM::Mask;
-  constexpr int NS = SM::NS, NACC = SM::NACC;
+  constexpr int NACC = SM::NACC;
   SM& sm = *st.sm;
   const uint32_t* winw = st.winw;
   const uint32_t* by_tab = st.by_tab;
@@ -626,7 +626,6 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
                    JobAux* __restrict__ aux)                      // per job: how K3 decodes the key
 {
   using SM = K2Smem<V, GRAN4>;
-  constexpr int NS = SM::NS;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const Group& g = groups[blockIdx.x];
   const int tid = threadIdx.x, lane = tid & 31;

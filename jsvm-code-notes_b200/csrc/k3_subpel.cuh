@@ -143,17 +143,21 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
   const int X0 = (BX - 2) & ~3, Y0 = BY - 2;                  // patch origin: 4-byte aligned column, even row
   const int relx = BX - X0;                                   // 2..5
   {
+    // 8 rows per pass, 4 lanes per row; a lane takes the words q, q+4, q+8 of its row (no runtime division)
     const int nwords = ((BX + 2 * w) - X0) / 4 + 1;           // <= 10
     const int nrows = 2 * h + 3;
-    const uint8_t* src = half_planes + (size_t)j.ref_slot * half_bytes + (size_t)(kHpOrigin + Y0) * half_stride + kHpOrigin + X0;
-    const int lr = lane / nwords, lk = lane - lr * nwords;     // one division per lane, then whole rows per pass
-    const int rows_per_pass = 32 / nwords;
-    if (lr < rows_per_pass) {
-      for (int r = lr; r < nrows; r += rows_per_pass) {
-        const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)r * half_stride + 4 * lk));
-        const int py = r & 1, pr = r >> 1;
-        *reinterpret_cast<uint16_t*>(&sw.plane[py * 2 + 0][pr][2 * lk]) = (uint16_t)__byte_perm(v, 0, 0x4420);   // bytes 0, 2: even X
-        *reinterpret_cast<uint16_t*>(&sw.plane[py * 2 + 1][pr][2 * lk]) = (uint16_t)__byte_perm(v, 0, 0x4431);   // bytes 1, 3: odd X
+    const int rr = lane >> 2, q = lane & 3;
+    const uint8_t* src = half_planes + (size_t)j.ref_slot * half_bytes + (size_t)(kHpOrigin + Y0) * half_stride + kHpOrigin + X0 + 4 * q;
+    for (int r = rr; r < nrows; r += 8) {
+      const uint8_t* rp = src + (size_t)r * half_stride;
+      uint8_t* d0 = &sw.plane[(r & 1) * 2][r >> 1][2 * q];     // even X of this row; odd X one plane further
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (q + 4 * k < nwords) {
+          const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(rp + 16 * k));
+          *reinterpret_cast<uint16_t*>(d0 + 8 * k) = (uint16_t)__byte_perm(v, 0, 0x4420);                                        // bytes 0, 2
+          *reinterpret_cast<uint16_t*>(d0 + 8 * k + kK3PlaneRows * kK3PlanePitch) = (uint16_t)__byte_perm(v, 0, 0x4431);       // bytes 1, 3
+        }
       }
     }
   }
@@ -169,6 +173,13 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
   for (int stage = 0; stage < 2; ++stage) {
     const int n0 = stage, ncand = 9 - stage;
     uint32_t stage_best = 0xffffffffu;
+    // the MV-rate term of the stage's candidates, once: lane i holds the one of candidate n0 + i
+    uint32_t my_rate = 0;
+    if (lane < ncand) {
+      const int n = n0 + lane;
+      const int th = mvh + (stage == 0 ? c_half_mv[n][0] : c_quarter_mv[n][0]), tv = mvv + (stage == 0 ? c_half_mv[n][1] : c_quarter_mv[n][1]);
+      my_rate = rate_cost(f, mv_component_bits(th - j.pred.hor) + mv_component_bits(tv - j.pred.ver));
+    }
     for (int t0 = 0; t0 < ncand * nb; t0 += 32) {
       const int t = t0 + lane;
       const bool active = t < ncand * nb;
@@ -203,14 +214,15 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
         }
       }
       // sum the 4x4 blocks of one candidate (nb is a power of two, groups are lane-aligned)
-      for (int off = 1; off < nb; off <<= 1) dist += __shfl_xor_sync(0xffffffffu, dist, off);
+#pragma unroll
+      for (int off = 1; off < 16; off <<= 1) {
+        const uint32_t o = __shfl_xor_sync(0xffffffffu, dist, off);
+        if (off < nb) dist += o;
+      }
+      const uint32_t rate = __shfl_sync(0xffffffffu, my_rate, n - n0);
       uint32_t k = 0xffffffffu;                           // (cost << 8) | n : cost < 2^17 in the 8-bit domain (N12), < 2^23 for
                                                           // originals in [-1024, 1023] (enforced by jsvm_me_search)
-      if (active && blk_b == 0) {
-        const int th = mvh + dx, tv = mvv + dy;
-        const uint32_t c = dist + rate_cost(f, mv_component_bits(th - j.pred.hor) + mv_component_bits(tv - j.pred.ver));
-        k = (c << 8) | (uint32_t)n;
-      }
+      if (active && blk_b == 0) k = ((dist + rate) << 8) | (uint32_t)n;
       k = __reduce_min_sync(0xffffffffu, k);
       stage_best = k < stage_best ? k : stage_best;
     }
