@@ -39,6 +39,9 @@ namespace jsvm {
 // Warps w and w + 4 of a CTA share an SM sub-partition.  After the prologue barrier all warps would run their
 // SAD pass (ALU pipe) and their rate / argmin pass (FMA pipe) in lockstep, leaving each pipe idle half of the time;
 // the upper half of the CTA therefore starts its first batch K2_STAGGER_NS later (the offset persists).
+#ifndef K2_COPY_UNROLL
+#define K2_COPY_UNROLL 4
+#endif
 #ifndef K2_STAGGER_NS
 #define K2_STAGGER_NS 0
 #endif
@@ -269,26 +272,40 @@ __device__ __forceinline__ void k2_build_stage(const Group& g, const K2Geo<V>& g
         planes + (size_t)g.ref_slot * plane_bytes + (size_t)py * plane_stride + (px - xa));
     const int stride_w = plane_stride >> 2;
     constexpr int kGroups = kWinRowWords / 4;                   // 10
-    for (int i = ptid; i < rows * kGroups; i += pthreads) {
-      const int r = i / kGroups, gq = i - r * kGroups;
-      const uint32_t* sp = src0 + (size_t)r * stride_w + 4 * gq;
-      uint32_t w[5];
+    // K2_COPY_UNROLL items per thread in flight: the loop is a chain of L2 round trips (the staging warps of the persistent
+    // kernel have to finish a window while the search warps work through the previous group)
+    const int n_items = rows * kGroups;
+    for (int i0 = ptid; i0 < n_items; i0 += K2_COPY_UNROLL * pthreads) {
+      uint32_t w[K2_COPY_UNROLL][5];
 #pragma unroll
-      for (int k = 0; k < 5; ++k) w[k] = __ldg(sp + k);
+      for (int u = 0; u < K2_COPY_UNROLL; ++u) {
+        const int i = min(i0 + u * pthreads, n_items - 1);       // clamped: a few redundant loads instead of a branch
+        const int r = i / kGroups, gq = i - r * kGroups;
+        const uint32_t* sp = src0 + (size_t)r * stride_w + 4 * gq;
 #pragma unroll
-      for (int sft = 0; sft < 4; ++sft) {
-        // copy_words is even (M is), not a multiple of 4: 8-byte stores
-        uint2* dst = reinterpret_cast<uint2*>(winw + sft * copy_words + r * kWinRowWords + 4 * gq);
-        dst[0] = make_uint2(__funnelshift_r(w[0], w[1], 8 * sft), __funnelshift_r(w[1], w[2], 8 * sft));
-        dst[1] = make_uint2(__funnelshift_r(w[2], w[3], 8 * sft), __funnelshift_r(w[3], w[4], 8 * sft));
+        for (int k = 0; k < 5; ++k) w[u][k] = __ldg(sp + k);
+      }
+#pragma unroll
+      for (int u = 0; u < K2_COPY_UNROLL; ++u) {
+        const int i = i0 + u * pthreads;
+        if (i < n_items) {
+          const int r = i / kGroups, gq = i - r * kGroups;
+#pragma unroll
+          for (int sft = 0; sft < 4; ++sft) {
+            // copy_words is even (M is), not a multiple of 4: 8-byte stores
+            uint2* dst = reinterpret_cast<uint2*>(winw + sft * copy_words + r * kWinRowWords + 4 * gq);
+            dst[0] = make_uint2(__funnelshift_r(w[u][0], w[u][1], 8 * sft), __funnelshift_r(w[u][1], w[u][2], 8 * sft));
+            dst[1] = make_uint2(__funnelshift_r(w[u][2], w[u][3], 8 * sft), __funnelshift_r(w[u][3], w[u][4], 8 * sft));
+          }
+        }
       }
     }
   }
 
   // ---- 3: the current macroblock (16 rows x 4 packed words); every unit re-reads it with 16 broadcast LDS.128 so that its
   //      64 registers are free during the rate / argmin pass ----
-  if (ptid < 64) {
-    const int r = ptid >> 2, k = ptid & 3;
+  for (int t = ptid; t < 64; t += pthreads) {
+    const int r = t >> 2, k = t & 3;
     uint32_t v;
     if (g.org_index < 0) {
       v = __ldg(reinterpret_cast<const uint32_t*>(planes + (size_t)g.cur_slot * plane_bytes + (size_t)(kMargin + 16 * g.mb_y + r) * plane_stride +
