@@ -321,7 +321,7 @@ int launch_search_persistent(jsvm_me_ctx* c, const Group* d_groups, int n_groups
 template <int V, bool GRAN4>
 int choose_persistent(jsvm_me_ctx* c, int n_groups, int max_uh, bool* persistent) {
   // JSVM_ME_K2 = group | persistent forces one of the two kernels (A/B measurements)
-  static const char* force = getenv("JSVM_ME_K2");
+  const char* force = getenv("JSVM_ME_K2");
   const bool fits = k2p_smem_bytes<V, GRAN4>(max_uh) <= kMaxDynSmem;
   // 4x4-granular groups (41 slots): staging 41 rate tables keeps 3 producer warps busier than 13 search warps; measured
   // 19 % slower than one CTA per group on C3, so the persistent kernel is only chosen for them when forced

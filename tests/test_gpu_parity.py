@@ -211,6 +211,25 @@ def test_large_configs_subset_bit_exact(me, oracle, synth, cfg_name, n_inner, fi
     assert np.array_equal(me.halfpel_plane(0), ses.halfpel(0))
 
 
+def test_persistent_and_per_group_kernels_agree(me, oracle, synth, monkeypatch):
+    """The same whole-picture job list through full_search_persistent_kernel (one CTA per SM, producer / consumer warps over two
+    shared-memory stages) and through full_search_kernel (one CTA per group): identical bytes, and both equal to the checker."""
+    cfg = synth.CONFIGS["C2"]
+    W, H = cfg["width"], cfg["height"]
+    ses, _ = _setup(me, oracle, synth, cfg, seed=1270)
+    jobs = np.concatenate([synth.make_jobs(W, H, cfg["parts"], cur_slot=1, ref_slot=0, qp=32, field=f, seed=3) for f in ("random", "split")])
+    out = {}
+    for mode in ("persistent", "group"):
+        monkeypatch.setenv("JSVM_ME_K2", mode)
+        out[mode] = me.search(jobs)
+        assert me.last_search_kernel().startswith("full_search_persistent_kernel" if mode == "persistent" else "full_search_kernel<")
+    monkeypatch.delenv("JSVM_ME_K2")
+    assert out["persistent"].tobytes() == out["group"].tobytes()
+    sub = np.arange(0, len(jobs), 7)                                      # every 7th job against the checker
+    want = ses.search(jobs[sub])
+    assert_results_equal(out["persistent"][sub], want, jobs[sub])
+
+
 # ---- full-size (1080p, SR 64, every macroblock) size-independent properties, no oracle needed ----
 @pytest.fixture(scope="module")
 def full_1080p(me, synth):
