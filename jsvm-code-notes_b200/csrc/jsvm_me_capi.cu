@@ -652,84 +652,96 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
   CU_OK(cudaEventRecord(c->ev_entry, c->stream));
   CU_OK(cudaStreamWaitEvent(c->up_stream, c->ev_entry, 0));
   CU_OK(cudaStreamWaitEvent(c->down_stream, c->ev_entry, 0));
-  // Pipeline over chunks of ~32 K jobs cut at macroblock boundaries.  Worker threads plan different chunks
-  // concurrently (chunk k is ready long before the GPU has finished chunk k-1); the calling thread uploads each
-  // chunk's jobs and groups right before its kernels and queues the copy-back of its results right after them.
-  // The first chunks are small so that the GPU starts early; later ones are large: a persistent K2 launch loses its pipeline
-  // fill and its last-wave imbalance once per launch (~1 group of ~25 per SM at 32 K jobs, of ~100 at 128 K jobs).
-  const int kChunk = 131072;
+  // Pipeline.  PLANNING happens in units of ~16 K jobs cut at macroblock boundaries, by worker threads, in order.
+  // LAUNCHES take every unit that is ready, up to kMaxUnits of them, as one batch: the calling thread never waits for more than
+  // the one unit it needs next, and once the planners are ahead of the GPU the launches grow to 128 K jobs (a persistent K2
+  // launch loses its pipeline fill and its last-wave imbalance once per launch: ~1 group of ~12 per SM at 16 K jobs, of ~100
+  // at 128 K).  Job / group uploads and result copy-backs run on their own streams next to the kernels.
+  int kUnit = 16384;
+  if (const char* e = getenv("JSVM_ME_CHUNK")) kUnit = std::max(1024, std::min(1 << 17, atoi(e)));     // tuning knob (jobs per planning unit)
+  constexpr int kMaxUnits = 8;
   std::vector<int> cut(1, 0);
   while (cut.back() < n_jobs) {
-    const int size = cut.size() == 1 ? kChunk / 4 : cut.size() == 2 ? kChunk / 2 : kChunk;
+    // the first units are small (2 K, 4 K, 8 K jobs): the GPU has nothing to do until unit 0 is planned and uploaded
+    const int size = std::min(kUnit, 2048 << std::min<size_t>(cut.size() - 1, 6));
     int end = std::min(n_jobs, cut.back() + size);
     while (end < n_jobs && same_mb(jobs[end], jobs[end - 1])) ++end;
     cut.push_back(end);
   }
-  const int n_chunks = (int)cut.size() - 1;
+  const int n_units = (int)cut.size() - 1;
   if (c->d_groups.reserve((size_t)n_jobs)) return JSVM_ME_ERR;                      // upper bound: one group per job
-  const size_t ring_cap = (size_t)kChunk + 256;             // a chunk never holds more groups than jobs (+ the MB it finishes)
+  const size_t ring_cap = (size_t)kMaxUnits * ((size_t)kUnit + 256);      // a unit never holds more groups than jobs (+ the MB it finishes)
   if (c->pinned_cap < ring_cap) {
     for (auto& pg : c->pinned_groups) { if (pg) cudaFreeHost(pg); pg = nullptr; }
     for (auto& pg : c->pinned_groups) CU_OK(cudaMallocHost((void**)&pg, ring_cap * sizeof(Group)));
     c->pinned_cap = ring_cap;
   }
-  std::vector<std::vector<Group>> plans(n_chunks);
-  std::vector<jsvm_me_plan_info> infos(n_chunks);
-  std::vector<int> status(n_chunks, 0);                     // 0 = pending, 1 = planned, -1 = failed (g_err of the worker copied below)
-  std::vector<std::string> errs(n_chunks);
+  std::vector<PlanChunk> plans(n_units);
+  std::vector<int> status(n_units, 0);                      // 0 = pending, 1 = planned, -1 = failed
   std::mutex mu; std::condition_variable cv;
-  const int n_workers = n_chunks <= 1 ? 0 : (int)std::min<unsigned>((unsigned)n_chunks, std::min(8u, std::max(1u, std::thread::hardware_concurrency())));
-  auto plan_chunk = [&](int k) {
-    PlanChunk pc;
-    plan_range(c->W, c->H, c->n_slots, c->search_range, jobs, cut[k], cut[k + 1], pc);
-    int st = 1;
-    if (pc.err_job >= 0) { st = -1; char b[256]; snprintf(b, sizeof(b), "job %d: %s", pc.err_job, pc.err); errs[k] = b; }
-    else {
-      std::vector<Group>& g = plans[k];
-      g.resize(pc.g8.size() + pc.g4.size());
-      if (!pc.g8.empty()) memcpy(g.data(), pc.g8.data(), pc.g8.size() * sizeof(Group));
-      if (!pc.g4.empty()) memcpy(g.data() + pc.g8.size(), pc.g4.data(), pc.g4.size() * sizeof(Group));
-      jsvm_me_plan_info& in = infos[k];
-      in.n_groups = (int32_t)g.size(); in.n_groups_8x8 = (int32_t)pc.g8.size();
-      in.max_uh_8x8 = in.max_uh_4x4 = 0; in.n_positions = pc.npos; in.n_group_positions = 0;
-      for (const Group& gg : g) { int32_t& mx = gg.gran4 ? in.max_uh_4x4 : in.max_uh_8x8; mx = std::max<int32_t>(mx, gg.uh); }
-    }
-    { std::lock_guard<std::mutex> lk(mu); status[k] = st; }
+  const int n_workers = n_units <= 1 ? 0 : (int)std::min<unsigned>((unsigned)n_units, std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
+  auto plan_unit = [&](int k) {
+    plan_range(c->W, c->H, c->n_slots, c->search_range, jobs, cut[k], cut[k + 1], plans[k]);
+    { std::lock_guard<std::mutex> lk(mu); status[k] = plans[k].err_job >= 0 ? -1 : 1; }
     cv.notify_all();
   };
   std::vector<std::thread> workers;
   for (int t = 0; t < n_workers; ++t)
-    workers.emplace_back([&, t]() { for (int k = t; k < n_chunks; k += n_workers) plan_chunk(k); });
+    workers.emplace_back([&, t]() { for (int k = t; k < n_units; k += n_workers) plan_unit(k); });
   struct Joiner { std::vector<std::thread>& w; ~Joiner() { for (auto& x : w) if (x.joinable()) x.join(); } } joiner{workers};
 
   size_t groups_done = 0;
-  for (int k = 0; k < n_chunks; ++k) {
-    if (n_workers == 0) plan_chunk(k);
-    { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return status[k] != 0; }); }
-    if (status[k] < 0) return fail("%s", errs[k].c_str());
-    const int begin = cut[k], end = cut[k + 1];
-    std::vector<Group>& hg = plans[k];
-    for (const Group& g : hg) {                             // one check per group: planes present, originals in range
-      if (g.org_index >= n_org_mbs) return fail("job %d: org_index %d >= n_org_mbs %d", g.first_job, g.org_index, n_org_mbs);
-      if (g.org_index < 0 && !c->slot_full[g.cur_slot]) return fail("job %d: cur_slot %d is empty", g.first_job, g.cur_slot);
-      if (!c->slot_half[g.ref_slot]) return fail("job %d: ref_slot %d has no half-pel plane", g.first_job, g.ref_slot);
+  int launch = 0;
+  for (int k = 0; k < n_units; ++launch) {
+    if (n_workers == 0) plan_unit(k);
+    int m = k;                                              // units [k, m) go into this launch
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return status[k] != 0; });
+      // 4x4-granular groups sit behind the 8x8-granular ones of their unit: such a unit is launched on its own
+      while (m < n_units && m - k < kMaxUnits && status[m] != 0 && (m == k || (plans[m].g4.empty() && plans[k].g4.empty()))) {
+        if (status[m] < 0) break;
+        ++m;
+      }
+      if (m == k) m = k + 1;                                // unit k failed: reported below
     }
-    if (hg.size() > ring_cap) return fail("internal: chunk plan larger than its ring slot");
-    Group* pg = c->pinned_groups[k & 3];
-    if (k >= 4) CU_OK(cudaEventSynchronize(c->chunk_done[k & 3]));                  // the slot's previous upload has been consumed
-    memcpy(pg, hg.data(), sizeof(Group) * hg.size());
+    for (int u = k; u < m; ++u)
+      if (status[u] < 0) return fail("job %d: %s", plans[u].err_job, plans[u].err);
+    const int begin = cut[k], end = cut[m];
+    Group* pg = c->pinned_groups[launch & 3];
+    if (launch >= 4) CU_OK(cudaEventSynchronize(c->chunk_done[launch & 3]));        // the slot's previous upload has been consumed
+    jsvm_me_plan_info info{};
+    size_t ng = 0;
+    for (int pass = 0; pass < 2; ++pass)                    // all 8x8-granular groups first, then the 4x4-granular ones
+      for (int u = k; u < m; ++u) {
+        const std::vector<Group>& v = pass == 0 ? plans[u].g8 : plans[u].g4;
+        if (ng + v.size() > ring_cap) return fail("internal: launch plan larger than its ring slot");
+        for (const Group& g : v) {                          // one check per group: planes present, originals in range
+          if (g.org_index >= n_org_mbs) return fail("job %d: org_index %d >= n_org_mbs %d", g.first_job, g.org_index, n_org_mbs);
+          if (g.org_index < 0 && !c->slot_full[g.cur_slot]) return fail("job %d: cur_slot %d is empty", g.first_job, g.cur_slot);
+          if (!c->slot_half[g.ref_slot]) return fail("job %d: ref_slot %d has no half-pel plane", g.first_job, g.ref_slot);
+          int32_t& mx = g.gran4 ? info.max_uh_4x4 : info.max_uh_8x8;
+          mx = std::max<int32_t>(mx, g.uh);
+        }
+        if (!v.empty()) memcpy(pg + ng, v.data(), sizeof(Group) * v.size());
+        ng += v.size();
+        if (pass == 0) info.n_groups_8x8 += (int32_t)v.size();
+        info.n_positions += pass == 0 ? plans[u].npos : 0;
+      }
+    info.n_groups = (int32_t)ng;
+    for (int u = k; u < m; ++u) { std::vector<Group>().swap(plans[u].g8); std::vector<Group>().swap(plans[u].g4); }
     CU_OK(cudaMemcpyAsync(c->d_jobs.p + begin, jobs + begin, sizeof(jsvm_me_job) * (end - begin), cudaMemcpyHostToDevice, c->up_stream));
-    CU_OK(cudaMemcpyAsync(c->d_groups.p + groups_done, pg, sizeof(Group) * hg.size(), cudaMemcpyHostToDevice, c->up_stream));
-    if (!c->chunk_done[k & 3]) CU_OK(cudaEventCreateWithFlags(&c->chunk_done[k & 3], cudaEventDisableTiming));
-    CU_OK(cudaEventRecord(c->chunk_done[k & 3], c->up_stream));                     // ring slot consumed; chunk k is on the device
-    CU_OK(cudaStreamWaitEvent(c->stream, c->chunk_done[k & 3], 0));
-    if (run_search(c, c->d_jobs.p, begin, end, c->d_groups.p + groups_done, &infos[k], c->d_org.p, c->d_keys.p, c->d_aux.p, c->d_results.p,
+    CU_OK(cudaMemcpyAsync(c->d_groups.p + groups_done, pg, sizeof(Group) * ng, cudaMemcpyHostToDevice, c->up_stream));
+    if (!c->chunk_done[launch & 3]) CU_OK(cudaEventCreateWithFlags(&c->chunk_done[launch & 3], cudaEventDisableTiming));
+    CU_OK(cudaEventRecord(c->chunk_done[launch & 3], c->up_stream));                // ring slot consumed; the batch is on the device
+    CU_OK(cudaStreamWaitEvent(c->stream, c->chunk_done[launch & 3], 0));
+    if (run_search(c, c->d_jobs.p, begin, end, c->d_groups.p + groups_done, &info, c->d_org.p, c->d_keys.p, c->d_aux.p, c->d_results.p,
                    want_preds ? c->d_preds.p : nullptr)) return JSVM_ME_ERR;
     CU_OK(cudaEventRecord(c->ev_kernels, c->stream));
     CU_OK(cudaStreamWaitEvent(c->down_stream, c->ev_kernels, 0));
     CU_OK(cudaMemcpyAsync(results + begin, c->d_results.p + begin, sizeof(jsvm_me_result) * (end - begin), cudaMemcpyDeviceToHost, c->down_stream));
-    groups_done += hg.size();
-    std::vector<Group>().swap(hg);
+    groups_done += ng;
+    k = m;
   }
   if (preds) CU_OK(cudaMemcpyAsync(preds, c->d_preds.p, (size_t)n_jobs * 256, cudaMemcpyDeviceToHost, c->stream));
   CU_OK(cudaStreamSynchronize(c->stream));
