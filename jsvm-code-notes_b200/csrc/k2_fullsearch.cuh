@@ -154,6 +154,8 @@ struct K2Smem {
   uint32_t cur[16][4];                            // the current macroblock, 16 packed bytes per row (16-byte aligned)
   uint32_t factor[NS];
   int16_t  xlo[NS], xhi[NS], ylo[NS], yhi[NS];    // relative to the union window origin (empty slot: xhi < xlo)
+  int16_t  ph[NS], pv[NS];                        // rcMvPred of the slot's job (quarter pel)
+  uint32_t inv[NS];                               // "bits" value of rows outside the job's window (0: exact row-by-row pass instead)
   int32_t  job[NS];                               // absolute job index or -1
   int32_t  next_unit;                             // work counter: warps pull batches of 32 units
   int16_t  ux0, uy0, uw, uh, xa, pad;             // geometry of the staged group (persistent kernel: consumers read it here)
@@ -207,58 +209,37 @@ struct K2Stage {
 };
 
 // ---- staging of one group: job parameters, the four window copies, the current macroblock, rate tables, masks ----
-// Executed by `pthreads` threads (whole warps; ptid = index among them); no barrier inside: every warp derives the
-// per-slot job parameters in its own lanes (lane l owns slots l and l + 32) and reads them back with shuffles.
-template <int V, bool GRAN4>
+// Executed by kThreads threads (whole warps; ptid = index among them), which meet once at named barrier 1: the first
+// warp derives the per-slot job parameters (lane l owns slots l and l + 32) and stores them in the stage record; after the
+// barrier every thread builds its share of the (slot, row) / (slot, column) table entries from the record.
+template <int V, bool GRAN4, int kThreads>
 __device__ __forceinline__ void k2_build_stage(const Group& g, const K2Geo<V>& geo, const K2Stage<V, GRAN4>& st,
                                                const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_stride,
                                                const jsvm_me_job* __restrict__ jobs, const int16_t* __restrict__ org_mbs,
                                                int mb_w, int mb_h, int default_range,
-                                               const int ptid, const int pthreads, const int first_unit)
+                                               const int ptid, const int first_unit)
 {
   using SM = K2Smem<V, GRAN4>;
   using Mask = typename SM::Mask;
   constexpr int NS = SM::NS;
+  constexpr int pthreads = kThreads;
   SM& sm = *st.sm;
   uint32_t* winw = st.winw;
   uint32_t* by_tab = st.by_tab;
-  const int xa = geo.xa, uh = geo.uh, uwx = geo.uwx, rows = geo.rows, copy_words = geo.copy_words, by_stride = geo.by_stride, nstrips = geo.nstrips;
+  const int xa = geo.xa, uwx = geo.uwx, rows = geo.rows, copy_words = geo.copy_words, by_stride = geo.by_stride, nstrips = geo.nstrips;
   const int px = kMargin + 16 * g.mb_x + g.ux0;                 // union window origin in plane coordinates
   const int py = kMargin + 16 * g.mb_y + g.uy0;
-  const int lane = ptid & 31;
 
-  // ---- 1: per-slot job parameters; the first warp also stores them for the search loop ----
+  // ---- 1a: the first warp fetches the job records of its slots (lane l owns slots l and l + 32); they are turned into
+  //      per-slot parameters in step 1b, after the window copies have been issued (both are chains of L2 round trips) ----
   constexpr int kSlotRegs = (NS + 31) / 32;
-  int p_present[kSlotRegs], p_xlo[kSlotRegs], p_xhi[kSlotRegs], p_ylo[kSlotRegs], p_yhi[kSlotRegs], p_ph[kSlotRegs], p_pv[kSlotRegs];
-  uint32_t p_inv[kSlotRegs];
+  jsvm_me_job slot_jobs[kSlotRegs];
+  int slot_jo[kSlotRegs];
 #pragma unroll
   for (int q = 0; q < kSlotRegs; ++q) {
-    const int sl = lane + 32 * q;
-    const int jo = sl < NS ? (int)g.slot_job[sl] : -1;
-    p_present[q] = jo >= 0; p_xlo[q] = 0; p_xhi[q] = -1; p_ylo[q] = 0; p_yhi[q] = -1; p_ph[q] = 0; p_pv[q] = 0; p_inv[q] = 0;
-    uint32_t fac = 0;
-    if (jo >= 0) {
-      const jsvm_me_job j = jobs[g.first_job + jo];
-      const Window w = job_window(j, mb_w, mb_h, default_range);
-      fac = j.cost_factor;
-      p_xlo[q] = w.xlo - g.ux0 + xa; p_xhi[q] = w.xhi - g.ux0 + xa;    // relative to the staged window origin
-      p_ylo[q] = w.ylo - g.uy0;      p_yhi[q] = w.yhi - g.uy0;
-      p_ph[q] = j.pred.hor; p_pv[q] = j.pred.ver;
-      // Rows of the union window outside this job's own window are neutralised through the rate table: their "bits" entry
-      // makes (f * bits) >> 16 >= kRowOutCost, more than any valid cost of a partition of at most 128 samples
-      // (SAD <= 32640, rate <= 62 bits * 2^22.5 / 65536 < 6000) and small enough for the 17-bit cost field
-      // (65280 + 40001 + 6000 < 2^17) and for f * bits + f * bits_x to stay below 2^32.  Not for the 16x16 partition
-      // (its valid costs reach 71000), not for f == 0 and not for factors beyond the SAD range (f > 7e6: QP 51 gives 5.5e6; an
-      // SSE-style factor could make the rate itself wrap, N5): those slots keep the exact row-by-row pass.
-      if (sl != 0 && fac != 0 && fac <= 7000000u) p_inv[q] = (kRowOutCost * 65536u + fac - 1u) / fac;
-    }
-    if (ptid < 32 && sl < NS) {
-      sm.job[sl] = jo < 0 ? -1 : g.first_job + jo;
-      sm.best[sl] = kKeyInvalid;
-      sm.factor[sl] = fac;
-      sm.xlo[sl] = (int16_t)p_xlo[q]; sm.xhi[sl] = (int16_t)p_xhi[q];
-      sm.ylo[sl] = (int16_t)p_ylo[q]; sm.yhi[sl] = (int16_t)p_yhi[q];
-    }
+    const int sl = ptid + 32 * q;
+    slot_jo[q] = (ptid < 32 && sl < NS) ? (int)g.slot_job[sl] : -1;
+    if (slot_jo[q] >= 0) slot_jobs[q] = jobs[g.first_job + slot_jo[q]];
   }
   if (ptid == 0) {
     sm.next_unit = first_unit;
@@ -319,59 +300,82 @@ __device__ __forceinline__ void k2_build_stage(const Group& g, const K2Geo<V>& g
     sm.cur[r][k] = v;
   }
 
-  // ---- 4: MV-rate tables and validity masks (no runtime divisions: slot loops outside, strided loops inside) ----
-#pragma unroll 1
-  for (int sl = 0; sl < (K2_ABLATE == 3 ? 0 : NS); ++sl) {
-    const int q = sl >> 5, src = sl & 31;
-    int present = 0, pv = 0, ph = 0, ylo = 0, yhi = -1;
-    uint32_t inv = 0;
+  // ---- 1b: per-slot job parameters (first warp) ----
+  if (ptid < 32) {
 #pragma unroll
-    for (int qq = 0; qq < kSlotRegs; ++qq) {
-      const int a = __shfl_sync(0xffffffffu, p_present[qq], src), b = __shfl_sync(0xffffffffu, p_pv[qq], src), c2 = __shfl_sync(0xffffffffu, p_ph[qq], src);
-      const int d = __shfl_sync(0xffffffffu, (p_ylo[qq] & 0xffff) | (p_yhi[qq] << 16), src);
-      const uint32_t e = __shfl_sync(0xffffffffu, p_inv[qq], src);
-      if (qq == q) { present = a; pv = b; ph = c2; ylo = (int)(int16_t)(d & 0xffff); yhi = d >> 16; inv = e; }
-    }
-    // xGetBits with m_uiMvScaleShift = 2: table index (y << 2) - pred (N6); rows outside the job's window: see p_inv
-    for (int y = ptid; y < by_stride; y += pthreads) {
-      uint32_t b = 0u;
-      if (present) b = (y >= ylo && y <= yhi) ? mv_component_bits(((g.uy0 + y) << 2) - pv) : inv;
-      by_tab[sl * by_stride + y] = b;
-    }
-    for (int ci = ptid; ci < 4 * kMaxM; ci += pthreads) {
-      const int sft = ci / kMaxM, m = ci - sft * kMaxM;         // division by a compile-time constant
-      const int x = 4 * m + sft;                                // staged column
-      sm.bx[sl][ci] = (present && x < uwx) ? (uint8_t)mv_component_bits(((g.ux0 - xa + x) << 2) - ph) : (uint8_t)0;
+    for (int q = 0; q < kSlotRegs; ++q) {
+      const int sl = ptid + 32 * q;
+      if (sl < NS) {
+        const int jo = slot_jo[q];
+        int xlo = 0, xhi = -1, ylo = 0, yhi = -1, ph = 0, pv = 0;
+        uint32_t fac = 0, inv = 0;
+        if (jo >= 0) {
+          const jsvm_me_job& j = slot_jobs[q];
+          const Window w = job_window(j, mb_w, mb_h, default_range);
+          fac = j.cost_factor;
+          xlo = w.xlo - g.ux0 + xa; xhi = w.xhi - g.ux0 + xa;         // relative to the staged window origin
+          ylo = w.ylo - g.uy0;      yhi = w.yhi - g.uy0;
+          ph = j.pred.hor; pv = j.pred.ver;
+          // Rows of the union window outside this job's own window are neutralised through the rate table: their "bits" entry
+          // makes (f * bits) >> 16 >= kRowOutCost, more than any valid cost of a partition of at most 128 samples
+          // (SAD <= 32640, rate <= 62 bits * 2^22.5 / 65536 < 6000) and small enough for the 17-bit cost field
+          // (65280 + 40001 + 6000 < 2^17) and for f * bits + f * bits_x to stay below 2^32.  Not for the 16x16 partition
+          // (its valid costs reach 71000), not for f == 0 and not for factors beyond the SAD range (f > 7e6: QP 51 gives 5.5e6; an
+          // SSE-style factor could make the rate itself wrap, N5): those slots keep the exact row-by-row pass.
+          if (sl != 0 && fac != 0 && fac <= 7000000u) inv = (kRowOutCost * 65536u + fac - 1u) / fac;
+        }
+        sm.job[sl] = jo < 0 ? -1 : g.first_job + jo;
+        sm.best[sl] = kKeyInvalid;
+        sm.factor[sl] = fac;
+        sm.xlo[sl] = (int16_t)xlo; sm.xhi[sl] = (int16_t)xhi;
+        sm.ylo[sl] = (int16_t)ylo; sm.yhi[sl] = (int16_t)yhi;
+        sm.ph[sl] = (int16_t)ph;   sm.pv[sl] = (int16_t)pv;
+        sm.inv[sl] = inv;
+      }
     }
   }
-  // column / strip validity masks: a thread evaluates its entries against all slots
-  for (int e0 = 0; e0 < 4 * kMaxM; e0 += pthreads) {              // warp-uniform trip count: the shuffles below need whole warps
-    const int ci = e0 + ptid, sft = ci / kMaxM, m = ci - sft * kMaxM, x = 4 * m + sft;
+
+  asm volatile("bar.sync 1, %0;" :: "n"(kThreads) : "memory");    // the per-slot parameters of step 1b are visible
+
+  // ---- 4: MV-rate tables: one (slot, row) or (slot, column) entry per thread and pass, parameters from the record ----
+  if (K2_ABLATE != 3) {
+    // bits of the vertical difference, xGetBits with m_uiMvScaleShift = 2: table index (y << 2) - pred (N6);
+    // rows outside the job's window: see step 1
+    const uint32_t inv_bs = (uint32_t)((0x100000000ull + by_stride - 1) / by_stride);      // exact division of i < 2^16
+    for (int i = ptid; i < NS * by_stride; i += pthreads) {
+      const int sl = (int)__umulhi((uint32_t)i, inv_bs), y = i - sl * by_stride;
+      uint32_t b = 0u;
+      if (sm.job[sl] >= 0) b = (y >= sm.ylo[sl] && y <= sm.yhi[sl]) ? mv_component_bits(((g.uy0 + y) << 2) - sm.pv[sl]) : sm.inv[sl];
+      by_tab[i] = b;
+    }
+    // bits of the horizontal difference, permuted [s][m]
+    for (int i = ptid; i < NS * 4 * kMaxM; i += pthreads) {
+      const int sl = i / (4 * kMaxM), ci = i - sl * (4 * kMaxM);   // divisions by compile-time constants
+      const int sft = ci / kMaxM, m = ci - sft * kMaxM;
+      const int x = 4 * m + sft;                                  // staged column
+      sm.bx[sl][ci] = (sm.job[sl] >= 0 && x < uwx) ? (uint8_t)mv_component_bits(((g.ux0 - xa + x) << 2) - sm.ph[sl]) : (uint8_t)0;
+    }
+  }
+  // ---- 5: column / strip validity masks: a thread evaluates its entries against all slots ----
+  for (int ci = ptid; ci < 4 * kMaxM; ci += pthreads) {
+    const int sft = ci / kMaxM, m = ci - sft * kMaxM, x = 4 * m + sft;
     const int y0 = ci * V, y1 = y0 + V - 1;                        // entry ci doubles as strip index for the row masks
     Mask mk = 0, full = 0, any = 0;
 #pragma unroll 1
     for (int sl = 0; sl < (K2_ABLATE == 3 ? 0 : NS); ++sl) {
-      const int q = sl >> 5, src = sl & 31;
-      int xlo = 0, xhi = -1, ylo = 0, yhi = -1;
-      uint32_t inv = 0;
-#pragma unroll
-      for (int qq = 0; qq < kSlotRegs; ++qq) {
-        const int a = __shfl_sync(0xffffffffu, p_xlo[qq], src), b = __shfl_sync(0xffffffffu, p_xhi[qq], src);
-        const int c2 = __shfl_sync(0xffffffffu, p_ylo[qq], src), d = __shfl_sync(0xffffffffu, p_yhi[qq], src);
-        const uint32_t e = __shfl_sync(0xffffffffu, p_inv[qq], src);
-        if (qq == q) { xlo = a; xhi = b; ylo = c2; yhi = d; inv = e; }
-      }
+      const int xlo = sm.xlo[sl], xhi = sm.xhi[sl];
       if (x >= xlo && x <= xhi) mk |= (Mask)1 << sl;
-      if (xhi >= xlo) {
+      if (ci < nstrips && xhi >= xlo) {
+        const int ylo = sm.ylo[sl], yhi = sm.yhi[sl];
         const bool some = ylo <= y1 && y0 <= yhi;
         // "full": the straight-line pass may commit all V rows of the strip -- every row is inside the job's window, or
         // the rows outside are neutralised through the rate table
-        if ((ylo <= y0 && y1 <= yhi) || (some && inv != 0)) full |= (Mask)1 << sl;
+        if ((ylo <= y0 && y1 <= yhi) || (some && sm.inv[sl] != 0)) full |= (Mask)1 << sl;
         if (some) any |= (Mask)1 << sl;
       }
     }
     if (K2_ABLATE == 3) { mk = full = any = (Mask)(~(Mask)0) >> (8 * sizeof(Mask) - NS); }
-    if (ci < 4 * kMaxM) sm.xmask[ci] = mk;
+    sm.xmask[ci] = mk;
     if (ci < nstrips) { sm.yfull[ci] = full; sm.yany[ci] = any; }
   }
 }
@@ -650,7 +654,7 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
   const K2Stage<V, GRAN4> st(smem_raw, geo);
 
   // the first batch of every warp is static (u0 = 32 * warp), the counter starts behind them
-  k2_build_stage<V, GRAN4>(g, geo, st, planes, plane_bytes, plane_stride, jobs, org_mbs, mb_w, mb_h, default_range, tid, kK2Threads, kK2Threads);
+  k2_build_stage<V, GRAN4, kK2Threads>(g, geo, st, planes, plane_bytes, plane_stride, jobs, org_mbs, mb_w, mb_h, default_range, tid, kK2Threads);
   __syncthreads();            // window copies and tables visible
 
   uint32_t best[SM::NBEST];
@@ -672,8 +676,15 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
 #ifndef K2P_PRODUCERS
 #define K2P_PRODUCERS 3
 #endif
-constexpr int kK2PConsumers = K2P_CONSUMERS, kK2PProducers = K2P_PRODUCERS;
-constexpr int kK2PThreads = 32 * (kK2PConsumers + kK2PProducers);
+// (8x8-granular groups: 13 + 3; 4x4-granular groups stage 41 rate tables per group and search a smaller window: K2P_PRODUCERS_G4)
+#ifndef K2P_PRODUCERS_G4
+#define K2P_PRODUCERS_G4 5
+#endif
+constexpr int kK2PThreads = 32 * (K2P_CONSUMERS + K2P_PRODUCERS);       // 16 warps: 512 threads x 128 registers
+template <bool GRAN4> struct K2PSplit {
+  static constexpr int kProducers = GRAN4 ? K2P_PRODUCERS_G4 : K2P_PRODUCERS;
+  static constexpr int kConsumers = kK2PThreads / 32 - kProducers;
+};
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
@@ -690,6 +701,7 @@ full_search_persistent_kernel(const uint8_t* __restrict__ planes, size_t plane_b
                               int stage_bytes)
 {
   using SM = K2Smem<V, GRAN4>;
+  constexpr int kK2PConsumers = K2PSplit<GRAN4>::kConsumers, kK2PProducers = K2PSplit<GRAN4>::kProducers;
     extern __shared__ __align__(128) uint8_t smem_raw[];
   // [0, 64): mbarriers full[2], done[2]; stages follow at 128
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
@@ -728,7 +740,7 @@ full_search_persistent_kernel(const uint8_t* __restrict__ planes, size_t plane_b
         const Group& g = groups[blockIdx.x + (size_t)k * gridDim.x];
         const K2Geo<V> geo((kMargin + 16 * g.mb_x + g.ux0) & 3, g.uw, g.uh);
         const K2Stage<V, GRAN4> st(K2P_STAGE(s), geo);
-        k2_build_stage<V, GRAN4>(g, geo, st, planes, plane_bytes, plane_stride, jobs, org_mbs, mb_w, mb_h, default_range, ptid, pthreads, 0);
+        k2_build_stage<V, GRAN4, pthreads>(g, geo, st, planes, plane_bytes, plane_stride, jobs, org_mbs, mb_w, mb_h, default_range, ptid, 0);
         mbar_arrive(&full[s]);                                // release: this thread's stage writes are visible to waiters
       }
     }
