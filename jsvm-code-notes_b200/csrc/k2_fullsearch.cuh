@@ -30,24 +30,11 @@
 
 namespace jsvm {
 
-#ifndef K2_FASTPATH
-#define K2_FASTPATH 0
-#endif
 #ifndef K2_THREADS
-#define K2_THREADS 256
+#define K2_THREADS 256              // threads of the one-CTA-per-group kernel
 #endif
-// Warps w and w + 4 of a CTA share an SM sub-partition.  After the prologue barrier all warps would run their
-// SAD pass (ALU pipe) and their rate / argmin pass (FMA pipe) in lockstep, leaving each pipe idle half of the time;
-// the upper half of the CTA therefore starts its first batch K2_STAGGER_NS later (the offset persists).
 #ifndef K2_COPY_UNROLL
-#define K2_COPY_UNROLL 4
-#endif
-#ifndef K2_STAGGER_NS
-#define K2_STAGGER_NS 0
-#endif
-// timing experiments only (results are wrong): 1 = no rate/argmin update, 2 = no SAD pass, 3 = no rate tables / masks
-#ifndef K2_ABLATE
-#define K2_ABLATE 0
+#define K2_COPY_UNROLL 4            // window-copy items a staging thread keeps in flight
 #endif
 constexpr int kK2Threads   = K2_THREADS;
 constexpr int kWinRowBytes = 160;                 // bytes per staged window row (max 145 positions + 15)
@@ -338,7 +325,7 @@ __device__ __forceinline__ void k2_build_stage(const Group& g, const K2Geo<V>& g
   asm volatile("bar.sync 1, %0;" :: "n"(kThreads) : "memory");    // the per-slot parameters of step 1b are visible
 
   // ---- 4: MV-rate tables: one (slot, row) or (slot, column) entry per thread and pass, parameters from the record ----
-  if (K2_ABLATE != 3) {
+  {
     // bits of the vertical difference, xGetBits with m_uiMvScaleShift = 2: table index (y << 2) - pred (N6);
     // rows outside the job's window: see step 1
     const uint32_t inv_bs = (uint32_t)((0x100000000ull + by_stride - 1) / by_stride);      // exact division of i < 2^16
@@ -362,7 +349,7 @@ __device__ __forceinline__ void k2_build_stage(const Group& g, const K2Geo<V>& g
     const int y0 = ci * V, y1 = y0 + V - 1;                        // entry ci doubles as strip index for the row masks
     Mask mk = 0, full = 0, any = 0;
 #pragma unroll 1
-    for (int sl = 0; sl < (K2_ABLATE == 3 ? 0 : NS); ++sl) {
+    for (int sl = 0; sl < NS; ++sl) {
       const int xlo = sm.xlo[sl], xhi = sm.xhi[sl];
       if (x >= xlo && x <= xhi) mk |= (Mask)1 << sl;
       if (ci < nstrips && xhi >= xlo) {
@@ -374,7 +361,6 @@ __device__ __forceinline__ void k2_build_stage(const Group& g, const K2Geo<V>& g
         if (some) any |= (Mask)1 << sl;
       }
     }
-    if (K2_ABLATE == 3) { mk = full = any = (Mask)(~(Mask)0) >> (8 * sizeof(Mask) - NS); }
     sm.xmask[ci] = mk;
     if (ci < nstrips) { sm.yfull[ci] = full; sm.yany[ci] = any; }
   }
@@ -431,12 +417,6 @@ __device__ __forceinline__ void k2_search_units(const K2Geo<V>& geo, const K2Sta
       for (int a = 0; a < NACC; ++a) acc[v][a] = 0;
 
     const uint32_t* rp = winw + s * copy_words + ys * kWinRowWords + m;
-#if K2_ABLATE == 2
-#pragma unroll
-    for (int v = 0; v < V; ++v)
-#pragma unroll
-      for (int a = 0; a < NACC; ++a) acc[v][a] = rp[0] + (uint32_t)(v * NACC + a);
-#else
     {
       uint32_t ref[V][4];
 #pragma unroll
@@ -458,19 +438,7 @@ __device__ __forceinline__ void k2_search_units(const K2Geo<V>& geo, const K2Sta
         }
       }
     }
-#endif
 
-#if K2_ABLATE == 1
-    {
-      uint32_t t = 0;
-#pragma unroll
-      for (int v = 0; v < V; ++v)
-#pragma unroll
-        for (int a = 0; a < NACC; ++a) t += acc[v][a];
-      best[0] = min(best[0], t);
-      continue;
-    }
-#endif
     // ---- per partition: SAD + rate, packed-key min ----
     // Pass 1 is straight-line code over all partition slots (no branches, so the loads of the next slot and the 8 x NS
     // independent rate / key chains overlap): every strip row is evaluated and the result is committed only for slots
