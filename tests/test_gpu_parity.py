@@ -149,6 +149,32 @@ def test_extreme_cost_factors_bit_exact(me, oracle, synth, parts_name):
     assert np.array_equal(gp, wp)
 
 
+def test_extreme_start_vectors_and_per_job_ranges_bit_exact(me, oracle, synth):
+    """Start vectors anywhere in the Short range (clamped to m_cMin / m_cMax per macroblock, N2, then '>> 2' on negatives) and
+    per-call search ranges 1 .. 16 (the bi-prediction iterations pass uiSearchRange != 0): windows collapse to a few
+    positions at the picture border, jobs of one macroblock get very different windows."""
+    cfg = synth.CONFIGS["C1"]
+    W, H = cfg["width"], cfg["height"]
+    ses, _ = _setup(me, oracle, synth, cfg, seed=1280)
+    jobs = synth.make_jobs(W, H, synth.PARTS_41, cur_slot=1, ref_slot=0, qp=28, field="zero", seed=1, bits_in=3)
+    rng = np.random.default_rng(9)
+    n = len(jobs)
+    wild = rng.random(n) < 0.3
+    jobs["start_hor"] = np.where(wild, rng.integers(-32768, 32768, n), rng.integers(-200, 201, n)).astype(np.int16)
+    jobs["start_ver"] = np.where(wild, rng.integers(-32768, 32768, n), rng.integers(-200, 201, n)).astype(np.int16)
+    # predictors stay near the clamped start, as the encoder's do (the reference's bit table only spans the search range)
+    mbw, mbh = W // 16, H // 16
+    min_h, max_h = (-16 * jobs["mb_x"].astype(np.int32) - 24) * 4, (16 * (mbw - jobs["mb_x"].astype(np.int32)) + 8) * 4
+    min_v, max_v = (-16 * jobs["mb_y"].astype(np.int32) - 24) * 4, (16 * (mbh - jobs["mb_y"].astype(np.int32)) + 8) * 4
+    jobs["pred_hor"] = (np.clip(jobs["start_hor"].astype(np.int32), min_h, max_h) + rng.integers(-64, 65, n)).astype(np.int16)
+    jobs["pred_ver"] = (np.clip(jobs["start_ver"].astype(np.int32), min_v, max_v) + rng.integers(-64, 65, n)).astype(np.int16)
+    jobs["search_range"] = rng.choice(np.array([0, 1, 2, 4, 7, 16], np.int16), n)
+    got, gp = me.search(jobs, want_preds=True)
+    want, wp = ses.search(jobs, want_preds=True)
+    assert_results_equal(got, want, jobs)
+    assert np.array_equal(gp, wp)
+
+
 def test_originals_outside_the_supported_range_are_refused(me, pkg):
     """|sample| >= 1024 cannot come from a residual-prediction pass; loud error, no fallback."""
     g = np.load(os.path.join(GOLDEN, "org_override_16bit.npz"))
