@@ -325,7 +325,9 @@ int choose_persistent(jsvm_me_ctx* c, int n_groups, int max_uh, bool* persistent
   const bool fits = k2p_smem_bytes<V, GRAN4>(max_uh) <= kMaxDynSmem;
   // 4x4-granular groups (41 slots): staging 41 rate tables keeps 3 producer warps busier than 13 search warps; measured
   // 19 % slower than one CTA per group on C3, so the persistent kernel is only chosen for them when forced
-  *persistent = n_groups >= 4 * c->sm_count && fits && !GRAN4;
+  // Small windows (search range <= ~40: union windows of at most 96 rows) leave a group too little work to hide the hand-over
+  // between stages: one CTA per group measured 8 % (CIF, SR 32) to 17 % (QCIF, SR 16) faster there.
+  *persistent = n_groups >= 4 * c->sm_count && fits && !GRAN4 && max_uh > 96;
   if (force && !strcmp(force, "group")) *persistent = false;
   if (force && !strcmp(force, "persistent")) {
     if (!fits) return fail("JSVM_ME_K2=persistent: union windows of %d rows do not fit two stages", max_uh);

@@ -240,7 +240,7 @@ def test_large_configs_subset_bit_exact(me, oracle, synth, cfg_name, n_inner, fi
 def test_persistent_and_per_group_kernels_agree(me, oracle, synth, monkeypatch):
     """The same whole-picture job list through full_search_persistent_kernel (one CTA per SM, producer / consumer warps over two
     shared-memory stages) and through full_search_kernel (one CTA per group): identical bytes, and both equal to the checker."""
-    cfg = synth.CONFIGS["C2"]
+    cfg = synth.CONFIGS["C2"]                                              # (SR 32: the default choice here is the per-group kernel)
     W, H = cfg["width"], cfg["height"]
     ses, _ = _setup(me, oracle, synth, cfg, seed=1270)
     jobs = np.concatenate([synth.make_jobs(W, H, cfg["parts"], cur_slot=1, ref_slot=0, qp=32, field=f, seed=3) for f in ("random", "split")])
