@@ -324,33 +324,18 @@ __device__ __forceinline__ void k2_build_stage(const Group& g, const K2Geo<V>& g
 
   asm volatile("bar.sync 1, %0;" :: "n"(kThreads) : "memory");    // the per-slot parameters of step 1b are visible
 
-  // ---- 4: MV-rate tables: one (slot, row) or (slot, column) entry per thread and pass, parameters from the record ----
-  {
-    // bits of the vertical difference, xGetBits with m_uiMvScaleShift = 2: table index (y << 2) - pred (N6);
-    // rows outside the job's window: see step 1
-    const uint32_t inv_bs = (uint32_t)((0x100000000ull + by_stride - 1) / by_stride);      // exact division of i < 2^16
-    for (int i = ptid; i < NS * by_stride; i += pthreads) {
-      const int sl = (int)__umulhi((uint32_t)i, inv_bs), y = i - sl * by_stride;
-      uint32_t b = 0u;
-      if (sm.job[sl] >= 0) b = (y >= sm.ylo[sl] && y <= sm.yhi[sl]) ? mv_component_bits(((g.uy0 + y) << 2) - sm.pv[sl]) : sm.inv[sl];
-      by_tab[i] = b;
-    }
-    // bits of the horizontal difference, permuted [s][m]
-    for (int i = ptid; i < NS * 4 * kMaxM; i += pthreads) {
-      const int sl = i / (4 * kMaxM), ci = i - sl * (4 * kMaxM);   // divisions by compile-time constants
-      const int sft = ci / kMaxM, m = ci - sft * kMaxM;
-      const int x = 4 * m + sft;                                  // staged column
-      sm.bx[sl][ci] = (sm.job[sl] >= 0 && x < uwx) ? (uint8_t)mv_component_bits(((g.ux0 - xa + x) << 2) - sm.ph[sl]) : (uint8_t)0;
-    }
-  }
-  // ---- 5: column / strip validity masks: a thread evaluates its entries against all slots ----
+  // ---- 4: per staged column: bits of the horizontal difference of every slot, and the column / strip validity masks.
+  //      A thread owns a column (no index arithmetic inside the slot loop); the slot parameters come from the record. ----
   for (int ci = ptid; ci < 4 * kMaxM; ci += pthreads) {
-    const int sft = ci / kMaxM, m = ci - sft * kMaxM, x = 4 * m + sft;
-    const int y0 = ci * V, y1 = y0 + V - 1;                        // entry ci doubles as strip index for the row masks
+    const int sft = ci / kMaxM, m = ci - sft * kMaxM, x = 4 * m + sft;     // staged column of entry [s][m]
+    const int dx4 = (g.ux0 - xa + x) << 2;                                  // quarter-pel displacement of the column
+    const int y0 = ci * V, y1 = y0 + V - 1;                                 // entry ci doubles as strip index for the row masks
     Mask mk = 0, full = 0, any = 0;
 #pragma unroll 1
     for (int sl = 0; sl < NS; ++sl) {
       const int xlo = sm.xlo[sl], xhi = sm.xhi[sl];
+      // xGetBits with m_uiMvScaleShift = 2: table index (x << 2) - pred (N6)
+      sm.bx[sl][ci] = (xhi >= xlo && x < uwx) ? (uint8_t)mv_component_bits(dx4 - sm.ph[sl]) : (uint8_t)0;
       if (x >= xlo && x <= xhi) mk |= (Mask)1 << sl;
       if (ci < nstrips && xhi >= xlo) {
         const int ylo = sm.ylo[sl], yhi = sm.yhi[sl];
@@ -363,6 +348,16 @@ __device__ __forceinline__ void k2_build_stage(const Group& g, const K2Geo<V>& g
     }
     sm.xmask[ci] = mk;
     if (ci < nstrips) { sm.yfull[ci] = full; sm.yany[ci] = any; }
+  }
+  // ---- 5: bits of the vertical difference, one (slot, row) entry per thread and pass; rows outside the job's window: step 1b ----
+  {
+    const uint32_t inv_bs = (uint32_t)((0x100000000ull + by_stride - 1) / by_stride);      // exact division of i < 2^16
+    for (int i = ptid; i < NS * by_stride; i += pthreads) {
+      const int sl = (int)__umulhi((uint32_t)i, inv_bs), y = i - sl * by_stride;
+      uint32_t b = 0u;
+      if (sm.job[sl] >= 0) b = (y >= sm.ylo[sl] && y <= sm.yhi[sl]) ? mv_component_bits(((g.uy0 + y) << 2) - sm.pv[sl]) : sm.inv[sl];
+      by_tab[i] = b;
+    }
   }
 }
 
