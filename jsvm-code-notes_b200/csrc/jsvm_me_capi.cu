@@ -116,6 +116,8 @@ struct jsvm_me_ctx {
   // measurement
   uint64_t launches = 0;
   const char* last_k2 = "";
+  // largest dynamic shared-memory size configured on THIS device for {group, persistent} x {8x8, 4x4} (the attribute is per device)
+  size_t smem_configured[4] = {0, 0, 0, 0};
   bool timing = false;
   struct Timed { cudaEvent_t e0, e1; int kind; };
   std::vector<Timed> timed;
@@ -280,7 +282,7 @@ int launch_search(jsvm_me_ctx* c, const Group* d_groups, int first_group, int n_
                   const jsvm_me_job* d_jobs, const int16_t* d_org, uint32_t* d_keys, JobAux* d_aux) {
   if (n_groups <= 0) return JSVM_ME_OK;
   const size_t smem = k2_smem_bytes<V, GRAN4>(max_uh);
-  static size_t configured = 0;
+  size_t& configured = c->smem_configured[GRAN4 ? 1 : 0];
   if (smem > configured) {
     CU_OK(cudaFuncSetAttribute(full_search_kernel<V, GRAN4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
@@ -302,7 +304,7 @@ template <int V, bool GRAN4>
 int launch_search_persistent(jsvm_me_ctx* c, const Group* d_groups, int n_groups, int max_uh,
                              const jsvm_me_job* d_jobs, const int16_t* d_org, uint32_t* d_keys, JobAux* d_aux) {
   const size_t smem = k2p_smem_bytes<V, GRAN4>(max_uh);
-  static size_t configured = 0;
+  size_t& configured = c->smem_configured[GRAN4 ? 3 : 2];
   if (smem > configured) {
     CU_OK(cudaFuncSetAttribute(full_search_persistent_kernel<V, GRAN4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
