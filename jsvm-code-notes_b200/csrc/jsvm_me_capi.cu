@@ -357,9 +357,9 @@ int run_search(jsvm_me_ctx* c, const jsvm_me_job* d_jobs, int job_begin, int job
   if (n <= 0) return JSVM_ME_OK;
   begin_timed(c, 2);
   const int ctas = (n + kK3WarpsPerCta - 1) / kK3WarpsPerCta;
-  subpel_kernel<<<ctas, 32 * kK3WarpsPerCta, 0, c->stream>>>(
+  (c->sub_dfunc == JSVM_DF_HADAMARD ? subpel_kernel<true> : subpel_kernel<false>)<<<ctas, 32 * kK3WarpsPerCta, 0, c->stream>>>(
       c->d_planes, c->plane_bytes, c->plane_stride, c->d_half, c->half_bytes, c->half_stride,
-      d_jobs + job_begin, d_aux + job_begin, n, d_org, d_keys + job_begin, c->sub_dfunc, d_results + job_begin,
+      d_jobs + job_begin, d_aux + job_begin, n, d_org, d_keys + job_begin, d_results + job_begin,
       d_preds ? d_preds + (size_t)job_begin * 256 : nullptr);
   end_timed(c);
   c->launches++;

@@ -27,7 +27,7 @@
 namespace jsvm {
 
 #ifndef K3_MIN_CTAS
-#define K3_MIN_CTAS 5
+#define K3_MIN_CTAS 4
 #endif
 constexpr int kK3WarpsPerCta = 8;
 constexpr int kK3PlaneRows = 18, kK3PlanePitch = 24;       // phase plane: (2*16+3+1)/2 rows, 4-byte aligned pitch
@@ -76,12 +76,13 @@ __device__ __forceinline__ uint32_t fetch4(const uint8_t* planes, int off) {
   return __funnelshift_r(q[0], q[1], 8 * (off & 3));
 }
 
+template <bool HAD>      // sub-pel distortion: Hadamard SATD (SearchFuncSubPel 2) or SAD (0)
 __global__ void __launch_bounds__(32 * kK3WarpsPerCta, K3_MIN_CTAS)
 subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_stride,
               const uint8_t* __restrict__ half_planes, size_t half_bytes, int half_stride,
               const jsvm_me_job* __restrict__ jobs, const JobAux* __restrict__ aux, int n_jobs,
               const int16_t* __restrict__ org_mbs,
-              const uint32_t* __restrict__ keys, int sub_dfunc,
+              const uint32_t* __restrict__ keys,
               jsvm_me_result* __restrict__ results, uint8_t* __restrict__ preds)
 {
   __shared__ __align__(16) K3Warp s_warp[kK3WarpsPerCta];
@@ -200,7 +201,7 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
           const uint32_t pa = fetch4(pl, offa + y * kK3PlanePitch);
           crow[y] = stage == 0 ? pa : __vavgu4(pa, fetch4(pl, offb + y * kK3PlanePitch));   // per byte (p + q + 1) >> 1
         }
-        if (sub_dfunc == JSVM_DF_HADAMARD) {
+        if (HAD) {
           int d[16];
 #pragma unroll
           for (int y = 0; y < 4; ++y)
