@@ -42,7 +42,6 @@ constexpr int kK1Threads = 256;
 constexpr int kK1VCols = 72;                             // phase A columns x0-4 .. x0+67 (taps of x0 .. x0+63 need x0-2 .. x0+66)
 constexpr int kK1VPitch = kK1VCols / 2 + 2;              // 32-bit words (int16 pairs) per row of s_v: 38 (even: 8-byte aligned rows)
 
-__device__ __forceinline__ int dp4a_u8s8(uint32_t a, uint32_t b, int c) { int d; asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 __device__ __forceinline__ int dp2a_lo_s16s8(uint32_t a, uint32_t b, int c) { int d; asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 __device__ __forceinline__ int dp2a_hi_s16s8(uint32_t a, uint32_t b, int c) { int d; asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 

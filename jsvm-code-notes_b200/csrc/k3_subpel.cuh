@@ -36,25 +36,29 @@ __constant__ int8_t c_half_mv[9][2]    = { {0,0}, {0,-2}, {0,2}, {-2,0}, {2,0}, 
 __constant__ int8_t c_quarter_mv[9][2] = { {0,0}, {0,-1}, {0,1}, {-1,-1}, {1,-1}, {-1,0}, {1,0}, {-1,1}, {1,1} };   // g_acQPSearchMv
 __constant__ uint8_t c_filter_of_half[9] = { 0, 2, 2, 1, 1, 3, 3, 3, 3 };                                          // g_aucFilter
 
-// XDistortion::xCalcHadamard4x4 on a 4x4 difference block (per-4x4 halving, N8).
-// The reference ends every row with the butterflies (a + b, a - b) and sums the absolute values; since
-// |a + b| + |a - b| = 2 max(|a|, |b|) the block sum is even, the reference's "/ 2" is exact, and the SATD is the sum of
-// max(|a|, |b|) over the 8 final pairs -- one butterfly stage and the halving disappear.
-__device__ __forceinline__ uint32_t hadamard4x4(const int (&d)[16]) {
-  int m[16];
-#pragma unroll
-  for (int n = 0; n < 4; ++n) {
-    const int t0 = d[0 + n] + d[12 + n], t1 = d[4 + n] + d[8 + n];
-    const int t2 = d[4 + n] - d[8 + n],  t3 = d[0 + n] - d[12 + n];
-    m[0 + n] = t0 + t1; m[8 + n] = t0 - t1; m[4 + n] = t3 + t2; m[12 + n] = t3 - t2;
-  }
+// XDistortion::xCalcHadamard4x4 (ENC/Distortion.cpp:291-340) of (original - prediction) on one 4x4 block, with the per-4x4
+// halving (N8).  The 2-D Hadamard transform is linear and separable in exact integers, so
+//   * the HORIZONTAL 4-point transform of a prediction row is four dot products of its packed bytes with (+-1) patterns
+//     (IDP.4A, u8 x s8) -- no unpacking -- and the transformed ORIGINAL row, computed once per job, goes in negated as the
+//     accumulator: e[row][k] = H_k( prediction row ) - H_k( original row );
+//   * the vertical transform of the e columns ends with the butterflies (a + b, a - b) whose absolute values are summed;
+//     |a + b| + |a - b| = 2 max(|a|, |b|), so the block sum is even, the reference's "/ 2" is exact, and the SATD is the
+//     sum of max(|a|, |b|) over the 8 final pairs: the last butterfly stage and the halving disappear.
+// (The reference transforms vertically first; the 16 coefficients are the same set.)
+// horizontal transform of one original row, negated: -( o0+o1+o2+o3, o0+o1-o2-o3, o0-o1-o2+o3, o0-o1+o2-o3 )
+__device__ __forceinline__ void neg_hrow(int o0, int o1, int o2, int o3, int (&out)[4]) {
+  const int s01 = o0 + o1, s23 = o2 + o3, d01 = o0 - o1, d23 = o2 - o3;
+  out[0] = -(s01 + s23); out[1] = -(s01 - s23); out[2] = -(d01 - d23); out[3] = -(d01 + d23);
+}
+__device__ __forceinline__ uint32_t satd4x4(const uint32_t (&crow)[4], const int (&nho)[16]) {
+  constexpr uint32_t kPat[4] = { 0x01010101u, 0xffff0101u, 0x01ffff01u, 0xff01ff01u };   // bytes (x0, x1, x2, x3) of the four patterns
   uint32_t sum = 0;
 #pragma unroll
-  for (int n = 0; n < 4; ++n) {
-    int a = m[4 * n] + m[4 * n + 3], b = m[4 * n + 1] + m[4 * n + 2];
-    sum += (uint32_t)max(abs(a), abs(b));
-    a = m[4 * n + 1] - m[4 * n + 2]; b = m[4 * n] - m[4 * n + 3];
-    sum += (uint32_t)max(abs(a), abs(b));
+  for (int k = 0; k < 4; ++k) {
+    const int e0 = dp4a_u8s8(crow[0], kPat[k], nho[0 + k]), e1 = dp4a_u8s8(crow[1], kPat[k], nho[4 + k]);
+    const int e2 = dp4a_u8s8(crow[2], kPat[k], nho[8 + k]), e3 = dp4a_u8s8(crow[3], kPat[k], nho[12 + k]);
+    const int t0 = e0 + e3, t1 = e1 + e2, t2 = e1 - e2, t3 = e0 - e3;
+    sum += (uint32_t)max(abs(t0), abs(t1)) + (uint32_t)max(abs(t3), abs(t2));
   }
   return sum;
 }
@@ -110,29 +114,35 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
   // each lane always works on the same 4x4 sub-block (32 % nb == 0): keep its original rows in registers
   const int blk_b = lane & (nb - 1);
   const int px0 = (blk_b & (nbx - 1)) * 4, py0 = (blk_b >> lg_nbx) * 4;
-  // The lane's 4x4 of the original: packed bytes for the SAD, plain ints for the Hadamard.  Originals supplied by the
+  // The lane's 4x4 of the original: packed bytes for the SAD, its (negated) row transforms for the Hadamard.  Originals supplied by the
   // caller (org_mbs) may be signed 16-bit (residual-prediction passes, N3): every prediction sample p lies in [0,255], so
   // |o - p| = |clip(o) - p| + |o - clip(o)|; the SAD runs on the clipped bytes and `excess` (a per-4x4 constant) is added.
   uint32_t orow[4];
-  int o16[16];
+  int nho[16];                                               // Hadamard variant: negated horizontal transform of the original rows
   uint32_t excess = 0;
   if (j.org_index >= 0) {
     const int16_t* op = org_mbs + (size_t)j.org_index * 256 + (4 * (j.blk >> 2) + py0) * 16 + 4 * (j.blk & 3) + px0;
 #pragma unroll
     for (int y = 0; y < 4; ++y) {
       const short4 s4 = __ldg(reinterpret_cast<const short4*>(op + y * 16));
-      o16[4 * y] = s4.x; o16[4 * y + 1] = s4.y; o16[4 * y + 2] = s4.z; o16[4 * y + 3] = s4.w;
+      const int o[4] = { s4.x, s4.y, s4.z, s4.w };
       orow[y] = pack_clip8(s4);
 #pragma unroll
-      for (int x = 0; x < 4; ++x) excess += (uint32_t)abs(o16[4 * y + x] - (int)((orow[y] >> (8 * x)) & 0xff));
+      for (int x = 0; x < 4; ++x) excess += (uint32_t)abs(o[x] - (int)((orow[y] >> (8 * x)) & 0xff));
+      int h[4];
+      neg_hrow(o[0], o[1], o[2], o[3], h);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) nho[4 * y + k] = h[k];
     }
   } else {
     const uint8_t* cp = planes + (size_t)j.cur_slot * plane_bytes + (size_t)(kMargin + by0 + py0) * plane_stride + kMargin + bx0 + px0;
 #pragma unroll
     for (int y = 0; y < 4; ++y) {
       orow[y] = __ldg(reinterpret_cast<const uint32_t*>(cp + (size_t)y * plane_stride));
+      int h[4];
+      neg_hrow((int)(orow[y] & 0xff), (int)((orow[y] >> 8) & 0xff), (int)((orow[y] >> 16) & 0xff), (int)(orow[y] >> 24), h);
 #pragma unroll
-      for (int x = 0; x < 4; ++x) o16[4 * y + x] = (int)((orow[y] >> (8 * x)) & 0xff);
+      for (int k = 0; k < 4; ++k) nho[4 * y + k] = h[k];
     }
   }
   uint32_t excess_block = excess;                            // the whole partition's constant (full-pel SAD)
@@ -202,12 +212,7 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
           crow[y] = stage == 0 ? pa : __vavgu4(pa, fetch4(pl, offb + y * kK3PlanePitch));   // per byte (p + q + 1) >> 1
         }
         if (HAD) {
-          int d[16];
-#pragma unroll
-          for (int y = 0; y < 4; ++y)
-#pragma unroll
-            for (int x = 0; x < 4; ++x) d[y * 4 + x] = o16[y * 4 + x] - (int)__byte_perm(crow[y], 0, 0x4440 + x);   // byte x, zero-extended
-          dist = hadamard4x4(d);
+          dist = satd4x4(crow, nho);
         } else {
 #pragma unroll
           for (int y = 0; y < 4; ++y) dist = __vsadu4(orow[y], crow[y]) + dist;

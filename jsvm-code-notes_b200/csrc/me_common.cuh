@@ -120,6 +120,12 @@ __host__ __device__ inline int partition_slot(int mode, int blk) {
 }
 
 #if defined(__CUDACC__)
+// c + dot product of four unsigned bytes (a) with four signed bytes (b): IDP.4A.U8.S8
+__device__ __forceinline__ int dp4a_u8s8(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
 // four int16 samples -> four bytes, each clipped to [0,255] (gClip, INCC/GlobalFunctions.h:37-44)
 __device__ __forceinline__ uint32_t pack_clip8(const short4 v) {
   const int a = min(max((int)v.x, 0), 255), b = min(max((int)v.y, 0), 255), c = min(max((int)v.z, 0), 255), d = min(max((int)v.w, 0), 255);
