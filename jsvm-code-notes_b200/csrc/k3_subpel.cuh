@@ -159,15 +159,26 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
     const int nrows = 2 * h + 3;
     const int rr = lane >> 2, q = lane & 3;
     const uint8_t* src = half_planes + (size_t)j.ref_slot * half_bytes + (size_t)(kHpOrigin + Y0) * half_stride + kHpOrigin + X0 + 4 * q;
-    for (int r = rr; r < nrows; r += 8) {
-      const uint8_t* rp = src + (size_t)r * half_stride;
-      uint8_t* d0 = &sw.plane[(r & 1) * 2][r >> 1][2 * q];     // even X of this row; odd X one plane further
+    // all loads first (up to 5 rows x 3 words per lane in flight), then the de-interleaving stores
+    uint32_t v[5][3];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        if (q + 4 * k < nwords) {
-          const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(rp + 16 * k));
-          *reinterpret_cast<uint16_t*>(d0 + 8 * k) = (uint16_t)__byte_perm(v, 0, 0x4420);                                        // bytes 0, 2
-          *reinterpret_cast<uint16_t*>(d0 + 8 * k + kK3PlaneRows * kK3PlanePitch) = (uint16_t)__byte_perm(v, 0, 0x4431);       // bytes 1, 3
+    for (int it = 0; it < 5; ++it) {
+      const int r = rr + 8 * it;
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        v[it][k] = (r < nrows && q + 4 * k < nwords) ? __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)r * half_stride + 16 * k)) : 0u;
+    }
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+      const int r = rr + 8 * it;
+      if (r < nrows) {
+        uint8_t* d0 = &sw.plane[(r & 1) * 2][r >> 1][2 * q];     // even X of this row; odd X one plane further
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          if (q + 4 * k < nwords) {
+            *reinterpret_cast<uint16_t*>(d0 + 8 * k) = (uint16_t)__byte_perm(v[it][k], 0, 0x4420);                                        // bytes 0, 2
+            *reinterpret_cast<uint16_t*>(d0 + 8 * k + kK3PlaneRows * kK3PlanePitch) = (uint16_t)__byte_perm(v[it][k], 0, 0x4431);       // bytes 1, 3
+          }
         }
       }
     }
