@@ -106,8 +106,11 @@ const char* jsvm_me_last_error(void);
 int jsvm_me_configure(jsvm_me_ctx* ctx, int width, int height, int n_slots);
 
 /* MotionEstimation::init reading MotionVectorSearchParams (ENC/MotionEstimation.cpp:38-66,
- * include/CodingParameter.h:41-89).  Only SearchMode 0 (BLOCK_SEARCH), full-pel DF_SAD and
- * sub-pel DF_SAD / DF_HADAMARD are on the hot path; anything else returns JSVM_ME_ERR. */
+ * include/CodingParameter.h:41-89).  SearchMode 0 (BLOCK_SEARCH) only.  Distortion functions: SAD (0) and HADAMARD (2) in any
+ * combination for the full-pel and the sub-pel stage, or SSD (1) for both (a job carries ONE cost factor: SAD and HADAMARD
+ * use the SAD factor, SSD the SSE factor, ENC/MotionEstimation.cpp:255, 325).  Full-pel SAD is the measured hot path
+ * (packed-byte kernels); full-pel HADAMARD / SSD run a plain one-CTA-per-job kernel.  YUV_SAD (3) and every other
+ * combination return JSVM_ME_ERR. */
 int jsvm_me_set_params(jsvm_me_ctx* ctx, int search_mode, int full_pel_dfunc, int sub_pel_dfunc, int search_range);
 
 /* Run every later call on this CUDA stream (a cudaStream_t / CUstream handle; NULL = default). */

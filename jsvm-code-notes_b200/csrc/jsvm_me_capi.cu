@@ -24,6 +24,7 @@
 #include "me_common.cuh"
 #include "k1_halfpel.cuh"
 #include "k2_fullsearch.cuh"
+#include "k2_generic.cuh"
 #include "k3_subpel.cuh"
 
 using namespace jsvm;
@@ -83,12 +84,13 @@ struct jsvm_me_ctx {
   CUtensorMap map_k1{};
   EncodeTiledFn encode = nullptr;
   // params
-  int search_range = 0, sub_dfunc = JSVM_DF_SAD;
+  int search_range = 0, sub_dfunc = JSVM_DF_SAD, full_dfunc = JSVM_DF_SAD;
   bool params_set = false;
   // per-call device buffers (host-buffer API)
   DevBuf<jsvm_me_job> d_jobs;
   DevBuf<Group> d_groups;
   DevBuf<uint32_t> d_keys;
+  DevBuf<uint32_t> d_full_costs;         // generic (SSD / Hadamard) full-pel search only
   DevBuf<JobAux> d_aux;
   DevBuf<jsvm_me_result> d_results;
   DevBuf<uint8_t> d_preds;
@@ -344,7 +346,22 @@ int run_search(jsvm_me_ctx* c, const jsvm_me_job* d_jobs, int job_begin, int job
                const int16_t* d_org, uint32_t* d_keys, JobAux* d_aux, jsvm_me_result* d_results, uint8_t* d_preds) {
   if (!c->params_set) return fail("jsvm_me_set_params has not been called");
   if (info->max_uh_8x8 > kMaxUH || info->max_uh_4x4 > kMaxUH) return fail("plan: union window taller than %d", kMaxUH);
-  const int n8 = info->n_groups_8x8, n4 = info->n_groups - info->n_groups_8x8;
+  const int n = job_end - job_begin;
+  if (n <= 0) return JSVM_ME_OK;
+  const bool generic = c->full_dfunc != JSVM_DF_SAD;         // SSD / Hadamard full-pel search: one CTA per job, no grouping
+  if (generic) {
+    if (c->d_full_costs.cap < (size_t)job_end) return fail("internal: full-pel cost buffer not reserved");
+    begin_timed(c, 1);
+    (c->full_dfunc == JSVM_DF_SSD ? full_search_generic_kernel<JSVM_DF_SSD> : full_search_generic_kernel<JSVM_DF_HADAMARD>)
+        <<<n, kK2GThreads, 0, c->stream>>>(c->d_planes, c->plane_bytes, c->plane_stride, d_jobs + job_begin, n, d_org,
+                                           c->W >> 4, c->H >> 4, c->search_range, d_keys + job_begin,
+                                           c->d_full_costs.p + job_begin, d_aux + job_begin);
+    end_timed(c);
+    c->launches++;
+    c->last_k2 = c->full_dfunc == JSVM_DF_SSD ? "full_search_generic_kernel<SSD>" : "full_search_generic_kernel<HADAMARD>";
+    CU_OK(cudaGetLastError());
+  }
+  const int n8 = generic ? 0 : info->n_groups_8x8, n4 = generic ? 0 : info->n_groups - info->n_groups_8x8;
   bool p8 = false, p4 = false;
   if (choose_persistent<kV8, false>(c, n8, info->max_uh_8x8, &p8) || choose_persistent<kV4, true>(c, n4, info->max_uh_4x4, &p4)) return JSVM_ME_ERR;
   if (n8 > 0) c->last_k2 = p8 ? "full_search_persistent_kernel<8,false>" : "full_search_kernel<8,false>";
@@ -353,13 +370,14 @@ int run_search(jsvm_me_ctx* c, const jsvm_me_job* d_jobs, int job_begin, int job
                     : launch_search<kV8, false>(c, d_groups, 0, n8, info->max_uh_8x8, d_jobs, d_org, d_keys, d_aux))) return JSVM_ME_ERR;
   if (n4 > 0 && (p4 ? launch_search_persistent<kV4, true>(c, d_groups + n8, n4, info->max_uh_4x4, d_jobs, d_org, d_keys, d_aux)
                     : launch_search<kV4, true>(c, d_groups, n8, n4, info->max_uh_4x4, d_jobs, d_org, d_keys, d_aux))) return JSVM_ME_ERR;
-  const int n = job_end - job_begin;
-  if (n <= 0) return JSVM_ME_OK;
   begin_timed(c, 2);
   const int ctas = (n + kK3WarpsPerCta - 1) / kK3WarpsPerCta;
-  (c->sub_dfunc == JSVM_DF_HADAMARD ? subpel_kernel<true> : subpel_kernel<false>)<<<ctas, 32 * kK3WarpsPerCta, 0, c->stream>>>(
+  auto k3 = c->sub_dfunc == JSVM_DF_HADAMARD ? subpel_kernel<JSVM_DF_HADAMARD>
+          : c->sub_dfunc == JSVM_DF_SSD ? subpel_kernel<JSVM_DF_SSD> : subpel_kernel<JSVM_DF_SAD>;
+  k3<<<ctas, 32 * kK3WarpsPerCta, 0, c->stream>>>(
       c->d_planes, c->plane_bytes, c->plane_stride, c->d_half, c->half_bytes, c->half_stride,
-      d_jobs + job_begin, d_aux + job_begin, n, d_org, d_keys + job_begin, d_results + job_begin,
+      d_jobs + job_begin, d_aux + job_begin, n, d_org, d_keys + job_begin,
+      generic ? c->d_full_costs.p + job_begin : nullptr, d_results + job_begin,
       d_preds ? d_preds + (size_t)job_begin * 256 : nullptr);
   end_timed(c);
   c->launches++;
@@ -390,7 +408,7 @@ int search_small(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const int1
     }
   memcpy(a->job, jobs, sizeof(jsvm_me_job) * n_jobs);
   if (n_org_mbs > 0) memcpy(a->org, org_mbs, sizeof(int16_t) * 256 * n_org_mbs);
-  if (c->d_keys.reserve(64) || c->d_aux.reserve(64)) return JSVM_ME_ERR;
+  if (c->d_keys.reserve(64) || c->d_full_costs.reserve(64) || c->d_aux.reserve(64)) return JSVM_ME_ERR;
   if (run_search(c, a->job, 0, n_jobs, a->group, &info, a->org, c->d_keys.p, c->d_aux.p, a->result, a->pred)) return JSVM_ME_ERR;
   CU_OK(cudaStreamSynchronize(c->stream));
   memcpy(results, a->result, sizeof(jsvm_me_result) * n_jobs);
@@ -439,7 +457,7 @@ int jsvm_me_destroy(jsvm_me_ctx* c) {
   if (c->d_half) cudaFree(c->d_half);
   if (c->d_slot_ids) cudaFree(c->d_slot_ids);
   if (c->d_bad) cudaFree(c->d_bad);
-  c->d_jobs.release(); c->d_groups.release(); c->d_keys.release(); c->d_aux.release();
+  c->d_jobs.release(); c->d_groups.release(); c->d_keys.release(); c->d_full_costs.release(); c->d_aux.release();
   c->d_results.release(); c->d_preds.release(); c->d_org.release(); c->d_stage.release();
   for (auto& t : c->timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
   for (auto& e : c->chunk_done) if (e) cudaEventDestroy(e);
@@ -479,10 +497,15 @@ int jsvm_me_configure(jsvm_me_ctx* c, int width, int height, int n_slots) {
 int jsvm_me_set_params(jsvm_me_ctx* c, int search_mode, int full_pel_dfunc, int sub_pel_dfunc, int search_range) {
   if (!c) return fail("null context");
   if (search_mode != JSVM_SEARCH_BLOCK) return fail("SearchMode %d: only BLOCK_SEARCH (0, full search) is implemented", search_mode);
-  if (full_pel_dfunc != JSVM_DF_SAD) return fail("SearchFuncFullPel %d: only SAD (0) is implemented", full_pel_dfunc);
-  if (sub_pel_dfunc != JSVM_DF_SAD && sub_pel_dfunc != JSVM_DF_HADAMARD) return fail("SearchFuncSubPel %d: only SAD (0) and HADAMARD (2) are implemented", sub_pel_dfunc);
+  // A job carries ONE cost factor, so both stages must use the same one (ENC/MotionEstimation.cpp:255, 325): SAD and HADAMARD
+  // take the SAD factor, SSD takes the SSE factor.  YUV_SAD (3) needs the chroma planes and is not implemented.
+  const bool full_sadlike = full_pel_dfunc == JSVM_DF_SAD || full_pel_dfunc == JSVM_DF_HADAMARD;
+  const bool sub_sadlike = sub_pel_dfunc == JSVM_DF_SAD || sub_pel_dfunc == JSVM_DF_HADAMARD;
+  if (!((full_sadlike && sub_sadlike) || (full_pel_dfunc == JSVM_DF_SSD && sub_pel_dfunc == JSVM_DF_SSD)))
+    return fail("SearchFuncFullPel %d / SearchFuncSubPel %d: implemented are SAD (0) and HADAMARD (2) in any combination, and SSD (1) "
+                "for both stages (one cost factor per job); YUV_SAD (3) is not implemented", full_pel_dfunc, sub_pel_dfunc);
   if (search_range < 1 || search_range > 64) return fail("SearchRange %d outside [1,64]", search_range);
-  c->search_range = search_range; c->sub_dfunc = sub_pel_dfunc; c->params_set = true;
+  c->search_range = search_range; c->sub_dfunc = sub_pel_dfunc; c->full_dfunc = full_pel_dfunc; c->params_set = true;
   return JSVM_ME_OK;
 }
 
@@ -623,7 +646,7 @@ int jsvm_me_search_device(jsvm_me_ctx* c, const jsvm_me_job* d_jobs, int n_jobs,
   if (!c || !d_jobs || !d_groups || !info || !d_results) return fail("null argument");
   if (n_jobs <= 0) return JSVM_ME_OK;
   CU_OK(cudaSetDevice(c->device));
-  if (c->d_keys.reserve(n_jobs) || c->d_aux.reserve(n_jobs)) return JSVM_ME_ERR;
+  if (c->d_keys.reserve(n_jobs) || c->d_full_costs.reserve(n_jobs) || c->d_aux.reserve(n_jobs)) return JSVM_ME_ERR;
   return run_search(c, d_jobs, 0, n_jobs, (const Group*)d_groups, info, d_org_mbs, c->d_keys.p, c->d_aux.p, d_results, d_preds);
 }
 
@@ -643,7 +666,7 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
   c->last_small = false;
   CU_OK(cudaSetDevice(c->device));
   const bool want_preds = preds != nullptr || n_jobs <= 4096;
-  if (c->d_jobs.reserve(n_jobs) || c->d_keys.reserve(n_jobs) || c->d_aux.reserve(n_jobs) ||
+  if (c->d_jobs.reserve(n_jobs) || c->d_keys.reserve(n_jobs) || c->d_full_costs.reserve(n_jobs) || c->d_aux.reserve(n_jobs) ||
       c->d_results.reserve(n_jobs) || (want_preds && c->d_preds.reserve((size_t)n_jobs * 256)) ||
       (n_org_mbs > 0 && c->d_org.reserve((size_t)n_org_mbs * 256))) return JSVM_ME_ERR;
   if (n_org_mbs > 0) CU_OK(cudaMemcpyAsync(c->d_org.p, org_mbs, sizeof(int16_t) * 256 * n_org_mbs, cudaMemcpyHostToDevice, c->stream));

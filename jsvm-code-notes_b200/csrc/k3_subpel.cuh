@@ -80,15 +80,18 @@ __device__ __forceinline__ uint32_t fetch4(const uint8_t* planes, int off) {
   return __funnelshift_r(q[0], q[1], 8 * (off & 3));
 }
 
-template <bool HAD>      // sub-pel distortion: Hadamard SATD (SearchFuncSubPel 2) or SAD (0)
+template <int DFUNC>     // sub-pel distortion: JSVM_DF_SAD (SearchFuncSubPel 0), JSVM_DF_SSD (1) or JSVM_DF_HADAMARD (2)
 __global__ void __launch_bounds__(32 * kK3WarpsPerCta, K3_MIN_CTAS)
 subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_stride,
               const uint8_t* __restrict__ half_planes, size_t half_bytes, int half_stride,
               const jsvm_me_job* __restrict__ jobs, const JobAux* __restrict__ aux, int n_jobs,
               const int16_t* __restrict__ org_mbs,
               const uint32_t* __restrict__ keys,
+              const uint32_t* __restrict__ full_costs,   // NULL: keys hold (cost << 15 | index) of the packed-byte SAD search;
+                                                         // else (generic SSD / Hadamard search): keys = index, full_costs = cost
               jsvm_me_result* __restrict__ results, uint8_t* __restrict__ preds)
 {
+  constexpr bool HAD = DFUNC == JSVM_DF_HADAMARD, SSD = DFUNC == JSVM_DF_SSD;
   __shared__ __align__(16) K3Warp s_warp[kK3WarpsPerCta];
   const int job_idx = blockIdx.x * kK3WarpsPerCta + (threadIdx.x >> 5);
   if (job_idx >= n_jobs) return;
@@ -104,9 +107,9 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
 
   // ---- decode the full-pel winner (xPelBlockSearch result) ----
   const uint32_t key = keys[job_idx];
-  const uint32_t idx = key & ((1u << kIdxBits) - 1);
+  const uint32_t idx = full_costs ? key : key & ((1u << kIdxBits) - 1);
   const int fx = a.ux0 + (int)(idx % (uint32_t)a.uw), fy = a.uy0 + (int)(idx / (uint32_t)a.uw);
-  const uint32_t full_cost = key >> kIdxBits;
+  const uint32_t full_cost = full_costs ? full_costs[job_idx] : key >> kIdxBits;
   const uint32_t full_rate = rate_cost(f, mv_component_bits((fx << 2) - j.pred.hor) + mv_component_bits((fy << 2) - j.pred.ver));
 
   const int bx0 = 16 * j.mb_x + 4 * (j.blk & 3), by0 = 16 * j.mb_y + 4 * (j.blk >> 2);
@@ -119,6 +122,7 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
   // |o - p| = |clip(o) - p| + |o - clip(o)|; the SAD runs on the clipped bytes and `excess` (a per-4x4 constant) is added.
   uint32_t orow[4];
   int nho[16];                                               // Hadamard variant: negated horizontal transform of the original rows
+  int osq[16];                                               // SSD variant: the original samples themselves
   uint32_t excess = 0;
   if (j.org_index >= 0) {
     const int16_t* op = org_mbs + (size_t)j.org_index * 256 + (4 * (j.blk >> 2) + py0) * 16 + 4 * (j.blk & 3) + px0;
@@ -132,17 +136,18 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
       int h[4];
       neg_hrow(o[0], o[1], o[2], o[3], h);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) nho[4 * y + k] = h[k];
+      for (int k = 0; k < 4; ++k) { nho[4 * y + k] = h[k]; osq[4 * y + k] = o[k]; }
     }
   } else {
     const uint8_t* cp = planes + (size_t)j.cur_slot * plane_bytes + (size_t)(kMargin + by0 + py0) * plane_stride + kMargin + bx0 + px0;
 #pragma unroll
     for (int y = 0; y < 4; ++y) {
       orow[y] = __ldg(reinterpret_cast<const uint32_t*>(cp + (size_t)y * plane_stride));
+      const int o[4] = { (int)(orow[y] & 0xff), (int)((orow[y] >> 8) & 0xff), (int)((orow[y] >> 16) & 0xff), (int)(orow[y] >> 24) };
       int h[4];
-      neg_hrow((int)(orow[y] & 0xff), (int)((orow[y] >> 8) & 0xff), (int)((orow[y] >> 16) & 0xff), (int)(orow[y] >> 24), h);
+      neg_hrow(o[0], o[1], o[2], o[3], h);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) nho[4 * y + k] = h[k];
+      for (int k = 0; k < 4; ++k) { nho[4 * y + k] = h[k]; osq[4 * y + k] = o[k]; }
     }
   }
   uint32_t excess_block = excess;                            // the whole partition's constant (full-pel SAD)
@@ -187,14 +192,14 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
 
   const uint8_t* pl = &sw.plane[0][0][0];
   int mvh = fx << 2, mvv = fy << 2;                           // cMv <<= 2
-  uint32_t best = 0xffffffffu;
+  unsigned long long best = ~0ull;                            // (cost << 8) | n, as the stage keys below
   uint32_t best_mode = 0;
   int cx = 0, cy = 0;                                         // half-pel winner, in half-pel units from the full-pel position
   bool axis_diag = false;
 
   for (int stage = 0; stage < 2; ++stage) {
     const int n0 = stage, ncand = 9 - stage;
-    uint32_t stage_best = 0xffffffffu;
+    unsigned long long stage_best = ~0ull;
     // the MV-rate term of the stage's candidates, once: lane i holds the one of candidate n0 + i
     uint32_t my_rate = 0;
     if (lane < ncand) {
@@ -224,6 +229,14 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
         }
         if (HAD) {
           dist = satd4x4(crow, nho);
+        } else if (SSD) {                                     // xGetSSE*: sum of squared differences on the true original
+#pragma unroll
+          for (int y = 0; y < 4; ++y)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+              const int d = osq[4 * y + x] - (int)__byte_perm(crow[y], 0, 0x4440 + x);
+              dist += (uint32_t)(d * d);
+            }
         } else {
 #pragma unroll
           for (int y = 0; y < 4; ++y) dist = __vsadu4(orow[y], crow[y]) + dist;
@@ -237,14 +250,24 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
         if (off < nb) dist += o;
       }
       const uint32_t rate = __shfl_sync(0xffffffffu, my_rate, n - n0);
-      uint32_t k = 0xffffffffu;                           // (cost << 8) | n : cost < 2^17 in the 8-bit domain (N12), < 2^23 for
-                                                          // originals in [-1024, 1023] (enforced by jsvm_me_search)
-      if (active && blk_b == 0) k = ((dist + rate) << 8) | (uint32_t)n;
-      k = __reduce_min_sync(0xffffffffu, k);
+      // warp minimum of (cost << 8) | n: lowest cost, then lowest candidate number.  SAD / Hadamard costs stay below 2^23
+      // (2^17 in the 8-bit domain, N12; originals in [-1024, 1023] are enforced by jsvm_me_search): one 32-bit REDUX.
+      // Squared differences reach 2^28: minimum cost first, then the lowest n among the lanes that hold it.
+      const bool valid = active && blk_b == 0;
+      const uint32_t c = dist + rate;
+      unsigned long long k;
+      if (!SSD) {
+        const uint32_t k32 = __reduce_min_sync(0xffffffffu, valid ? ((c << 8) | (uint32_t)n) : 0xffffffffu);
+        k = k32 == 0xffffffffu ? ~0ull : (unsigned long long)k32;
+      } else {
+        const uint32_t cmin = __reduce_min_sync(0xffffffffu, valid ? c : 0xffffffffu);
+        const uint32_t nmin = __reduce_min_sync(0xffffffffu, (valid && c == cmin) ? (uint32_t)n : 0xffu);
+        k = cmin == 0xffffffffu ? ~0ull : (((unsigned long long)cmin << 8) | nmin);
+      }
       stage_best = k < stage_best ? k : stage_best;
     }
     if (stage == 0) {
-      best = stage_best & ~0xffu;                         // incumbent for the quarter-pel stage (n field 0 wins ties)
+      best = stage_best & ~0xffull;                       // incumbent for the quarter-pel stage (n field 0 wins ties)
       best_mode = (uint32_t)(stage_best & 0xff);
       mvh += c_half_mv[best_mode][0]; mvv += c_half_mv[best_mode][1];
       cx = c_half_mv[best_mode][0] / 2; cy = c_half_mv[best_mode][1] / 2;   // ENC/MotionEstimationQuarterPel.cpp:137-139
@@ -258,14 +281,14 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
     }
   }
 
-  const uint32_t min_sad = best >> 8;
+  const uint32_t min_sad = (uint32_t)(best >> 8);
   if (lane == 0) {
     // ENC/MotionEstimation.cpp:331-337 with fWeight = 1.0
     const uint32_t mv_bits = mv_component_bits(mvh - j.pred.hor) + mv_component_bits(mvv - j.pred.ver);
     jsvm_me_result r;
     r.mv.hor = (int16_t)mvh; r.mv.ver = (int16_t)mvv;
     r.mv_fullpel.hor = (int16_t)fx; r.mv_fullpel.ver = (int16_t)fy;
-    r.sad_fullpel = full_cost - full_rate + excess_block;
+    r.sad_fullpel = full_cost - full_rate + (full_costs ? 0u : excess_block);    // the generic search works on the true original
     r.min_sad = min_sad;
     r.mv_bits = mv_bits;
     r.bits = j.bits_in + mv_bits;

@@ -47,14 +47,14 @@ struct LayerStore {
 
 struct B200State {
   std::map<std::pair<int, int>, LayerStore*> layers;
-  int search_range, sub_dfunc;
+  int search_range, sub_dfunc, full_dfunc;
   bool params_valid;
   int device;
   // the buffers compensateBlock serves from (the reference keeps m_aXHPelSearch / m_aXQPelSearch)
   unsigned char last_pred[256];
   bool last_valid;
   unsigned long long n_calls, n_calls_16bit, n_calls_bipred, n_frames;
-  B200State() : search_range(0), sub_dfunc(0), params_valid(false), device(0), last_valid(false), n_calls(0), n_calls_16bit(0),
+  B200State() : search_range(0), sub_dfunc(0), full_dfunc(0), params_valid(false), device(0), last_valid(false), n_calls(0), n_calls_16bit(0),
                 n_calls_bipred(0), n_frames(0) {
     const char* d = getenv("JSVM_ME_DEVICE");
     if (d) device = atoi(d);
@@ -175,16 +175,19 @@ ErrVal MotionEstimation::init( XDistortion*      pcXDistortion,
   B200State& st = state();
   st.params_valid = false;
   // only what the device path implements; anything else is an error, not a silent CPU search
-  if( m_cParams.getSearchMode() != BLOCK_SEARCH || m_cParams.getFullPelDFunc() != DF_SAD ||
-      ( m_cParams.getSubPelDFunc() != DF_SAD && m_cParams.getSubPelDFunc() != DF_HADAMARD ) ||
+  const UInt uiFull = m_cParams.getFullPelDFunc(), uiSub = m_cParams.getSubPelDFunc();
+  const Bool bSadClass = ( uiFull == DF_SAD || uiFull == DF_HADAMARD ) && ( uiSub == DF_SAD || uiSub == DF_HADAMARD );
+  const Bool bSseClass = ( uiFull == DF_SSD && uiSub == DF_SSD );      // one cost factor per job: no mixing of the two classes
+  if( m_cParams.getSearchMode() != BLOCK_SEARCH || !( bSadClass || bSseClass ) ||
       m_cParams.getSearchRange() < 1 || m_cParams.getSearchRange() > 64 || m_cParams.getFastBiSearch() )
   {
-    fprintf( stderr, "jsvm_me_b200: unsupported MotionVectorSearchParams (need SearchMode 0, SearchFuncFullPel 0, "
-                     "SearchFuncSubPel 0|2, SearchRange 1..64, FastBiSearch 0)\n" );
+    fprintf( stderr, "jsvm_me_b200: unsupported MotionVectorSearchParams (need SearchMode 0, SearchFuncFullPel / SearchFuncSubPel "
+                     "both in {0, 2} or both 1, SearchRange 1..64, FastBiSearch 0)\n" );
     return Err::m_nERR;
   }
   st.search_range = (int)m_cParams.getSearchRange();
-  st.sub_dfunc    = (int)m_cParams.getSubPelDFunc();
+  st.sub_dfunc    = (int)uiSub;
+  st.full_dfunc   = (int)uiFull;
   st.params_valid = true;
   return Err::m_nOK;
 }
@@ -288,7 +291,7 @@ MotionEstimation::estimateBlockWithStart( const MbDataAccess&          rcMbDataA
   }
   if( st.n_calls == 0 || st.search_range != 0 )
   {
-    if( jsvm_me_set_params( ls->ctx, JSVM_SEARCH_BLOCK, JSVM_DF_SAD, st.sub_dfunc, st.search_range ) != JSVM_ME_OK )
+    if( jsvm_me_set_params( ls->ctx, JSVM_SEARCH_BLOCK, st.full_dfunc, st.sub_dfunc, st.search_range ) != JSVM_ME_OK )
       return reportFailure( "jsvm_me_set_params" );
   }
   st.n_calls++;
@@ -297,7 +300,8 @@ MotionEstimation::estimateBlockWithStart( const MbDataAccess&          rcMbDataA
   const Int iMbX = ( -( m_cMin.getHor() >> 2 ) - 24 ) >> 4;
   const Int iMbY = ( -( m_cMin.getVer() >> 2 ) - 24 ) >> 4;
 
-  xSetMEPars( 0, true );                                   // SAD factor for SAD and HADAMARD (N7); used below for the final cost
+  xSetMEPars( 0, st.sub_dfunc != JSVM_DF_SSD );            // SAD factor for SAD and HADAMARD (N7), SSE factor for SSD (both stages then);
+                                                           // also used below for the final cost
   jsvm_me_job cJob;
   cJob.cur_slot     = (int16_t)it->second;                 // unused: the original comes from org_mbs
   cJob.ref_slot     = (int16_t)it->second;

@@ -59,6 +59,25 @@ def main():
         np.savez_compressed(os.path.join(HERE, nm + ".npz"), width=W, height=H, search_range=sr, sub_dfunc=2,
                             frame0=f0, frame1=f1, jobs=jobs, results=res, preds=preds, org_mbs=org)
         print(nm, len(jobs), "jobs")
+    # full-pel Hadamard / SSD searches (generic full-search kernel), 8-bit and signed 16-bit originals
+    W, H, sr = 64, 48, 8
+    seq = synth.Sequence(W, H, 33)
+    f0, f1 = seq.frame(0), seq.frame(1)
+    org16b = np.random.default_rng(33).integers(-255, 511, (12, 16, 16)).astype(np.int16)
+    for nm, full, sub, parts, org in (("fullpel_had_had", 2, 2, "PARTS_9", None), ("fullpel_had_sad_all41", 2, 0, "PARTS_41", None),
+                                      ("fullpel_ssd_ssd", 1, 1, "PARTS_9", None), ("fullpel_ssd_ssd_16bit", 1, 1, "PARTS_9", org16b),
+                                      ("fullpel_had_had_16bit", 2, 2, "PARTS_9", org16b)):
+        ses = oracle_lib.CpuSession(ref, W, H, 2, sr, sub, full)
+        ses.set_plane(0, f0); ses.set_plane(1, f1)
+        jobs = synth.make_jobs(W, H, getattr(synth, parts), 1, 0, qp=29, field="random", seed=6, bits_in=1)
+        extra = {}
+        if org is not None:
+            jobs["org_index"] = np.repeat(np.arange(12), len(getattr(synth, parts)))
+            extra["org_mbs"] = org
+        res, preds = ses.search(jobs, org_mbs=org, want_preds=True)
+        np.savez_compressed(os.path.join(HERE, nm + ".npz"), width=W, height=H, search_range=sr, sub_dfunc=sub, full_dfunc=full,
+                            frame0=f0, frame1=f1, jobs=jobs, results=res, preds=preds, **extra)
+        print(nm, len(jobs), "jobs")
     # distortion function table (XDistortion SAD / SSD / HADAMARD for all 7 block modes) and cost factors
     orgs = rng.integers(0, 256, (8, 16, 16)).astype(np.int16)
     refs = rng.integers(0, 256, (8, 20, 24)).astype(np.int16)

@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SEARCH_CASES = ["tiny_all41_had", "tiny_9_sad", "qcif_9_had", "qcif_9_zero_sr32", "org_override_8bit", "org_override_16bit"]
+SEARCH_CASES = ["tiny_all41_had", "tiny_9_sad", "qcif_9_had", "qcif_9_zero_sr32", "org_override_8bit", "org_override_16bit",
+                "fullpel_had_had", "fullpel_had_sad_all41", "fullpel_ssd_ssd", "fullpel_ssd_ssd_16bit", "fullpel_had_had_16bit"]
 
 
 def load(name):
@@ -15,14 +16,14 @@ def load(name):
 
 
 def test_fixtures_present():
-    assert len(glob.glob(os.path.join(HERE, "golden", "*.npz"))) >= 7
+    assert len(glob.glob(os.path.join(HERE, "golden", "*.npz"))) >= 12
 
 
 @pytest.mark.parametrize("name", SEARCH_CASES)
 def test_oracle_search_matches_reference_golden(oracle, name):
     g = load(name)
     W, H = int(g["width"]), int(g["height"])
-    ses = oracle.session(W, H, 2, int(g["search_range"]), int(g["sub_dfunc"]))
+    ses = oracle.session(W, H, 2, int(g["search_range"]), int(g["sub_dfunc"]), int(g["full_dfunc"]) if "full_dfunc" in g.files else 0)
     ses.set_plane(0, g["frame0"])
     ses.set_plane(1, g["frame1"])
     org = g["org_mbs"] if "org_mbs" in g.files else None

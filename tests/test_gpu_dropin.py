@@ -20,7 +20,10 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
     # C5 in small: spatial + quality (CGS) layers, 2 reference frames, inter-layer motion prediction
     ["--width", "352", "--height", "288", "--layers", "2", "--quality-layers", "1", "--refs", "2", "--frames", "5", "--gop", "4",
      "--sr", "16", "--subpel", "2"],
-], ids=["C1-qcif-hierB-satd", "all41-2refs-sad", "C2-two-spatial-layers", "C5-spatial+quality-2refs"])
+    # the other distortion functions of XDistortion: Hadamard for both stages, SSD for both stages (SSE cost factor)
+    ["--frames", "5", "--gop", "4", "--sr", "8", "--subpel", "2", "--fullpel", "2"],
+    ["--frames", "5", "--gop", "4", "--sr", "8", "--subpel", "1", "--fullpel", "1"],
+], ids=["C1-qcif-hierB-satd", "all41-2refs-sad", "C2-two-spatial-layers", "C5-spatial+quality-2refs", "fullpel-hadamard", "ssd-ssd"])
 def test_encoder_with_dropin_is_bit_identical(args):
     import system_parity
     if not (os.path.exists(system_parity.STOCK) and os.path.exists(system_parity.B200)):

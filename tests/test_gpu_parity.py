@@ -86,12 +86,13 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 @pytest.mark.parametrize("name", ["tiny_all41_had", "tiny_9_sad", "qcif_9_had", "qcif_9_zero_sr32", "org_override_8bit",
-                                  "org_override_16bit"])
+                                  "org_override_16bit", "fullpel_had_had", "fullpel_had_sad_all41", "fullpel_ssd_ssd",
+                                  "fullpel_ssd_ssd_16bit", "fullpel_had_had_16bit"])
 def test_cuda_matches_reference_golden(me, name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     W, H = int(g["width"]), int(g["height"])
     me.configure(W, H, 2)
-    me.set_params(int(g["search_range"]), int(g["sub_dfunc"]))
+    me.set_params(int(g["search_range"]), int(g["sub_dfunc"]), int(g["full_dfunc"]) if "full_dfunc" in g.files else 0)
     me.upload_plane(0, g["frame0"]); me.upload_plane(1, g["frame1"])
     me.interp_halfpel([0, 1])
     org = g["org_mbs"] if "org_mbs" in g.files else None
@@ -147,6 +148,45 @@ def test_extreme_cost_factors_bit_exact(me, oracle, synth, parts_name):
     want, wp = ses.search(jobs, want_preds=True)
     assert_results_equal(got, want, jobs)
     assert np.array_equal(gp, wp)
+
+
+@pytest.mark.parametrize("full_dfunc,sub_dfunc", [(2, 2), (2, 0), (1, 1)])
+def test_fullpel_hadamard_and_ssd_search_bit_exact(me, oracle, synth, full_dfunc, sub_dfunc):
+    """SearchFuncFullPel 2 (Hadamard) and 1 (SSD) through the generic full-search kernel, all 41 partitions, picture corners and
+    edges, SR 16, plane-sourced and signed 16-bit originals, against the checker (pinned against the reference for these
+    modes by the fullpel_* golden vectors)."""
+    cfg = synth.CONFIGS["C1"]
+    W, H = cfg["width"], cfg["height"]
+    seq = synth.Sequence(W, H, 1290)
+    frames = [seq.frame(0), seq.frame(1)]
+    me.configure(W, H, 2)
+    me.set_params(cfg["search_range"], sub_dfunc, full_dfunc)
+    ses = oracle.session(W, H, 2, cfg["search_range"], sub_dfunc, full_dfunc)
+    for s, f in enumerate(frames):
+        me.upload_plane(s, f); ses.set_plane(s, f)
+    me.interp_halfpel([0, 1])
+    mbs = [(0, 0), (0, 10), (8, 0), (8, 10), (4, 5), (3, 7)]
+    jobs = synth.make_jobs(W, H, synth.PARTS_41, cur_slot=1, ref_slot=0, qp=30, field="split", seed=17, mb_subset=mbs, bits_in=2)
+    got, gp = me.search(jobs, want_preds=True)
+    want, wp = ses.search(jobs, want_preds=True)
+    assert_results_equal(got, want, jobs)
+    assert np.array_equal(gp, wp)
+    assert me.last_search_kernel().startswith("full_search_generic_kernel")
+    org = np.random.default_rng(4).integers(-255, 511, (len(mbs), 16, 16)).astype(np.int16)
+    jobs["org_index"] = np.repeat(np.arange(len(mbs)), len(synth.PARTS_41))
+    got, gp = me.search(jobs, org_mbs=org, want_preds=True)
+    want, wp = ses.search(jobs, org_mbs=org, want_preds=True)
+    assert_results_equal(got, want, jobs)
+    assert np.array_equal(gp, wp)
+
+
+def test_unsupported_distortion_combinations_are_refused(me, pkg):
+    """One cost factor per job: SAD-class (SAD, Hadamard) and SSE-class (SSD) functions cannot be mixed between the stages;
+    YUV_SAD needs chroma planes.  Loud errors, no fallback."""
+    for full, sub in [(0, 1), (1, 0), (1, 2), (2, 1), (3, 0), (0, 3), (3, 3)]:
+        with pytest.raises(pkg.MotionEstimationError):
+            me.set_params(16, sub, full)
+    me.set_params(16, 2, 0)
 
 
 def test_extreme_start_vectors_and_per_job_ranges_bit_exact(me, oracle, synth):

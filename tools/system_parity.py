@@ -36,7 +36,7 @@ NumberReferenceFrames {refs}
 BaseLayerMode 2
 ConstrainedIntraUps 1
 SearchMode 0
-SearchFuncFullPel 0
+SearchFuncFullPel {fullpel}
 SearchFuncSubPel {subpel}
 SearchRange {sr}
 ELSearchRange 0
@@ -156,7 +156,7 @@ def run(exe, workdir, tag, a):
                                                 lt8=0 if a.all_partitions else 1, ilpred=0 if i == 0 else a.ilpred,
                                                 profile=100 if i == 0 else 86))
         lines += f"LayerCfg {layer}\n"
-    open(main_cfg, "w").write(MAIN_CFG.format(out=out, frames=a.frames, gop=a.gop, refs=a.refs, sr=a.sr, subpel=a.subpel,
+    open(main_cfg, "w").write(MAIN_CFG.format(out=out, frames=a.frames, gop=a.gop, refs=a.refs, sr=a.sr, subpel=a.subpel, fullpel=a.fullpel,
                                               nlayers=len(plan), layercfgs=lines))
     t0 = time.perf_counter()
     p = subprocess.run([exe, "-pf", main_cfg], cwd=workdir, capture_output=True, text=True, timeout=a.timeout,
@@ -182,6 +182,7 @@ def compare(argv=None):
     ap.add_argument("--refs", type=int, default=1)
     ap.add_argument("--sr", type=int, default=16)
     ap.add_argument("--subpel", type=int, default=2)
+    ap.add_argument("--fullpel", type=int, default=0, help="SearchFuncFullPel: 0 SAD, 1 SSD, 2 HADAMARD")
     ap.add_argument("--qp", type=float, default=32.0)
     ap.add_argument("--all-partitions", action="store_true")
     ap.add_argument("--seed", type=int, default=1235)
