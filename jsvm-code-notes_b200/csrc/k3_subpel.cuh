@@ -22,6 +22,7 @@
 //     n, and the quarter-pel stage can only strictly beat the half-pel winner (N1).
 #pragma once
 
+#include <type_traits>
 #include "me_common.cuh"
 
 namespace jsvm {
@@ -133,10 +134,16 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
       orow[y] = pack_clip8(s4);
 #pragma unroll
       for (int x = 0; x < 4; ++x) excess += (uint32_t)abs(o[x] - (int)((orow[y] >> (8 * x)) & 0xff));
-      int h[4];
-      neg_hrow(o[0], o[1], o[2], o[3], h);
+      if (HAD) {
+        int h[4];
+        neg_hrow(o[0], o[1], o[2], o[3], h);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { nho[4 * y + k] = h[k]; osq[4 * y + k] = o[k]; }
+        for (int k = 0; k < 4; ++k) nho[4 * y + k] = h[k];
+      }
+      if (SSD) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) osq[4 * y + k] = o[k];
+      }
     }
   } else {
     const uint8_t* cp = planes + (size_t)j.cur_slot * plane_bytes + (size_t)(kMargin + by0 + py0) * plane_stride + kMargin + bx0 + px0;
@@ -144,10 +151,16 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
     for (int y = 0; y < 4; ++y) {
       orow[y] = __ldg(reinterpret_cast<const uint32_t*>(cp + (size_t)y * plane_stride));
       const int o[4] = { (int)(orow[y] & 0xff), (int)((orow[y] >> 8) & 0xff), (int)((orow[y] >> 16) & 0xff), (int)(orow[y] >> 24) };
-      int h[4];
-      neg_hrow(o[0], o[1], o[2], o[3], h);
+      if (HAD) {
+        int h[4];
+        neg_hrow(o[0], o[1], o[2], o[3], h);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { nho[4 * y + k] = h[k]; osq[4 * y + k] = o[k]; }
+        for (int k = 0; k < 4; ++k) nho[4 * y + k] = h[k];
+      }
+      if (SSD) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) osq[4 * y + k] = o[k];
+      }
     }
   }
   uint32_t excess_block = excess;                            // the whole partition's constant (full-pel SAD)
@@ -192,14 +205,17 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
 
   const uint8_t* pl = &sw.plane[0][0][0];
   int mvh = fx << 2, mvv = fy << 2;                           // cMv <<= 2
-  unsigned long long best = ~0ull;                            // (cost << 8) | n, as the stage keys below
+  // stage keys (cost << 8) | n: 32 bits for SAD / Hadamard costs (< 2^23), 64 bits for squared differences (up to 2^28)
+  typedef typename std::conditional<SSD, unsigned long long, uint32_t>::type Key;
+  constexpr Key kNoKey = ~(Key)0;
+  Key best = kNoKey;
   uint32_t best_mode = 0;
   int cx = 0, cy = 0;                                         // half-pel winner, in half-pel units from the full-pel position
   bool axis_diag = false;
 
   for (int stage = 0; stage < 2; ++stage) {
     const int n0 = stage, ncand = 9 - stage;
-    unsigned long long stage_best = ~0ull;
+    Key stage_best = kNoKey;
     // the MV-rate term of the stage's candidates, once: lane i holds the one of candidate n0 + i
     uint32_t my_rate = 0;
     if (lane < ncand) {
@@ -255,19 +271,18 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
       // Squared differences reach 2^28: minimum cost first, then the lowest n among the lanes that hold it.
       const bool valid = active && blk_b == 0;
       const uint32_t c = dist + rate;
-      unsigned long long k;
+      Key k;
       if (!SSD) {
-        const uint32_t k32 = __reduce_min_sync(0xffffffffu, valid ? ((c << 8) | (uint32_t)n) : 0xffffffffu);
-        k = k32 == 0xffffffffu ? ~0ull : (unsigned long long)k32;
+        k = (Key)__reduce_min_sync(0xffffffffu, valid ? ((c << 8) | (uint32_t)n) : 0xffffffffu);
       } else {
         const uint32_t cmin = __reduce_min_sync(0xffffffffu, valid ? c : 0xffffffffu);
         const uint32_t nmin = __reduce_min_sync(0xffffffffu, (valid && c == cmin) ? (uint32_t)n : 0xffu);
-        k = cmin == 0xffffffffu ? ~0ull : (((unsigned long long)cmin << 8) | nmin);
+        k = cmin == 0xffffffffu ? kNoKey : (Key)(((unsigned long long)cmin << 8) | nmin);
       }
       stage_best = k < stage_best ? k : stage_best;
     }
     if (stage == 0) {
-      best = stage_best & ~0xffull;                       // incumbent for the quarter-pel stage (n field 0 wins ties)
+      best = stage_best & ~(Key)0xff;                     // incumbent for the quarter-pel stage (n field 0 wins ties)
       best_mode = (uint32_t)(stage_best & 0xff);
       mvh += c_half_mv[best_mode][0]; mvv += c_half_mv[best_mode][1];
       cx = c_half_mv[best_mode][0] / 2; cy = c_half_mv[best_mode][1] / 2;   // ENC/MotionEstimationQuarterPel.cpp:137-139
