@@ -45,8 +45,11 @@ extern "C" {
 #define JSVM_DF_YUV_SAD  3
 #define JSVM_SEARCH_BLOCK 0   /* SearchMode BLOCK_SEARCH = full search (xPelBlockSearch) */
 
-/* Luma plane geometry, INCC/CommonDefs.h:246-247 + COM/YuvBufferCtrl.cpp:134-157:
- * stride = width + 2*32, 32 filled margin samples on every side. */
+/* Luma plane geometry, INCC/CommonDefs.h:246-247 + COM/YuvBufferCtrl.cpp:134-157: stride = width + 2*YUV_X_MARGIN (32).
+ * The reference ALLOCATES YUV_Y_MARGIN = 64 rows above and below the picture (m_uiLumBaseOffset = stride*64 + 32) but, for
+ * frame pictures, fills and reads only m_uiYMargin = 64/2 = 32 of them (YuvPicBuffer::fillMargin, filterFrame uses getLXMargin for
+ * both axes).  The device plane therefore keeps 32 margin samples on every side; jsvm_me_upload_plane_xpel addresses the source
+ * relative to `origin` with the caller's stride, so a real YuvPicBuffer (64 allocated rows) is read correctly: rows -32..H+31. */
 #define JSVM_ME_MARGIN 32
 
 typedef struct jsvm_me_ctx jsvm_me_ctx;

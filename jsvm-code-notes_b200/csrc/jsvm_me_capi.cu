@@ -46,6 +46,7 @@ int fail(const char* fmt, ...) {
 constexpr int kV8 = 8;        // strip height of the 8x8-granular search kernel
 constexpr int kV4 = 4;        // strip height of the 4x4-granular search kernel
 constexpr int kMaxUH = 176;   // tallest union window one CTA handles (by-table rows, shared memory)
+constexpr int kMaxSearchRange = 64;   // windows of at most 129 x 129 positions per job (k2_generic.cuh stages 129 + 15 columns)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -118,14 +119,28 @@ struct jsvm_me_ctx {
   // measurement
   uint64_t launches = 0;
   const char* last_k2 = "";
-  // largest dynamic shared-memory size configured on THIS device for {group, persistent} x {8x8, 4x4} (the attribute is per device)
-  size_t smem_configured[4] = {0, 0, 0, 0};
   bool timing = false;
   struct Timed { cudaEvent_t e0, e1; int kind; };
   std::vector<Timed> timed;
 };
 
 namespace {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to (function, device), not to a context: several contexts on one device (the
+// drop-in keeps one per spatial layer) share it, so the configured maximum is process-wide state per device and is only ever raised.
+constexpr int kMaxDevices = 64;
+std::mutex g_smem_mu;
+size_t g_smem_configured[kMaxDevices][4] = {};      // {group, persistent} x {8x8, 4x4}
+template <typename Fn>
+int raise_dyn_smem(int device, int which, Fn* fn, size_t smem) {
+  std::lock_guard<std::mutex> lk(g_smem_mu);
+  size_t& configured = g_smem_configured[device % kMaxDevices][which];
+  if (smem > configured) {
+    CU_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  return JSVM_ME_OK;
+}
 
 int make_map(jsvm_me_ctx* c, CUtensorMap* map, void* base, int box_w, int box_h) {
   const cuuint64_t dims[3]    = { (cuuint64_t)c->plane_stride, (cuuint64_t)c->plane_rows, (cuuint64_t)c->n_slots };
@@ -205,6 +220,8 @@ void plan_range(int width, int height, int n_slots, int search_range, const jsvm
     if (slot < 0) return bad(i, "blk %d is not a legal origin for mode %d", (int)j.blk, (int)j.mode);
     if (j.cur_slot < 0 || j.cur_slot >= n_slots || j.ref_slot < 0 || j.ref_slot >= n_slots) return bad(i, "plane slot out of range");
     if (j.mb_x < 0 || j.mb_x >= mbw || j.mb_y < 0 || j.mb_y >= mbh) return bad(i, "macroblock (%d,%d) outside the picture", j.mb_x, j.mb_y);
+    // the staged windows of every full-search kernel (packed-byte and generic) are sized for search ranges up to kMaxSearchRange
+    if (j.search_range < 0 || j.search_range > kMaxSearchRange) return bad(i, "per-job search range %d outside [0,%d]", (int)j.search_range, kMaxSearchRange);
     const Window w1 = job_window(j, mbw, mbh, search_range);
     const int ww = w1.xhi - w1.xlo + 1, wh = w1.yhi - w1.ylo + 1;
     if (ww < 1 || wh < 1) return bad(i, "empty search window");
@@ -284,11 +301,7 @@ int launch_search(jsvm_me_ctx* c, const Group* d_groups, int first_group, int n_
                   const jsvm_me_job* d_jobs, const int16_t* d_org, uint32_t* d_keys, JobAux* d_aux) {
   if (n_groups <= 0) return JSVM_ME_OK;
   const size_t smem = k2_smem_bytes<V, GRAN4>(max_uh);
-  size_t& configured = c->smem_configured[GRAN4 ? 1 : 0];
-  if (smem > configured) {
-    CU_OK(cudaFuncSetAttribute(full_search_kernel<V, GRAN4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  if (raise_dyn_smem(c->device, GRAN4 ? 1 : 0, full_search_kernel<V, GRAN4>, smem)) return JSVM_ME_ERR;
   begin_timed(c, 1);
   full_search_kernel<V, GRAN4><<<n_groups, kK2Threads, smem, c->stream>>>(
       c->d_planes, c->plane_bytes, c->plane_stride, d_groups + first_group, d_jobs, d_org,
@@ -306,11 +319,7 @@ template <int V, bool GRAN4>
 int launch_search_persistent(jsvm_me_ctx* c, const Group* d_groups, int n_groups, int max_uh,
                              const jsvm_me_job* d_jobs, const int16_t* d_org, uint32_t* d_keys, JobAux* d_aux) {
   const size_t smem = k2p_smem_bytes<V, GRAN4>(max_uh);
-  size_t& configured = c->smem_configured[GRAN4 ? 3 : 2];
-  if (smem > configured) {
-    CU_OK(cudaFuncSetAttribute(full_search_persistent_kernel<V, GRAN4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  if (raise_dyn_smem(c->device, GRAN4 ? 3 : 2, full_search_persistent_kernel<V, GRAN4>, smem)) return JSVM_ME_ERR;
   begin_timed(c, 1);
   full_search_persistent_kernel<V, GRAN4><<<std::min(n_groups, c->sm_count), kK2PThreads, smem, c->stream>>>(
       c->d_planes, c->plane_bytes, c->plane_stride, d_groups, n_groups, d_jobs, d_org,
@@ -504,7 +513,7 @@ int jsvm_me_set_params(jsvm_me_ctx* c, int search_mode, int full_pel_dfunc, int 
   if (!((full_sadlike && sub_sadlike) || (full_pel_dfunc == JSVM_DF_SSD && sub_pel_dfunc == JSVM_DF_SSD)))
     return fail("SearchFuncFullPel %d / SearchFuncSubPel %d: implemented are SAD (0) and HADAMARD (2) in any combination, and SSD (1) "
                 "for both stages (one cost factor per job); YUV_SAD (3) is not implemented", full_pel_dfunc, sub_pel_dfunc);
-  if (search_range < 1 || search_range > 64) return fail("SearchRange %d outside [1,64]", search_range);
+  if (search_range < 1 || search_range > kMaxSearchRange) return fail("SearchRange %d outside [1,%d]", search_range, kMaxSearchRange);
   c->search_range = search_range; c->sub_dfunc = sub_pel_dfunc; c->full_dfunc = full_pel_dfunc; c->params_set = true;
   return JSVM_ME_OK;
 }
@@ -633,7 +642,7 @@ int jsvm_me_plan_host(int width, int height, int n_slots, int search_range, cons
                       void* groups_out, jsvm_me_plan_info* info) {
   if (!jobs || !groups_out || !info) return fail("null argument");
   if (width <= 0 || height <= 0 || (width & 15) || (height & 15)) return fail("picture size %dx%d must be a positive multiple of 16", width, height);
-  if (search_range < 1 || search_range > 64) return fail("SearchRange %d outside [1,64]", search_range);
+  if (search_range < 1 || search_range > kMaxSearchRange) return fail("SearchRange %d outside [1,%d]", search_range, kMaxSearchRange);
   std::vector<Group> g;
   if (plan_jobs(width, height, n_slots, search_range, jobs, n_jobs, g, info)) return JSVM_ME_ERR;
   memcpy(groups_out, g.data(), g.size() * sizeof(Group));
@@ -656,6 +665,7 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
   if (!c->d_planes) return fail("jsvm_me_configure has not been called");
   if (!c->params_set) return fail("jsvm_me_set_params has not been called");
   if (n_jobs <= 0) return JSVM_ME_OK;
+  c->last_jobs.clear(); c->last_has_preds = false;     // a failed call leaves no prediction to fetch (compensateBlock contract)
   if (n_org_mbs > 0) {
     if (!org_mbs) return fail("org_mbs is null");
     for (size_t i = 0; i < (size_t)n_org_mbs * 256; ++i)
@@ -665,6 +675,17 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
   if (n_jobs <= 64 && n_org_mbs <= 64) return search_small(c, jobs, n_jobs, org_mbs, n_org_mbs, results, preds);
   c->last_small = false;
   CU_OK(cudaSetDevice(c->device));
+  // every error exit below: nothing may still be copying into the caller's buffers, and no prediction of an earlier call may be served
+  struct ExitGuard {
+    jsvm_me_ctx* c; bool ok = false;
+    ~ExitGuard() {
+      if (ok) return;
+      cudaStreamSynchronize(c->stream);
+      if (c->up_stream) cudaStreamSynchronize(c->up_stream);
+      if (c->down_stream) cudaStreamSynchronize(c->down_stream);
+      c->last_jobs.clear(); c->last_has_preds = false;
+    }
+  } guard{c};
   const bool want_preds = preds != nullptr || n_jobs <= 4096;
   if (c->d_jobs.reserve(n_jobs) || c->d_keys.reserve(n_jobs) || c->d_full_costs.reserve(n_jobs) || c->d_aux.reserve(n_jobs) ||
       c->d_results.reserve(n_jobs) || (want_preds && c->d_preds.reserve((size_t)n_jobs * 256)) ||
@@ -775,6 +796,7 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
   CU_OK(cudaStreamSynchronize(c->down_stream));
   if (want_preds && n_jobs <= 4096) c->last_jobs.assign(jobs, jobs + n_jobs); else c->last_jobs.clear();
   c->last_has_preds = want_preds && n_jobs <= 4096;
+  guard.ok = true;
   return JSVM_ME_OK;
 }
 

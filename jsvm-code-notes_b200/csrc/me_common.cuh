@@ -1,8 +1,9 @@
 // me_common.cuh -- shared definitions of the B200 motion-estimation kernels.
 //
 // Plane geometry mirrors the reference (R = /root/reference/JSVM/H264Extension):
-//   full-pel luma plane : (H+64) x (W+64) bytes, picture origin at (32,32)
-//                         (INCC/CommonDefs.h:246-247, COM/YuvBufferCtrl.cpp:134-157)
+//   full-pel luma plane : (H+64) x (W+64) bytes, picture origin at (32,32): the 32 margin rows / columns the reference fills and
+//                         reads (INCC/CommonDefs.h:246-247 YUV_X_MARGIN 32; YUV_Y_MARGIN 64 is the ALLOCATED vertical margin, of
+//                         which frame pictures use m_uiYMargin = 64/2, COM/YuvBufferCtrl.cpp:134-157)
 //   half-pel luma plane : 2(H+64) x 2(W+64) bytes, picture origin at (64,64)
 //                         (YuvBufferCtrl with uiResolution = 1, ENC/ControlMngH264AVCEncoder.cpp:56-57)
 // Samples are stored as bytes on the device: reference planes hold reconstructed pictures

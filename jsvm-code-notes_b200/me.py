@@ -96,13 +96,16 @@ class MotionEstimator:
     def set_plane_device(self, slot, dev_ptr, stride=None):
         self._check(self._lib.jsvm_me_set_plane_device_u8(self._ctx, slot, C.c_void_p(int(dev_ptr)), self.width, self.height, stride or self.width))
 
-    def upload_plane_xpel(self, slot, plane_with_margin):
-        """plane_with_margin: (H+64, W+64) int16 ndarray laid out like a YuvPicBuffer luma plane."""
+    def upload_plane_xpel(self, slot, plane_with_margin, v_margin=None):
+        """plane_with_margin: (H + 2*v_margin, W + 64) int16 ndarray laid out like a YuvPicBuffer luma plane.  v_margin is the
+        number of rows above the picture: 64 for a real YuvPicBuffer dump (YUV_Y_MARGIN rows are allocated), 32 for the rows the
+        reference actually fills; inferred from the shape when omitted.  Only the inner 32 rows are read."""
         p = np.ascontiguousarray(plane_with_margin, dtype=np.int16)
         s = self.width + 2 * abi.MARGIN
-        if p.shape != (self.height + 2 * abi.MARGIN, s):
-            raise MotionEstimationError(f"plane shape {p.shape}")
-        origin = p.ctypes.data + 2 * (abi.MARGIN * s + abi.MARGIN)
+        vm = (p.shape[0] - self.height) // 2 if v_margin is None else int(v_margin)
+        if p.ndim != 2 or p.shape[1] != s or vm < abi.MARGIN or p.shape[0] != self.height + 2 * vm:
+            raise MotionEstimationError(f"plane shape {p.shape}: expected ({self.height} + 2*v_margin, {s}) with v_margin >= {abi.MARGIN}")
+        origin = p.ctypes.data + 2 * (vm * s + abi.MARGIN)
         self._check(self._lib.jsvm_me_upload_plane_xpel(self._ctx, slot, C.c_void_p(origin), self.width, self.height, s))
 
     def interp_halfpel(self, slots):
@@ -116,11 +119,14 @@ class MotionEstimator:
         self._check(self._lib.jsvm_me_download_halfpel_u8(self._ctx, slot, _ptr(out), out.shape[1]))
         return out
 
-    def halfpel_plane_xpel(self, slot):
-        """Half-pel YuvPicBuffer layout: (2(H+64), 2(W+64)) int16 with origin at (64, 64)."""
+    def halfpel_plane_xpel(self, slot, v_margin=abi.MARGIN):
+        """Half-pel YuvPicBuffer layout: (2(H + 2*v_margin), 2(W+64)) int16 with origin at (2*v_margin, 64); v_margin = 64 gives
+        the allocation of a real half-pel YuvPicBuffer (see upload_plane_xpel)."""
+        if v_margin < abi.MARGIN:
+            raise MotionEstimationError(f"v_margin {v_margin} < {abi.MARGIN}")
         s = 2 * (self.width + 2 * abi.MARGIN)
-        out = np.zeros((2 * (self.height + 2 * abi.MARGIN), s), np.int16)
-        origin = out.ctypes.data + 2 * (2 * abi.MARGIN * s + 2 * abi.MARGIN)
+        out = np.zeros((2 * (self.height + 2 * v_margin), s), np.int16)
+        origin = out.ctypes.data + 2 * (2 * v_margin * s + 2 * abi.MARGIN)
         self._check(self._lib.jsvm_me_download_halfpel_xpel(self._ctx, slot, C.c_void_p(origin), s))
         return out
 

@@ -20,14 +20,33 @@ def pair_owner(global_index, world):
     return global_index % world
 
 
-def gather_results(local, dst=0, group=None):
-    """Gather equally sized per-rank result tensors on `dst`; returns the list (rank order) there, else None."""
+def pairs_of_rank(n_pairs, rank, world):
+    """How many of n_pairs round-robin pairs rank `rank` owns."""
+    return (n_pairs - rank + world - 1) // world if rank < n_pairs else 0
+
+
+def gather_results(local, dst=0, group=None, n_pairs=None, jobs_per_pair=None):
+    """Gather per-rank result tensors on `dst`; returns the list (rank order) there, else None.
+
+    Round-robin dealing gives ranks different numbers of pairs whenever n_pairs % world != 0 while the gather needs equal
+    sizes: with n_pairs / jobs_per_pair given every rank pads its records to ceil(n_pairs / world) pairs and the returned
+    tensors are trimmed back to what each rank owns (assemble_level expects exactly that).  Without them the sizes must
+    already agree."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return [local]
     rank = dist.get_rank(group)
-    out = [torch.empty_like(local) for _ in range(world)] if rank == dst else None
-    dist.gather(local, out, dst=dst, group=group)
+    send = local
+    if n_pairs is not None:
+        rows = -(-n_pairs // world) * jobs_per_pair
+        if local.shape[0] != pairs_of_rank(n_pairs, rank, world) * jobs_per_pair:
+            raise ValueError(f"rank {rank} holds {local.shape[0]} records, expected {pairs_of_rank(n_pairs, rank, world) * jobs_per_pair}")
+        if local.shape[0] < rows:
+            send = torch.cat([local, local.new_zeros((rows - local.shape[0],) + tuple(local.shape[1:]))])
+    out = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+    dist.gather(send, out, dst=dst, group=group)
+    if out is not None and n_pairs is not None:
+        out = [t[: pairs_of_rank(n_pairs, r, world) * jobs_per_pair] for r, t in enumerate(out)]
     return out
 
 

@@ -3,7 +3,7 @@
 /root/reference by `make -C oracle ref`).  Run in the build container only; the fixtures are committed so
 that the GPU box (which has no /root/reference) can pin the oracle and the CUDA path against them.
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [group ...]      groups: search, org, fullpel, table (default: all)
 """
 import importlib
 import os
@@ -26,11 +26,14 @@ CASES = {
     "tiny_9_sad": (64, 48, 16, 0, "PARTS_9", "random", 22, None, 36),
     "qcif_9_had": (176, 144, 16, 2, "PARTS_9", "random", 23, [(0, 0), (0, 10), (8, 0), (8, 10), (4, 5), (3, 7), (0, 5), (8, 4)], 30),
     "qcif_9_zero_sr32": (176, 144, 32, 2, "PARTS_9", "zero", 24, [(0, 0), (8, 10), (4, 5), (2, 9)], 33),
+    # SR 64 (the search range of C4 / C5): CIF, all four corners, edges and interior macroblocks, windows clipped on every side
+    "cif_9_sr64": (352, 288, 64, 2, "PARTS_9", "random", 25,
+                   [(0, 0), (0, 21), (17, 0), (17, 21), (0, 9), (17, 12), (8, 0), (9, 21), (4, 4), (8, 11), (13, 17), (5, 16)], 35),
 }
+PLANE_FREE = {"cif_9_sr64"}          # fixtures that do not carry the half-pel / margin planes (size)
 
 
-def main():
-    ref = oracle_lib.CpuBackend(os.path.join(ROOT, "oracle", "_ref", "libjsvm_ref.so"), "jsvm_ref_")
+def gen_search(ref):
     for name, (W, H, sr, sub, parts, field, seed, subset, qp) in CASES.items():
         seq = synth.Sequence(W, H, seed)
         f0, f1 = seq.frame(0), seq.frame(1)
@@ -39,10 +42,13 @@ def main():
         ses.set_plane(1, f1)
         jobs = synth.make_jobs(W, H, getattr(synth, parts), 1, 0, qp=qp, field=field, seed=seed, mb_subset=subset, bits_in=2)
         res, preds = ses.search(jobs, want_preds=True)
+        planes = {} if name in PLANE_FREE else dict(halfpel0=ses.halfpel(0), fullpel0=ses.fullpel(0))
         np.savez_compressed(os.path.join(HERE, name + ".npz"), width=W, height=H, search_range=sr, sub_dfunc=sub,
-                            frame0=f0, frame1=f1, jobs=jobs, results=res, preds=preds,
-                            halfpel0=ses.halfpel(0), fullpel0=ses.fullpel(0))
+                            frame0=f0, frame1=f1, jobs=jobs, results=res, preds=preds, **planes)
         print(name, len(jobs), "jobs")
+
+
+def gen_org(ref):
     # weighted / bi-pred style originals handed in by the caller (8-bit range) and a signed 16-bit one
     W, H, sr = 64, 48, 8
     seq = synth.Sequence(W, H, 31)
@@ -59,6 +65,9 @@ def main():
         np.savez_compressed(os.path.join(HERE, nm + ".npz"), width=W, height=H, search_range=sr, sub_dfunc=2,
                             frame0=f0, frame1=f1, jobs=jobs, results=res, preds=preds, org_mbs=org)
         print(nm, len(jobs), "jobs")
+
+
+def gen_fullpel(ref):
     # full-pel Hadamard / SSD searches (generic full-search kernel), 8-bit and signed 16-bit originals
     W, H, sr = 64, 48, 8
     seq = synth.Sequence(W, H, 33)
@@ -78,7 +87,12 @@ def main():
         np.savez_compressed(os.path.join(HERE, nm + ".npz"), width=W, height=H, search_range=sr, sub_dfunc=sub, full_dfunc=full,
                             frame0=f0, frame1=f1, jobs=jobs, results=res, preds=preds, **extra)
         print(nm, len(jobs), "jobs")
+
+
+def gen_table(ref):
     # distortion function table (XDistortion SAD / SSD / HADAMARD for all 7 block modes) and cost factors
+    rng = np.random.default_rng(31)
+    rng.integers(0, 256, (3, 16, 16)); rng.integers(-255, 511, (3, 16, 16))      # (the draws gen_org makes from the same stream)
     orgs = rng.integers(0, 256, (8, 16, 16)).astype(np.int16)
     refs = rng.integers(0, 256, (8, 20, 24)).astype(np.int16)
     rows = []
@@ -93,6 +107,15 @@ def main():
     np.savez_compressed(os.path.join(HERE, "distortion_and_factors.npz"), orgs=orgs, refs=refs,
                         rows=np.array(rows, np.int64), factors=factors)
     print("distortion rows", len(rows))
+
+
+GROUPS = {"search": gen_search, "org": gen_org, "fullpel": gen_fullpel, "table": gen_table}
+
+
+def main():
+    ref = oracle_lib.CpuBackend(os.path.join(ROOT, "oracle", "_ref", "libjsvm_ref.so"), "jsvm_ref_")
+    for g in (sys.argv[1:] or list(GROUPS)):
+        GROUPS[g](ref)
 
 
 if __name__ == "__main__":

@@ -78,3 +78,64 @@ class CpuBackend:
 
     def session(self, width, height, n_slots, search_range, sub_dfunc, full_dfunc=0):
         return CpuSession(self, width, height, n_slots, search_range, sub_dfunc, full_dfunc)
+
+
+# ---- the checker on many host cores: full-frame comparisons (tests) and bench.py's parity sample ----
+_POOL_STATE = {}
+
+
+def _pool_worker(task):
+    begin, end = task
+    st = _POOL_STATE
+    be = CpuBackend(st["path"], st["prefix"])
+    ses = CpuSession(be, st["W"], st["H"], st["n_slots"], st["sr"], st["sub"], st["full"], st.get("search_mode", 0))
+    for slot, luma in st["planes"].items():
+        ses.set_plane(slot, luma)
+    out = ses.search(st["jobs"][begin:end], org_mbs=st["org"], want_preds=st["want_preds"])
+    ses.close()
+    return (begin, end) + (out if st["want_preds"] else (out, None))
+
+
+def parallel_search(path, prefix, W, H, n_slots, sr, sub, planes, jobs, full=0, org_mbs=None, want_preds=False, n_proc=None, search_mode=0):
+    """estimateBlockWithStart of the CPU checker for every job, spread over host cores (fork pool; job list cut at
+    macroblock boundaries).  `planes`: {slot: (H, W) uint8}.  Returns results (and prediction blocks)."""
+    import multiprocessing as mp
+    import os
+    jobs = np.ascontiguousarray(jobs, JOB_DTYPE)
+    n = len(jobs)
+    n_proc = n_proc or min(os.cpu_count() or 1, 64)
+    used = sorted({int(s) for s in np.unique(jobs["ref_slot"])} | {int(s) for s in np.unique(jobs["cur_slot"])})
+    _POOL_STATE.update(path=path, prefix=prefix, W=W, H=H, n_slots=n_slots, sr=sr, sub=sub, full=full, search_mode=search_mode,
+                       planes={s: planes[s] for s in used if s in planes}, jobs=jobs, org=org_mbs, want_preds=want_preds)
+    n_tasks = max(1, min(n // 64, n_proc * 6))
+    cuts = [0]
+    for t in range(1, n_tasks):
+        i = max(cuts[-1], n * t // n_tasks)
+        while 0 < i < n and (jobs["mb_x"][i] == jobs["mb_x"][i - 1] and jobs["mb_y"][i] == jobs["mb_y"][i - 1]
+                             and jobs["ref_slot"][i] == jobs["ref_slot"][i - 1]):
+            i += 1
+        cuts.append(i)
+    cuts.append(n)
+    tasks = [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+    res = np.zeros(n, RESULT_DTYPE)
+    preds = np.zeros((n, 16, 16), np.uint8) if want_preds else None
+    if n_proc == 1 or len(tasks) == 1:
+        outs = [_pool_worker(t) for t in tasks]
+    else:
+        with mp.get_context("fork").Pool(min(n_proc, len(tasks))) as pool:
+            outs = pool.map(_pool_worker, tasks, chunksize=1)
+    for a, b, r, p in outs:
+        res[a:b] = r
+        if want_preds:
+            preds[a:b] = p
+    _POOL_STATE.clear()
+    return (res, preds) if want_preds else res
+
+
+def best_checker(root):
+    """(path, prefix, kind): the compiled unmodified reference when oracle/_ref was built (it travels to the GPU box), else the C port."""
+    import os
+    ref = os.path.join(root, "oracle", "_ref", "libjsvm_ref.so")
+    if os.path.exists(ref):
+        return ref, "jsvm_ref_", "reference"
+    return os.path.join(root, "oracle", "libme_oracle.so"), "jsvm_ora_", "port"

@@ -85,7 +85,7 @@ import os
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("name", ["tiny_all41_had", "tiny_9_sad", "qcif_9_had", "qcif_9_zero_sr32", "org_override_8bit",
+@pytest.mark.parametrize("name", ["tiny_all41_had", "tiny_9_sad", "qcif_9_had", "qcif_9_zero_sr32", "cif_9_sr64", "org_override_8bit",
                                   "org_override_16bit", "fullpel_had_had", "fullpel_had_sad_all41", "fullpel_ssd_ssd",
                                   "fullpel_ssd_ssd_16bit", "fullpel_had_had_16bit"])
 def test_cuda_matches_reference_golden(me, name):

@@ -20,9 +20,10 @@ def _worker(rank, world, port, n_pairs, jobs_per_pair, out_path):
     pairs = [(2 * i + 1, 2 * i) for i in range(n_pairs)]
     mine = sharding.shard_pairs(pairs, rank, world)
     # fake "results": one int32 record per job carrying (global pair index, job index)
-    local = torch.cat([torch.stack([torch.full((jobs_per_pair,), gi, dtype=torch.int32),
+    local = torch.cat([torch.zeros((0, 2), dtype=torch.int32)] +
+                      [torch.stack([torch.full((jobs_per_pair,), gi, dtype=torch.int32),
                                     torch.arange(jobs_per_pair, dtype=torch.int32)], 1) for gi, _ in mine])
-    gathered = sharding.gather_results(local, dst=0)
+    gathered = sharding.gather_results(local, dst=0, n_pairs=n_pairs, jobs_per_pair=jobs_per_pair)
     if rank == 0:
         full = sharding.assemble_level(gathered, len(mine), jobs_per_pair, world, n_pairs)
         np.save(out_path, full.numpy())
@@ -32,10 +33,14 @@ def _worker(rank, world, port, n_pairs, jobs_per_pair, out_path):
     dist.destroy_process_group()
 
 
-def test_shard_and_gather_two_ranks(tmp_path):
-    n_pairs, jobs_per_pair, world = 8, 5, 2
+import pytest
+
+
+@pytest.mark.parametrize("n_pairs,port", [(8, 29531), (7, 29533), (1, 29535)])     # even, ragged (4 + 3 pairs) and one rank without work
+def test_shard_and_gather_two_ranks(tmp_path, n_pairs, port):
+    jobs_per_pair, world = 5, 2
     out = str(tmp_path / "full.npy")
-    mp.spawn(_worker, args=(world, 29531, n_pairs, jobs_per_pair, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, n_pairs, jobs_per_pair, out), nprocs=world, join=True)
     full = np.load(out)
     assert full.shape == (n_pairs * jobs_per_pair, 2)
     want_pair = np.repeat(np.arange(n_pairs), jobs_per_pair)

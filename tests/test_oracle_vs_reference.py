@@ -22,6 +22,24 @@ def test_search_and_planes_identical(oracle, reference, synth, sub_dfunc, parts_
     assert np.array_equal(pa, pb)
 
 
+def test_search_range_64_identical(oracle, reference, synth):
+    """SR 64 (C4 / C5): 129 x 129 windows clipped by the picture on every side, CIF, a macroblock subset with corners and edges."""
+    W, H, sr = 352, 288, 64
+    seq = synth.Sequence(W, H, 141)
+    f0, f1 = seq.frame(0), seq.frame(3)
+    a, b = oracle.session(W, H, 2, sr, 2), reference.session(W, H, 2, sr, 2)
+    for s in (a, b):
+        s.set_plane(0, f0); s.set_plane(1, f1)
+    mbs = [(0, 0), (0, 21), (17, 0), (17, 21), (0, 10), (17, 7), (9, 0), (6, 21), (3, 3), (9, 12), (14, 18), (7, 5)]
+    for field, seed in (("random", 1), ("split", 2), ("zero", 3)):
+        jobs = synth.make_jobs(W, H, synth.PARTS_9, 1, 0, qp=35, field=field, seed=seed, mb_subset=mbs, bits_in=2)
+        ra, pa = a.search(jobs, want_preds=True)
+        rb, pb = b.search(jobs, want_preds=True)
+        for f in ra.dtype.names:
+            assert np.array_equal(ra[f], rb[f]), (field, f)
+        assert np.array_equal(pa, pb)
+
+
 def test_extreme_content(oracle, reference, synth):
     """Flat, saturated and checkerboard pictures: SAD ties everywhere, clipping in the 6-tap filter."""
     W, H, sr = 64, 48, 8
