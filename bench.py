@@ -32,7 +32,24 @@ METRIC = "1080p full-search ME frame-pairs/s (SR+-64, QPel)"
 UNIT = "frame-pairs/s"
 OPS_PER_POS_9 = 87       # 64 packed abs-diff-acc + 5 tree adds + 9 rate adds + 9 compare/selects
 OPS_PER_POS_41 = 171
+# K3: INT32 lane-ops per (candidate, 4x4 block).  SAD: 4 packed abs-diff-accumulate (pixels / 4).  Hadamard
+# (xCalcHadamard4x4, ENC/Distortion.cpp:291-340, in its cheapest exact form): 16 horizontal dot products on packed
+# bytes + 16 vertical first-stage adds + 16 abs + 8 max (= last butterfly + halving) + 8 accumulates = 64.
+OPS_4x4_SAD = 4
+OPS_4x4_HADAMARD = 64
 INT32_PEAK_FALLBACK = 1.855e13   # lane-ops/s, tools/int32_peak on this pool's B200 (profiles/int32_peak_r01.json)
+
+
+def light_module(name):
+    """`synth` / `abi` of the package WITHOUT running the package __init__ (which dlopens the CUDA library): the reference arm
+    and the CPU checker must not map any of the product's native code."""
+    import types
+    alias = "jsvm_me_b200_light"
+    if alias not in sys.modules:
+        m = types.ModuleType(alias)
+        m.__path__ = [os.path.join(ROOT, PKG)]
+        sys.modules[alias] = m
+    return importlib.import_module(f"{alias}.{name}")
 
 
 def parse_args():
@@ -47,6 +64,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-mbs", type=int, default=0, help="macroblocks in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--parity-fraction", type=float, default=0.05, help="fraction of the macroblocks of a step that is re-computed by "
+                    "the CPU checker after the timed legs (0 = skip)")
     return ap.parse_args()
 
 
@@ -80,7 +99,7 @@ def _cpu_worker(args):
     kind, path, prefix, W, H, sr, sub, cur, ref, jobs_bytes = args
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
-    abi = importlib.import_module(PKG + ".abi")
+    abi = light_module("abi")
     be = oracle_lib.CpuBackend(path, prefix)
     ses = be.session(W, H, 2, sr, sub)
     ses.set_plane(0, ref)
@@ -116,7 +135,7 @@ def cpu_baseline(synth, cfg, field, sample_mbs, steps=1):
     mbs = [(int(i) // mbw, int(i) % mbw) for i in sorted(pick)]
     chunks = [mbs[i::cores] for i in range(cores)]
     chunks = [c for c in chunks if c]
-    values = []
+    values, walls = [], []
     for _ in range(steps):
         tasks = []
         for i, c in enumerate(chunks):
@@ -127,11 +146,36 @@ def cpu_baseline(synth, cfg, field, sample_mbs, steps=1):
             times = pool.map(_cpu_worker, tasks)
         wall = max(times)                                   # search time only (plane set-up excluded), slowest worker
         values.append((sample_mbs / (mbw * mbh)) / wall)
-        _ = time.perf_counter() - t0
+        walls.append(time.perf_counter() - t0)                # the whole sample step incl. process start-up and plane set-up
     v = float(np.mean(values))
     return {"value": v, "unit": UNIT, "cores": len(chunks), "kind": kind,
             "sample": f"{sample_mbs} of {mbw * mbh} macroblocks of one 1080p pair x {len(cfg['parts'])} partitions, SR+-{cfg['search_range']}, "
-                      f"{len(chunks)} processes x 1 thread, search time only"}, values
+                      f"{len(chunks)} processes x 1 thread, search time only"}, values, walls
+
+
+def parity_check(cfg, frames, slot_of, jobs, legs, fraction, seed=4242):
+    """Re-computes a seeded sample of the step's macroblocks (all their partitions) with the CPU checker -- the compiled unmodified
+    reference when oracle/_ref is present, else the C restatement -- and compares every result field of every timed leg with it.
+    Runs after the timed regions; the checker is never the thing measured."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    W, H = cfg["width"], cfg["height"]
+    per_mb = len(cfg["parts"])
+    n_units = len(jobs) // per_mb                                  # (pair, macroblock) units, jobs are MB-major inside a pair
+    rng = np.random.default_rng(seed)
+    pick = np.sort(rng.choice(n_units, size=max(1, int(round(fraction * n_units))), replace=False))
+    idx = (pick[:, None] * per_mb + np.arange(per_mb)[None, :]).reshape(-1)
+    path, prefix, kind = oracle_lib.best_checker(ROOT)
+    planes = {slot_of[p]: f for p, f in frames.items()}
+    want = oracle_lib.parallel_search(path, prefix, W, H, len(frames), cfg["search_range"], cfg["sub_dfunc"], planes, jobs[idx])
+    bad = {}
+    for name, got in legs.items():
+        g = got[idx]
+        n_bad = int(sum(np.count_nonzero(g[f] != want[f]) for f in want.dtype.names))
+        if n_bad:
+            bad[name] = n_bad
+    return {"jobs": int(len(idx)), "macroblocks": int(len(pick)), "fraction": float(len(pick) / n_units), "checker": kind,
+            "legs": sorted(legs), "fields": list(want.dtype.names), "mismatches": bad}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -201,19 +245,28 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    synth = importlib.import_module(PKG + ".synth")
+    # (the reference arm never imports the package itself: its __init__ dlopens the CUDA library)
+    synth = light_module("synth") if args.impl == "reference" else importlib.import_module(PKG + ".synth")
     cfg = synth.CONFIGS[args.config]
     workload = f"{args.config}: {cfg['name']}, top temporal level of GOP 16, {args.pairs} (cur,ref) pairs/GPU/step, " \
                f"{len(cfg['parts'])} partitions/MB, start=pred field '{args.field}'"
+    n_mb = (cfg["width"] // 16) * (cfg["height"] // 16)
+    config = {"workload": workload, "jobs_per_step_per_gpu": args.pairs * n_mb * len(cfg["parts"])}      # the same dict in both arms
 
     if args.impl == "reference":
+        # One step of this arm = ONE bounded sample of the workload (the macroblocks of about one pair, spread over all host
+        # cores); `value` extrapolates it to pairs/s, `ms_per_step` is the measured wall time of a sample step (so that
+        # steps x ms_per_step is what this run really took), `ms_per_workload_step` what a whole 16-pair step would take.
         if rank != 0:
             return
-        base, values = cpu_baseline(synth, cfg, args.field, args.cpu_sample_mbs, steps=max(1, min(args.steps, 3)))
+        for _ in range(max(0, min(args.warmup, 1))):
+            cpu_baseline(synth, cfg, args.field, args.cpu_sample_mbs, steps=1)
+        base, values, walls = cpu_baseline(synth, cfg, args.field, args.cpu_sample_mbs, steps=max(1, args.steps))
         line = {"metric": METRIC, "value": base["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / base["value"] if base["value"] else None,
+                "steps": len(values), "warmup": max(0, min(args.warmup, 1)), "ms_per_step": 1e3 * float(np.mean(walls)),
+                "ms_per_workload_step": 1e3 * args.pairs / base["value"] if base["value"] else None,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": workload}, "cpu_baseline": base,
+                "config": config, "cpu_baseline": base,
                 "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -283,6 +336,10 @@ def main():
     ms_per_step = total_ms / args.steps
     value = args.pairs * world / (ms_per_step * 1e-3)
 
+    legs = {}
+    if rank == 0 and args.parity_fraction > 0:
+        legs["value (jsvm_me_search_device)"] = d_results.cpu().numpy().view(pkg.RESULT_DTYPE).copy()
+
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
@@ -309,6 +366,8 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
         h2d = sum(int(tns.numel()) for tns in host_planes.values()) + n_jobs * 32 + len(groups)
+        if rank == 0 and args.parity_fraction > 0:
+            legs["e2e (jsvm_me_search)"] = hr.copy()
         e2e = {"value": args.pairs * world * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": n_jobs * 32, "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3}
 
@@ -343,22 +402,44 @@ def main():
                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                    "share_of_step": kt["interp_ms"] / total_ms}
 
+    # ---- what was timed is what the reference computes: a seeded sample of the step against the CPU checker ----
+    parity = None
+    if legs:
+        parity = parity_check(cfg, frames, slot_of, jobs, legs, args.parity_fraction)
+
+    # K3 (sub-pel refinement): algorithmic INT32 lane-ops per job = 17 candidates x (4x4 blocks of the partition) x OPS_4x4, plus
+    # the 8 quarter-pel candidates' byte-wise averages (one lane-op per 4 samples) -- DESIGN.md section 3
+    part_px = {1: 256, 2: 128, 3: 128, 8: 64, 9: 32, 10: 32, 11: 16}
+    ops_4x4 = OPS_4x4_HADAMARD if cfg["sub_dfunc"] == 2 else OPS_4x4_SAD
+    k3_ops_per_mb = sum(17 * (part_px[m] // 16) * ops_4x4 + 8 * (part_px[m] // 4) for m, _ in cfg["parts"])
+    k3_ops = k3_ops_per_mb * (n_jobs // len(cfg["parts"]))
+    k3_ms = kt["subpel_ms"] / max(1, kt["subpel_launches"])
+    roofline_k3 = {"bound": "int32", "kernel": "subpel_kernel", "achieved": k3_ops / (k3_ms * 1e-3) / 1e12, "peak": peak / 1e12,
+                   "unit": "Tlane-op/s", "frac": k3_ops / (k3_ms * 1e-3) / peak, "traffic": traffic.get("k3_subpel"),
+                   "alg_ops_per_launch": k3_ops, "alg_ops_per_4x4_candidate": ops_4x4, "ms_per_launch": k3_ms, "peak_source": peak_how,
+                   "share_of_step": kt["subpel_ms"] / total_ms}
+
     base = None
     if not args.no_cpu_baseline and world == 1:
-        base, _ = cpu_baseline(synth, cfg, args.field, args.cpu_sample_mbs)
+        base, _, _ = cpu_baseline(synth, cfg, args.field, args.cpu_sample_mbs)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": workload, "jobs_per_step_per_gpu": n_jobs, "l2": "256 MiB L2 flush between timed iterations",
+            "config": config,
+            "method": {"l2": "256 MiB L2 flush between timed iterations",
                        "timing": "CUDA events per step on the launching stream, summed; max over ranks"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": roofline, "roofline_k1": roofline_k1, "cpu_baseline": base,
+            "roofline": roofline, "roofline_k1": roofline_k1, "roofline_k3": roofline_k3, "cpu_baseline": base,
+            "parity_checked": parity["jobs"] if parity else 0, "parity": parity,
             "kernel_ms_per_step": {"k1_halfpel": kt["interp_ms"] / args.steps, "k2_full_search": kt["search_ms"] / args.steps,
                                    "k3_subpel": kt["subpel_ms"] / args.steps}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if parity and parity["mismatches"]:
+        sys.stderr.write(f"PARITY FAILURE: {parity['mismatches']} result fields differ from the {parity['checker']} checker\n")
+        sys.exit(3)
 
 
 if __name__ == "__main__":

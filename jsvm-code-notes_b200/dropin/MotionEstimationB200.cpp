@@ -54,16 +54,18 @@ struct B200State {
   unsigned char last_pred[256];
   bool last_valid;
   unsigned long long n_calls, n_calls_16bit, n_calls_bipred, n_frames;
+  unsigned long long n_wp_uni, n_wp_bi_explicit, n_wp_bi_implicit;     // calls whose original went through weightInverseLumaSamples
   B200State() : search_range(0), sub_dfunc(0), full_dfunc(0), params_valid(false), device(0), last_valid(false), n_calls(0), n_calls_16bit(0),
-                n_calls_bipred(0), n_frames(0) {
+                n_calls_bipred(0), n_frames(0), n_wp_uni(0), n_wp_bi_explicit(0), n_wp_bi_implicit(0) {
     const char* d = getenv("JSVM_ME_DEVICE");
     if (d) device = atoi(d);
   }
   ~B200State() {
     // JSVM_ME_STATS=1: what went through the device (evidence for the system parity runs)
     if (getenv("JSVM_ME_STATS"))
-      fprintf(stderr, "jsvm_me_b200 stats: filterFrame %llu, estimateBlockWithStart %llu (signed 16-bit originals %llu, bi-pred %llu), layers %zu\n",
-              n_frames, n_calls, n_calls_16bit, n_calls_bipred, layers.size());
+      fprintf(stderr, "jsvm_me_b200 stats: filterFrame %llu, estimateBlockWithStart %llu (signed 16-bit originals %llu, bi-pred %llu, weighted uni %llu, weighted bi explicit %llu, "
+                      "weighted bi implicit %llu), layers %zu\n",
+              n_frames, n_calls, n_calls_16bit, n_calls_bipred, n_wp_uni, n_wp_bi_explicit, n_wp_bi_implicit, layers.size());
   }
 };
 
@@ -251,11 +253,13 @@ MotionEstimation::estimateBlockWithStart( const MbDataAccess&          rcMbDataA
       PredWeight acIPW[2];
       acIPW[1].scaleL1Weight( iScale );
       acIPW[0].scaleL0Weight( acIPW[1] );
+      st.n_wp_bi_implicit++;
       m_pcSampleWeighting->weightInverseLumaSamples( &cPrepared, pcOrg, pcBSP->pcAltRefPelData,
                                                      &acIPW[pcBSP->uiL1Search], &acIPW[1 - pcBSP->uiL1Search], fWeight, iYSize, iXSize );
     }
     else if( bExplicit )
     {
+      st.n_wp_bi_explicit++;
       m_pcSampleWeighting->weightInverseLumaSamples( &cPrepared, pcOrg, pcBSP->pcAltRefPelData,
                                                      pcBSP->apcWeight[pcBSP->uiL1Search], pcBSP->apcWeight[1 - pcBSP->uiL1Search], fWeight, iYSize, iXSize );
     }
@@ -273,6 +277,7 @@ MotionEstimation::estimateBlockWithStart( const MbDataAccess&          rcMbDataA
     {
       cPrepared.set4x4Block( cIdx );
       m_pcXDistortion->set4x4Block( cIdx );
+      st.n_wp_uni++;
       m_pcSampleWeighting->weightInverseLumaSamples( &cPrepared, pcOrg, pcPW, fWeight, iYSize, iXSize );
       pcOrg = &cPrepared;
     }

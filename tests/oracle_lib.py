@@ -5,11 +5,17 @@ or oracle/_ref/libjsvm_ref.so (prefix jsvm_ref_, the unmodified reference behind
 Both take the product's job / result records (include/jsvm_me_b200.h).
 """
 import ctypes as C
-import importlib
+import importlib.util
+import os
 
 import numpy as np
 
-abi = importlib.import_module("jsvm-code-notes_b200.abi")
+# the record layouts only: abi.py is loaded by path so that the checker never runs the product package's __init__ (which dlopens
+# the CUDA library) -- bench.py's reference arm must not map any of the product's native code
+_spec = importlib.util.spec_from_file_location(
+    "jsvm_me_abi_records", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "jsvm-code-notes_b200", "abi.py"))
+abi = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(abi)
 JOB_DTYPE, RESULT_DTYPE = abi.JOB_DTYPE, abi.RESULT_DTYPE
 
 

@@ -23,7 +23,12 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
     # the other distortion functions of XDistortion: Hadamard for both stages, SSD for both stages (SSE cost factor)
     ["--frames", "5", "--gop", "4", "--sr", "8", "--subpel", "2", "--fullpel", "2"],
     ["--frames", "5", "--gop", "4", "--sr", "8", "--subpel", "1", "--fullpel", "1"],
-], ids=["C1-qcif-hierB-satd", "all41-2refs-sad", "C2-two-spatial-layers", "C5-spatial+quality-2refs", "fullpel-hadamard", "ssd-ssd"])
+    # weighted prediction on a fading sequence (ENC/MotionEstimation.cpp:163-247): explicit weights for P and B pictures, and
+    # implicit bi-prediction weights (hierarchical B with unequal temporal distances needs refs > 1)
+    ["--frames", "9", "--gop", "4", "--sr", "8", "--subpel", "2", "--wp", "1", "--wbp", "1", "--fade", "0.04"],
+    ["--frames", "9", "--gop", "4", "--sr", "8", "--subpel", "2", "--wp", "1", "--wbp", "2", "--fade", "0.04", "--refs", "2"],
+], ids=["C1-qcif-hierB-satd", "all41-2refs-sad", "C2-two-spatial-layers", "C5-spatial+quality-2refs", "fullpel-hadamard", "ssd-ssd",
+        "weighted-explicit", "weighted-implicit"])
 def test_encoder_with_dropin_is_bit_identical(args):
     import system_parity
     if not (os.path.exists(system_parity.STOCK) and os.path.exists(system_parity.B200)):
@@ -35,4 +40,8 @@ def test_encoder_with_dropin_is_bit_identical(args):
     assert res["b200"]["device_path"] and "estimateBlockWithStart 0 " not in res["b200"]["device_path"]     # the search really ran on the device
     if "--saturate" in args:                                   # residual prediction reached the search with signed 16-bit originals (N3)
         assert "signed 16-bit originals 0," not in res["b200"]["device_path"], res["b200"]["device_path"]
+    if "--wp" in args:                                         # the weighted originals (a14) really went through the device search
+        assert "weighted uni 0," not in res["b200"]["device_path"], res["b200"]["device_path"]
+        which = "weighted bi explicit 0," if args[args.index("--wbp") + 1] == "1" else "weighted bi implicit 0)"
+        assert which not in res["b200"]["device_path"], res["b200"]["device_path"]
     print(res["b200"]["device_path"])

@@ -50,8 +50,8 @@ InterLayerLoopFilterDisable 2
 InterLayerLoopFilterAlphaC0Offset 0
 InterLayerLoopFilterBetaOffset 0
 NumLayers {nlayers}
-{layercfgs}WeightedPrediction 0
-WeightedBiprediction 0
+{layercfgs}WeightedPrediction {wp}
+WeightedBiprediction {wbp}
 LARDO 0
 MultiLayerLambdaSel 0
 PreAndSuffixUnitEnable 0
@@ -130,6 +130,10 @@ def write_inputs(workdir, a):
     synth = importlib.import_module("jsvm-code-notes_b200.synth")
     seq = synth.Sequence(a.width, a.height, a.seed)
     top = [seq.frame(n) for n in range(a.frames)]
+    if a.fade:
+        # linear fade to black / brightening: picture n is scaled by (1 - fade * n) so that the encoder's weight estimation
+        # (explicit WeightedPrediction / WeightedBiprediction) finds non-default weights and offsets
+        top = [np.clip(np.rint(f.astype(np.float64) * (1.0 - a.fade * n)), 0, 255).astype(np.uint8) for n, f in enumerate(top)]
     if a.saturate:
         # contrast x3 around mid-grey with hard clipping: large areas at 0 and 255, so that "original minus base-layer
         # residual" leaves [0,255] in the residual-prediction passes (N3)
@@ -157,7 +161,7 @@ def run(exe, workdir, tag, a):
                                                 profile=100 if i == 0 else 86))
         lines += f"LayerCfg {layer}\n"
     open(main_cfg, "w").write(MAIN_CFG.format(out=out, frames=a.frames, gop=a.gop, refs=a.refs, sr=a.sr, subpel=a.subpel, fullpel=a.fullpel,
-                                              nlayers=len(plan), layercfgs=lines))
+                                              nlayers=len(plan), layercfgs=lines, wp=a.wp, wbp=a.wbp))
     t0 = time.perf_counter()
     p = subprocess.run([exe, "-pf", main_cfg], cwd=workdir, capture_output=True, text=True, timeout=a.timeout,
                        env=dict(os.environ, JSVM_ME_STATS="1"))
@@ -190,6 +194,9 @@ def compare(argv=None):
     ap.add_argument("--layers", type=int, default=1, help="dyadic spatial layers; --width/--height name the TOP layer")
     ap.add_argument("--quality-layers", type=int, default=0, help="extra CGS quality layers at the top resolution")
     ap.add_argument("--ilpred", type=int, default=2, help="InterLayerPred / ILModePred / ILMotionPred / ILResidualPred of enhancement layers")
+    ap.add_argument("--wp", type=int, default=0, help="WeightedPrediction (P pictures): 0 off, 1 explicit")
+    ap.add_argument("--wbp", type=int, default=0, help="WeightedBiprediction (B pictures): 0 off, 1 explicit, 2 implicit")
+    ap.add_argument("--fade", type=float, default=0.0, help="per-picture luma fade factor (exercises weighted prediction)")
     ap.add_argument("--only", choices=["stock", "b200"], default=None)
     ap.add_argument("--timeout", type=int, default=1500)
     a = ap.parse_args(argv)
