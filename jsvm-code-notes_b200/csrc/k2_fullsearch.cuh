@@ -68,19 +68,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   } while (!done);
 }
-// the same with a pause between polls: for waiters that have nothing urgent to do (they must not steal issue slots)
+// the same for waiters that have nothing urgent to do (the staging warps of the persistent kernel): they must not steal issue
+// slots from the search warps.  try_wait with a suspend-time hint parks the warp in hardware until the phase completes or the
+// hint elapses; the nanosleep between attempts covers implementations that return early.  (Round 1 polled with nanosleep(200),
+// which returned after ~30 ns: 82 warp-instructions of polling per search-loop iteration, 6 % of all issue slots.)
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
   uint32_t done;
   for (;;) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(100000u) : "memory");
     if (done) break;
-    __nanosleep(200);
+    __nanosleep(2000);
   }
+}
+// shared-memory atomics issued by ONE lane as plain PTX: atomicAdd / atomicMin in a lane-0 branch make the compiler emit its
+// warp-aggregation sequence (VOTE, FLO, POPC, S2R LTMASK, SHFL: ~14 instructions per call) around a single active lane
+__device__ __forceinline__ int smem_fetch_add(int32_t* p, int v) {
+  int old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void smem_min(uint32_t* p, uint32_t v) {
+  asm volatile("red.shared.min.u32 [%0], %1;" :: "r"(smem_u32(p)), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -351,7 +364,7 @@ __device__ __forceinline__ void k2_build_stage(const Group& g, const K2Geo<V>& g
   }
   // ---- 5: bits of the vertical difference, one (slot, row) entry per thread and pass; rows outside the job's window: step 1b ----
   {
-    const uint32_t inv_bs = (uint32_t)((0x100000000ull + by_stride - 1) / by_stride);      // exact division of i < 2^16
+    const uint32_t inv_bs = 0xffffffffu / (uint32_t)by_stride + 1u;      // ceil(2^32 / d), d >= 2: exact division of i < 2^16
     for (int i = ptid; i < NS * by_stride; i += pthreads) {
       const int sl = (int)__umulhi((uint32_t)i, inv_bs), y = i - sl * by_stride;
       uint32_t b = 0u;
@@ -378,19 +391,19 @@ __device__ __forceinline__ void k2_search_units(const K2Geo<V>& geo, const K2Sta
   const int units_per_strip = 4 * M;
   const int nunits = geo.nstrips * units_per_strip;
   // exact division of u < 2^16 by d < 2^16: (u * ceil(2^32 / d)) >> 32
-  const uint32_t inv_ups = (uint32_t)((0x100000000ull + units_per_strip - 1) / units_per_strip);
-  const uint32_t inv_m = (uint32_t)((0x100000000ull + M - 1) / M);
+  const uint32_t inv_ups = 0xffffffffu / (uint32_t)units_per_strip + 1u;     // = ceil(2^32 / d) for d >= 2
+  const uint32_t inv_m = 0xffffffffu / (uint32_t)M + 1u;
 
   int u0 = first_u0, u0_next = 0;
   if (first_u0 < 0) {                                             // no static first batch: fetch it
-    if (lane == 0) u0 = atomicAdd(&sm.next_unit, 32);
+    if (lane == 0) u0 = smem_fetch_add(&sm.next_unit, 32);
     u0 = __shfl_sync(0xffffffffu, u0, 0);
   }
-  if (lane == 0) u0_next = atomicAdd(&sm.next_unit, 32);
+  if (lane == 0) u0_next = smem_fetch_add(&sm.next_unit, 32);
   for (;;) {
     if (u0 >= nunits) break;
     const int fetched = __shfl_sync(0xffffffffu, u0_next, 0);
-    if (lane == 0) u0_next = atomicAdd(&sm.next_unit, 32);        // prefetch the batch after the next one
+    if (lane == 0) u0_next = smem_fetch_add(&sm.next_unit, 32);   // prefetch the batch after the next one
     const bool live = u0 + lane < nunits;
     const int u = live ? u0 + lane : nunits - 1;                  // idle lanes redo the last unit with every slot masked off
     u0 = fetched;
@@ -572,13 +585,13 @@ __device__ __forceinline__ void k2_warp_reduce(K2Smem<V, GRAN4>& sm, const int l
 #pragma unroll
     for (int sl = 0; sl < SM::NBEST; ++sl) {
       const uint32_t w = __reduce_min_sync(0xffffffffu, best[sl]);
-      if (lane == 0 && w != kKeyInvalid) atomicMin(&sm.best[sl], w);
+      if (lane == 0 && w != kKeyInvalid) smem_min(&sm.best[sl], w);
     }
   } else {
 #pragma unroll
     for (int q = 0; q < SM::NBEST; ++q) {
       const int sl = lane + 32 * q;
-      if (sl < SM::NS && best[q] != kKeyInvalid) atomicMin(&sm.best[sl], best[q]);
+      if (sl < SM::NS && best[q] != kKeyInvalid) smem_min(&sm.best[sl], best[q]);
     }
   }
 }
