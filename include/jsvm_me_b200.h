@@ -109,12 +109,20 @@ const char* jsvm_me_last_error(void);
 int jsvm_me_configure(jsvm_me_ctx* ctx, int width, int height, int n_slots);
 
 /* MotionEstimation::init reading MotionVectorSearchParams (ENC/MotionEstimation.cpp:38-66,
- * include/CodingParameter.h:41-89).  SearchMode 0 (BLOCK_SEARCH) only.  Distortion functions: SAD (0) and HADAMARD (2) in any
- * combination for the full-pel and the sub-pel stage, or SSD (1) for both (a job carries ONE cost factor: SAD and HADAMARD
- * use the SAD factor, SSD the SSE factor, ENC/MotionEstimation.cpp:255, 325).  Full-pel SAD is the measured hot path
- * (packed-byte kernels); full-pel HADAMARD / SSD run a plain one-CTA-per-job kernel.  YUV_SAD (3) and every other
- * combination return JSVM_ME_ERR. */
+ * include/CodingParameter.h:41-89; value ranges checked as MotionVectorSearchParams::check, ENC/CodingParameter.cpp:17-36).
+ * SearchMode 0 (BLOCK_SEARCH) only.  SearchFuncFullPel: SAD (0), SSD (1), HADAMARD (2), YUV_SAD (3); SearchFuncSubPel: SAD (0),
+ * SSD (1), HADAMARD (2) -- every combination.  Full-pel SAD is the measured hot path (packed-byte kernels); the other full-pel
+ * functions run a plain one-CTA-per-job kernel.  YUV_SAD needs the chroma planes of the slots (jsvm_me_upload_chroma_*).
+ * A job carries ONE cost factor, the one of the FULL-PEL stage (ENC/MotionEstimation.cpp:255: the SAD factor unless
+ * SearchFuncFullPel is SSD).  When the sub-pel stage uses the other factor class (:325: the SSE factor iff SearchFuncSubPel is
+ * SSD) the pairs must be registered with jsvm_me_map_cost_factor. */
 int jsvm_me_set_params(jsvm_me_ctx* ctx, int search_mode, int full_pel_dfunc, int sub_pel_dfunc, int search_range);
+
+/* RateDistortionIf::getMotionCostShift( bSad ) for both classes (ENC/RateDistortion.cpp:59-70, RateDistortion.h:30): registers that
+ * jobs whose cost_factor (full-pel stage) is `factor_full_pel` use `factor_sub_pel` in the sub-pel stage and in the final cost
+ * (xSetMEPars( 0, ... ), ENC/MotionEstimation.cpp:325-335).  Both values come from the host (double arithmetic, N11).  Only
+ * consulted when the two stages use different factor classes; up to 256 pairs per context, re-registering a factor replaces it. */
+int jsvm_me_map_cost_factor(jsvm_me_ctx* ctx, uint32_t factor_full_pel, uint32_t factor_sub_pel);
 
 /* Run every later call on this CUDA stream (a cudaStream_t / CUstream handle; NULL = default). */
 int jsvm_me_set_stream(jsvm_me_ctx* ctx, void* cuda_stream);
@@ -132,6 +140,19 @@ int jsvm_me_upload_plane_xpel(jsvm_me_ctx* ctx, int slot, const int16_t* origin,
 int jsvm_me_upload_plane_u8  (jsvm_me_ctx* ctx, int slot, const uint8_t* host, int width, int height, int stride);
 /* Same as upload_plane_u8 but the source is already in device memory (bench "resident in HBM" leg). */
 int jsvm_me_set_plane_device_u8(jsvm_me_ctx* ctx, int slot, const uint8_t* dev, int width, int height, int stride);
+
+/* Chroma planes of a slot (4:2:0; YuvPicBuffer Cb / Cr with stride (W+64)/2 and 16 margin samples, COM/YuvBufferCtrl.cpp:134-157,
+ * INCC/YuvPicBuffer.h:32,68-69).  Read by the YUV_SAD full-pel search (xGetYuvSAD*, ENC/Distortion.cpp:435-505, 593-647, 718-764;
+ * chroma displacement ( y>>1, x>>1 ), ENC/MotionEstimation.cpp:386-387) and by jsvm_me_compensate.
+ * upload_chroma_u8  : dense (W/2) x (H/2) planes; margins are generated on the device as fillMargin does.
+ * upload_chroma_xpel: `cb_origin` / `cr_origin` point at sample (0,0) of the YuvPicBuffer planes (getMbCbAddr / getMbCrAddr after
+ *                     initMb(0,0)) whose 16-sample margins are already filled. */
+int jsvm_me_upload_chroma_u8  (jsvm_me_ctx* ctx, int slot, const uint8_t* cb, const uint8_t* cr, int stride);
+int jsvm_me_upload_chroma_xpel(jsvm_me_ctx* ctx, int slot, const int16_t* cb_origin, const int16_t* cr_origin, int stride);
+/* Chroma originals of the caller-prepared macroblocks (pUOrg / pVOrg of a weighted original, ENC/MotionEstimation.cpp:259-260):
+ * n_org_mbs x (Cb 8x8, Cr 8x8) int16, HOST memory, for jobs with org_index >= 0.  Only read by jsvm_me_search when
+ * SearchFuncFullPel is YUV_SAD; the pointer must stay valid until that call returns.  NULL clears it. */
+int jsvm_me_set_org_chroma(jsvm_me_ctx* ctx, const int16_t* org_chroma_mbs, int n_org_mbs);
 
 /* QuarterPelFilter::filterFrame( full, half ) (COM/QuarterPelFilter.cpp:61-149): builds the half-pel
  * plane of the slot; it stays on the device (its only consumer is ME). */
@@ -178,6 +199,35 @@ int jsvm_me_search_device(jsvm_me_ctx* ctx, const jsvm_me_job* d_jobs, int n_job
  * (the reference's stateful contract): writes w x h samples to dst (XPel, dst_stride). */
 int jsvm_me_fetch_pred(jsvm_me_ctx* ctx, int job_idx, int16_t* dst, int dst_stride);
 
+/* ---- motion-compensated prediction ----
+ * One job == the prediction of one luma block and its two chroma blocks as MotionCompensation::compensateMb / compensateSubMb
+ * produce it (COM/MotionCompensation.cpp:1200-1405): MV limited to the macroblock's range (xGetMbPredData -> limitComponents,
+ * :1390), luma by QuarterPelFilter::predBlk (COM/QuarterPelFilter.cpp:266-619: 6-tap half samples, averaged quarter samples),
+ * chroma by xPredChroma / xPredChromaPel (:171-260: 1/8-sample bilinear), then SampleWeighting::weightLumaSamples /
+ * weightChromaSamples (COM/SampleWeighting.cpp:159-265, 332-372: xMixB, xMixBWeight, xWeight).
+ * Luma comes from the slot's half-pel plane (the same integers predBlk computes from the full-pel plane: the plane IS
+ * filterFrame's output), so the reference slots need jsvm_me_interp_halfpel; chroma needs jsvm_me_upload_chroma_*. */
+/* SampleWeighting::initSlice state (COM/SampleWeighting.cpp:77-138): which prediction types are weighted in this slice */
+#define JSVM_MC_DEFAULT    0   /* one list: plain prediction; two lists: ( a + b + 1 ) >> 1 (xMixB) */
+#define JSVM_MC_WEIGHT_UNI 1   /* !m_bWeightedPredDisableP: one-list blocks go through xWeight when the list's weight_flag is set */
+#define JSVM_MC_WEIGHT_BI  2   /* !m_bWeightedPredDisableB: two-list blocks go through xMixBWeight (explicit or implicit weights) */
+typedef struct jsvm_mc_job {
+  int16_t ref_slot[2];     /* LIST_0 / LIST_1 reference slot, -1 = list not used */
+  int16_t mb_x, mb_y;      /* initMb( uiMbY, uiMbX ): MV clamp m_cMin / m_cMax and block position */
+  uint8_t blk;             /* cIdx: 4x4 raster index of the block's top-left 4x4 */
+  uint8_t size_x, size_y;  /* luma block size: 16, 8 or 4 (chroma: half) */
+  uint8_t weighting;       /* JSVM_MC_DEFAULT or JSVM_MC_WEIGHT_UNI | JSVM_MC_WEIGHT_BI */
+  jsvm_mv mv[2];           /* quarter-pel MV per list (before the clamp) */
+  int16_t weight[2][3];    /* PredWeight::getLumaWeight / getChromaCbWeight / getChromaCrWeight per list */
+  int16_t offset[2][3];    /* ... Offset */
+  uint8_t log_denom[2];    /* m_uiLumaLogWeightDenom, m_uiChromaLogWeightDenom (5 / 5 for implicit weights) */
+  uint8_t weight_flag[2];  /* one-list case: getLumaWeightFlag / getChromaWeightFlag of the list's PredWeight */
+} jsvm_mc_job;
+/* pred_y: n x 256 bytes (stride 16, top-left aligned, zero padded); pred_cb / pred_cr: n x 64 bytes (stride 8) or NULL. */
+int jsvm_me_compensate(jsvm_me_ctx* ctx, const jsvm_mc_job* jobs, int n_jobs, uint8_t* pred_y, uint8_t* pred_cb, uint8_t* pred_cr);
+/* The same with every buffer in device memory, asynchronous on the ctx stream. */
+int jsvm_me_compensate_device(jsvm_me_ctx* ctx, const jsvm_mc_job* d_jobs, int n_jobs, uint8_t* d_pred_y, uint8_t* d_pred_cb, uint8_t* d_pred_cr);
+
 int jsvm_me_sync(jsvm_me_ctx* ctx);
 
 /* Measurement helpers (bench.py): kernel launches issued so far, and CUDA-event timing of the
@@ -191,6 +241,8 @@ const char* jsvm_me_last_search_kernel(jsvm_me_ctx* ctx);
 int jsvm_me_timing_begin(jsvm_me_ctx* ctx);                  /* start accumulating per-kernel event times */
 int jsvm_me_timing_end(jsvm_me_ctx* ctx, double* ms_interp, double* ms_search, double* ms_subpel,
                        uint64_t* n_interp, uint64_t* n_search, uint64_t* n_subpel);
+/* Time and launch count of the motion-compensation kernel inside the last timing_begin / timing_end bracket. */
+int jsvm_me_timing_compensate(jsvm_me_ctx* ctx, double* ms_compensate, uint64_t* n_compensate);
 
 #ifdef __cplusplus
 }

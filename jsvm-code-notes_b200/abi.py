@@ -53,6 +53,14 @@ RESULT_DTYPE = np.dtype([("mv_hor", "<i2"), ("mv_ver", "<i2"), ("full_hor", "<i2
                          ("cost", "<u4"), ("best_mode", "<u4")])
 assert JOB_DTYPE.itemsize == 32 and RESULT_DTYPE.itemsize == 32
 
+# jsvm_mc_job (motion-compensated prediction of one block, COM/MotionCompensation.cpp:1200-1405)
+MC_DEFAULT, MC_WEIGHT_UNI, MC_WEIGHT_BI = 0, 1, 2
+MC_JOB_DTYPE = np.dtype([("ref_slot", "<i2", (2,)), ("mb_x", "<i2"), ("mb_y", "<i2"), ("blk", "u1"), ("size_x", "u1"), ("size_y", "u1"),
+                         ("weighting", "u1"), ("mv", "<i2", (2, 2)),            # mv[list] = (hor, ver)
+                         ("weight", "<i2", (2, 3)), ("offset", "<i2", (2, 3)),  # [list][Y, Cb, Cr]
+                         ("log_denom", "u1", (2,)), ("weight_flag", "u1", (2,))])
+assert MC_JOB_DTYPE.itemsize == 48
+
 # every symbol the header declares: (name, restype, argtypes)
 PROTOTYPES = [
     ("jsvm_me_create", C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
@@ -64,6 +72,13 @@ PROTOTYPES = [
     ("jsvm_me_upload_plane_xpel", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     ("jsvm_me_upload_plane_u8", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     ("jsvm_me_set_plane_device_u8", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    ("jsvm_me_map_cost_factor", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    ("jsvm_me_upload_chroma_u8", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    ("jsvm_me_upload_chroma_xpel", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    ("jsvm_me_set_org_chroma", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    ("jsvm_me_compensate", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("jsvm_me_compensate_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("jsvm_me_timing_compensate", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     ("jsvm_me_interp_halfpel", C.c_int, [C.c_void_p, C.c_int]),
     ("jsvm_me_interp_halfpel_batch", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     ("jsvm_me_download_halfpel_xpel", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),

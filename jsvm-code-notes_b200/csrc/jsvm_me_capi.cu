@@ -26,6 +26,7 @@
 #include "k2_fullsearch.cuh"
 #include "k2_generic.cuh"
 #include "k3_subpel.cuh"
+#include "k4_mc.cuh"
 
 using namespace jsvm;
 
@@ -81,7 +82,20 @@ struct jsvm_me_ctx {
   uint8_t* d_planes = nullptr;
   uint8_t* d_half = nullptr;
   int* d_slot_ids = nullptr;            // scratch list of slots for batched launches (n_slots entries)
-  std::vector<char> slot_full, slot_half;
+  std::vector<char> slot_full, slot_half, slot_chroma;
+  // chroma planes [slot][Cb, Cr][H/2 + 32][W/2 + 32], origin (16,16); allocated by the first chroma upload
+  uint8_t* d_chroma = nullptr;
+  int chroma_stride = 0, chroma_rows = 0; size_t chroma_bytes = 0;     // per plane
+  // full-pel -> sub-pel cost-factor pairs (jsvm_me_map_cost_factor) and their device copy
+  std::vector<uint2> factor_map;
+  DevBuf<uint2> d_factor_map;
+  bool factor_map_dirty = false;
+  // chroma originals of caller-prepared macroblocks (jsvm_me_set_org_chroma)
+  const int16_t* org_chroma = nullptr; int n_org_chroma = 0;
+  DevBuf<int16_t> d_org_chroma;
+  // jsvm_me_compensate (host-buffer form)
+  DevBuf<jsvm_mc_job> d_mc_jobs;
+  DevBuf<uint8_t> d_mc_pred;
   CUtensorMap map_k1{};
   EncodeTiledFn encode = nullptr;
   // params
@@ -122,6 +136,7 @@ struct jsvm_me_ctx {
   bool timing = false;
   struct Timed { cudaEvent_t e0, e1; int kind; };
   std::vector<Timed> timed;
+  double last_mc_ms = 0; uint64_t last_mc_n = 0;
 };
 
 namespace {
@@ -351,23 +366,42 @@ int choose_persistent(jsvm_me_ctx* c, int n_groups, int max_uh, bool* persistent
 
 // K2 for the groups of a plan, then K3 for the jobs [job_begin, job_end) they cover (K2 reaches jobs through the groups'
 // absolute first_job; all per-job arrays are indexed by the absolute job number).
+// the two stages use different cost-factor classes (ENC/MotionEstimation.cpp:255, 325): SSE factor iff the stage's function is SSD
+inline bool mixed_factor_classes(const jsvm_me_ctx* c) { return (c->full_dfunc == JSVM_DF_SSD) != (c->sub_dfunc == JSVM_DF_SSD); }
+
+int sync_factor_map(jsvm_me_ctx* c) {
+  if (!c->factor_map_dirty) return JSVM_ME_OK;
+  if (c->d_factor_map.reserve(std::max<size_t>(1, c->factor_map.size()))) return JSVM_ME_ERR;
+  if (!c->factor_map.empty())
+    CU_OK(cudaMemcpyAsync(c->d_factor_map.p, c->factor_map.data(), sizeof(uint2) * c->factor_map.size(), cudaMemcpyHostToDevice, c->stream));
+  CU_OK(cudaStreamSynchronize(c->stream));                  // the host vector may change again right after this call
+  c->factor_map_dirty = false;
+  return JSVM_ME_OK;
+}
+
 int run_search(jsvm_me_ctx* c, const jsvm_me_job* d_jobs, int job_begin, int job_end, const Group* d_groups, const jsvm_me_plan_info* info,
-               const int16_t* d_org, uint32_t* d_keys, JobAux* d_aux, jsvm_me_result* d_results, uint8_t* d_preds) {
+               const int16_t* d_org, uint32_t* d_keys, JobAux* d_aux, jsvm_me_result* d_results, uint8_t* d_preds,
+               const int16_t* d_org_chroma = nullptr) {
   if (!c->params_set) return fail("jsvm_me_set_params has not been called");
   if (info->max_uh_8x8 > kMaxUH || info->max_uh_4x4 > kMaxUH) return fail("plan: union window taller than %d", kMaxUH);
   const int n = job_end - job_begin;
   if (n <= 0) return JSVM_ME_OK;
-  const bool generic = c->full_dfunc != JSVM_DF_SAD;         // SSD / Hadamard full-pel search: one CTA per job, no grouping
+  if (sync_factor_map(c)) return JSVM_ME_ERR;
+  const bool generic = c->full_dfunc != JSVM_DF_SAD;         // SSD / Hadamard / YUV-SAD full-pel search: one CTA per job, no grouping
   if (generic) {
     if (c->d_full_costs.cap < (size_t)job_end) return fail("internal: full-pel cost buffer not reserved");
+    if (c->full_dfunc == JSVM_DF_YUV_SAD && !c->d_chroma) return fail("SearchFuncFullPel 3 (YUV_SAD) needs the chroma planes (jsvm_me_upload_chroma_*)");
+    auto k2g = c->full_dfunc == JSVM_DF_SSD ? full_search_generic_kernel<JSVM_DF_SSD>
+             : c->full_dfunc == JSVM_DF_HADAMARD ? full_search_generic_kernel<JSVM_DF_HADAMARD> : full_search_generic_kernel<JSVM_DF_YUV_SAD>;
     begin_timed(c, 1);
-    (c->full_dfunc == JSVM_DF_SSD ? full_search_generic_kernel<JSVM_DF_SSD> : full_search_generic_kernel<JSVM_DF_HADAMARD>)
-        <<<n, kK2GThreads, 0, c->stream>>>(c->d_planes, c->plane_bytes, c->plane_stride, d_jobs + job_begin, n, d_org,
-                                           c->W >> 4, c->H >> 4, c->search_range, d_keys + job_begin,
-                                           c->d_full_costs.p + job_begin, d_aux + job_begin);
+    k2g<<<n, kK2GThreads, 0, c->stream>>>(c->d_planes, c->plane_bytes, c->plane_stride, c->d_chroma, c->chroma_bytes, c->chroma_stride,
+                                          d_jobs + job_begin, n, d_org, d_org_chroma,
+                                          c->W >> 4, c->H >> 4, c->search_range, d_keys + job_begin,
+                                          c->d_full_costs.p + job_begin, d_aux + job_begin);
     end_timed(c);
     c->launches++;
-    c->last_k2 = c->full_dfunc == JSVM_DF_SSD ? "full_search_generic_kernel<SSD>" : "full_search_generic_kernel<HADAMARD>";
+    c->last_k2 = c->full_dfunc == JSVM_DF_SSD ? "full_search_generic_kernel<SSD>"
+               : c->full_dfunc == JSVM_DF_HADAMARD ? "full_search_generic_kernel<HADAMARD>" : "full_search_generic_kernel<YUV_SAD>";
     CU_OK(cudaGetLastError());
   }
   const int n8 = generic ? 0 : info->n_groups_8x8, n4 = generic ? 0 : info->n_groups - info->n_groups_8x8;
@@ -387,10 +421,48 @@ int run_search(jsvm_me_ctx* c, const jsvm_me_job* d_jobs, int job_begin, int job
       c->d_planes, c->plane_bytes, c->plane_stride, c->d_half, c->half_bytes, c->half_stride,
       d_jobs + job_begin, d_aux + job_begin, n, d_org, d_keys + job_begin,
       generic ? c->d_full_costs.p + job_begin : nullptr, d_results + job_begin,
-      d_preds ? d_preds + (size_t)job_begin * 256 : nullptr);
+      d_preds ? d_preds + (size_t)job_begin * 256 : nullptr,
+      c->d_factor_map.p, mixed_factor_classes(c) ? (int)c->factor_map.size() : 0);
   end_timed(c);
   c->launches++;
   CU_OK(cudaGetLastError());
+  return JSVM_ME_OK;
+}
+
+// What a host-buffer search needs beyond the plan when the distortion functions are not plain SAD / SAD-class:
+//  * YUV_SAD: chroma planes of every slot the jobs touch, and the chroma originals (if registered) on the device;
+//  * mixed factor classes: every job's full-pel factor must have a registered sub-pel partner.
+int prepare_search_extras(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, int n_org_mbs, const int16_t** d_org_chroma) {
+  *d_org_chroma = nullptr;
+  if (c->full_dfunc == JSVM_DF_YUV_SAD) {
+    if (!c->d_chroma) return fail("SearchFuncFullPel 3 (YUV_SAD) needs the chroma planes (jsvm_me_upload_chroma_*)");
+    const bool have_org = c->org_chroma != nullptr;
+    for (int i = 0; i < n_jobs; ++i) {
+      const jsvm_me_job& j = jobs[i];
+      if (j.ref_slot < 0 || j.ref_slot >= c->n_slots || j.cur_slot < 0 || j.cur_slot >= c->n_slots) return fail("job %d: plane slot out of range", i);
+      if (j.org_index >= 0 && !have_org) continue;                         // luma-only job (bi-pred / unequal weights)
+      if (!c->slot_chroma[j.ref_slot]) return fail("job %d: ref_slot %d has no chroma planes", i, (int)j.ref_slot);
+      if (j.org_index < 0 && !c->slot_chroma[j.cur_slot]) return fail("job %d: cur_slot %d has no chroma planes", i, (int)j.cur_slot);
+    }
+    if (have_org && n_org_mbs > 0) {
+      if (c->n_org_chroma < n_org_mbs) return fail("jsvm_me_set_org_chroma registered %d macroblocks, the call passes %d", c->n_org_chroma, n_org_mbs);
+      if (c->d_org_chroma.reserve((size_t)n_org_mbs * 128)) return JSVM_ME_ERR;
+      CU_OK(cudaMemcpyAsync(c->d_org_chroma.p, c->org_chroma, sizeof(int16_t) * 128 * n_org_mbs, cudaMemcpyHostToDevice, c->stream));
+      *d_org_chroma = c->d_org_chroma.p;
+    }
+  }
+  if (mixed_factor_classes(c)) {
+    uint32_t last = 0; bool have_last = false;
+    for (int i = 0; i < n_jobs; ++i) {
+      const uint32_t f = jobs[i].cost_factor;
+      if (have_last && f == last) continue;
+      bool found = false;
+      for (const uint2& e : c->factor_map) if (e.x == f) { found = true; break; }
+      if (!found) return fail("job %d: cost factor %u has no sub-pel partner (SearchFuncFullPel %d / SearchFuncSubPel %d use different "
+                              "factor classes: register the pair with jsvm_me_map_cost_factor)", i, f, c->full_dfunc, c->sub_dfunc);
+      last = f; have_last = true;
+    }
+  }
   return JSVM_ME_OK;
 }
 
@@ -418,7 +490,9 @@ int search_small(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const int1
   memcpy(a->job, jobs, sizeof(jsvm_me_job) * n_jobs);
   if (n_org_mbs > 0) memcpy(a->org, org_mbs, sizeof(int16_t) * 256 * n_org_mbs);
   if (c->d_keys.reserve(64) || c->d_full_costs.reserve(64) || c->d_aux.reserve(64)) return JSVM_ME_ERR;
-  if (run_search(c, a->job, 0, n_jobs, a->group, &info, a->org, c->d_keys.p, c->d_aux.p, a->result, a->pred)) return JSVM_ME_ERR;
+  const int16_t* d_org_chroma = nullptr;
+  if (prepare_search_extras(c, jobs, n_jobs, n_org_mbs, &d_org_chroma)) return JSVM_ME_ERR;
+  if (run_search(c, a->job, 0, n_jobs, a->group, &info, a->org, c->d_keys.p, c->d_aux.p, a->result, a->pred, d_org_chroma)) return JSVM_ME_ERR;
   CU_OK(cudaStreamSynchronize(c->stream));
   memcpy(results, a->result, sizeof(jsvm_me_result) * n_jobs);
   if (preds) memcpy(preds, a->pred, (size_t)n_jobs * 256);
@@ -464,8 +538,10 @@ int jsvm_me_destroy(jsvm_me_ctx* c) {
   cudaStreamSynchronize(c->stream);
   if (c->d_planes) cudaFree(c->d_planes);
   if (c->d_half) cudaFree(c->d_half);
+  if (c->d_chroma) cudaFree(c->d_chroma);
   if (c->d_slot_ids) cudaFree(c->d_slot_ids);
   if (c->d_bad) cudaFree(c->d_bad);
+  c->d_factor_map.release(); c->d_org_chroma.release(); c->d_mc_jobs.release(); c->d_mc_pred.release();
   c->d_jobs.release(); c->d_groups.release(); c->d_keys.release(); c->d_full_costs.release(); c->d_aux.release();
   c->d_results.release(); c->d_preds.release(); c->d_org.release(); c->d_stage.release();
   for (auto& t : c->timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
@@ -487,6 +563,7 @@ int jsvm_me_configure(jsvm_me_ctx* c, int width, int height, int n_slots) {
   CU_OK(cudaStreamSynchronize(c->stream));
   if (c->d_planes) { cudaFree(c->d_planes); c->d_planes = nullptr; }
   if (c->d_half) { cudaFree(c->d_half); c->d_half = nullptr; }
+  if (c->d_chroma) { cudaFree(c->d_chroma); c->d_chroma = nullptr; }
   if (c->d_slot_ids) { cudaFree(c->d_slot_ids); c->d_slot_ids = nullptr; }
   c->W = width; c->H = height; c->n_slots = n_slots;
   c->plane_stride = width + 2 * kMargin; c->plane_rows = height + 2 * kMargin;
@@ -498,7 +575,9 @@ int jsvm_me_configure(jsvm_me_ctx* c, int width, int height, int n_slots) {
   CU_OK(cudaMalloc((void**)&c->d_slot_ids, sizeof(int) * n_slots));
   CU_OK(cudaMemsetAsync(c->d_planes, 0, c->plane_bytes * n_slots + 256, c->stream));
   CU_OK(cudaMemsetAsync(c->d_half, 0, c->half_bytes * n_slots, c->stream));     // samples outside the written region stay 0 (reference: memset at allocation)
-  c->slot_full.assign(n_slots, 0); c->slot_half.assign(n_slots, 0);
+  c->slot_full.assign(n_slots, 0); c->slot_half.assign(n_slots, 0); c->slot_chroma.assign(n_slots, 0);
+  c->chroma_stride = width / 2 + 2 * kCMargin; c->chroma_rows = height / 2 + 2 * kCMargin;
+  c->chroma_bytes = (size_t)c->chroma_stride * c->chroma_rows;
   if (make_map(c, &c->map_k1, c->d_planes, kK1BoxW, kK1BoxH)) return JSVM_ME_ERR;
   return JSVM_ME_OK;
 }
@@ -506,13 +585,9 @@ int jsvm_me_configure(jsvm_me_ctx* c, int width, int height, int n_slots) {
 int jsvm_me_set_params(jsvm_me_ctx* c, int search_mode, int full_pel_dfunc, int sub_pel_dfunc, int search_range) {
   if (!c) return fail("null context");
   if (search_mode != JSVM_SEARCH_BLOCK) return fail("SearchMode %d: only BLOCK_SEARCH (0, full search) is implemented", search_mode);
-  // A job carries ONE cost factor, so both stages must use the same one (ENC/MotionEstimation.cpp:255, 325): SAD and HADAMARD
-  // take the SAD factor, SSD takes the SSE factor.  YUV_SAD (3) needs the chroma planes and is not implemented.
-  const bool full_sadlike = full_pel_dfunc == JSVM_DF_SAD || full_pel_dfunc == JSVM_DF_HADAMARD;
-  const bool sub_sadlike = sub_pel_dfunc == JSVM_DF_SAD || sub_pel_dfunc == JSVM_DF_HADAMARD;
-  if (!((full_sadlike && sub_sadlike) || (full_pel_dfunc == JSVM_DF_SSD && sub_pel_dfunc == JSVM_DF_SSD)))
-    return fail("SearchFuncFullPel %d / SearchFuncSubPel %d: implemented are SAD (0) and HADAMARD (2) in any combination, and SSD (1) "
-                "for both stages (one cost factor per job); YUV_SAD (3) is not implemented", full_pel_dfunc, sub_pel_dfunc);
+  // MotionVectorSearchParams::check (ENC/CodingParameter.cpp:17-36)
+  if (full_pel_dfunc < 0 || full_pel_dfunc > 3) return fail("No Such Search Func (Full Pel) %d: 0==SAD, 1==SSE, 2==Hadamard, 3==YUV-SAD", full_pel_dfunc);
+  if (sub_pel_dfunc < 0 || sub_pel_dfunc > 2) return fail("No Such Search Func (Sub Pel) %d: 0==SAD, 1==SSE, 2==Hadamard", sub_pel_dfunc);
   if (search_range < 1 || search_range > kMaxSearchRange) return fail("SearchRange %d outside [1,%d]", search_range, kMaxSearchRange);
   c->search_range = search_range; c->sub_dfunc = sub_pel_dfunc; c->full_dfunc = full_pel_dfunc; c->params_set = true;
   return JSVM_ME_OK;
@@ -573,6 +648,135 @@ int jsvm_me_set_plane_device_u8(jsvm_me_ctx* c, int slot, const uint8_t* dev, in
   CU_OK(cudaMemcpyAsync(c->d_slot_ids, &s, sizeof(int), cudaMemcpyHostToDevice, c->stream));
   if (launch_margin_fill(c, c->d_slot_ids, 1)) return JSVM_ME_ERR;
   c->slot_full[slot] = 1; c->slot_half[slot] = 0;
+  return JSVM_ME_OK;
+}
+
+// ---- chroma planes (YUV_SAD search, motion-compensated prediction) ----
+static int ensure_chroma(jsvm_me_ctx* c) {
+  if (c->d_chroma) return JSVM_ME_OK;
+  CU_OK(cudaMalloc((void**)&c->d_chroma, c->chroma_bytes * 2 * c->n_slots));
+  CU_OK(cudaMemsetAsync(c->d_chroma, 0, c->chroma_bytes * 2 * c->n_slots, c->stream));
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_upload_chroma_u8(jsvm_me_ctx* c, int slot, const uint8_t* cb, const uint8_t* cr, int stride) {
+  if (check_slot(c, slot)) return JSVM_ME_ERR;
+  if (!cb || !cr) return fail("null chroma plane");
+  const int cw = c->W / 2, ch = c->H / 2;
+  if (stride < cw) return fail("stride %d smaller than the chroma width %d", stride, cw);
+  CU_OK(cudaSetDevice(c->device));
+  if (ensure_chroma(c)) return JSVM_ME_ERR;
+  for (int comp = 0; comp < 2; ++comp) {
+    uint8_t* plane = c->d_chroma + ((size_t)slot * 2 + comp) * c->chroma_bytes;
+    CU_OK(cudaMemcpy2DAsync(plane + (size_t)kCMargin * c->chroma_stride + kCMargin, c->chroma_stride, comp ? cr : cb, stride, cw, ch,
+                            cudaMemcpyHostToDevice, c->stream));
+    dim3 grid(1, c->chroma_rows), block(256);
+    plane_margin_fill_kernel<<<grid, block, 0, c->stream>>>(plane, c->chroma_stride, cw, ch, kCMargin);
+    c->launches++;
+    CU_OK(cudaGetLastError());
+  }
+  c->slot_chroma[slot] = 1;
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_upload_chroma_xpel(jsvm_me_ctx* c, int slot, const int16_t* cb_origin, const int16_t* cr_origin, int stride) {
+  if (check_slot(c, slot)) return JSVM_ME_ERR;
+  if (!cb_origin || !cr_origin) return fail("null chroma plane");
+  if (stride < c->chroma_stride) return fail("stride %d smaller than width / 2 + 32", stride);
+  CU_OK(cudaSetDevice(c->device));
+  if (ensure_chroma(c)) return JSVM_ME_ERR;
+  const size_t n16 = (size_t)c->chroma_stride * c->chroma_rows;
+  if (c->d_stage.reserve(n16 * 2)) return JSVM_ME_ERR;
+  CU_OK(cudaMemsetAsync(c->d_bad, 0, sizeof(int), c->stream));
+  for (int comp = 0; comp < 2; ++comp) {
+    const int16_t* top = (comp ? cr_origin : cb_origin) - (ptrdiff_t)kCMargin * stride - kCMargin;
+    CU_OK(cudaMemcpy2DAsync(c->d_stage.p, (size_t)c->chroma_stride * 2, top, (size_t)stride * 2, (size_t)c->chroma_stride * 2, c->chroma_rows,
+                            cudaMemcpyHostToDevice, c->stream));
+    dim3 grid((c->chroma_stride + 255) / 256, c->chroma_rows), block(256);
+    xpel_to_u8_kernel<<<grid, block, 0, c->stream>>>((const int16_t*)c->d_stage.p, c->chroma_stride,
+                                                     c->d_chroma + ((size_t)slot * 2 + comp) * c->chroma_bytes, c->chroma_stride,
+                                                     c->chroma_stride, c->chroma_rows, c->d_bad);
+    c->launches++;
+    CU_OK(cudaGetLastError());
+  }
+  int bad = 0;
+  CU_OK(cudaMemcpyAsync(&bad, c->d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU_OK(cudaStreamSynchronize(c->stream));
+  if (bad) return fail("chroma planes hold %d samples outside [0,255]", bad);
+  c->slot_chroma[slot] = 1;
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_set_org_chroma(jsvm_me_ctx* c, const int16_t* org_chroma_mbs, int n_org_mbs) {
+  if (!c) return fail("null context");
+  if (org_chroma_mbs && n_org_mbs <= 0) return fail("n_org_mbs %d", n_org_mbs);
+  c->org_chroma = org_chroma_mbs; c->n_org_chroma = org_chroma_mbs ? n_org_mbs : 0;
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_map_cost_factor(jsvm_me_ctx* c, uint32_t factor_full_pel, uint32_t factor_sub_pel) {
+  if (!c) return fail("null context");
+  for (uint2& e : c->factor_map)
+    if (e.x == factor_full_pel) { if (e.y != factor_sub_pel) { e.y = factor_sub_pel; c->factor_map_dirty = true; } return JSVM_ME_OK; }
+  if (c->factor_map.size() >= 256) return fail("more than 256 cost-factor pairs registered");
+  c->factor_map.push_back(make_uint2(factor_full_pel, factor_sub_pel));
+  c->factor_map_dirty = true;
+  return JSVM_ME_OK;
+}
+
+// ---- K4: motion-compensated prediction ----
+int jsvm_me_compensate_device(jsvm_me_ctx* c, const jsvm_mc_job* d_jobs, int n_jobs, uint8_t* d_pred_y, uint8_t* d_pred_cb, uint8_t* d_pred_cr) {
+  if (!c || !d_jobs || !d_pred_y) return fail("null argument");
+  if (!c->d_planes) return fail("jsvm_me_configure has not been called");
+  if ((d_pred_cb == nullptr) != (d_pred_cr == nullptr)) return fail("pred_cb and pred_cr must both be given or both be NULL");
+  if (d_pred_cb && !c->d_chroma) return fail("chroma prediction needs the chroma planes (jsvm_me_upload_chroma_*)");
+  if (n_jobs <= 0) return JSVM_ME_OK;
+  CU_OK(cudaSetDevice(c->device));
+  begin_timed(c, 3);
+  compensate_kernel<<<n_jobs, kK4Threads, 0, c->stream>>>(c->d_half, c->half_bytes, c->half_stride, c->d_chroma, c->chroma_bytes, c->chroma_stride,
+                                                          d_jobs, n_jobs, c->W >> 4, c->H >> 4, d_pred_y, d_pred_cb, d_pred_cr);
+  end_timed(c);
+  c->launches++;
+  CU_OK(cudaGetLastError());
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_compensate(jsvm_me_ctx* c, const jsvm_mc_job* jobs, int n_jobs, uint8_t* pred_y, uint8_t* pred_cb, uint8_t* pred_cr) {
+  if (!c || !jobs || !pred_y) return fail("null argument");
+  if (!c->d_planes) return fail("jsvm_me_configure has not been called");
+  if ((pred_cb == nullptr) != (pred_cr == nullptr)) return fail("pred_cb and pred_cr must both be given or both be NULL");
+  if (n_jobs <= 0) return JSVM_ME_OK;
+  const int mbw = c->W >> 4, mbh = c->H >> 4;
+  for (int i = 0; i < n_jobs; ++i) {
+    const jsvm_mc_job& j = jobs[i];
+    if (j.mb_x < 0 || j.mb_x >= mbw || j.mb_y < 0 || j.mb_y >= mbh) return fail("job %d: macroblock (%d,%d) outside the picture", i, j.mb_x, j.mb_y);
+    if (j.blk > 15) return fail("job %d: blk %d out of range", i, (int)j.blk);
+    const bool sx = j.size_x == 16 || j.size_x == 8 || j.size_x == 4, sy = j.size_y == 16 || j.size_y == 8 || j.size_y == 4;
+    if (!sx || !sy || 4 * (j.blk & 3) + j.size_x > 16 || 4 * (j.blk >> 2) + j.size_y > 16)
+      return fail("job %d: block %dx%d at blk %d does not fit the macroblock", i, (int)j.size_x, (int)j.size_y, (int)j.blk);
+    if (j.ref_slot[0] < 0 && j.ref_slot[1] < 0) return fail("job %d: no reference list used", i);
+    if (j.log_denom[0] > 7 || j.log_denom[1] > 7) return fail("job %d: log2 weight denominator above 7", i);
+    for (int l = 0; l < 2; ++l) {
+      if (j.ref_slot[l] < 0) continue;
+      if (j.ref_slot[l] >= c->n_slots) return fail("job %d: ref_slot %d out of range", i, (int)j.ref_slot[l]);
+      if (!c->slot_half[j.ref_slot[l]]) return fail("job %d: ref_slot %d has no half-pel plane", i, (int)j.ref_slot[l]);
+      if (pred_cb && !c->slot_chroma[j.ref_slot[l]]) return fail("job %d: ref_slot %d has no chroma planes", i, (int)j.ref_slot[l]);
+    }
+  }
+  CU_OK(cudaSetDevice(c->device));
+  const size_t per_job = pred_cb ? 384 : 256;
+  if (c->d_mc_jobs.reserve(n_jobs) || c->d_mc_pred.reserve((size_t)n_jobs * per_job)) return JSVM_ME_ERR;
+  CU_OK(cudaMemcpyAsync(c->d_mc_jobs.p, jobs, sizeof(jsvm_mc_job) * n_jobs, cudaMemcpyHostToDevice, c->stream));
+  uint8_t* dy = c->d_mc_pred.p;
+  uint8_t* dcb = pred_cb ? dy + (size_t)n_jobs * 256 : nullptr;
+  uint8_t* dcr = pred_cb ? dcb + (size_t)n_jobs * 64 : nullptr;
+  if (jsvm_me_compensate_device(c, c->d_mc_jobs.p, n_jobs, dy, dcb, dcr)) return JSVM_ME_ERR;
+  CU_OK(cudaMemcpyAsync(pred_y, dy, (size_t)n_jobs * 256, cudaMemcpyDeviceToHost, c->stream));
+  if (pred_cb) {
+    CU_OK(cudaMemcpyAsync(pred_cb, dcb, (size_t)n_jobs * 64, cudaMemcpyDeviceToHost, c->stream));
+    CU_OK(cudaMemcpyAsync(pred_cr, dcr, (size_t)n_jobs * 64, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU_OK(cudaStreamSynchronize(c->stream));
   return JSVM_ME_OK;
 }
 
@@ -691,6 +895,8 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
       c->d_results.reserve(n_jobs) || (want_preds && c->d_preds.reserve((size_t)n_jobs * 256)) ||
       (n_org_mbs > 0 && c->d_org.reserve((size_t)n_org_mbs * 256))) return JSVM_ME_ERR;
   if (n_org_mbs > 0) CU_OK(cudaMemcpyAsync(c->d_org.p, org_mbs, sizeof(int16_t) * 256 * n_org_mbs, cudaMemcpyHostToDevice, c->stream));
+  const int16_t* d_org_chroma = nullptr;
+  if (prepare_search_extras(c, jobs, n_jobs, n_org_mbs, &d_org_chroma)) return JSVM_ME_ERR;
   if (!c->up_stream) {
     CU_OK(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
     CU_OK(cudaStreamCreateWithFlags(&c->down_stream, cudaStreamNonBlocking));
@@ -784,7 +990,7 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
     CU_OK(cudaEventRecord(c->chunk_done[launch & 3], c->up_stream));                // ring slot consumed; the batch is on the device
     CU_OK(cudaStreamWaitEvent(c->stream, c->chunk_done[launch & 3], 0));
     if (run_search(c, c->d_jobs.p, begin, end, c->d_groups.p + groups_done, &info, c->d_org.p, c->d_keys.p, c->d_aux.p, c->d_results.p,
-                   want_preds ? c->d_preds.p : nullptr)) return JSVM_ME_ERR;
+                   want_preds ? c->d_preds.p : nullptr, d_org_chroma)) return JSVM_ME_ERR;
     CU_OK(cudaEventRecord(c->ev_kernels, c->stream));
     CU_OK(cudaStreamWaitEvent(c->down_stream, c->ev_kernels, 0));
     CU_OK(cudaMemcpyAsync(results + begin, c->d_results.p + begin, sizeof(jsvm_me_result) * (end - begin), cudaMemcpyDeviceToHost, c->down_stream));
@@ -841,7 +1047,7 @@ int jsvm_me_timing_end(jsvm_me_ctx* c, double* ms_interp, double* ms_search, dou
   if (!c) return fail("null context");
   CU_OK(cudaSetDevice(c->device));
   CU_OK(cudaStreamSynchronize(c->stream));
-  double ms[3] = {0, 0, 0}; uint64_t n[3] = {0, 0, 0};
+  double ms[4] = {0, 0, 0, 0}; uint64_t n[4] = {0, 0, 0, 0};
   for (auto& t : c->timed) {
     float f = 0;
     CU_OK(cudaEventElapsedTime(&f, t.e0, t.e1));
@@ -852,6 +1058,14 @@ int jsvm_me_timing_end(jsvm_me_ctx* c, double* ms_interp, double* ms_search, dou
   c->timing = false;
   if (ms_interp) *ms_interp = ms[0]; if (ms_search) *ms_search = ms[1]; if (ms_subpel) *ms_subpel = ms[2];
   if (n_interp) *n_interp = n[0]; if (n_search) *n_search = n[1]; if (n_subpel) *n_subpel = n[2];
+  c->last_mc_ms = ms[3]; c->last_mc_n = n[3];
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_timing_compensate(jsvm_me_ctx* c, double* ms_compensate, uint64_t* n_compensate) {
+  if (!c) return fail("null context");
+  if (ms_compensate) *ms_compensate = c->last_mc_ms;
+  if (n_compensate) *n_compensate = c->last_mc_n;
   return JSVM_ME_OK;
 }
 

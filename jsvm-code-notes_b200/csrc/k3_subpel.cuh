@@ -90,7 +90,8 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
               const uint32_t* __restrict__ keys,
               const uint32_t* __restrict__ full_costs,   // NULL: keys hold (cost << 15 | index) of the packed-byte SAD search;
                                                          // else (generic SSD / Hadamard search): keys = index, full_costs = cost
-              jsvm_me_result* __restrict__ results, uint8_t* __restrict__ preds)
+              jsvm_me_result* __restrict__ results, uint8_t* __restrict__ preds,
+              const uint2* __restrict__ factor_map, int n_factor_map)    // (full-pel factor, sub-pel factor) pairs; 0: one factor for both stages
 {
   constexpr bool HAD = DFUNC == JSVM_DF_HADAMARD, SSD = DFUNC == JSVM_DF_SSD;
   __shared__ __align__(16) K3Warp s_warp[kK3WarpsPerCta];
@@ -104,14 +105,25 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
   mode_size(j.mode, w, h);
   const int nbx = w >> 2, nb = nbx * (h >> 2);               // 4x4 sub-blocks per row / per block: powers of two
   const int lg_nbx = 31 - __clz(nbx), lg_nb = 31 - __clz(nb);
-  const uint32_t f = j.cost_factor;
+  // The job carries the factor of the full-pel stage; the sub-pel stage and the final cost use the factor xSetMEPars( 0, ... )
+  // selects (ENC/MotionEstimation.cpp:325): the same one unless the two stages are of different classes (SAD-type vs SSE),
+  // in which case the host registered the pair (jsvm_me_map_cost_factor).  An unmapped factor was rejected before the launch.
+  const uint32_t f_full = j.cost_factor;
+  uint32_t f = f_full;
+  if (n_factor_map > 0) {
+    uint32_t hit = 0xffffffffu;
+    for (int i = lane; i < n_factor_map; i += 32)
+      if (factor_map[i].x == f_full) hit = (uint32_t)i;
+    hit = __reduce_min_sync(0xffffffffu, hit);
+    if (hit != 0xffffffffu) f = factor_map[hit].y;
+  }
 
   // ---- decode the full-pel winner (xPelBlockSearch result) ----
   const uint32_t key = keys[job_idx];
   const uint32_t idx = full_costs ? key : key & ((1u << kIdxBits) - 1);
   const int fx = a.ux0 + (int)(idx % (uint32_t)a.uw), fy = a.uy0 + (int)(idx / (uint32_t)a.uw);
   const uint32_t full_cost = full_costs ? full_costs[job_idx] : key >> kIdxBits;
-  const uint32_t full_rate = rate_cost(f, mv_component_bits((fx << 2) - j.pred.hor) + mv_component_bits((fy << 2) - j.pred.ver));
+  const uint32_t full_rate = rate_cost(f_full, mv_component_bits((fx << 2) - j.pred.hor) + mv_component_bits((fy << 2) - j.pred.ver));
 
   const int bx0 = 16 * j.mb_x + 4 * (j.blk & 3), by0 = 16 * j.mb_y + 4 * (j.blk >> 2);
 

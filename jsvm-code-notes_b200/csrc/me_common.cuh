@@ -18,6 +18,7 @@ namespace jsvm {
 
 constexpr int kMargin   = JSVM_ME_MARGIN;   // 32
 constexpr int kHpOrigin = 2 * kMargin;      // 64
+constexpr int kCMargin  = kMargin / 2;      // chroma plane margin: 16 samples on every side (INCC/YuvPicBuffer.h:68-69)
 
 // Partition slots of one macroblock (41 = 1 + 2 + 2 + 4 + 8 + 8 + 16).
 //   0        16x16

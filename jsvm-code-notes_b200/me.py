@@ -17,7 +17,7 @@ import ctypes as C
 import numpy as np
 
 from . import abi
-from .abi import JOB_DTYPE, RESULT_DTYPE, PlanInfo
+from .abi import JOB_DTYPE, RESULT_DTYPE, MC_JOB_DTYPE, PlanInfo
 
 
 class MotionEstimationError(RuntimeError):
@@ -107,6 +107,48 @@ class MotionEstimator:
             raise MotionEstimationError(f"plane shape {p.shape}: expected ({self.height} + 2*v_margin, {s}) with v_margin >= {abi.MARGIN}")
         origin = p.ctypes.data + 2 * (vm * s + abi.MARGIN)
         self._check(self._lib.jsvm_me_upload_plane_xpel(self._ctx, slot, C.c_void_p(origin), self.width, self.height, s))
+
+    def upload_chroma(self, slot, cb, cr):
+        """cb, cr: (H/2, W/2) uint8 ndarrays (no margins): the slot's chroma planes (YUV_SAD search, compensate)."""
+        cb = np.ascontiguousarray(cb, dtype=np.uint8)
+        cr = np.ascontiguousarray(cr, dtype=np.uint8)
+        shape = (self.height // 2, self.width // 2)
+        if cb.shape != shape or cr.shape != shape:
+            raise MotionEstimationError(f"chroma plane shapes {cb.shape} / {cr.shape} != {shape}")
+        self._check(self._lib.jsvm_me_upload_chroma_u8(self._ctx, slot, _ptr(cb), _ptr(cr), shape[1]))
+
+    def upload_chroma_xpel(self, slot, cb_with_margin, cr_with_margin):
+        """(H/2 + 32, W/2 + 32) int16 planes laid out like YuvPicBuffer chroma planes with their 16-sample margins filled."""
+        planes = [np.ascontiguousarray(p, dtype=np.int16) for p in (cb_with_margin, cr_with_margin)]
+        s = self.width // 2 + abi.MARGIN
+        for p in planes:
+            if p.shape != (self.height // 2 + abi.MARGIN, s):
+                raise MotionEstimationError(f"chroma plane shape {p.shape}: expected {(self.height // 2 + abi.MARGIN, s)}")
+        org = [p.ctypes.data + 2 * ((abi.MARGIN // 2) * s + abi.MARGIN // 2) for p in planes]
+        self._check(self._lib.jsvm_me_upload_chroma_xpel(self._ctx, slot, C.c_void_p(org[0]), C.c_void_p(org[1]), s))
+
+    def set_org_chroma(self, org_chroma_mbs):
+        """(n, 2, 8, 8) int16 chroma originals of the caller-prepared macroblocks (or None); kept alive until replaced."""
+        if org_chroma_mbs is None:
+            self._org_chroma = None
+            self._check(self._lib.jsvm_me_set_org_chroma(self._ctx, None, 0))
+            return
+        self._org_chroma = np.ascontiguousarray(org_chroma_mbs, dtype=np.int16).reshape(-1, 2, 8, 8)
+        self._check(self._lib.jsvm_me_set_org_chroma(self._ctx, _ptr(self._org_chroma), len(self._org_chroma)))
+
+    def map_cost_factor(self, factor_full_pel, factor_sub_pel):
+        self._check(self._lib.jsvm_me_map_cost_factor(self._ctx, int(factor_full_pel), int(factor_sub_pel)))
+
+    def compensate(self, mc_jobs, chroma=True):
+        """MotionCompensation (predBlk / xPredChromaPel / SampleWeighting) for every MC_JOB_DTYPE record.
+        Returns (pred_y (n,16,16), pred_cb (n,8,8), pred_cr (n,8,8)) uint8 (chroma None when chroma=False)."""
+        jobs = np.ascontiguousarray(mc_jobs, dtype=MC_JOB_DTYPE)
+        n = len(jobs)
+        py = np.zeros((n, 16, 16), np.uint8)
+        pcb = np.zeros((n, 8, 8), np.uint8) if chroma else None
+        pcr = np.zeros((n, 8, 8), np.uint8) if chroma else None
+        self._check(self._lib.jsvm_me_compensate(self._ctx, _ptr(jobs), n, _ptr(py), _ptr(pcb), _ptr(pcr)))
+        return py, pcb, pcr
 
     def interp_halfpel(self, slots):
         """QuarterPelFilter::filterFrame for one slot or a list of slots (one launch)."""

@@ -12,7 +12,7 @@ import math
 
 import numpy as np
 
-from .abi import (JOB_DTYPE, MODE_16x16, MODE_16x8, MODE_8x16, BLK_8x8, BLK_8x4, BLK_4x8, BLK_4x4, DF_SAD, DF_HADAMARD)
+from .abi import (MC_JOB_DTYPE, MC_WEIGHT_UNI, MC_WEIGHT_BI, JOB_DTYPE, MODE_16x16, MODE_16x8, MODE_8x16, BLK_8x8, BLK_8x4, BLK_4x8, BLK_4x4, DF_SAD, DF_HADAMARD)
 
 # (mode, blk) of the 9-partition set {16x16, 2 x 16x8, 2 x 8x16, 4 x 8x8} and of all 41 partitions
 PARTS_9 = [(MODE_16x16, 0), (MODE_16x8, 0), (MODE_16x8, 8), (MODE_8x16, 0), (MODE_8x16, 2),
@@ -78,6 +78,75 @@ class Sequence:
         rng = np.random.default_rng(self.seed * 1000003 + n)
         f = f + rng.normal(0.0, 2.0, f.shape)
         return np.clip(np.rint(f), 0, 255).astype(np.uint8)
+
+
+def chroma_planes(width, height, seed):
+    """Seeded (Cb, Cr) planes of a 4:2:0 picture: smooth texture with full 8-bit range (YUV_SAD search, chroma MC)."""
+    rng = np.random.default_rng(seed * 7919 + 17)
+    out = []
+    for _ in range(2):
+        coarse = rng.integers(0, 256, (height // 8 + 2, width // 8 + 2)).astype(np.float64)
+        fine = _box_blur(np.kron(coarse, np.ones((4, 4)))[:height // 2, :width // 2], 5)
+        fine = (fine - fine.min()) / max(1e-9, fine.max() - fine.min()) * 255.0 + rng.normal(0.0, 2.0, fine.shape)
+        out.append(np.clip(np.rint(fine), 0, 255).astype(np.uint8))
+    return out[0], out[1]
+
+
+def make_mc_jobs(width, height, n, n_slots, seed=0, kind="uni", mv_range=96, sizes=((16, 16), (16, 8), (8, 16), (8, 8), (8, 4), (4, 8), (4, 4))):
+    """n motion-compensation jobs with seeded random macroblocks, block sizes and quarter-pel MVs (every fractional phase;
+    |mv| up to mv_range quarter-pels plus a few far outliers that the per-MB clamp catches).
+
+    kind: "uni" (one list, plain), "bi" (two lists, (a+b+1)>>1), "uni_w" (explicit weights, one list),
+          "bi_w" (explicit weights, two lists), "bi_implicit" (implicit weights: w0 + w1 = 64, denominators 5)."""
+    rng = np.random.default_rng(seed)
+    mbw, mbh = width // 16, height // 16
+    jobs = np.zeros(n, MC_JOB_DTYPE)
+    jobs["mb_x"] = rng.integers(0, mbw, n)
+    jobs["mb_y"] = rng.integers(0, mbh, n)
+    # corners and edges first
+    fixed = [(0, 0), (mbw - 1, 0), (0, mbh - 1), (mbw - 1, mbh - 1)]
+    for i, (x, y) in enumerate(fixed[:n]):
+        jobs["mb_x"][i], jobs["mb_y"][i] = x, y
+    for i in range(n):
+        sx, sy = sizes[rng.integers(0, len(sizes))]
+        if kind.startswith("bi") and (sx < 8 or sy < 8) and kind == "bi":
+            sx, sy = 8, 8                      # the reference mixes bi-pred sub-8x8 blocks per 8x8 (compensateSubMb)
+        bx = rng.integers(0, (16 - sx) // 4 + 1)
+        by = rng.integers(0, (16 - sy) // 4 + 1)
+        jobs["blk"][i] = by * 4 + bx
+        jobs["size_x"][i], jobs["size_y"][i] = sx, sy
+    mv = rng.integers(-mv_range, mv_range + 1, (n, 2, 2))
+    far = rng.random(n) < 0.05
+    mv[far] = rng.integers(-4000, 4001, (int(far.sum()), 2, 2))
+    jobs["mv"] = mv.astype(np.int16)
+    two = kind.startswith("bi")
+    jobs["ref_slot"][:, 0] = rng.integers(0, n_slots, n)
+    jobs["ref_slot"][:, 1] = rng.integers(0, n_slots, n) if two else -1
+    if kind == "uni":
+        flip = rng.random(n) < 0.3                                       # some blocks predicted from LIST_1 only
+        jobs["ref_slot"][flip, 1] = jobs["ref_slot"][flip, 0]
+        jobs["ref_slot"][flip, 0] = -1
+    jobs["log_denom"] = 0
+    if kind in ("uni_w", "bi_w"):
+        jobs["weighting"] = MC_WEIGHT_UNI | MC_WEIGHT_BI if kind == "bi_w" else MC_WEIGHT_UNI
+        jobs["log_denom"][:, 0] = rng.integers(0, 8, n)
+        jobs["log_denom"][:, 1] = rng.integers(0, 8, n)
+        for l in range(2):
+            for comp in range(3):
+                d = jobs["log_denom"][:, 1 if comp else 0].astype(np.int64)
+                hi = np.minimum(127, (1 << d) * 2)
+                # explicit weights: -128..127 in general; two lists: w0 + w1 <= 127 / 128 (COM/SampleWeighting.cpp:443-444)
+                jobs["weight"][:, l, comp] = rng.integers(-hi // (2 if two else 1), hi // (2 if two else 1) + 1)
+                jobs["offset"][:, l, comp] = rng.integers(-20, 21, n)
+        jobs["weight_flag"] = rng.integers(0, 2, (n, 2))
+    elif kind == "bi_implicit":
+        jobs["weighting"] = MC_WEIGHT_BI
+        jobs["log_denom"] = 5
+        w1 = rng.integers(-64, 129, n)                                  # implicit: w1 = DistScaleFactor >> 2, w0 = 64 - w1
+        for comp in range(3):
+            jobs["weight"][:, 1, comp] = w1
+            jobs["weight"][:, 0, comp] = 64 - w1
+    return jobs
 
 
 def make_jobs(width, height, parts, cur_slot, ref_slot, qp=30, field="random", seed=0, mb_subset=None, bits_in=0):

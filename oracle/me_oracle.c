@@ -18,9 +18,12 @@
 #define MARGIN   JSVM_ME_MARGIN          /* INCC/CommonDefs.h:246 YUV_X_MARGIN; y margin = 64/2 (COM/YuvBufferCtrl.cpp:134-135) */
 #define HP_ORG   (2 * MARGIN)            /* origin offset inside our half-pel plane (both axes) */
 
+#define CMARGIN  (MARGIN / 2)            /* chroma margin, INCC/YuvPicBuffer.h:68-69 */
+
 typedef struct {
   uint8_t* full;   /* (H+64) x (W+64), origin at (32,32) */
   uint8_t* half;   /* 2(H+64) x 2(W+64), origin at (64,64); only [-56, 2(W+28)) x [-56, 2(H+28)) is written */
+  uint8_t* chroma[2];   /* Cb, Cr: (H/2+32) x (W/2+32), origin at (16,16); 128 until jsvm_ora_set_chroma_u8 */
   int      valid;
 } ora_plane;
 
@@ -28,6 +31,8 @@ struct jsvm_ora_ctx {
   int width, height, n_slots;
   int search_mode, full_dfunc, sub_dfunc, search_range;
   ora_plane* planes;
+  uint32_t factor_map[256][2]; int n_factor_map;   /* full-pel stage factor -> sub-pel stage factor */
+  const int16_t* org_chroma; int n_org_chroma;
 };
 
 static inline int clip255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }   /* gClip, INCC/GlobalFunctions.h:37-44 */
@@ -150,32 +155,37 @@ jsvm_ora_ctx* jsvm_ora_create(int width, int height, int n_slots,
   for (int s = 0; s < n_slots; ++s) {
     c->planes[s].full = (uint8_t*)calloc((size_t)(width + 2 * MARGIN) * (height + 2 * MARGIN), 1);
     c->planes[s].half = (uint8_t*)calloc((size_t)4 * (width + 2 * MARGIN) * (height + 2 * MARGIN), 1);
+    for (int k = 0; k < 2; ++k) {
+      c->planes[s].chroma[k] = (uint8_t*)malloc((size_t)(width / 2 + 2 * CMARGIN) * (height / 2 + 2 * CMARGIN));
+      memset(c->planes[s].chroma[k], 128, (size_t)(width / 2 + 2 * CMARGIN) * (height / 2 + 2 * CMARGIN));
+    }
   }
   return c;
 }
 
 void jsvm_ora_destroy(jsvm_ora_ctx* c) {
   if (!c) return;
-  for (int s = 0; s < c->n_slots; ++s) { free(c->planes[s].full); free(c->planes[s].half); }
+  for (int s = 0; s < c->n_slots; ++s) { free(c->planes[s].full); free(c->planes[s].half); free(c->planes[s].chroma[0]); free(c->planes[s].chroma[1]); }
   free(c->planes);
   free(c);
 }
 
 /* YuvPicBuffer::xFillPlaneMargin (COM/YuvPicBuffer.cpp:1608-1641): left/right replicate per row,
  * then whole padded rows are copied down / up. */
-static void fill_margin(uint8_t* full, int W, int H) {
-  const int S = W + 2 * MARGIN;
-  uint8_t* org = full + MARGIN * S + MARGIN;
+static void fill_margin_m(uint8_t* full, int W, int H, int M) {
+  const int S = W + 2 * M;
+  uint8_t* org = full + M * S + M;
   for (int y = 0; y < H; ++y) {
     uint8_t* r = org + y * S;
-    for (int m = -MARGIN; m < 0; ++m) r[m] = r[0];
-    for (int m = W; m < W + MARGIN; ++m) r[m] = r[W - 1];
+    for (int m = -M; m < 0; ++m) r[m] = r[0];
+    for (int m = W; m < W + M; ++m) r[m] = r[W - 1];
   }
-  for (int n = 0; n < MARGIN; ++n) {
-    memcpy(org - MARGIN + (H + n) * S, org - MARGIN + (H - 1) * S, (size_t)S);
-    memcpy(org - MARGIN - (n + 1) * S, org - MARGIN, (size_t)S);
+  for (int n = 0; n < M; ++n) {
+    memcpy(org - M + (H + n) * S, org - M + (H - 1) * S, (size_t)S);
+    memcpy(org - M - (n + 1) * S, org - M, (size_t)S);
   }
 }
+static void fill_margin(uint8_t* full, int W, int H) { fill_margin_m(full, W, H, MARGIN); }
 
 /* a12 QuarterPelFilter::filterFrame (COM/QuarterPelFilter.cpp:61-149).
  * Pass 1 (:83-102): per picture row, x in [-28, W+28): tmp[2x] = s[x] << 5,
@@ -241,6 +251,35 @@ int jsvm_ora_set_plane_u8(jsvm_ora_ctx* c, int slot, const uint8_t* luma, int st
   memset(p->half, 0, (size_t)4 * S * (H + 2 * MARGIN));
   filter_frame(p->full, p->half, W, H);
   p->valid = 1;
+  return 0;
+}
+
+/* Chroma planes of a slot and their margins (YuvPicBuffer::fillMargin, COM/YuvPicBuffer.cpp:1595-1606: the same replication
+ * with the chroma margin). */
+int jsvm_ora_set_chroma_u8(jsvm_ora_ctx* c, int slot, const uint8_t* cb, const uint8_t* cr, int stride) {
+  if (!c || slot < 0 || slot >= c->n_slots) return -1;
+  const int CW = c->width / 2, CH = c->height / 2, CS = CW + 2 * CMARGIN;
+  for (int k = 0; k < 2; ++k) {
+    uint8_t* p = c->planes[slot].chroma[k];
+    for (int y = 0; y < CH; ++y) memcpy(p + (size_t)(CMARGIN + y) * CS + CMARGIN, (k ? cr : cb) + (size_t)y * stride, (size_t)CW);
+    fill_margin_m(p, CW, CH, CMARGIN);
+  }
+  return 0;
+}
+
+int jsvm_ora_set_org_chroma(jsvm_ora_ctx* c, const int16_t* org_chroma_mbs, int n_org_mbs) {
+  if (!c) return -1;
+  c->org_chroma = org_chroma_mbs; c->n_org_chroma = org_chroma_mbs ? n_org_mbs : 0;
+  return 0;
+}
+
+int jsvm_ora_map_cost_factor(jsvm_ora_ctx* c, uint32_t factor_full_pel, uint32_t factor_sub_pel) {
+  if (!c) return -1;
+  for (int k = 0; k < c->n_factor_map; ++k)
+    if (c->factor_map[k][0] == factor_full_pel) { c->factor_map[k][1] = factor_sub_pel; return 0; }
+  if (c->n_factor_map >= 256) return -1;
+  c->factor_map[c->n_factor_map][0] = factor_full_pel; c->factor_map[c->n_factor_map][1] = factor_sub_pel;
+  c->n_factor_map++;
   return 0;
 }
 
@@ -349,7 +388,35 @@ int jsvm_ora_search(jsvm_ora_ctx* c, const jsvm_me_job* jobs, int n_jobs,
         else
           org[y * 16 + x] = cur->full[(size_t)(MARGIN + by0 + y) * S + MARGIN + bx0 + x];
       }
-    const uint32_t f = j->cost_factor;
+    /* xSetMEPars( 2, 1 != FullPelDFunc ) / xSetMEPars( 0, 1 != ( 1 & SubPelDFunc ) ) (ENC/MotionEstimation.cpp:255, 325): the job
+     * carries the factor of the full-pel stage; when the sub-pel stage is of the other class its factor comes from the map */
+    const uint32_t f_full = j->cost_factor;
+    uint32_t f = f_full;
+    if ((c->full_dfunc == JSVM_DF_SSD) != (c->sub_dfunc == JSVM_DF_SSD)) {
+      int found = 0;
+      for (int k = 0; k < c->n_factor_map; ++k) if (c->factor_map[k][0] == f_full) { f = c->factor_map[k][1]; found = 1; }
+      if (!found) return -1;
+    }
+    /* a5 YUV_SAD (xGetYuvSAD16x/8x/4x, ENC/Distortion.cpp:435-505, 593-647, 718-764): luma SAD + SAD of the (w/2) x (h/2) Cb and
+     * Cr blocks displaced by ( x>>1, y>>1 ) (ENC/MotionEstimation.cpp:386-387).  Falls back to SAD for originals prepared
+     * without chroma (bi-pred / unequal weights, :250-253). */
+    int full_dfunc = c->full_dfunc;
+    int16_t corg[2][64];
+    memset(corg, 0, sizeof(corg));
+    if (full_dfunc == JSVM_DF_YUV_SAD) {
+      if (j->org_index >= 0 && !c->org_chroma) full_dfunc = JSVM_DF_SAD;
+      else {
+        if (j->org_index >= 0 && j->org_index >= c->n_org_chroma) return -1;
+        const int CS = W / 2 + 2 * CMARGIN;
+        for (int k = 0; k < 2; ++k)
+          for (int y = 0; y < h / 2; ++y)
+            for (int x = 0; x < w / 2; ++x) {
+              const int cy = 2 * (j->blk >> 2) + y, cx = 2 * (j->blk & 3) + x;
+              corg[k][y * 8 + x] = j->org_index >= 0 ? c->org_chroma[(size_t)j->org_index * 128 + k * 64 + cy * 8 + cx]
+                                                     : cur->chroma[k][(size_t)(CMARGIN + 8 * j->mb_y + cy) * CS + CMARGIN + 8 * j->mb_x + cx];
+            }
+      }
+    }
 
     /* ---- a2 xPelBlockSearch (ENC/MotionEstimation.cpp:351-412) ---- */
     int cx, cy; search_rect r;
@@ -360,20 +427,28 @@ int jsvm_ora_search(jsvm_ora_ctx* c, const jsvm_me_job* jobs, int n_jobs,
     for (int y = -r.neg_ver; y <= r.pos_ver; ++y)
       for (int x = -r.neg_hor; x <= r.pos_hor; ++x) {
         uint32_t sad;
-        if (c->full_dfunc == JSVM_DF_SAD) {                 /* same sums as distortion(); direct loops keep the checker fast */
+        if (full_dfunc == JSVM_DF_SAD || full_dfunc == JSVM_DF_YUV_SAD) {   /* same sums as distortion(); direct loops keep the checker fast */
           const uint8_t* rp = ref0 + y * S + x;
           sad = 0;
           for (int yy = 0; yy < h; ++yy)
             for (int xx = 0; xx < w; ++xx) sad += (uint32_t)abs(org[yy * 16 + xx] - rp[yy * S + xx]);
+          if (full_dfunc == JSVM_DF_YUV_SAD) {
+            const int CS = W / 2 + 2 * CMARGIN;
+            for (int k = 0; k < 2; ++k) {
+              const uint8_t* cp = ref->chroma[k] + (size_t)(CMARGIN + by0 / 2 + (y >> 1)) * CS + CMARGIN + bx0 / 2 + (x >> 1);
+              for (int yy = 0; yy < h / 2; ++yy)
+                for (int xx = 0; xx < w / 2; ++xx) sad += (uint32_t)abs(corg[k][yy * 8 + xx] - cp[yy * CS + xx]);
+            }
+          }
         } else {
           u8_src s = { ref0 + y * S + x, S };
-          sad = distortion(org, get_u8, &s, w, h, c->full_dfunc);
+          sad = distortion(org, get_u8, &s, w, h, full_dfunc);
         }
         /* xGetCost( x, y ) with m_uiMvScaleShift = 2 (N6): table index (x<<2) - pred */
-        sad += rate_cost(f, jsvm_ora_component_bits((x << 2) - j->pred.hor) + jsvm_ora_component_bits((y << 2) - j->pred.ver));
+        sad += rate_cost(f_full, jsvm_ora_component_bits((x << 2) - j->pred.hor) + jsvm_ora_component_bits((y << 2) - j->pred.ver));
         if (best > sad) { best = sad; best_x = x; best_y = y; }       /* first strict minimum in raster order (N1) */
       }
-    best -= rate_cost(f, jsvm_ora_component_bits((best_x << 2) - j->pred.hor) + jsvm_ora_component_bits((best_y << 2) - j->pred.ver));
+    best -= rate_cost(f_full, jsvm_ora_component_bits((best_x << 2) - j->pred.hor) + jsvm_ora_component_bits((best_y << 2) - j->pred.ver));
     jsvm_me_result* out = &results[i];
     out->mv_fullpel.hor = (int16_t)best_x; out->mv_fullpel.ver = (int16_t)best_y;
     out->sad_fullpel = best;
@@ -425,6 +500,116 @@ int jsvm_ora_search(jsvm_ora_ctx* c, const jsvm_me_job* jobs, int n_jobs,
       } else {
         qp_src s = { qc, HS, kQuarterMv[q_winner][0], kQuarterMv[q_winner][1], axis_diag };
         for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) dp[y * 16 + x] = (uint8_t)get_qp(&s, x, y);
+      }
+    }
+  }
+  return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * f3  Motion-compensated prediction: MotionCompensation::xGetMbPredData (limitComponents, COM/MotionCompensation.cpp:1390),
+ *     QuarterPelFilter::predBlk and its helpers (COM/QuarterPelFilter.cpp:266-619), xPredChromaPel (COM/MotionCompensation.cpp:206-276),
+ *     SampleWeighting::weightLumaSamples / weightChromaSamples (COM/SampleWeighting.cpp:159-265) with xMixB / xMixBWeight / xWeight
+ *     (:382-461).  Luma is filtered from the FULL-pel plane as predBlk does (the product gathers from the half-pel plane).
+ * ------------------------------------------------------------------------------------------- */
+static int tap6(int a, int b, int c2, int d, int e, int f) { return a - 5 * b + 20 * c2 + 20 * d - 5 * e + f; }
+static int h6(const uint8_t* p) { return tap6(p[-2], p[-1], p[0], p[1], p[2], p[3]); }
+static int v6(const uint8_t* p, int S) { return tap6(p[-2 * S], p[-S], p[0], p[S], p[2 * S], p[3 * S]); }
+
+static int pred_luma_sample(const uint8_t* p /* integer sample at floor(mv) */, int S, int dx, int dy) {
+  if (dy == 0) {
+    if (dx == 0) return p[0];
+    const int b = clip255((h6(p) + 16) / 32);
+    return dx == 2 ? b : (b + p[dx >> 1] + 1) / 2;                       /* xPredDy0Dx2 / xPredDy0Dx13 */
+  }
+  if (dx == 0) {
+    const int hh = clip255((v6(p, S) + 16) / 32);
+    return dy == 2 ? hh : (hh + p[(dy >> 1) * S] + 1) / 2;               /* xPredDx0Dy2 / xPredDx0Dy13 */
+  }
+  if (dx == 2) {                                                       /* xPredDx2Dy2 / xPredDx2Dy13: rows of unrounded H-6-taps */
+    int t[6];
+    for (int n = 0; n < 6; ++n) t[n] = h6(p + (n - 2) * S);
+    const int jj = clip255((tap6(t[0], t[1], t[2], t[3], t[4], t[5]) + 512) / 1024);
+    if (dy == 2) return jj;
+    return (jj + clip255((t[dy == 1 ? 2 : 3] + 16) / 32) + 1) / 2;
+  }
+  if (dy == 2) {                                                       /* xPredDy2Dx13: columns of unrounded V-6-taps */
+    int t[6];
+    for (int n = 0; n < 6; ++n) t[n] = v6(p + n - 2, S);
+    const int jj = clip255((tap6(t[0], t[1], t[2], t[3], t[4], t[5]) + 512) / 1024);
+    return (jj + clip255((t[dx == 1 ? 2 : 3] + 16) / 32) + 1) / 2;
+  }
+  /* xPredElse: H-half sample of row (dy==1 ? 0 : 1), V-half sample of column (dx==1 ? 0 : 1) */
+  const int bx = clip255((h6(p + (dy == 1 ? 0 : S)) + 16) / 32);
+  const int hy = clip255((v6(p + (dx == 1 ? 0 : 1), S) + 16) / 32);
+  return (bx + hy + 1) >> 1;
+}
+
+static int pred_chroma_sample(const uint8_t* p, int S, int xF1, int yF1) {        /* xPredChromaPel, all four branches */
+  if (xF1 == 0 && yF1 == 0) return p[0];
+  if (xF1 == 0) return ((8 - yF1) * p[0] + yF1 * p[S] + 4) >> 3;
+  if (yF1 == 0) return ((8 - xF1) * p[0] + xF1 * p[1] + 4) >> 3;
+  const int xF0 = 8 - xF1, yF0 = 8 - yF1;
+  return (xF0 * (yF0 * p[0] + yF1 * p[S]) + xF1 * (yF0 * p[1] + yF1 * p[S + 1]) + 0x20) >> 6;
+}
+
+static int weight_samples(const jsvm_mc_job* j, int comp, int a, int b, int has0, int has1) {
+  const int d = j->log_denom[comp ? 1 : 0];
+  if (has0 && has1) {
+    if (!(j->weighting & JSVM_MC_WEIGHT_BI)) return (a + b + 1) >> 1;                              /* xMixB */
+    const int off = (j->offset[0][comp] + j->offset[1][comp] + 1) >> 1;                           /* xMixBWeight */
+    return clip255(((j->weight[0][comp] * a + j->weight[1][comp] * b + (1 << d)) >> (d + 1)) + off);
+  }
+  const int l = has0 ? 0 : 1, v = has0 ? a : b;
+  if ((j->weighting & JSVM_MC_WEIGHT_UNI) && j->weight_flag[comp ? 1 : 0])                         /* xWeight */
+    return clip255((j->weight[l][comp] * v + (((1 + j->offset[l][comp] * 2) << d) >> 1)) >> d);
+  return v;
+}
+
+int jsvm_ora_compensate(jsvm_ora_ctx* c, const jsvm_mc_job* jobs, int n_jobs, uint8_t* pred_y, uint8_t* pred_cb, uint8_t* pred_cr) {
+  if (!c) return -1;
+  const int W = c->width, H = c->height, S = W + 2 * MARGIN, CS = W / 2 + 2 * CMARGIN;
+  const int mbw = W >> 4, mbh = H >> 4;
+  for (int i = 0; i < n_jobs; ++i) {
+    const jsvm_mc_job* j = &jobs[i];
+    if (j->mb_x < 0 || j->mb_x >= mbw || j->mb_y < 0 || j->mb_y >= mbh || j->blk > 15) return -1;
+    const int16_t min_h = sat16(((-(int)j->mb_x << 4) - 24) << 2), min_v = sat16(((-(int)j->mb_y << 4) - 24) << 2);
+    const int16_t max_h = sat16((((mbw - j->mb_x) << 4) + 8) << 2), max_v = sat16((((mbh - j->mb_y) << 4) + 8) << 2);
+    const int bx0 = 16 * j->mb_x + 4 * (j->blk & 3), by0 = 16 * j->mb_y + 4 * (j->blk >> 2);
+    int has[2], mvx[2], mvy[2];
+    for (int l = 0; l < 2; ++l) {
+      has[l] = j->ref_slot[l] >= 0;
+      if (has[l] && (j->ref_slot[l] >= c->n_slots || !c->planes[j->ref_slot[l]].valid)) return -1;
+      mvx[l] = imin(max_h, imax(min_h, j->mv[l].hor));
+      mvy[l] = imin(max_v, imax(min_v, j->mv[l].ver));
+    }
+    if (!has[0] && !has[1]) return -1;
+    uint8_t* dy = pred_y + (size_t)i * 256;
+    memset(dy, 0, 256);
+    for (int y = 0; y < j->size_y; ++y)
+      for (int x = 0; x < j->size_x; ++x) {
+        int v[2] = { 0, 0 };
+        for (int l = 0; l < 2; ++l)
+          if (has[l]) {
+            const uint8_t* p = c->planes[j->ref_slot[l]].full + (size_t)(MARGIN + by0 + y + (mvy[l] >> 2)) * S + MARGIN + bx0 + x + (mvx[l] >> 2);
+            v[l] = pred_luma_sample(p, S, mvx[l] & 3, mvy[l] & 3);
+          }
+        dy[y * 16 + x] = (uint8_t)weight_samples(j, 0, v[0], v[1], has[0], has[1]);
+      }
+    if (pred_cb && pred_cr) {
+      uint8_t* d[2] = { pred_cb + (size_t)i * 64, pred_cr + (size_t)i * 64 };
+      for (int k = 0; k < 2; ++k) {
+        memset(d[k], 0, 64);
+        for (int y = 0; y < j->size_y / 2; ++y)
+          for (int x = 0; x < j->size_x / 2; ++x) {
+            int v[2] = { 0, 0 };
+            for (int l = 0; l < 2; ++l)
+              if (has[l]) {
+                const uint8_t* p = c->planes[j->ref_slot[l]].chroma[k] + (size_t)(CMARGIN + by0 / 2 + y + (mvy[l] >> 3)) * CS + CMARGIN + bx0 / 2 + x + (mvx[l] >> 3);
+                v[l] = pred_chroma_sample(p, CS, mvx[l] & 7, mvy[l] & 7);
+              }
+            d[k][y * 8 + x] = (uint8_t)weight_samples(j, 1 + k, v[0], v[1], has[0], has[1]);
+          }
       }
     }
   }

@@ -40,6 +40,12 @@ uint32_t jsvm_ora_component_bits(int d);
 /* number of integer search positions of one job (clipped window size), for ALG_OPS accounting */
 int jsvm_ora_window_positions(jsvm_ora_ctx* ctx, const jsvm_me_job* job);
 
+/* chroma planes, chroma originals, cost-factor pairs, motion-compensated prediction: see ref_harness.h */
+int jsvm_ora_set_chroma_u8(jsvm_ora_ctx* ctx, int slot, const uint8_t* cb, const uint8_t* cr, int stride);
+int jsvm_ora_set_org_chroma(jsvm_ora_ctx* ctx, const int16_t* org_chroma_mbs, int n_org_mbs);
+int jsvm_ora_map_cost_factor(jsvm_ora_ctx* ctx, uint32_t factor_full_pel, uint32_t factor_sub_pel);
+int jsvm_ora_compensate(jsvm_ora_ctx* ctx, const jsvm_mc_job* jobs, int n_jobs, uint8_t* pred_y, uint8_t* pred_cb, uint8_t* pred_cr);
+
 #ifdef __cplusplus
 }
 #endif

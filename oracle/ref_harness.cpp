@@ -36,14 +36,15 @@ namespace {
 // real RateDistortion::setMbQpLambda would have produced; jsvm_ref_cost_factor pins that mapping).
 class FixedRateDistortion : public RateDistortionIf {
 public:
-  FixedRateDistortion() : m_uiFactor(0) {}
+  FixedRateDistortion() : m_uiFactor(0), m_uiFactorSse(0) {}
   virtual ~FixedRateDistortion() {}
   ErrVal  setMbQpLambda(MbDataAccess&, UInt, Double) { return Err::m_nOK; }
   Double  getCost (UInt, UInt) { return 0; }
   Double  getFCost(UInt, UInt) { return 0; }
-  UInt    getMotionCostShift(Bool) { return m_uiFactor; }
+  UInt    getMotionCostShift(Bool bSad) { return bSad ? m_uiFactor : m_uiFactorSse; }
   ErrVal  fixMacroblockQP(MbDataAccess&) { return Err::m_nOK; }
-  UInt m_uiFactor;
+  UInt m_uiFactor;       // SAD-class factor
+  UInt m_uiFactorSse;    // SSE-class factor
 };
 
 // Probe subclass: records what xPelBlockSearch handed to xSubPelSearch and what came back.
@@ -58,6 +59,25 @@ public:
     m_uiMinSad = ruiSAD;
   }
   UInt bestMode() const { return m_uiBestMode; }
+  UInt fullPelDFunc() const { return m_cParams.getFullPelDFunc(); }
+  UInt subPelDFunc() const { return m_cParams.getSubPelDFunc(); }
+  Void setFullPelDFunc(UInt ui) { m_cParams.setFullPelDFunc(ui); }
+  // MotionCompensation::compensateMb's inner sequence for one block (COM/MotionCompensation.cpp:1217-1224, 1363-1405):
+  // limitComponents, xPredLuma (predBlk + weightLumaSamples), xPredChroma (xPredChromaPel + weightChromaSamples)
+  Void predictBlock(YuvMbBuffer* pcRec, UInt uiBlk, Int iSizeX, Int iSizeY, YuvPicBuffer* apcRef[2], const Mv acMv[2], const PredWeight* apcPW[2], Bool bChroma) {
+    MC8x8 cMC(B_8x8_0);
+    cMC.m_cIdx = B4x4Idx(uiBlk);
+    for (Int n = 0; n < 2; n++) {
+      if (!apcRef[n]) continue;
+      cMC.m_aacMv[n][0].set(acMv[n], 1);
+      cMC.m_aacMv[n][0].limitComponents(m_cMin, m_cMax);
+      cMC.m_sChromaOffset[n] = 0;
+      cMC.m_apcRefBuffer[n] = apcRef[n];
+      cMC.m_apcPW[n] = apcPW[n];
+    }
+    xPredLuma(pcRec, iSizeX, iSizeY, cMC);
+    if (bChroma) xPredChroma(pcRec, iSizeX >> 1, iSizeY >> 1, cMC);
+  }
   Mv   m_cFullPelMv;
   UInt m_uiFullPelSad;
   UInt m_uiMinSad;
@@ -83,6 +103,9 @@ struct jsvm_ref_ctx {
   CodingParameter*      cp;
   std::vector<Frame*>   frames;
   PredWeight            pw;
+  std::vector<std::pair<uint32_t, uint32_t> > factor_map;   // full-pel stage factor -> sub-pel stage factor (other class)
+  const int16_t*        org_chroma;
+  int                   n_org_chroma;
 };
 
 #define CHK(x) do { if ((x) != Err::m_nOK) { fprintf(stderr, "ref_harness: %s failed (%s:%d)\n", #x, __FILE__, __LINE__); return 0; } } while (0)
@@ -92,7 +115,7 @@ extern "C" jsvm_ref_ctx* jsvm_ref_create(int width, int height, int n_slots,
                                          int search_mode, int full_pel_dfunc, int sub_pel_dfunc, int search_range) {
   if (width <= 0 || height <= 0 || (width & 15) || (height & 15) || n_slots <= 0) return 0;
   jsvm_ref_ctx* c = new jsvm_ref_ctx();
-  c->width = width; c->height = height; c->n_slots = n_slots;
+  c->width = width; c->height = height; c->n_slots = n_slots; c->org_chroma = 0; c->n_org_chroma = 0;
   c->mbw = width >> 4; c->mbh = height >> 4;
 
   CHK(SequenceParameterSet::create(c->sps));
@@ -262,12 +285,31 @@ extern "C" int jsvm_ref_search(jsvm_ref_ctx* c, const jsvm_me_job* jobs, int n_j
         for (int x = 0; x < 16; ++x) d[r * org->getLStride() + x] = src[r * 16 + x];
     }
 
-    c->rd->m_uiFactor = j.cost_factor;
+    // the job carries the factor of the full-pel stage (:255: SSE class iff SearchFuncFullPel is SSD); the other class comes
+    // from the registered pairs (identity if none: both stages of one class)
+    uint32_t other = j.cost_factor;
+    for (size_t k = 0; k < c->factor_map.size(); ++k) if (c->factor_map[k].first == j.cost_factor) other = c->factor_map[k].second;
+    const bool full_sse = c->me->fullPelDFunc() == DF_SSD;
+    c->rd->m_uiFactor    = full_sse ? other : j.cost_factor;
+    c->rd->m_uiFactorSse = full_sse ? j.cost_factor : other;
+    const UInt cfg_full = c->me->fullPelDFunc();
+    if (cfg_full == DF_YUV_SAD && j.org_index >= 0) {
+      if (c->org_chroma) {
+        if (j.org_index >= c->n_org_chroma) return -1;
+        const int16_t* src = c->org_chroma + (size_t)j.org_index * 128;
+        XPel* u = org->getMbCbAddr(); XPel* v = org->getMbCrAddr();
+        for (int r = 0; r < 8; ++r)
+          for (int x = 0; x < 8; ++x) { u[r * org->getCStride() + x] = src[r * 8 + x]; v[r * org->getCStride() + x] = src[64 + r * 8 + x]; }
+      } else {
+        c->me->setFullPelDFunc(DF_SAD);     // what ENC/MotionEstimation.cpp:250-253 does for bi-pred / unequally weighted originals
+      }
+    }
     Mv   mv(j.start.hor, j.start.ver);
     Mv   pred(j.pred.hor, j.pred.ver);
     UInt bits = j.bits_in, cost = 0;
     CHKI(c->me->estimateBlockWithStart(*mba, *c->frames[j.ref_slot], mv, pred, bits, cost,
                                        j.blk, j.mode, (UInt)j.search_range, &c->pw, 0));
+    c->me->setFullPelDFunc(cfg_full);
     jsvm_me_result& r = results[i];
     r.mv.hor = mv.getHor(); r.mv.ver = mv.getVer();
     r.mv_fullpel.hor = c->me->m_cFullPelMv.getHor() >> 2;
@@ -338,4 +380,93 @@ extern "C" uint32_t jsvm_ref_distortion(const int16_t* org16x16, const int16_t* 
   uint32_t v = s.Func(&s);
   d->destroy();
   return v;
+}
+
+extern "C" int jsvm_ref_set_chroma_u8(jsvm_ref_ctx* c, int slot, const uint8_t* cb_src, const uint8_t* cr_src, int stride) {
+  if (!c || slot < 0 || slot >= c->n_slots) return -1;
+  Frame* f = c->frames[slot];
+  CHKI(c->full_ctrl->initMb());
+  CHKI(c->half_ctrl->initMb());
+  YuvPicBuffer* pb = f->getFullPelYuvBuffer();
+  XPel* cb = pb->getMbCbAddr();
+  XPel* cr = pb->getMbCrAddr();
+  const int cs = pb->getCStride();
+  for (int r = 0; r < c->height / 2; ++r)
+    for (int x = 0; x < c->width / 2; ++x) { cb[r * cs + x] = cb_src[r * stride + x]; cr[r * cs + x] = cr_src[r * stride + x]; }
+  CHKI(f->extendFrame(c->filter));          // fillMargin of all three planes (+ the unchanged half-pel plane again)
+  return 0;
+}
+
+extern "C" int jsvm_ref_set_org_chroma(jsvm_ref_ctx* c, const int16_t* org_chroma_mbs, int n_org_mbs) {
+  if (!c) return -1;
+  c->org_chroma = org_chroma_mbs; c->n_org_chroma = org_chroma_mbs ? n_org_mbs : 0;
+  return 0;
+}
+
+extern "C" int jsvm_ref_map_cost_factor(jsvm_ref_ctx* c, uint32_t factor_full_pel, uint32_t factor_sub_pel) {
+  if (!c) return -1;
+  for (size_t k = 0; k < c->factor_map.size(); ++k)
+    if (c->factor_map[k].first == factor_full_pel) { c->factor_map[k].second = factor_sub_pel; return 0; }
+  c->factor_map.push_back(std::make_pair(factor_full_pel, factor_sub_pel));
+  return 0;
+}
+
+// MotionCompensation (luma predBlk, chroma xPredChromaPel, SampleWeighting) for every job.  The slice-level weighting state is
+// produced by the reference's own SampleWeighting::initSlice from a slice header that matches the job's `weighting` flags.
+extern "C" int jsvm_ref_compensate(jsvm_ref_ctx* c, const jsvm_mc_job* jobs, int n_jobs, uint8_t* pred_y, uint8_t* pred_cb, uint8_t* pred_cr) {
+  if (!c) return -1;
+  const bool old_flag = c->pps->getWeightedPredFlag();
+  const UInt old_idc = c->pps->getWeightedBiPredIdc();
+  int rc = 0;
+  for (int i = 0; i < n_jobs && rc == 0; ++i) {
+    const jsvm_mc_job& j = jobs[i];
+    if (j.mb_x < 0 || j.mb_x >= (int)c->mbw || j.mb_y < 0 || j.mb_y >= (int)c->mbh || j.blk > 15) { rc = -1; break; }
+    const bool uni = (j.weighting & JSVM_MC_WEIGHT_UNI) != 0, bi = (j.weighting & JSVM_MC_WEIGHT_BI) != 0;
+    if (bi && !uni && (j.log_denom[0] != 5 || j.log_denom[1] != 5)) { rc = -1; break; }     // implicit weights: denominators are 5 / 5
+    c->pps->setWeightedPredFlag(uni);
+    c->pps->setWeightedBiPredIdc(bi ? (uni ? 1 : 2) : 0);
+    SliceHeader sh(*c->sps, *c->pps);
+    sh.setSliceType(bi ? B_SLICE : P_SLICE);
+    sh.setLumaLog2WeightDenom(j.log_denom[0]);
+    sh.setChromaLog2WeightDenom(j.log_denom[1]);
+    if (c->weighting->initSlice(sh) != Err::m_nOK) { rc = -1; break; }
+
+    MbDataAccess* mba = 0;
+    if (c->mbctrl->initMb(mba, j.mb_y, j.mb_x) != Err::m_nOK || c->full_ctrl->initMb(j.mb_y, j.mb_x, false) != Err::m_nOK ||
+        c->me->initMb(j.mb_y, j.mb_x, *mba) != Err::m_nOK) { rc = -1; break; }
+    YuvPicBuffer* refs[2] = { 0, 0 };
+    Mv mvs[2];
+    PredWeight pw[2];
+    const PredWeight* ppw[2] = { 0, 0 };
+    for (int l = 0; l < 2; ++l) {
+      if (j.ref_slot[l] < 0) continue;
+      if (j.ref_slot[l] >= c->n_slots) { rc = -1; break; }
+      refs[l] = c->frames[j.ref_slot[l]]->getFullPelYuvBuffer();
+      mvs[l] = Mv(j.mv[l].hor, j.mv[l].ver);
+      pw[l].setLumaWeightFlag(j.weight_flag[0] != 0); pw[l].setChromaWeightFlag(j.weight_flag[1] != 0);
+      pw[l].setLumaWeight(j.weight[l][0]); pw[l].setChromaCbWeight(j.weight[l][1]); pw[l].setChromaCrWeight(j.weight[l][2]);
+      pw[l].setLumaOffset(j.offset[l][0]); pw[l].setChromaCbOffset(j.offset[l][1]); pw[l].setChromaCrOffset(j.offset[l][2]);
+      ppw[l] = &pw[l];
+    }
+    if (rc) break;
+    YuvMbBuffer rec;
+    c->me->predictBlock(&rec, j.blk, j.size_x, j.size_y, refs, mvs, ppw, pred_cb != 0);
+    const B4x4Idx idx(j.blk);
+    const XPel* y = rec.getYBlk(idx);
+    uint8_t* dy = pred_y + (size_t)i * 256;
+    memset(dy, 0, 256);
+    for (int r = 0; r < j.size_y; ++r)
+      for (int x = 0; x < j.size_x; ++x) dy[r * 16 + x] = (uint8_t)y[r * rec.getLStride() + x];
+    if (pred_cb) {
+      const XPel* u = rec.getUBlk(idx); const XPel* v = rec.getVBlk(idx);
+      uint8_t* du = pred_cb + (size_t)i * 64; uint8_t* dv = pred_cr + (size_t)i * 64;
+      memset(du, 0, 64); memset(dv, 0, 64);
+      for (int r = 0; r < j.size_y / 2; ++r)
+        for (int x = 0; x < j.size_x / 2; ++x) { du[r * 8 + x] = (uint8_t)u[r * rec.getCStride() + x]; dv[r * 8 + x] = (uint8_t)v[r * rec.getCStride() + x]; }
+    }
+  }
+  c->pps->setWeightedPredFlag(old_flag);
+  c->pps->setWeightedBiPredIdc(old_idc);
+  c->weighting->initSlice(*c->sh);
+  return rc;
 }

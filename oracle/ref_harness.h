@@ -48,6 +48,16 @@ uint32_t jsvm_ref_cost_factor(double lambda, int sad);
  * org: 16x16 int16 dense; ref: pointer + stride. */
 uint32_t jsvm_ref_distortion(const int16_t* org16x16, const int16_t* ref, int ref_stride, int mode, int dfunc, int blk);
 
+/* Chroma planes of a slot (dense (W/2) x (H/2) bytes); jsvm_ref_set_plane_u8 sets them to 128.  Margins are refilled. */
+int jsvm_ref_set_chroma_u8(jsvm_ref_ctx* ctx, int slot, const uint8_t* cb, const uint8_t* cr, int stride);
+/* Chroma originals (Cb 8x8, Cr 8x8 int16 per macroblock) of the caller-prepared originals, for SearchFuncFullPel = YUV_SAD.
+ * Without them a job with org_index >= 0 is searched with the luma SAD (ENC/MotionEstimation.cpp:250-253). */
+int jsvm_ref_set_org_chroma(jsvm_ref_ctx* ctx, const int16_t* org_chroma_mbs, int n_org_mbs);
+/* The cost factor of the other class for jobs carrying `factor_full_pel` (see jsvm_me_map_cost_factor). */
+int jsvm_ref_map_cost_factor(jsvm_ref_ctx* ctx, uint32_t factor_full_pel, uint32_t factor_sub_pel);
+/* MotionCompensation::xPredLuma / xPredChroma (predBlk, xPredChromaPel, SampleWeighting) for every job. */
+int jsvm_ref_compensate(jsvm_ref_ctx* ctx, const jsvm_mc_job* jobs, int n_jobs, uint8_t* pred_y, uint8_t* pred_cb, uint8_t* pred_cr);
+
 #ifdef __cplusplus
 }
 #endif

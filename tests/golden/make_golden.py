@@ -3,7 +3,7 @@
 /root/reference by `make -C oracle ref`).  Run in the build container only; the fixtures are committed so
 that the GPU box (which has no /root/reference) can pin the oracle and the CUDA path against them.
 
-    python tests/golden/make_golden.py [group ...]      groups: search, org, fullpel, table (default: all)
+    python tests/golden/make_golden.py [group ...]      groups: search, org, fullpel, table, yuv, mc (default: all)
 """
 import importlib
 import os
@@ -109,7 +109,61 @@ def gen_table(ref):
     print("distortion rows", len(rows))
 
 
-GROUPS = {"search": gen_search, "org": gen_org, "fullpel": gen_fullpel, "table": gen_table}
+def gen_yuv(ref):
+    # SearchFuncFullPel = YUV_SAD (chroma planes), and the mixed cost-factor classes (SAD-class full-pel + SSD sub-pel and back)
+    W, H, sr = 64, 48, 8
+    seq = synth.Sequence(W, H, 35)
+    f0, f1 = seq.frame(0), seq.frame(1)
+    c0, c1 = synth.chroma_planes(W, H, 35), synth.chroma_planes(W, H, 36)
+    rng = np.random.default_rng(35)
+    org = rng.integers(0, 256, (12, 16, 16)).astype(np.int16)
+    orgc = rng.integers(0, 256, (12, 2, 8, 8)).astype(np.int16)
+    fs, fe = synth.cost_factor_for_qp(29), ref.cost_factor(synth.lambda_for_qp(29), 0)
+    cases = (("yuvsad_had_all41", 3, 2, "PARTS_41", None, None), ("yuvsad_sad_org_chroma", 3, 0, "PARTS_9", org, orgc),
+             ("yuvsad_had_org_lumaonly", 3, 2, "PARTS_9", org, None), ("yuvsad_ssd_mixed", 3, 1, "PARTS_9", None, None),
+             ("sad_ssd_mixed", 0, 1, "PARTS_41", None, None), ("ssd_had_mixed", 1, 2, "PARTS_9", None, None))
+    for nm, full, sub, parts, o, oc in cases:
+        ses = oracle_lib.CpuSession(ref, W, H, 2, sr, sub, full)
+        ses.set_plane(0, f0); ses.set_plane(1, f1)
+        ses.set_chroma(0, *c0); ses.set_chroma(1, *c1)
+        jobs = synth.make_jobs(W, H, getattr(synth, parts), 1, 0, qp=29, field="split", seed=7, bits_in=1)
+        mixed = (full == 1) != (sub == 1)
+        if full == 1:
+            jobs["cost_factor"] = fe
+        if mixed:
+            ses.map_cost_factor(fe if full == 1 else fs, fs if full == 1 else fe)
+        extra = dict(factor_pair=np.array([fe if full == 1 else fs, fs if full == 1 else fe], np.uint32)) if mixed else {}
+        if o is not None:
+            jobs["org_index"] = np.repeat(np.arange(12), len(getattr(synth, parts)))
+            extra["org_mbs"] = o
+        if oc is not None:
+            ses.set_org_chroma(oc)
+            extra["org_chroma"] = oc
+        res, preds = ses.search(jobs, org_mbs=o, want_preds=True)
+        np.savez_compressed(os.path.join(HERE, nm + ".npz"), width=W, height=H, search_range=sr, sub_dfunc=sub, full_dfunc=full,
+                            frame0=f0, frame1=f1, cb0=c0[0], cr0=c0[1], cb1=c1[0], cr1=c1[1], jobs=jobs, results=res, preds=preds, **extra)
+        print(nm, len(jobs), "jobs")
+
+
+def gen_mc(ref):
+    # MotionCompensation: predBlk (all 16 fractional phases), chroma 1/8-sample filter, SampleWeighting variants
+    W, H = 64, 48
+    seq = synth.Sequence(W, H, 37)
+    frames = [seq.frame(i) for i in range(3)]
+    chroma = [synth.chroma_planes(W, H, 40 + i) for i in range(3)]
+    ses = ref.session(W, H, 3, 8, 0)
+    for s in range(3):
+        ses.set_plane(s, frames[s]); ses.set_chroma(s, *chroma[s])
+    out = dict(width=W, height=H, frames=np.stack(frames), cb=np.stack([c[0] for c in chroma]), cr=np.stack([c[1] for c in chroma]))
+    for kind in ("uni", "bi", "uni_w", "bi_w", "bi_implicit"):
+        jobs = synth.make_mc_jobs(W, H, 400, 3, seed=len(kind), kind=kind)
+        py, pcb, pcr = ses.compensate(jobs)
+        out["jobs_" + kind], out["y_" + kind], out["cb_" + kind], out["cr_" + kind] = jobs, py, pcb, pcr
+        print("mc", kind, len(jobs), "jobs")
+    np.savez_compressed(os.path.join(HERE, "mc_blocks.npz"), **out)
+
+
+GROUPS = {"yuv": gen_yuv, "mc": gen_mc, "search": gen_search, "org": gen_org, "fullpel": gen_fullpel, "table": gen_table}
 
 
 def main():

@@ -16,7 +16,7 @@ _spec = importlib.util.spec_from_file_location(
     "jsvm_me_abi_records", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "jsvm-code-notes_b200", "abi.py"))
 abi = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(abi)
-JOB_DTYPE, RESULT_DTYPE = abi.JOB_DTYPE, abi.RESULT_DTYPE
+JOB_DTYPE, RESULT_DTYPE, MC_JOB_DTYPE = abi.JOB_DTYPE, abi.RESULT_DTYPE, abi.MC_JOB_DTYPE
 
 
 class CpuSession:
@@ -38,6 +38,31 @@ class CpuSession:
         luma = np.ascontiguousarray(luma, np.uint8)
         assert luma.shape == (self.height, self.width)
         assert self.be.set_plane_u8(self.ctx, slot, luma.ctypes.data, self.width) == 0
+
+    def set_chroma(self, slot, cb, cr):
+        cb = np.ascontiguousarray(cb, np.uint8)
+        cr = np.ascontiguousarray(cr, np.uint8)
+        assert cb.shape == cr.shape == (self.height // 2, self.width // 2)
+        assert self.be.set_chroma_u8(self.ctx, slot, cb.ctypes.data, cr.ctypes.data, self.width // 2) == 0
+
+    def set_org_chroma(self, org_chroma_mbs):
+        self._org_chroma = None if org_chroma_mbs is None else np.ascontiguousarray(org_chroma_mbs, np.int16).reshape(-1, 2, 8, 8)
+        assert self.be.set_org_chroma(self.ctx, None if self._org_chroma is None else self._org_chroma.ctypes.data,
+                                      0 if self._org_chroma is None else len(self._org_chroma)) == 0
+
+    def map_cost_factor(self, factor_full_pel, factor_sub_pel):
+        assert self.be.map_cost_factor(self.ctx, int(factor_full_pel), int(factor_sub_pel)) == 0
+
+    def compensate(self, mc_jobs, chroma=True):
+        jobs = np.ascontiguousarray(mc_jobs, MC_JOB_DTYPE)
+        n = len(jobs)
+        py = np.zeros((n, 16, 16), np.uint8)
+        pcb = np.zeros((n, 8, 8), np.uint8) if chroma else None
+        pcr = np.zeros((n, 8, 8), np.uint8) if chroma else None
+        rc = self.be.compensate(self.ctx, jobs.ctypes.data, n, py.ctypes.data,
+                                pcb.ctypes.data if chroma else None, pcr.ctypes.data if chroma else None)
+        assert rc == 0, "checker compensate() failed"
+        return py, pcb, pcr
 
     def fullpel(self, slot):
         out = np.zeros((self.height + 64, self.width + 64), np.uint8)
@@ -75,6 +100,10 @@ class CpuBackend:
                   ("get_fullpel_u8", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
                   ("get_halfpel_u8", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
                   ("search", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+                  ("set_chroma_u8", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+                  ("set_org_chroma", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+                  ("map_cost_factor", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+                  ("compensate", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
                   ("cost_factor", C.c_uint32, [C.c_double, C.c_int]),
                   ("distortion", C.c_uint32, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int])]
         for name, rt, at in protos:

@@ -8,7 +8,21 @@ import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SEARCH_CASES = ["tiny_all41_had", "tiny_9_sad", "qcif_9_had", "qcif_9_zero_sr32", "cif_9_sr64", "org_override_8bit", "org_override_16bit",
-                "fullpel_had_had", "fullpel_had_sad_all41", "fullpel_ssd_ssd", "fullpel_ssd_ssd_16bit", "fullpel_had_had_16bit"]
+                "fullpel_had_had", "fullpel_had_sad_all41", "fullpel_ssd_ssd", "fullpel_ssd_ssd_16bit", "fullpel_had_had_16bit",
+                "yuvsad_had_all41", "yuvsad_sad_org_chroma", "yuvsad_had_org_lumaonly", "yuvsad_ssd_mixed", "sad_ssd_mixed", "ssd_had_mixed"]
+MC_KINDS = ["uni", "bi", "uni_w", "bi_w", "bi_implicit"]
+
+
+def prepare_session(ses, g):
+    """Planes, chroma planes, chroma originals and cost-factor pairs of a search fixture (shared with the GPU tests)."""
+    ses.set_plane(0, g["frame0"])
+    ses.set_plane(1, g["frame1"])
+    if "cb0" in g.files:
+        ses.set_chroma(0, g["cb0"], g["cr0"])
+        ses.set_chroma(1, g["cb1"], g["cr1"])
+    if "factor_pair" in g.files:
+        ses.map_cost_factor(int(g["factor_pair"][0]), int(g["factor_pair"][1]))
+    ses.set_org_chroma(g["org_chroma"] if "org_chroma" in g.files else None)
 
 
 def load(name):
@@ -16,7 +30,7 @@ def load(name):
 
 
 def test_fixtures_present():
-    assert len(glob.glob(os.path.join(HERE, "golden", "*.npz"))) >= 12
+    assert len(glob.glob(os.path.join(HERE, "golden", "*.npz"))) >= 19
 
 
 @pytest.mark.parametrize("name", SEARCH_CASES)
@@ -24,8 +38,7 @@ def test_oracle_search_matches_reference_golden(oracle, name):
     g = load(name)
     W, H = int(g["width"]), int(g["height"])
     ses = oracle.session(W, H, 2, int(g["search_range"]), int(g["sub_dfunc"]), int(g["full_dfunc"]) if "full_dfunc" in g.files else 0)
-    ses.set_plane(0, g["frame0"])
-    ses.set_plane(1, g["frame1"])
+    prepare_session(ses, g)
     org = g["org_mbs"] if "org_mbs" in g.files else None
     res, preds = ses.search(g["jobs"], org_mbs=org, want_preds=True)
     for f in res.dtype.names:
@@ -34,6 +47,29 @@ def test_oracle_search_matches_reference_golden(oracle, name):
     if "halfpel0" in g.files:
         assert np.array_equal(ses.halfpel(0), g["halfpel0"])       # QuarterPelFilter::filterFrame
         assert np.array_equal(ses.fullpel(0), g["fullpel0"])       # YuvPicBuffer::fillMargin
+
+
+@pytest.mark.parametrize("kind", MC_KINDS)
+def test_oracle_compensate_matches_reference_golden(oracle, kind):
+    """MotionCompensation (predBlk, chroma bilinear, SampleWeighting) of the C port against the compiled reference."""
+    g = load("mc_blocks")
+    W, H = int(g["width"]), int(g["height"])
+    ses = oracle.session(W, H, 3, 8, 0)
+    for s in range(3):
+        ses.set_plane(s, g["frames"][s])
+        ses.set_chroma(s, g["cb"][s], g["cr"][s])
+    py, pcb, pcr = ses.compensate(g["jobs_" + kind])
+    assert np.array_equal(py, g["y_" + kind]) and np.array_equal(pcb, g["cb_" + kind]) and np.array_equal(pcr, g["cr_" + kind])
+
+
+def test_mc_golden_covers_all_phases_and_clamps():
+    g = load("mc_blocks")
+    j = g["jobs_uni"]
+    l = np.where(j["ref_slot"][:, 0] >= 0, 0, 1)
+    mv = j["mv"][np.arange(len(j)), l]
+    assert len({(int(a) & 3, int(b) & 3) for a, b in mv}) == 16 and len({(int(a) & 7, int(b) & 7) for a, b in mv}) >= 60
+    assert (np.abs(mv) > 1000).any()                                  # MVs the per-macroblock clamp limits
+    assert (g["jobs_uni_w"]["weight_flag"] == 0).any() and (g["jobs_uni_w"]["weight_flag"] == 1).any()
 
 
 def test_oracle_distortion_table_and_factors(oracle):

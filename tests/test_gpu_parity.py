@@ -87,7 +87,9 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 @pytest.mark.parametrize("name", ["tiny_all41_had", "tiny_9_sad", "qcif_9_had", "qcif_9_zero_sr32", "cif_9_sr64", "org_override_8bit",
                                   "org_override_16bit", "fullpel_had_had", "fullpel_had_sad_all41", "fullpel_ssd_ssd",
-                                  "fullpel_ssd_ssd_16bit", "fullpel_had_had_16bit"])
+                                  "fullpel_ssd_ssd_16bit", "fullpel_had_had_16bit",
+                                  "yuvsad_had_all41", "yuvsad_sad_org_chroma", "yuvsad_had_org_lumaonly", "yuvsad_ssd_mixed",
+                                  "sad_ssd_mixed", "ssd_had_mixed"])
 def test_cuda_matches_reference_golden(me, name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     W, H = int(g["width"]), int(g["height"])
@@ -95,6 +97,11 @@ def test_cuda_matches_reference_golden(me, name):
     me.set_params(int(g["search_range"]), int(g["sub_dfunc"]), int(g["full_dfunc"]) if "full_dfunc" in g.files else 0)
     me.upload_plane(0, g["frame0"]); me.upload_plane(1, g["frame1"])
     me.interp_halfpel([0, 1])
+    if "cb0" in g.files:                                  # YUV_SAD: chroma planes (+ chroma originals of prepared macroblocks)
+        me.upload_chroma(0, g["cb0"], g["cr0"]); me.upload_chroma(1, g["cb1"], g["cr1"])
+    if "factor_pair" in g.files:                          # the two stages use different cost-factor classes
+        me.map_cost_factor(int(g["factor_pair"][0]), int(g["factor_pair"][1]))
+    me.set_org_chroma(g["org_chroma"] if "org_chroma" in g.files else None)
     org = g["org_mbs"] if "org_mbs" in g.files else None
     res, preds = me.search(g["jobs"], org_mbs=org, want_preds=True)
     assert_results_equal(res, g["results"], g["jobs"])
@@ -180,10 +187,9 @@ def test_fullpel_hadamard_and_ssd_search_bit_exact(me, oracle, synth, full_dfunc
     assert np.array_equal(gp, wp)
 
 
-def test_unsupported_distortion_combinations_are_refused(me, pkg):
-    """One cost factor per job: SAD-class (SAD, Hadamard) and SSE-class (SSD) functions cannot be mixed between the stages;
-    YUV_SAD needs chroma planes.  Loud errors, no fallback."""
-    for full, sub in [(0, 1), (1, 0), (1, 2), (2, 1), (3, 0), (0, 3), (3, 3)]:
+def test_invalid_distortion_functions_are_refused(me, pkg):
+    """MotionVectorSearchParams::check (ENC/CodingParameter.cpp:17-36): full-pel functions 0..3, sub-pel functions 0..2.  Loud errors."""
+    for full, sub in [(0, 3), (3, 3), (4, 0), (-1, 0), (0, -1)]:
         with pytest.raises(pkg.MotionEstimationError):
             me.set_params(16, sub, full)
     me.set_params(16, 2, 0)

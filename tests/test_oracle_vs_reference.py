@@ -56,3 +56,41 @@ def test_extreme_content(oracle, reference, synth):
             ra, rb = a.search(jobs), b.search(jobs)
             for f in ra.dtype.names:
                 assert np.array_equal(ra[f], rb[f]), f
+
+
+@pytest.mark.parametrize("full,sub", [(3, 2), (3, 1), (0, 1), (1, 2)])
+def test_optional_distortion_functions_identical(oracle, reference, synth, full, sub):
+    """a5: YUV-SAD (chroma planes, ( x>>1, y>>1 ) displacement) and the mixed cost-factor classes, fresh seeds."""
+    import oracle_lib
+    W, H, sr = 96, 80, 12
+    seq = synth.Sequence(W, H, 300 + full)
+    sessions = [oracle_lib.CpuSession(be, W, H, 2, sr, sub, full) for be in (oracle, reference)]
+    f_sad, f_sse = reference.cost_factor(synth.lambda_for_qp(34), 1), reference.cost_factor(synth.lambda_for_qp(34), 0)
+    for s in sessions:
+        for slot in range(2):
+            s.set_plane(slot, seq.frame(slot))
+            s.set_chroma(slot, *synth.chroma_planes(W, H, 70 + slot))
+        if (full == 1) != (sub == 1):
+            s.map_cost_factor(*((f_sse, f_sad) if full == 1 else (f_sad, f_sse)))
+    jobs = synth.make_jobs(W, H, synth.PARTS_41, 1, 0, qp=34, field="split", seed=9, bits_in=1)
+    jobs["cost_factor"] = f_sse if full == 1 else f_sad
+    (ra, pa), (rb, pb) = [s.search(jobs, want_preds=True) for s in sessions]
+    for f in ra.dtype.names:
+        assert np.array_equal(ra[f], rb[f]), f
+    assert np.array_equal(pa, pb)
+
+
+@pytest.mark.parametrize("kind", ["uni", "bi", "uni_w", "bi_w", "bi_implicit"])
+def test_compensate_identical(oracle, reference, synth, kind):
+    """f3: predBlk / chroma MC / SampleWeighting of the C port against the reference's MotionCompensation, fresh seeds."""
+    W, H = 96, 80
+    seq = synth.Sequence(W, H, 500)
+    sessions = [be.session(W, H, 2, 8, 0) for be in (oracle, reference)]
+    for s in sessions:
+        for slot in range(2):
+            s.set_plane(slot, seq.frame(slot))
+            s.set_chroma(slot, *synth.chroma_planes(W, H, 80 + slot))
+    jobs = synth.make_mc_jobs(W, H, 1500, 2, seed=17, kind=kind, mv_range=160)
+    a, b = [s.compensate(jobs) for s in sessions]
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
