@@ -43,7 +43,18 @@ extern "C" {
 #define JSVM_DF_SSD      1
 #define JSVM_DF_HADAMARD 2
 #define JSVM_DF_YUV_SAD  3
-#define JSVM_SEARCH_BLOCK 0   /* SearchMode BLOCK_SEARCH = full search (xPelBlockSearch) */
+#define JSVM_SEARCH_BLOCK  0   /* SearchMode BLOCK_SEARCH = full search (xPelBlockSearch) */
+#define JSVM_SEARCH_SPIRAL 1   /* xPelSpiralSearch */
+#define JSVM_SEARCH_LOG    2   /* xPelLogSearch */
+#define JSVM_SEARCH_FAST   3   /* xPelLogSearch seeded with the MV predictor and the neighbours' MVs */
+#define JSVM_SEARCH_TZ     4   /* xTZSearch (the default of the shipped encoder.cfg) */
+
+/* Per-call state of estimateBlockWithStart that the fast searches read, carried in the two top bits of jsvm_me_job.mode:
+ * pcBSP != NULL (bi-predictive search: halves the first step of LOG / FAST, ENC/MotionEstimation.cpp:289, 296) and
+ * m_bELWithBLMv (setEL( true ): TZ uses ELSearchRange, :1112-1117). */
+#define JSVM_JOB_MODE_MASK 0x3f
+#define JSVM_JOB_EL        0x40
+#define JSVM_JOB_BIPRED    0x80
 
 /* Luma plane geometry, INCC/CommonDefs.h:246-247 + COM/YuvBufferCtrl.cpp:134-157: stride = width + 2*YUV_X_MARGIN (32).
  * The reference ALLOCATES YUV_Y_MARGIN = 64 rows above and below the picture (m_uiLumBaseOffset = stride*64 + 32) but, for
@@ -110,7 +121,9 @@ int jsvm_me_configure(jsvm_me_ctx* ctx, int width, int height, int n_slots);
 
 /* MotionEstimation::init reading MotionVectorSearchParams (ENC/MotionEstimation.cpp:38-66,
  * include/CodingParameter.h:41-89; value ranges checked as MotionVectorSearchParams::check, ENC/CodingParameter.cpp:17-36).
- * SearchMode 0 (BLOCK_SEARCH) only.  SearchFuncFullPel: SAD (0), SSD (1), HADAMARD (2), YUV_SAD (3); SearchFuncSubPel: SAD (0),
+ * SearchMode: BLOCK_SEARCH (0, the measured hot path), SPIRAL (1), LOG (2), FAST (3), TZ (4; one warp per job, see
+ * jsvm_me_set_fast_search_params / jsvm_me_set_mv_candidates; LOG and FAST refuse YUV_SAD as the reference is undefined there).
+ * SearchFuncFullPel: SAD (0), SSD (1), HADAMARD (2), YUV_SAD (3); SearchFuncSubPel: SAD (0),
  * SSD (1), HADAMARD (2) -- every combination.  Full-pel SAD is the measured hot path (packed-byte kernels); the other full-pel
  * functions run a plain one-CTA-per-job kernel.  YUV_SAD needs the chroma planes of the slots (jsvm_me_upload_chroma_*).
  * A job carries ONE cost factor, the one of the FULL-PEL stage (ENC/MotionEstimation.cpp:255: the SAD factor unless
@@ -123,6 +136,19 @@ int jsvm_me_set_params(jsvm_me_ctx* ctx, int search_mode, int full_pel_dfunc, in
  * (xSetMEPars( 0, ... ), ENC/MotionEstimation.cpp:325-335).  Both values come from the host (double arithmetic, N11).  Only
  * consulted when the two stages use different factor classes; up to 256 pairs per context, re-registering a factor replaces it. */
 int jsvm_me_map_cost_factor(jsvm_me_ctx* ctx, uint32_t factor_full_pel, uint32_t factor_sub_pel);
+
+/* The remaining MotionVectorSearchParams the fast searches read (include/CodingParameter.h:41-89): ELSearchRange (0 = SearchRange,
+ * ENC/CodingParameter.cpp:25-28; used by TZ_SEARCH for jobs flagged JSVM_JOB_EL) and FastBiSearch (jobs with a per-call search
+ * range -- the refinement searches of the bi-prediction iterations, ENC/MotionEstimation.cpp:264-274 -- run xTZSearch with an empty
+ * candidate list instead of xPelBlockSearch). */
+int jsvm_me_set_fast_search_params(jsvm_me_ctx* ctx, int el_search_range, int fast_bi_search);
+
+/* MbDataAccess::addMvPredictors (COM/MbDataAccess.cpp:423-428): the MVs m_cMv3D_A / B / C of the left, above and above-right (or
+ * above-left) neighbours that getMvPredictor left behind, three per job, quarter-pel.  FAST_SEARCH and TZ_SEARCH test them next
+ * to rcMvPred (ENC/MotionEstimation.cpp:293-305).  HOST memory read by the next jsvm_me_search calls (must stay valid; job i uses
+ * abc[3i .. 3i+2]); NULL = all zero.  The _device form takes device memory and serves jsvm_me_search_device. */
+int jsvm_me_set_mv_candidates(jsvm_me_ctx* ctx, const jsvm_mv* abc, int n_jobs);
+int jsvm_me_set_mv_candidates_device(jsvm_me_ctx* ctx, const jsvm_mv* d_abc);
 
 /* Run every later call on this CUDA stream (a cudaStream_t / CUstream handle; NULL = default). */
 int jsvm_me_set_stream(jsvm_me_ctx* ctx, void* cuda_stream);

@@ -16,7 +16,8 @@ LIB_PATH = os.environ.get("JSVM_ME_LIB", os.path.join(_HERE, "libjsvm_me_b200.so
 MODE_16x16, MODE_16x8, MODE_8x16 = 1, 2, 3
 BLK_8x8, BLK_8x4, BLK_4x8, BLK_4x4 = 8, 9, 10, 11
 DF_SAD, DF_SSD, DF_HADAMARD, DF_YUV_SAD = 0, 1, 2, 3
-SEARCH_BLOCK = 0
+SEARCH_BLOCK, SEARCH_SPIRAL, SEARCH_LOG, SEARCH_FAST, SEARCH_TZ = 0, 1, 2, 3, 4
+JOB_MODE_MASK, JOB_EL, JOB_BIPRED = 0x3F, 0x40, 0x80
 MARGIN = 32
 
 
@@ -72,6 +73,9 @@ PROTOTYPES = [
     ("jsvm_me_upload_plane_xpel", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     ("jsvm_me_upload_plane_u8", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     ("jsvm_me_set_plane_device_u8", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    ("jsvm_me_set_fast_search_params", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    ("jsvm_me_set_mv_candidates", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    ("jsvm_me_set_mv_candidates_device", C.c_int, [C.c_void_p, C.c_void_p]),
     ("jsvm_me_map_cost_factor", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     ("jsvm_me_upload_chroma_u8", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     ("jsvm_me_upload_chroma_xpel", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),

@@ -27,6 +27,7 @@
 #include "k2_generic.cuh"
 #include "k3_subpel.cuh"
 #include "k4_mc.cuh"
+#include "k5_fastsearch.cuh"
 
 using namespace jsvm;
 
@@ -100,7 +101,12 @@ struct jsvm_me_ctx {
   EncodeTiledFn encode = nullptr;
   // params
   int search_range = 0, sub_dfunc = JSVM_DF_SAD, full_dfunc = JSVM_DF_SAD;
+  int search_mode = JSVM_SEARCH_BLOCK, el_search_range = 0, fast_bi_search = 0;
   bool params_set = false;
+  // neighbour MVs (A, B, C per job) for FAST_SEARCH / TZ_SEARCH: host pointer for jsvm_me_search, device pointer for jsvm_me_search_device
+  const jsvm_mv* cands = nullptr; int n_cands = 0;
+  const jsvm_mv* d_cands_user = nullptr;
+  DevBuf<jsvm_mv> d_cands;
   // per-call device buffers (host-buffer API)
   DevBuf<jsvm_me_job> d_jobs;
   DevBuf<Group> d_groups;
@@ -381,16 +387,38 @@ int sync_factor_map(jsvm_me_ctx* c) {
 
 int run_search(jsvm_me_ctx* c, const jsvm_me_job* d_jobs, int job_begin, int job_end, const Group* d_groups, const jsvm_me_plan_info* info,
                const int16_t* d_org, uint32_t* d_keys, JobAux* d_aux, jsvm_me_result* d_results, uint8_t* d_preds,
-               const int16_t* d_org_chroma = nullptr) {
+               const int16_t* d_org_chroma = nullptr, const jsvm_mv* d_cands = nullptr) {
   if (!c->params_set) return fail("jsvm_me_set_params has not been called");
-  if (info->max_uh_8x8 > kMaxUH || info->max_uh_4x4 > kMaxUH) return fail("plan: union window taller than %d", kMaxUH);
+  const bool fast = c->search_mode != JSVM_SEARCH_BLOCK;     // SPIRAL / LOG / FAST / TZ: one warp per job (K5), no plan
+  const bool refine = !fast && c->fast_bi_search;            // BLOCK_SEARCH + FastBiSearch: the jobs with a per-call range are redone by K5
+  if (!fast && (info->max_uh_8x8 > kMaxUH || info->max_uh_4x4 > kMaxUH)) return fail("plan: union window taller than %d", kMaxUH);
   const int n = job_end - job_begin;
   if (n <= 0) return JSVM_ME_OK;
   if (sync_factor_map(c)) return JSVM_ME_ERR;
-  const bool generic = c->full_dfunc != JSVM_DF_SAD;         // SSD / Hadamard / YUV-SAD full-pel search: one CTA per job, no grouping
+  if ((fast || refine) && c->d_full_costs.cap < (size_t)job_end) return fail("internal: full-pel cost buffer not reserved");
+  if (c->full_dfunc == JSVM_DF_YUV_SAD && !c->d_chroma) return fail("SearchFuncFullPel 3 (YUV_SAD) needs the chroma planes (jsvm_me_upload_chroma_*)");
+  auto launch_k5 = [&](int only_refinement) -> int {
+    auto k5 = c->full_dfunc == JSVM_DF_SAD ? fast_search_kernel<JSVM_DF_SAD> : c->full_dfunc == JSVM_DF_SSD ? fast_search_kernel<JSVM_DF_SSD>
+            : c->full_dfunc == JSVM_DF_HADAMARD ? fast_search_kernel<JSVM_DF_HADAMARD> : fast_search_kernel<JSVM_DF_YUV_SAD>;
+    begin_timed(c, 1);
+    k5<<<(n + kK5WarpsPerCta - 1) / kK5WarpsPerCta, 32 * kK5WarpsPerCta, 0, c->stream>>>(
+        c->d_planes, c->plane_bytes, c->plane_stride, c->d_chroma, c->chroma_bytes, c->chroma_stride,
+        d_jobs + job_begin, n, d_org, d_org_chroma, d_cands ? d_cands + 3 * (size_t)job_begin : nullptr,
+        c->W >> 4, c->H >> 4, c->search_mode, c->search_range, c->el_search_range ? c->el_search_range : c->search_range, c->fast_bi_search,
+        only_refinement, d_keys + job_begin, c->d_full_costs.p + job_begin, d_aux + job_begin);
+    end_timed(c);
+    c->launches++;
+    CU_OK(cudaGetLastError());
+    return JSVM_ME_OK;
+  };
+  if (fast) {
+    if (launch_k5(0)) return JSVM_ME_ERR;
+    static const char* const names[5] = {"", "fast_search_kernel(SPIRAL)", "fast_search_kernel(LOG)", "fast_search_kernel(FAST)", "fast_search_kernel(TZ)"};
+    c->last_k2 = names[c->search_mode];
+  }
+  const bool generic = !fast && c->full_dfunc != JSVM_DF_SAD;         // SSD / Hadamard / YUV-SAD full search: one CTA per job, no grouping
   if (generic) {
     if (c->d_full_costs.cap < (size_t)job_end) return fail("internal: full-pel cost buffer not reserved");
-    if (c->full_dfunc == JSVM_DF_YUV_SAD && !c->d_chroma) return fail("SearchFuncFullPel 3 (YUV_SAD) needs the chroma planes (jsvm_me_upload_chroma_*)");
     auto k2g = c->full_dfunc == JSVM_DF_SSD ? full_search_generic_kernel<JSVM_DF_SSD>
              : c->full_dfunc == JSVM_DF_HADAMARD ? full_search_generic_kernel<JSVM_DF_HADAMARD> : full_search_generic_kernel<JSVM_DF_YUV_SAD>;
     begin_timed(c, 1);
@@ -404,7 +432,7 @@ int run_search(jsvm_me_ctx* c, const jsvm_me_job* d_jobs, int job_begin, int job
                : c->full_dfunc == JSVM_DF_HADAMARD ? "full_search_generic_kernel<HADAMARD>" : "full_search_generic_kernel<YUV_SAD>";
     CU_OK(cudaGetLastError());
   }
-  const int n8 = generic ? 0 : info->n_groups_8x8, n4 = generic ? 0 : info->n_groups - info->n_groups_8x8;
+  const int n8 = generic || fast ? 0 : info->n_groups_8x8, n4 = generic || fast ? 0 : info->n_groups - info->n_groups_8x8;
   bool p8 = false, p4 = false;
   if (choose_persistent<kV8, false>(c, n8, info->max_uh_8x8, &p8) || choose_persistent<kV4, true>(c, n4, info->max_uh_4x4, &p4)) return JSVM_ME_ERR;
   if (n8 > 0) c->last_k2 = p8 ? "full_search_persistent_kernel<8,false>" : "full_search_kernel<8,false>";
@@ -413,6 +441,7 @@ int run_search(jsvm_me_ctx* c, const jsvm_me_job* d_jobs, int job_begin, int job
                     : launch_search<kV8, false>(c, d_groups, 0, n8, info->max_uh_8x8, d_jobs, d_org, d_keys, d_aux))) return JSVM_ME_ERR;
   if (n4 > 0 && (p4 ? launch_search_persistent<kV4, true>(c, d_groups + n8, n4, info->max_uh_4x4, d_jobs, d_org, d_keys, d_aux)
                     : launch_search<kV4, true>(c, d_groups, n8, n4, info->max_uh_4x4, d_jobs, d_org, d_keys, d_aux))) return JSVM_ME_ERR;
+  if (refine && launch_k5(1)) return JSVM_ME_ERR;
   begin_timed(c, 2);
   const int ctas = (n + kK3WarpsPerCta - 1) / kK3WarpsPerCta;
   auto k3 = c->sub_dfunc == JSVM_DF_HADAMARD ? subpel_kernel<JSVM_DF_HADAMARD>
@@ -420,7 +449,7 @@ int run_search(jsvm_me_ctx* c, const jsvm_me_job* d_jobs, int job_begin, int job
   k3<<<ctas, 32 * kK3WarpsPerCta, 0, c->stream>>>(
       c->d_planes, c->plane_bytes, c->plane_stride, c->d_half, c->half_bytes, c->half_stride,
       d_jobs + job_begin, d_aux + job_begin, n, d_org, d_keys + job_begin,
-      generic ? c->d_full_costs.p + job_begin : nullptr, d_results + job_begin,
+      generic || fast || refine ? c->d_full_costs.p + job_begin : nullptr, d_results + job_begin,
       d_preds ? d_preds + (size_t)job_begin * 256 : nullptr,
       c->d_factor_map.p, mixed_factor_classes(c) ? (int)c->factor_map.size() : 0);
   end_timed(c);
@@ -463,6 +492,58 @@ int prepare_search_extras(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, i
       last = f; have_last = true;
     }
   }
+  return JSVM_ME_OK;
+}
+
+// jsvm_me_search for SPIRAL / LOG / FAST / TZ: no plan, one batch (these searches touch a few hundred points per job).
+int search_fast_host(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const int16_t* org_mbs, int n_org_mbs,
+                     jsvm_me_result* results, uint8_t* preds) {
+  CU_OK(cudaSetDevice(c->device));
+  const int mbw = c->W >> 4, mbh = c->H >> 4;
+  for (int i = 0; i < n_jobs; ++i) {
+    const jsvm_me_job& j = jobs[i];
+    int w, h;
+    if (!mode_size(j.mode, w, h)) return fail("job %d: unsupported mode %d", i, (int)(j.mode & JSVM_JOB_MODE_MASK));
+    if (j.blk > 15 || partition_slot(j.mode, j.blk) < 0) return fail("job %d: blk %d is not a legal origin for mode %d", i, (int)j.blk, (int)(j.mode & JSVM_JOB_MODE_MASK));
+    if (j.cur_slot < 0 || j.cur_slot >= c->n_slots || j.ref_slot < 0 || j.ref_slot >= c->n_slots) return fail("job %d: plane slot out of range", i);
+    if (j.mb_x < 0 || j.mb_x >= mbw || j.mb_y < 0 || j.mb_y >= mbh) return fail("job %d: macroblock (%d,%d) outside the picture", i, j.mb_x, j.mb_y);
+    if (j.search_range < 0 || j.search_range > kMaxSearchRange) return fail("job %d: per-job search range %d outside [0,%d]", i, (int)j.search_range, kMaxSearchRange);
+    if (j.org_index >= n_org_mbs) return fail("job %d: org_index %d >= n_org_mbs %d", i, j.org_index, n_org_mbs);
+    if (j.org_index < 0 && !c->slot_full[j.cur_slot]) return fail("job %d: cur_slot %d is empty", i, (int)j.cur_slot);
+    if (!c->slot_half[j.ref_slot]) return fail("job %d: ref_slot %d has no half-pel plane", i, (int)j.ref_slot);
+    if (c->search_mode == JSVM_SEARCH_SPIRAL && j.search_range == 0) {
+      // xPelSpiralSearch limits the start to [ m_cMin + 4 SR, m_cMax - 4 SR ] and then reads (2 SR + 1)^2 positions unchecked
+      const int lo_h = ((-16 * j.mb_x - 24) + c->search_range) * 4, hi_h = ((16 * (mbw - j.mb_x) + 8) - c->search_range) * 4;
+      const int lo_v = ((-16 * j.mb_y - 24) + c->search_range) * 4, hi_v = ((16 * (mbh - j.mb_y) + 8) - c->search_range) * 4;
+      if (lo_h > hi_h || lo_v > hi_v)
+        return fail("job %d: spiral search with range %d does not fit the padded %dx%d picture (the reference reads outside its planes here)",
+                    i, c->search_range, c->W, c->H);
+    }
+  }
+  const bool need_cands = c->search_mode == JSVM_SEARCH_FAST || c->search_mode == JSVM_SEARCH_TZ;
+  if (need_cands && c->cands && c->n_cands < n_jobs) return fail("jsvm_me_set_mv_candidates registered %d jobs, the call passes %d", c->n_cands, n_jobs);
+  const bool want_preds = preds != nullptr || n_jobs <= 4096;
+  if (c->d_jobs.reserve(n_jobs) || c->d_keys.reserve(n_jobs) || c->d_full_costs.reserve(n_jobs) || c->d_aux.reserve(n_jobs) ||
+      c->d_results.reserve(n_jobs) || (want_preds && c->d_preds.reserve((size_t)n_jobs * 256)) ||
+      (n_org_mbs > 0 && c->d_org.reserve((size_t)n_org_mbs * 256)) || (need_cands && c->cands && c->d_cands.reserve((size_t)n_jobs * 3))) return JSVM_ME_ERR;
+  const int16_t* d_org_chroma = nullptr;
+  if (prepare_search_extras(c, jobs, n_jobs, n_org_mbs, &d_org_chroma)) return JSVM_ME_ERR;
+  if (n_org_mbs > 0) CU_OK(cudaMemcpyAsync(c->d_org.p, org_mbs, sizeof(int16_t) * 256 * n_org_mbs, cudaMemcpyHostToDevice, c->stream));
+  CU_OK(cudaMemcpyAsync(c->d_jobs.p, jobs, sizeof(jsvm_me_job) * n_jobs, cudaMemcpyHostToDevice, c->stream));
+  const jsvm_mv* d_cands = nullptr;
+  if (need_cands && c->cands) {
+    CU_OK(cudaMemcpyAsync(c->d_cands.p, c->cands, sizeof(jsvm_mv) * 3 * n_jobs, cudaMemcpyHostToDevice, c->stream));
+    d_cands = c->d_cands.p;
+  }
+  jsvm_me_plan_info none{};
+  if (run_search(c, c->d_jobs.p, 0, n_jobs, nullptr, &none, c->d_org.p, c->d_keys.p, c->d_aux.p, c->d_results.p, want_preds ? c->d_preds.p : nullptr,
+                 d_org_chroma, d_cands)) { cudaStreamSynchronize(c->stream); return JSVM_ME_ERR; }
+  CU_OK(cudaMemcpyAsync(results, c->d_results.p, sizeof(jsvm_me_result) * n_jobs, cudaMemcpyDeviceToHost, c->stream));
+  if (preds) CU_OK(cudaMemcpyAsync(preds, c->d_preds.p, (size_t)n_jobs * 256, cudaMemcpyDeviceToHost, c->stream));
+  CU_OK(cudaStreamSynchronize(c->stream));
+  c->last_small = false;
+  if (want_preds && n_jobs <= 4096) c->last_jobs.assign(jobs, jobs + n_jobs); else c->last_jobs.clear();
+  c->last_has_preds = want_preds && n_jobs <= 4096;
   return JSVM_ME_OK;
 }
 
@@ -541,7 +622,7 @@ int jsvm_me_destroy(jsvm_me_ctx* c) {
   if (c->d_chroma) cudaFree(c->d_chroma);
   if (c->d_slot_ids) cudaFree(c->d_slot_ids);
   if (c->d_bad) cudaFree(c->d_bad);
-  c->d_factor_map.release(); c->d_org_chroma.release(); c->d_mc_jobs.release(); c->d_mc_pred.release();
+  c->d_cands.release(); c->d_factor_map.release(); c->d_org_chroma.release(); c->d_mc_jobs.release(); c->d_mc_pred.release();
   c->d_jobs.release(); c->d_groups.release(); c->d_keys.release(); c->d_full_costs.release(); c->d_aux.release();
   c->d_results.release(); c->d_preds.release(); c->d_org.release(); c->d_stage.release();
   for (auto& t : c->timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
@@ -566,6 +647,7 @@ int jsvm_me_configure(jsvm_me_ctx* c, int width, int height, int n_slots) {
   if (c->d_chroma) { cudaFree(c->d_chroma); c->d_chroma = nullptr; }
   if (c->d_slot_ids) { cudaFree(c->d_slot_ids); c->d_slot_ids = nullptr; }
   c->W = width; c->H = height; c->n_slots = n_slots;
+  c->cands = nullptr; c->n_cands = 0; c->d_cands_user = nullptr; c->org_chroma = nullptr; c->n_org_chroma = 0;   // per-call inputs of the old geometry
   c->plane_stride = width + 2 * kMargin; c->plane_rows = height + 2 * kMargin;
   c->plane_bytes = (size_t)c->plane_stride * c->plane_rows;
   c->half_stride = 2 * c->plane_stride; c->half_rows = 2 * c->plane_rows;
@@ -584,12 +666,35 @@ int jsvm_me_configure(jsvm_me_ctx* c, int width, int height, int n_slots) {
 
 int jsvm_me_set_params(jsvm_me_ctx* c, int search_mode, int full_pel_dfunc, int sub_pel_dfunc, int search_range) {
   if (!c) return fail("null context");
-  if (search_mode != JSVM_SEARCH_BLOCK) return fail("SearchMode %d: only BLOCK_SEARCH (0, full search) is implemented", search_mode);
   // MotionVectorSearchParams::check (ENC/CodingParameter.cpp:17-36)
+  if (search_mode < JSVM_SEARCH_BLOCK || search_mode > JSVM_SEARCH_TZ) return fail("No Such Search Mode %d: 0==Block, 1==Spiral, 2==Log, 3==Fast, 4==TZ", search_mode);
+  if ((search_mode == JSVM_SEARCH_LOG || search_mode == JSVM_SEARCH_FAST) && full_pel_dfunc == JSVM_DF_YUV_SAD)
+    return fail("SearchMode %d with SearchFuncFullPel 3: xPelLogSearch never sets the chroma search pointers (ENC/MotionEstimation.cpp:472-709), "
+                "the reference's result is undefined there", search_mode);
   if (full_pel_dfunc < 0 || full_pel_dfunc > 3) return fail("No Such Search Func (Full Pel) %d: 0==SAD, 1==SSE, 2==Hadamard, 3==YUV-SAD", full_pel_dfunc);
   if (sub_pel_dfunc < 0 || sub_pel_dfunc > 2) return fail("No Such Search Func (Sub Pel) %d: 0==SAD, 1==SSE, 2==Hadamard", sub_pel_dfunc);
   if (search_range < 1 || search_range > kMaxSearchRange) return fail("SearchRange %d outside [1,%d]", search_range, kMaxSearchRange);
-  c->search_range = search_range; c->sub_dfunc = sub_pel_dfunc; c->full_dfunc = full_pel_dfunc; c->params_set = true;
+  c->search_range = search_range; c->sub_dfunc = sub_pel_dfunc; c->full_dfunc = full_pel_dfunc; c->search_mode = search_mode; c->params_set = true;
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_set_fast_search_params(jsvm_me_ctx* c, int el_search_range, int fast_bi_search) {
+  if (!c) return fail("null context");
+  if (el_search_range < 0 || el_search_range > kMaxSearchRange) return fail("ELSearchRange %d outside [0,%d]", el_search_range, kMaxSearchRange);
+  c->el_search_range = el_search_range; c->fast_bi_search = fast_bi_search != 0;
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_set_mv_candidates(jsvm_me_ctx* c, const jsvm_mv* abc, int n_jobs) {
+  if (!c) return fail("null context");
+  if (abc && n_jobs <= 0) return fail("n_jobs %d", n_jobs);
+  c->cands = abc; c->n_cands = abc ? n_jobs : 0;
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_set_mv_candidates_device(jsvm_me_ctx* c, const jsvm_mv* d_abc) {
+  if (!c) return fail("null context");
+  c->d_cands_user = d_abc;
   return JSVM_ME_OK;
 }
 
@@ -856,11 +961,15 @@ int jsvm_me_plan_host(int width, int height, int n_slots, int search_range, cons
 int jsvm_me_search_device(jsvm_me_ctx* c, const jsvm_me_job* d_jobs, int n_jobs, const void* d_groups, const jsvm_me_plan_info* info,
                           const int16_t* d_org_mbs, int n_org_mbs, jsvm_me_result* d_results, uint8_t* d_preds) {
   (void)n_org_mbs;
-  if (!c || !d_jobs || !d_groups || !info || !d_results) return fail("null argument");
+  if (!c || !d_jobs || !d_results) return fail("null argument");
+  const bool fast = c->search_mode != JSVM_SEARCH_BLOCK;     // the fast searches need no plan
+  if (!fast && (!d_groups || !info)) return fail("null argument");
   if (n_jobs <= 0) return JSVM_ME_OK;
   CU_OK(cudaSetDevice(c->device));
   if (c->d_keys.reserve(n_jobs) || c->d_full_costs.reserve(n_jobs) || c->d_aux.reserve(n_jobs)) return JSVM_ME_ERR;
-  return run_search(c, d_jobs, 0, n_jobs, (const Group*)d_groups, info, d_org_mbs, c->d_keys.p, c->d_aux.p, d_results, d_preds);
+  jsvm_me_plan_info none{};
+  return run_search(c, d_jobs, 0, n_jobs, (const Group*)d_groups, info ? info : &none, d_org_mbs, c->d_keys.p, c->d_aux.p, d_results, d_preds,
+                    nullptr, c->d_cands_user);
 }
 
 int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const int16_t* org_mbs, int n_org_mbs,
@@ -876,6 +985,7 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
       if (org_mbs[i] < -1024 || org_mbs[i] > 1023)      // residual-prediction originals span [-255, 510] (N3); the key widths assume |v| < 1024
         return fail("org_mbs sample %zu = %d outside [-1024,1023]", i, (int)org_mbs[i]);
   }
+  if (c->search_mode != JSVM_SEARCH_BLOCK) return search_fast_host(c, jobs, n_jobs, org_mbs, n_org_mbs, results, preds);
   if (n_jobs <= 64 && n_org_mbs <= 64) return search_small(c, jobs, n_jobs, org_mbs, n_org_mbs, results, preds);
   c->last_small = false;
   CU_OK(cudaSetDevice(c->device));

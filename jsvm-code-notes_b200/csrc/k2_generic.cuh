@@ -64,8 +64,9 @@ full_search_generic_kernel(const uint8_t* __restrict__ planes, size_t plane_byte
   const jsvm_me_job j = jobs[job_idx];
   // ENC/MotionEstimation.cpp:250-253: with a bi-predictive or unequally weighted original the YUV-SAD search falls back to the
   // luma SAD; those are the jobs whose original is caller-prepared (org_index >= 0) WITHOUT chroma originals
-  // (jsvm_me_set_org_chroma).  Equal-weight originals come with their chroma (weightInverseChromaSamples, :236-241).
-  const bool YUV = YUV_FN && !(j.org_index >= 0 && org_chroma_mbs == nullptr);
+  // (jsvm_me_set_org_chroma), and every job flagged JSVM_JOB_BIPRED.  Equal-weight originals come with their chroma
+  // (weightInverseChromaSamples, :236-241).
+  const bool YUV = YUV_FN && !(j.org_index >= 0 && org_chroma_mbs == nullptr) && !(j.mode & JSVM_JOB_BIPRED);
   const int tid = threadIdx.x;
   int w = 16, h = 16;
   mode_size(j.mode, w, h);
@@ -157,7 +158,7 @@ full_search_generic_kernel(const uint8_t* __restrict__ planes, size_t plane_byte
   if (tid == 0) {
     keys[job_idx] = (uint32_t)(s_best & 0xffffffffu);
     full_costs[job_idx] = (uint32_t)(s_best >> 32);
-    JobAux a; a.ux0 = (int16_t)win.xlo; a.uy0 = (int16_t)win.ylo; a.uw = (int16_t)ww; a.pad = 0;
+    JobAux a; a.ux0 = (int16_t)win.xlo; a.uy0 = (int16_t)win.ylo; a.uw = (int16_t)ww; a.pad = 1;
     aux[job_idx] = a;
   }
 }

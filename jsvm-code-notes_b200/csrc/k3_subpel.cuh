@@ -88,8 +88,8 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
               const jsvm_me_job* __restrict__ jobs, const JobAux* __restrict__ aux, int n_jobs,
               const int16_t* __restrict__ org_mbs,
               const uint32_t* __restrict__ keys,
-              const uint32_t* __restrict__ full_costs,   // NULL: keys hold (cost << 15 | index) of the packed-byte SAD search;
-                                                         // else (generic SSD / Hadamard search): keys = index, full_costs = cost
+              const uint32_t* __restrict__ full_costs,   // jobs whose aux.pad is 0: keys hold (cost << 15 | index) of the packed-byte SAD
+                                                         // search; aux.pad 1 (generic and fast searches): keys = index, full_costs = cost
               jsvm_me_result* __restrict__ results, uint8_t* __restrict__ preds,
               const uint2* __restrict__ factor_map, int n_factor_map)    // (full-pel factor, sub-pel factor) pairs; 0: one factor for both stages
 {
@@ -120,9 +120,10 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
 
   // ---- decode the full-pel winner (xPelBlockSearch result) ----
   const uint32_t key = keys[job_idx];
-  const uint32_t idx = full_costs ? key : key & ((1u << kIdxBits) - 1);
+  const bool wide = full_costs != nullptr && a.pad != 0;
+  const uint32_t idx = wide ? key : key & ((1u << kIdxBits) - 1);
   const int fx = a.ux0 + (int)(idx % (uint32_t)a.uw), fy = a.uy0 + (int)(idx / (uint32_t)a.uw);
-  const uint32_t full_cost = full_costs ? full_costs[job_idx] : key >> kIdxBits;
+  const uint32_t full_cost = wide ? full_costs[job_idx] : key >> kIdxBits;
   const uint32_t full_rate = rate_cost(f_full, mv_component_bits((fx << 2) - j.pred.hor) + mv_component_bits((fy << 2) - j.pred.ver));
 
   const int bx0 = 16 * j.mb_x + 4 * (j.blk & 3), by0 = 16 * j.mb_y + 4 * (j.blk >> 2);
@@ -315,7 +316,7 @@ subpel_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int plane_
     jsvm_me_result r;
     r.mv.hor = (int16_t)mvh; r.mv.ver = (int16_t)mvv;
     r.mv_fullpel.hor = (int16_t)fx; r.mv_fullpel.ver = (int16_t)fy;
-    r.sad_fullpel = full_cost - full_rate + (full_costs ? 0u : excess_block);    // the generic search works on the true original
+    r.sad_fullpel = full_cost - full_rate + (wide ? 0u : excess_block);    // the generic search works on the true original
     r.min_sad = min_sad;
     r.mv_bits = mv_bits;
     r.bits = j.bits_in + mv_bits;

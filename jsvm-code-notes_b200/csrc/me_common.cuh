@@ -93,7 +93,7 @@ __host__ __device__ inline uint32_t mv_component_bits(int d) {
 __host__ __device__ inline uint32_t rate_cost(uint32_t factor, uint32_t bits) { return (factor * bits) >> 16; }
 
 __host__ __device__ inline bool mode_size(int mode, int& w, int& h) {
-  switch (mode) {          // XDistortion::init m_aiRows / m_aiCols, ENC/Distortion.cpp:50-74
+  switch (mode & JSVM_JOB_MODE_MASK) {          // XDistortion::init m_aiRows / m_aiCols, ENC/Distortion.cpp:50-74
     case JSVM_MODE_16x16: w = 16; h = 16; return true;
     case JSVM_MODE_16x8:  w = 16; h = 8;  return true;
     case JSVM_MODE_8x16:  w = 8;  h = 16; return true;
@@ -109,7 +109,7 @@ __host__ __device__ inline bool mode_size(int mode, int& w, int& h) {
 __host__ __device__ inline int partition_slot(int mode, int blk) {
   const int bx = blk & 3, by = blk >> 2;
   const int b8 = (by >> 1) * 2 + (bx >> 1);           // which 8x8
-  switch (mode) {
+  switch (mode & JSVM_JOB_MODE_MASK) {
     case JSVM_MODE_16x16: return blk == 0 ? 0 : -1;
     case JSVM_MODE_16x8:  return (bx == 0 && (by == 0 || by == 2)) ? 1 + (by >> 1) : -1;
     case JSVM_MODE_8x16:  return (by == 0 && (bx == 0 || bx == 2)) ? 3 + (bx >> 1) : -1;

@@ -139,6 +139,18 @@ class MotionEstimator:
     def map_cost_factor(self, factor_full_pel, factor_sub_pel):
         self._check(self._lib.jsvm_me_map_cost_factor(self._ctx, int(factor_full_pel), int(factor_sub_pel)))
 
+    def set_fast_search_params(self, el_search_range=0, fast_bi_search=0):
+        self._check(self._lib.jsvm_me_set_fast_search_params(self._ctx, int(el_search_range), int(fast_bi_search)))
+
+    def set_mv_candidates(self, abc):
+        """(n_jobs, 3, 2) int16 MVs of the neighbours A, B, C per job for FAST / TZ searches (or None); kept alive until replaced."""
+        if abc is None:
+            self._cands = None
+            self._check(self._lib.jsvm_me_set_mv_candidates(self._ctx, None, 0))
+            return
+        self._cands = np.ascontiguousarray(abc, dtype=np.int16).reshape(-1, 3, 2)
+        self._check(self._lib.jsvm_me_set_mv_candidates(self._ctx, _ptr(self._cands), len(self._cands)))
+
     def compensate(self, mc_jobs, chroma=True):
         """MotionCompensation (predBlk / xPredChromaPel / SampleWeighting) for every MC_JOB_DTYPE record.
         Returns (pred_y (n,16,16), pred_cb (n,8,8), pred_cr (n,8,8)) uint8 (chroma None when chroma=False)."""

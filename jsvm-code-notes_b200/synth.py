@@ -186,6 +186,27 @@ def make_jobs(width, height, parts, cur_slot, ref_slot, qp=30, field="random", s
     return jobs
 
 
+def make_fast_search_extras(jobs, search_range, seed=0, p_el=0.2, p_bipred=0.25, p_iter=0.15, iter_range=8, far=0.1):
+    """What the fast searches (SPIRAL / LOG / FAST / TZ) read beyond the plain job: returns (jobs', cands).
+    jobs': a copy with the per-call flags in the top bits of `mode` (JSVM_JOB_EL, JSVM_JOB_BIPRED) on a seeded share of the jobs and
+    a non-zero per-call search range (the bi-prediction refinement) on another share; cands: (n, 3, 2) MVs of the neighbours A, B, C
+    near the predictor, a share of them far away (outside the search window, clamped per macroblock) -- but inside the span of
+    the reference's bit-count table, |4x - pred| < (4 SR + 4) * 16 quarter-pels (ENC/MotionEstimationCost.cpp:33-41): beyond it
+    the reference reads outside the table (undefined), while the device evaluates the Exp-Golomb length analytically."""
+    rng = np.random.default_rng(seed)
+    n = len(jobs)
+    out = jobs.copy()
+    flags = np.where(rng.random(n) < p_el, 0x40, 0) | np.where(rng.random(n) < p_bipred, 0x80, 0)
+    out["mode"] = out["mode"] | flags.astype(np.uint8)
+    out["search_range"] = np.where(rng.random(n) < p_iter, rng.integers(1, iter_range + 1, n), 0).astype(np.int16)
+    base = np.stack([out["pred_hor"], out["pred_ver"]], -1).astype(np.int64)[:, None, :]
+    cands = base + rng.integers(-24, 25, (n, 3, 2))
+    wild = rng.random((n, 3)) < far
+    span = min(600, (4 * search_range + 4) * 16 - 48)
+    cands[wild] = (np.broadcast_to(base, cands.shape)[wild] + rng.integers(-span, span + 1, (int(wild.sum()), 2)))
+    return out, np.clip(cands, -32768, 32767).astype(np.int16)
+
+
 def hierarchical_b_pairs(gop, refs=1):
     """(current, reference) picture pairs of one GOP, grouped by temporal level (coarsest first).
 

@@ -33,6 +33,8 @@ struct jsvm_ora_ctx {
   ora_plane* planes;
   uint32_t factor_map[256][2]; int n_factor_map;   /* full-pel stage factor -> sub-pel stage factor */
   const int16_t* org_chroma; int n_org_chroma;
+  int el_search_range, fast_bi_search;              /* MotionVectorSearchParams ELSearchRange / FastBiSearch */
+  const jsvm_mv* cands; int n_cands;                /* 3 per job: m_cMv3D_A / B / C (MbDataAccess::addMvPredictors) */
 };
 
 static inline int clip255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }   /* gClip, INCC/GlobalFunctions.h:37-44 */
@@ -64,7 +66,7 @@ uint32_t jsvm_ora_cost_factor(double lambda, int sad) {
  * Block geometry: XDistortion::init tables m_aiRows / m_aiCols (ENC/Distortion.cpp:50-74).
  * ------------------------------------------------------------------------------------------- */
 static int mode_size(int mode, int* w, int* h) {
-  switch (mode) {
+  switch (mode & JSVM_JOB_MODE_MASK) {
     case JSVM_MODE_16x16: *w = 16; *h = 16; return 0;
     case JSVM_MODE_16x8:  *w = 16; *h = 8;  return 0;
     case JSVM_MODE_8x16:  *w = 8;  *h = 16; return 0;
@@ -150,7 +152,7 @@ jsvm_ora_ctx* jsvm_ora_create(int width, int height, int n_slots,
   if (width <= 0 || height <= 0 || (width & 15) || (height & 15) || n_slots <= 0) return NULL;
   jsvm_ora_ctx* c = (jsvm_ora_ctx*)calloc(1, sizeof(*c));
   c->width = width; c->height = height; c->n_slots = n_slots;
-  c->search_mode = search_mode; c->full_dfunc = full_pel_dfunc; c->sub_dfunc = sub_pel_dfunc; c->search_range = search_range;
+  c->search_mode = search_mode; c->el_search_range = search_range; c->full_dfunc = full_pel_dfunc; c->sub_dfunc = sub_pel_dfunc; c->search_range = search_range;
   c->planes = (ora_plane*)calloc((size_t)n_slots, sizeof(ora_plane));
   for (int s = 0; s < n_slots; ++s) {
     c->planes[s].full = (uint8_t*)calloc((size_t)(width + 2 * MARGIN) * (height + 2 * MARGIN), 1);
@@ -360,11 +362,270 @@ static const uint8_t kFilterOfHalf[9] = { 0, 2, 2, 1, 1, 3, 3, 3, 3 };
 static const int8_t kHalfMv[9][2] = { {0,0}, {0,-2}, {0,2}, {-2,0}, {2,0}, {-2,-2}, {2,-2}, {-2,2}, {2,2} };
 static const int8_t kQuarterMv[9][2] = { {0,0}, {0,-1}, {0,1}, {-1,-1}, {1,-1}, {-1,0}, {1,0}, {-1,1}, {1,1} };
 
+
+/* ---------------------------------------------------------------------------------------------
+ * Full-pel stage.  fp_cost() is m_cXDSS.Func + xGetCost( x, y ) at one integer displacement; the strategies below restate
+ *   xPelBlockSearch  ENC/MotionEstimation.cpp:351-412      xPelSpiralSearch :415-468 (spiral table built in init, :69-113)
+ *   xPelLogSearch    :472-709 (LOG_SEARCH and, with the candidate list, FAST_SEARCH)
+ *   xTZSearch        :1106-1292 with xTZCheckPoint :733-757, xTZ2PointSearch :760-880, xTZ8PointDiamondSearch :929-1103 and
+ *                    the TZ_SEARCH_CONFIGURATION constants :713-730
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const jsvm_ora_ctx* c; const jsvm_me_job* j;
+  int w, h, dfunc, S, CS;
+  uint32_t f;
+  const int16_t* org; const int16_t* corg;       /* org: stride 16; corg: [2][64], stride 8 */
+  const uint8_t* ref0; const uint8_t* cref0[2];
+} fp_eval;
+
+static uint32_t fp_cost(const fp_eval* e, int x, int y) {
+  uint32_t sad;
+  if (e->dfunc == JSVM_DF_SAD || e->dfunc == JSVM_DF_YUV_SAD) {   /* same sums as distortion(); direct loops keep the checker fast */
+    const uint8_t* rp = e->ref0 + y * e->S + x;
+    sad = 0;
+    for (int yy = 0; yy < e->h; ++yy)
+      for (int xx = 0; xx < e->w; ++xx) sad += (uint32_t)abs(e->org[yy * 16 + xx] - rp[yy * e->S + xx]);
+    if (e->dfunc == JSVM_DF_YUV_SAD)
+      for (int k = 0; k < 2; ++k) {
+        const uint8_t* cp = e->cref0[k] + (y >> 1) * e->CS + (x >> 1);
+        for (int yy = 0; yy < e->h / 2; ++yy)
+          for (int xx = 0; xx < e->w / 2; ++xx) sad += (uint32_t)abs(e->corg[k * 64 + yy * 8 + xx] - cp[yy * e->CS + xx]);
+      }
+  } else {
+    u8_src s = { e->ref0 + y * e->S + x, e->S };
+    sad = distortion(e->org, get_u8, &s, e->w, e->h, e->dfunc);
+  }
+  /* xGetCost( x, y ) with m_uiMvScaleShift = 2 (N6): table index (x<<2) - pred */
+  return sad + rate_cost(e->f, jsvm_ora_component_bits((x << 2) - e->j->pred.hor) + jsvm_ora_component_bits((y << 2) - e->j->pred.ver));
+}
+static uint32_t fp_rate(const fp_eval* e, int x, int y) {
+  return rate_cost(e->f, jsvm_ora_component_bits((x << 2) - e->j->pred.hor) + jsvm_ora_component_bits((y << 2) - e->j->pred.ver));
+}
+
+static void mb_limits(const jsvm_ora_ctx* c, const jsvm_me_job* j, int16_t* min_h, int16_t* min_v, int16_t* max_h, int16_t* max_v) {
+  const int mbw = c->width >> 4, mbh = c->height >> 4;
+  *min_h = sat16(((-(int)j->mb_x << 4) - 24) << 2); *min_v = sat16(((-(int)j->mb_y << 4) - 24) << 2);
+  *max_h = sat16((((mbw - j->mb_x) << 4) + 8) << 2); *max_v = sat16((((mbh - j->mb_y) << 4) + 8) << 2);
+}
+/* Mv::limitComponents + '>>= 2' of one vector */
+static void limit_pel(const jsvm_ora_ctx* c, const jsvm_me_job* j, jsvm_mv mv, int* x, int* y) {
+  int16_t a, b, cc, d; mb_limits(c, j, &a, &b, &cc, &d);
+  *x = (int16_t)imin(cc, imax(a, mv.hor)) >> 2; *y = (int16_t)imin(d, imax(b, mv.ver)) >> 2;
+}
+/* SearchRect::init around the clipped start with range `lim` */
+static void rect_init(const jsvm_ora_ctx* c, const jsvm_me_job* j, int lim_in, int* cx, int* cy, search_rect* r) {
+  int16_t min_h, min_v, max_h, max_v; mb_limits(c, j, &min_h, &min_v, &max_h, &max_v);
+  limit_pel(c, j, j->start, cx, cy);
+  const int16_t h = (int16_t)*cx, v = (int16_t)*cy, lim = (int16_t)lim_in;
+  const int16_t mnh = min_h >> 2, mnv = min_v >> 2, mxh = max_h >> 2, mxv = max_v >> 2;
+  const int16_t pos_v = (int16_t)(mxv - v), neg_v = (int16_t)(v - mnv), pos_h = (int16_t)(mxh - h), neg_h = (int16_t)(h - mnh);
+  r->neg_ver = imin(lim, neg_v) - v; r->pos_ver = imin(lim, pos_v) + v;
+  r->neg_hor = imin(lim, neg_h) - h; r->pos_hor = imin(lim, pos_h) + h;
+}
+
+static const jsvm_mv kZeroCands[3] = { {0, 0}, {0, 0}, {0, 0} };
+
+static void search_block(const fp_eval* e, int* bx, int* by, uint32_t* best_io) {
+  int cx, cy; search_rect r;
+  search_window(e->c, e->j, &cx, &cy, &r);
+  uint32_t best = 0xffffffffu;
+  int best_x = cx, best_y = cy;                             /* rcMv keeps the clipped start if the window is empty */
+  for (int y = -r.neg_ver; y <= r.pos_ver; ++y)
+    for (int x = -r.neg_hor; x <= r.pos_hor; ++x) {
+      const uint32_t sad = fp_cost(e, x, y);
+      if (best > sad) { best = sad; best_x = x; best_y = y; }           /* first strict minimum in raster order (N1) */
+    }
+  *best_io = best - fp_rate(e, best_x, best_y); *bx = best_x; *by = best_y;
+}
+
+/* xPelSpiralSearch: the start is limited to [ m_cMin + 4 SR, m_cMax - 4 SR ], then all (2 SR + 1)^2 offsets of the spiral table
+ * are tried in table order; SR is always the configured range.  Returns -1 where the reference would read outside its planes
+ * (picture too small for the range: the limited interval is empty). */
+static int search_spiral(const fp_eval* e, int* bx, int* by, uint32_t* best_io) {
+  const int sr = e->c->search_range;
+  int16_t min_h, min_v, max_h, max_v; mb_limits(e->c, e->j, &min_h, &min_v, &max_h, &max_v);
+  const int16_t lo_h = (int16_t)(min_h + 4 * sr), lo_v = (int16_t)(min_v + 4 * sr), hi_h = (int16_t)(max_h - 4 * sr), hi_v = (int16_t)(max_v - 4 * sr);
+  if (lo_h > hi_h || lo_v > hi_v) return -1;
+  const int cx = (int16_t)imin(hi_h, imax(lo_h, e->j->start.hor)) >> 2, cy = (int16_t)imin(hi_v, imax(lo_v, e->j->start.ver)) >> 2;
+  uint32_t best = fp_cost(e, cx, cy);                        /* entry 0 = (0,0) */
+  int ox = 0, oy = 0;
+#define SPIRAL_TRY(dx, dy) do { const uint32_t sad_ = fp_cost(e, cx + (dx), cy + (dy)); if (best > sad_) { best = sad_; ox = (dx); oy = (dy); } } while (0)
+  for (int off = 1; off <= sr; ++off) {
+    for (int l = -off + 1; l < off; ++l) { SPIRAL_TRY(l, -off); SPIRAL_TRY(l, off); }
+    for (int l = -off; l <= off; ++l)    { SPIRAL_TRY(-off, l); SPIRAL_TRY(off, l); }
+  }
+#undef SPIRAL_TRY
+  *bx = cx + ox; *by = cy + oy; *best_io = best - fp_rate(e, *bx, *by);
+  return 0;
+}
+
+/* MotionEstimation::init, :50-58 */
+static int max_log_step(int search_range) {
+  unsigned lim = (unsigned)search_range >> 4; int step = 1;
+  while (lim) { lim >>= 1; step <<= 1; }
+  return step;
+}
+
+/* xPelLogSearch( ..., bFme = (cands != NULL), uiStep ) */
+static void search_log(const fp_eval* e, const jsvm_mv* cands, int step_start, int* bx, int* by, uint32_t* best_io) {
+  int x, y; search_rect r;
+  rect_init(e->c, e->j, e->c->search_range, &x, &y, &r);
+  uint32_t best = fp_cost(e, x, y);
+  if (cands) {
+    jsvm_mv list[4] = { e->j->pred, cands[0], cands[1], cands[2] };       /* :283-284: rcMvPred, then A, B, C */
+    for (int n = 0; n < 4; ++n) {
+      int px, py; limit_pel(e->c, e->j, list[n], &px, &py);
+      const uint32_t sad = fp_cost(e, px, py);
+      if (best > sad) { best = sad; x = px; y = py; }
+    }
+  }
+  int dx_old = 0, dy_old = 0;
+  for (int step = step_start; step != 0; step >>= 1) {
+    int go = 1;
+    dx_old = 0; dy_old = 0;
+    while (go) {
+      int dx = 0, dy = 0;
+      uint32_t sad;
+      if (dx_old <= 0 && -x <= r.neg_hor - step) { sad = fp_cost(e, x - step, y); if (best > sad) { best = sad; dx = -step; } }
+      if (dx_old >= 0 && x < r.pos_hor - step)   { sad = fp_cost(e, x + step, y); if (best > sad) { best = sad; dx = step; } }
+      if (dy_old <= 0 && -y <= r.neg_ver - step) { sad = fp_cost(e, x, y - step); if (best > sad) { best = sad; dx = 0; dy = -step; } }
+      if (dy_old >= 0 && y < r.pos_ver - step)   { sad = fp_cost(e, x, y + step); if (best > sad) { best = sad; dx = 0; dy = step; } }
+      go = (dx != 0 || dy != 0);
+      if (go) { dx_old = dx; dy_old = dy; x += dx; y += dy; }
+    }
+  }
+  {                                                         /* the four diagonal neighbours, once */
+    int dx = 0, dy = 0;
+    uint32_t sad;
+    if (dx_old != 1 && -x <= r.neg_hor - 1) {
+      if (dy_old != 1 && -y <= r.neg_ver - 1) { sad = fp_cost(e, x - 1, y - 1); if (best > sad) { best = sad; dx = -1; dy = -1; } }
+      if (dy_old != -1 && y < r.pos_ver - 1)  { sad = fp_cost(e, x - 1, y + 1); if (best > sad) { best = sad; dx = -1; dy = 1; } }
+    }
+    if (dx_old != -1 && x < r.pos_hor - 1) {
+      if (dy_old != 1 && -y <= r.neg_ver - 1) { sad = fp_cost(e, x + 1, y - 1); if (best > sad) { best = sad; dx = 1; dy = -1; } }
+      if (dy_old != -1 && y < r.pos_ver - 1)  { sad = fp_cost(e, x + 1, y + 1); if (best > sad) { best = sad; dx = 1; dy = 1; } }
+    }
+    x += dx; y += dy;
+  }
+  *bx = x; *by = y; *best_io = best - fp_rate(e, x, y);
+}
+
+/* ---- xTZSearch ---- */
+typedef struct { const fp_eval* e; search_rect r; uint32_t best; int bx, by; unsigned dist; int nr; } tz_state;
+
+static void tz_check(tz_state* t, int x, int y, int nr, unsigned dist) {                         /* xTZCheckPoint */
+  const uint32_t sad = fp_cost(t->e, x, y);
+  if (t->best > sad) { t->best = sad; t->bx = x; t->by = y; t->dist = dist; t->nr = nr; }
+}
+
+static void tz_two_points(tz_state* t) {                                                          /* xTZ2PointSearch */
+  const int x = t->bx, y = t->by;
+  const int l = (x - 1) >= -t->r.neg_hor, rr = (x + 1) <= t->r.pos_hor, u = (y - 1) >= -t->r.neg_ver, d = (y + 1) <= t->r.pos_ver;
+  switch (t->nr) {
+    case 1: if (l) tz_check(t, x - 1, y, 0, 2); if (u) tz_check(t, x, y - 1, 0, 2); break;
+    case 2: if (u) { if (l) tz_check(t, x - 1, y - 1, 0, 2); if (rr) tz_check(t, x + 1, y - 1, 0, 2); } break;
+    case 3: if (u) tz_check(t, x, y - 1, 0, 2); if (rr) tz_check(t, x + 1, y, 0, 2); break;
+    case 4: if (l) { if (d) tz_check(t, x - 1, y + 1, 0, 2); if (u) tz_check(t, x - 1, y - 1, 0, 2); } break;
+    case 5: if (rr) { if (u) tz_check(t, x + 1, y - 1, 0, 2); if (d) tz_check(t, x + 1, y + 1, 0, 2); } break;
+    case 6: if (l) tz_check(t, x - 1, y, 0, 2); if (d) tz_check(t, x, y + 1, 0, 2); break;
+    case 7: if (d) { if (l) tz_check(t, x - 1, y + 1, 0, 2); if (rr) tz_check(t, x + 1, y + 1, 0, 2); } break;
+    case 8: if (rr) tz_check(t, x + 1, y, 0, 2); if (d) tz_check(t, x, y + 1, 0, 2); break;
+    default: break;                                          /* AF() in the reference: not reachable (see search_tz) */
+  }
+}
+
+static void tz_diamond(tz_state* t, int sx, int sy, int dist) {                                   /* xTZ8PointDiamondSearch */
+  const search_rect* r = &t->r;
+  const int top = sy - dist, bot = sy + dist, left = sx - dist, right = sx + dist;
+  const int t_ok = top >= -r->neg_ver, b_ok = bot <= r->pos_ver, l_ok = left >= -r->neg_hor, r_ok = right <= r->pos_hor;
+  if (dist == 1) {
+    if (t_ok) tz_check(t, sx, top, 2, 1);
+    if (l_ok) tz_check(t, left, sy, 4, 1);
+    if (r_ok) tz_check(t, right, sy, 5, 1);
+    if (b_ok) tz_check(t, sx, bot, 7, 1);
+  } else if (dist <= 8) {
+    const int h = dist >> 1, top2 = sy - h, bot2 = sy + h, left2 = sx - h, right2 = sx + h;
+    if (t_ok && l_ok && r_ok && b_ok) {
+      tz_check(t, sx, top, 2, dist); tz_check(t, left2, top2, 1, h); tz_check(t, right2, top2, 3, h); tz_check(t, left, sy, 4, dist);
+      tz_check(t, right, sy, 5, dist); tz_check(t, left2, bot2, 6, h); tz_check(t, right2, bot2, 8, h); tz_check(t, sx, bot, 7, dist);
+    } else {
+      if (t_ok) tz_check(t, sx, top, 2, dist);
+      if (top2 >= -r->neg_ver) {
+        if (left2 >= -r->neg_hor) tz_check(t, left2, top2, 1, h);
+        if (right2 <= r->pos_hor) tz_check(t, right2, top2, 3, h);
+      }
+      if (l_ok) tz_check(t, left, sy, 4, dist);
+      if (r_ok) tz_check(t, right, sy, 5, dist);
+      if (bot2 <= r->pos_ver) {
+        if (left2 >= -r->neg_hor) tz_check(t, left2, bot2, 6, h);
+        if (right2 <= r->pos_hor) tz_check(t, right2, bot2, 8, h);
+      }
+      if (b_ok) tz_check(t, sx, bot, 7, dist);
+    }
+  } else {
+    const int q = dist >> 2;
+    const int all = t_ok && l_ok && r_ok && b_ok;
+    if (all || t_ok) tz_check(t, sx, top, 0, dist);
+    if (all || l_ok) tz_check(t, left, sy, 0, dist);
+    if (all || r_ok) tz_check(t, right, sy, 0, dist);
+    if (all || b_ok) tz_check(t, sx, bot, 0, dist);
+    for (int k = 1; k < 4; ++k) {
+      const int yt = top + q * k, yb = bot - q * k, xl = sx - q * k, xr = sx + q * k;
+      if (all) { tz_check(t, xl, yt, 0, dist); tz_check(t, xr, yt, 0, dist); tz_check(t, xl, yb, 0, dist); tz_check(t, xr, yb, 0, dist); }
+      else {
+        if (yt >= -r->neg_ver) { if (xl >= -r->neg_hor) tz_check(t, xl, yt, 0, dist); if (xr <= r->pos_hor) tz_check(t, xr, yt, 0, dist); }
+        if (yb <= r->pos_ver)  { if (xl >= -r->neg_hor) tz_check(t, xl, yb, 0, dist); if (xr <= r->pos_hor) tz_check(t, xr, yb, 0, dist); }
+      }
+    }
+  }
+}
+
+/* cands == NULL: empty candidate list (the FastBiSearch refinement).  Configuration constants of :713-730: raster 3, other
+ * predicted MVs and the zero vector tested, diamond first search without early stop, raster search when the best distance
+ * exceeds 3, star refinement with diamonds. */
+static void search_tz(const fp_eval* e, const jsvm_mv* cands, int range, int* bx, int* by, uint32_t* best_io) {
+  tz_state t; int sx, sy;
+  t.e = e; t.best = 0xffffffffu; t.bx = t.by = 0; t.dist = 0; t.nr = 0;
+  rect_init(e->c, e->j, range, &sx, &sy, &t.r);
+  tz_check(&t, sx, sy, 0, 0);
+  if (cands) {
+    jsvm_mv list[4] = { e->j->pred, cands[0], cands[1], cands[2] };
+    for (int n = 0; n < 4; ++n) { int px, py; limit_pel(e->c, e->j, list[n], &px, &py); tz_check(&t, px, py, 0, 0); }
+  }
+  tz_check(&t, 0, 0, 0, 0);
+  sx = t.bx; sy = t.by;
+  for (int dist = 1; dist <= range; dist *= 2) tz_diamond(&t, sx, sy, dist);
+  if (t.dist == 1) { t.dist = 0; tz_two_points(&t); }
+  if (t.dist > 3) {
+    t.dist = 3;
+    for (int y = -t.r.neg_ver; y <= t.r.pos_ver; y += 3)
+      for (int x = -t.r.neg_hor; x <= t.r.pos_hor; x += 3) tz_check(&t, x, y, 0, 3);
+  }
+  while (t.dist > 0) {
+    sx = t.bx; sy = t.by; t.dist = 0; t.nr = 0;
+    for (int dist = 1; dist < range + 1; dist *= 2) tz_diamond(&t, sx, sy, dist);
+    if (t.dist == 1) { t.dist = 0; if (t.nr != 0) tz_two_points(&t); }
+  }
+  *bx = t.bx; *by = t.by; *best_io = t.best - fp_rate(e, t.bx, t.by);
+}
+
+int jsvm_ora_set_fast_search_params(jsvm_ora_ctx* c, int el_search_range, int fast_bi_search) {
+  if (!c) return -1;
+  c->el_search_range = el_search_range ? el_search_range : c->search_range;      /* ENC/CodingParameter.cpp:25-28 */
+  c->fast_bi_search = fast_bi_search;
+  return 0;
+}
+
+int jsvm_ora_set_mv_candidates(jsvm_ora_ctx* c, const jsvm_mv* abc, int n_jobs) {
+  if (!c) return -1;
+  c->cands = abc; c->n_cands = abc ? n_jobs : 0;
+  return 0;
+}
+
 int jsvm_ora_search(jsvm_ora_ctx* c, const jsvm_me_job* jobs, int n_jobs,
                     const int16_t* org_mbs, int n_org_mbs,
                     jsvm_me_result* results, uint8_t* preds) {
   if (!c) return -1;
-  if (c->search_mode != JSVM_SEARCH_BLOCK) return -1;     /* only xPelBlockSearch is on the hot path */
   const int W = c->width, H = c->height, S = W + 2 * MARGIN, HS = 2 * S;
   for (int i = 0; i < n_jobs; ++i) {
     const jsvm_me_job* j = &jobs[i];
@@ -404,7 +665,7 @@ int jsvm_ora_search(jsvm_ora_ctx* c, const jsvm_me_job* jobs, int n_jobs,
     int16_t corg[2][64];
     memset(corg, 0, sizeof(corg));
     if (full_dfunc == JSVM_DF_YUV_SAD) {
-      if (j->org_index >= 0 && !c->org_chroma) full_dfunc = JSVM_DF_SAD;
+      if ((j->org_index >= 0 && !c->org_chroma) || (j->mode & JSVM_JOB_BIPRED)) full_dfunc = JSVM_DF_SAD;
       else {
         if (j->org_index >= 0 && j->org_index >= c->n_org_chroma) return -1;
         const int CS = W / 2 + 2 * CMARGIN;
@@ -418,37 +679,30 @@ int jsvm_ora_search(jsvm_ora_ctx* c, const jsvm_me_job* jobs, int n_jobs,
       }
     }
 
-    /* ---- a2 xPelBlockSearch (ENC/MotionEstimation.cpp:351-412) ---- */
-    int cx, cy; search_rect r;
-    search_window(c, j, &cx, &cy, &r);
+    /* ---- full-pel stage: the search strategy of ENC/MotionEstimation.cpp:262-307 ---- */
+    fp_eval ev;
+    ev.c = c; ev.j = j; ev.w = w; ev.h = h; ev.org = org; ev.corg = &corg[0][0]; ev.dfunc = full_dfunc; ev.f = f_full;
+    ev.S = S; ev.ref0 = ref->full + (size_t)(MARGIN + by0) * S + MARGIN + bx0;
+    ev.CS = W / 2 + 2 * CMARGIN;
+    for (int k = 0; k < 2; ++k) ev.cref0[k] = ref->chroma[k] + (size_t)(CMARGIN + by0 / 2) * ev.CS + CMARGIN + bx0 / 2;
     uint32_t best = 0xffffffffu;                            /* MSYS_UINT_MAX */
-    int best_x = cx, best_y = cy;                           /* rcMv keeps the clipped start if the window is empty */
-    const uint8_t* ref0 = ref->full + (size_t)(MARGIN + by0) * S + MARGIN + bx0;
-    for (int y = -r.neg_ver; y <= r.pos_ver; ++y)
-      for (int x = -r.neg_hor; x <= r.pos_hor; ++x) {
-        uint32_t sad;
-        if (full_dfunc == JSVM_DF_SAD || full_dfunc == JSVM_DF_YUV_SAD) {   /* same sums as distortion(); direct loops keep the checker fast */
-          const uint8_t* rp = ref0 + y * S + x;
-          sad = 0;
-          for (int yy = 0; yy < h; ++yy)
-            for (int xx = 0; xx < w; ++xx) sad += (uint32_t)abs(org[yy * 16 + xx] - rp[yy * S + xx]);
-          if (full_dfunc == JSVM_DF_YUV_SAD) {
-            const int CS = W / 2 + 2 * CMARGIN;
-            for (int k = 0; k < 2; ++k) {
-              const uint8_t* cp = ref->chroma[k] + (size_t)(CMARGIN + by0 / 2 + (y >> 1)) * CS + CMARGIN + bx0 / 2 + (x >> 1);
-              for (int yy = 0; yy < h / 2; ++yy)
-                for (int xx = 0; xx < w / 2; ++xx) sad += (uint32_t)abs(corg[k][yy * 8 + xx] - cp[yy * CS + xx]);
-            }
-          }
-        } else {
-          u8_src s = { ref0 + y * S + x, S };
-          sad = distortion(org, get_u8, &s, w, h, full_dfunc);
-        }
-        /* xGetCost( x, y ) with m_uiMvScaleShift = 2 (N6): table index (x<<2) - pred */
-        sad += rate_cost(f_full, jsvm_ora_component_bits((x << 2) - j->pred.hor) + jsvm_ora_component_bits((y << 2) - j->pred.ver));
-        if (best > sad) { best = sad; best_x = x; best_y = y; }       /* first strict minimum in raster order (N1) */
-      }
-    best -= rate_cost(f_full, jsvm_ora_component_bits((best_x << 2) - j->pred.hor) + jsvm_ora_component_bits((best_y << 2) - j->pred.ver));
+    int best_x = 0, best_y = 0;
+    const jsvm_mv* cand = (c->cands && i < c->n_cands) ? c->cands + 3 * (size_t)i : NULL;
+    const int bipred = (j->mode & JSVM_JOB_BIPRED) != 0, el = (j->mode & JSVM_JOB_EL) != 0;
+    if (j->search_range) {                                  /* :264-274: the iterative bi-prediction refinement */
+      if (c->fast_bi_search) search_tz(&ev, NULL, j->search_range, &best_x, &best_y, &best);
+      else search_block(&ev, &best_x, &best_y, &best);
+    } else switch (c->search_mode) {
+      case JSVM_SEARCH_BLOCK:  search_block(&ev, &best_x, &best_y, &best); break;
+      case JSVM_SEARCH_SPIRAL: if (search_spiral(&ev, &best_x, &best_y, &best)) return -1; break;
+      case JSVM_SEARCH_LOG: case JSVM_SEARCH_FAST:
+        if (full_dfunc == JSVM_DF_YUV_SAD) return -1;       /* xPelLogSearch leaves pUSearch / pVSearch unset: undefined in the reference */
+        if (c->search_mode == JSVM_SEARCH_LOG) search_log(&ev, NULL, max_log_step(c->search_range) << (bipred ? 0 : 1), &best_x, &best_y, &best);
+        else search_log(&ev, cand ? cand : kZeroCands, bipred ? 1 : 2, &best_x, &best_y, &best);
+        break;
+      case JSVM_SEARCH_TZ:     search_tz(&ev, cand ? cand : kZeroCands, el ? c->el_search_range : c->search_range, &best_x, &best_y, &best); break;
+      default: return -1;
+    }
     jsvm_me_result* out = &results[i];
     out->mv_fullpel.hor = (int16_t)best_x; out->mv_fullpel.ver = (int16_t)best_y;
     out->sad_fullpel = best;

@@ -46,6 +46,10 @@ int jsvm_ora_set_org_chroma(jsvm_ora_ctx* ctx, const int16_t* org_chroma_mbs, in
 int jsvm_ora_map_cost_factor(jsvm_ora_ctx* ctx, uint32_t factor_full_pel, uint32_t factor_sub_pel);
 int jsvm_ora_compensate(jsvm_ora_ctx* ctx, const jsvm_mc_job* jobs, int n_jobs, uint8_t* pred_y, uint8_t* pred_cb, uint8_t* pred_cr);
 
+/* ELSearchRange / FastBiSearch of MotionVectorSearchParams; the three neighbour MVs of every job (3 per job, host pointer kept) */
+int jsvm_ora_set_fast_search_params(jsvm_ora_ctx* ctx, int el_search_range, int fast_bi_search);
+int jsvm_ora_set_mv_candidates(jsvm_ora_ctx* ctx, const jsvm_mv* abc, int n_jobs);
+
 #ifdef __cplusplus
 }
 #endif

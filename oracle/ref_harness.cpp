@@ -62,6 +62,8 @@ public:
   UInt fullPelDFunc() const { return m_cParams.getFullPelDFunc(); }
   UInt subPelDFunc() const { return m_cParams.getSubPelDFunc(); }
   Void setFullPelDFunc(UInt ui) { m_cParams.setFullPelDFunc(ui); }
+  Void setFastSearchParams(UInt uiEL, UInt uiFastBi) { m_cParams.setELSearchRange(uiEL); m_cParams.setFastBiSearch(uiFastBi); }
+  UInt searchRange() const { return m_cParams.getSearchRange(); }
   // MotionCompensation::compensateMb's inner sequence for one block (COM/MotionCompensation.cpp:1217-1224, 1363-1405):
   // limitComponents, xPredLuma (predBlk + weightLumaSamples), xPredChroma (xPredChromaPel + weightChromaSamples)
   Void predictBlock(YuvMbBuffer* pcRec, UInt uiBlk, Int iSizeX, Int iSizeY, YuvPicBuffer* apcRef[2], const Mv acMv[2], const PredWeight* apcPW[2], Bool bChroma) {
@@ -106,6 +108,8 @@ struct jsvm_ref_ctx {
   std::vector<std::pair<uint32_t, uint32_t> > factor_map;   // full-pel stage factor -> sub-pel stage factor (other class)
   const int16_t*        org_chroma;
   int                   n_org_chroma;
+  const jsvm_mv*        cands;              // 3 per job: the neighbours' MVs MbDataAccess::addMvPredictors hands to FAST / TZ
+  int                   n_cands;
 };
 
 #define CHK(x) do { if ((x) != Err::m_nOK) { fprintf(stderr, "ref_harness: %s failed (%s:%d)\n", #x, __FILE__, __LINE__); return 0; } } while (0)
@@ -115,7 +119,7 @@ extern "C" jsvm_ref_ctx* jsvm_ref_create(int width, int height, int n_slots,
                                          int search_mode, int full_pel_dfunc, int sub_pel_dfunc, int search_range) {
   if (width <= 0 || height <= 0 || (width & 15) || (height & 15) || n_slots <= 0) return 0;
   jsvm_ref_ctx* c = new jsvm_ref_ctx();
-  c->width = width; c->height = height; c->n_slots = n_slots; c->org_chroma = 0; c->n_org_chroma = 0;
+  c->width = width; c->height = height; c->n_slots = n_slots; c->org_chroma = 0; c->n_org_chroma = 0; c->cands = 0; c->n_cands = 0;
   c->mbw = width >> 4; c->mbh = height >> 4;
 
   CHK(SequenceParameterSet::create(c->sps));
@@ -307,8 +311,28 @@ extern "C" int jsvm_ref_search(jsvm_ref_ctx* c, const jsvm_me_job* jobs, int n_j
     Mv   mv(j.start.hor, j.start.ver);
     Mv   pred(j.pred.hor, j.pred.ver);
     UInt bits = j.bits_in, cost = 0;
-    CHKI(c->me->estimateBlockWithStart(*mba, *c->frames[j.ref_slot], mv, pred, bits, cost,
-                                       j.blk, j.mode, (UInt)j.search_range, &c->pw, 0));
+    // the neighbours' MVs that FAST_SEARCH / TZ_SEARCH read through MbDataAccess::addMvPredictors (public members, normally left
+    // there by getMvPredictor)
+    for (int k = 0; k < 3; ++k) {
+      const jsvm_mv m = (c->cands && i < c->n_cands) ? c->cands[3 * (size_t)i + k] : jsvm_mv{0, 0};
+      (k == 0 ? mba->m_cMv3D_A : k == 1 ? mba->m_cMv3D_B : mba->m_cMv3D_C).set(Mv(m.hor, m.ver), 1);
+    }
+    const UInt mode = j.mode & JSVM_JOB_MODE_MASK;
+    if (j.mode & JSVM_JOB_EL) c->me->setEL(true);                    // one-shot m_bELWithBLMv
+    if (j.mode & JSVM_JOB_BIPRED) {
+      // a bi-predictive call whose prepared original equals the job's: gClip( 2 * org - alt ) with alt = org (8-bit originals)
+      YuvMbBuffer alt;
+      alt.loadLuma(*org);
+      MotionEstimation::MEBiSearchParameters bsp;
+      bsp.pcAltRefPelData = &alt; bsp.uiL1Search = 0; bsp.pcAltRefFrame = c->frames[j.ref_slot];
+      bsp.apcWeight[0] = &c->pw; bsp.apcWeight[1] = &c->pw;
+      CHKI(c->me->estimateBlockWithStart(*mba, *c->frames[j.ref_slot], mv, pred, bits, cost, j.blk, mode, (UInt)j.search_range, &c->pw, &bsp));
+      // ruiCost was formed with fWeight = 0.5; the records carry the fWeight = 1 value (the drop-in applies the weight on the host)
+      const UInt f = c->rd->getMotionCostShift(c->me->subPelDFunc() != DF_SSD);
+      cost = (c->me->m_uiMinSad - ((f * (bits - j.bits_in)) >> 16)) + ((f * bits) >> 16);
+    } else {
+      CHKI(c->me->estimateBlockWithStart(*mba, *c->frames[j.ref_slot], mv, pred, bits, cost, j.blk, mode, (UInt)j.search_range, &c->pw, 0));
+    }
     c->me->setFullPelDFunc(cfg_full);
     jsvm_me_result& r = results[i];
     r.mv.hor = mv.getHor(); r.mv.ver = mv.getVer();
@@ -322,10 +346,10 @@ extern "C" int jsvm_ref_search(jsvm_ref_ctx* c, const jsvm_me_job* jobs, int n_j
     r.best_mode   = c->me->bestMode();
 
     if (preds) {
-      CHKI(c->me->compensateBlock(&rec, j.blk, j.mode, NULL));
+      CHKI(c->me->compensateBlock(&rec, j.blk, mode, NULL));
       rec.set4x4Block(B4x4Idx(j.blk));
       const XPel* p = rec.getLumBlk();
-      const int w = c->dist->getBlockWidth(j.mode), h = c->dist->getBlockHeight(j.mode);
+      const int w = c->dist->getBlockWidth(mode), h = c->dist->getBlockHeight(mode);
       uint8_t* dp = preds + (size_t)i * 256;
       memset(dp, 0, 256);
       for (int y = 0; y < h; ++y)
@@ -469,4 +493,16 @@ extern "C" int jsvm_ref_compensate(jsvm_ref_ctx* c, const jsvm_mc_job* jobs, int
   c->pps->setWeightedBiPredIdc(old_idc);
   c->weighting->initSlice(*c->sh);
   return rc;
+}
+
+extern "C" int jsvm_ref_set_fast_search_params(jsvm_ref_ctx* c, int el_search_range, int fast_bi_search) {
+  if (!c) return -1;
+  c->me->setFastSearchParams(el_search_range ? el_search_range : c->me->searchRange(), fast_bi_search);   // ENC/CodingParameter.cpp:25-28
+  return 0;
+}
+
+extern "C" int jsvm_ref_set_mv_candidates(jsvm_ref_ctx* c, const jsvm_mv* abc, int n_jobs) {
+  if (!c) return -1;
+  c->cands = abc; c->n_cands = abc ? n_jobs : 0;
+  return 0;
 }

@@ -58,6 +58,10 @@ int jsvm_ref_map_cost_factor(jsvm_ref_ctx* ctx, uint32_t factor_full_pel, uint32
 /* MotionCompensation::xPredLuma / xPredChroma (predBlk, xPredChromaPel, SampleWeighting) for every job. */
 int jsvm_ref_compensate(jsvm_ref_ctx* ctx, const jsvm_mc_job* jobs, int n_jobs, uint8_t* pred_y, uint8_t* pred_cb, uint8_t* pred_cr);
 
+/* MotionVectorSearchParams ELSearchRange (0 = SearchRange) / FastBiSearch; the neighbours' MVs (A, B, C per job) for FAST / TZ. */
+int jsvm_ref_set_fast_search_params(jsvm_ref_ctx* ctx, int el_search_range, int fast_bi_search);
+int jsvm_ref_set_mv_candidates(jsvm_ref_ctx* ctx, const jsvm_mv* abc, int n_jobs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,7 +3,7 @@
 /root/reference by `make -C oracle ref`).  Run in the build container only; the fixtures are committed so
 that the GPU box (which has no /root/reference) can pin the oracle and the CUDA path against them.
 
-    python tests/golden/make_golden.py [group ...]      groups: search, org, fullpel, table, yuv, mc (default: all)
+    python tests/golden/make_golden.py [group ...]      groups: search, org, fullpel, table, yuv, mc, fast (default: all)
 """
 import importlib
 import os
@@ -163,7 +163,44 @@ def gen_mc(ref):
     np.savez_compressed(os.path.join(HERE, "mc_blocks.npz"), **out)
 
 
-GROUPS = {"yuv": gen_yuv, "mc": gen_mc, "search": gen_search, "org": gen_org, "fullpel": gen_fullpel, "table": gen_table}
+FAST_CASES = {
+    # name: (search_mode, SR, EL range, FastBiSearch, full dfunc, sub dfunc, parts)
+    "fast_spiral_sr8": (1, 8, 0, 0, 0, 2, "PARTS_9"),
+    "fast_log_sr16": (2, 16, 0, 0, 0, 2, "PARTS_41"),
+    "fast_log_sr64_had": (2, 64, 0, 1, 2, 0, "PARTS_9"),
+    "fast_fme_sr32": (3, 32, 0, 0, 0, 2, "PARTS_41"),
+    "fast_tz_sr32": (4, 32, 8, 0, 0, 2, "PARTS_41"),
+    "fast_tz_sr64_fastbi": (4, 64, 16, 1, 0, 0, "PARTS_9"),
+    "fast_tz_sr16_yuv": (4, 16, 4, 0, 3, 2, "PARTS_9"),
+    "block_fastbi_sr16": (0, 16, 0, 1, 0, 2, "PARTS_41"),
+}
+
+
+def gen_fast(ref):
+    # SPIRAL / LOG / FAST / TZ searches (and the FastBiSearch refinement under BLOCK_SEARCH) on QCIF: neighbour-MV candidates,
+    # EL ranges, bi-predictive calls, per-call ranges; macroblock subset with the corners and edges
+    W, H = 176, 144
+    mbs = [(0, 0), (0, 10), (8, 0), (8, 10), (4, 5), (3, 7), (0, 5), (8, 4), (5, 0), (2, 10)]
+    for name, (mode, sr, el, fastbi, full, sub, parts) in FAST_CASES.items():
+        seq = synth.Sequence(W, H, 44 + mode)
+        f0, f1 = seq.frame(0), seq.frame(2)
+        c0, c1 = synth.chroma_planes(W, H, 45), synth.chroma_planes(W, H, 46)
+        ses = oracle_lib.CpuSession(ref, W, H, 2, sr, sub, full, mode)
+        ses.set_plane(0, f0); ses.set_plane(1, f1)
+        ses.set_chroma(0, *c0); ses.set_chroma(1, *c1)
+        subset = [(4, 5), (3, 7), (5, 4), (4, 6)] if mode == 1 else mbs       # spiral: interior only (un-clipped window)
+        jobs = synth.make_jobs(W, H, getattr(synth, parts), 1, 0, qp=31, field="split", seed=mode + sr, mb_subset=subset, bits_in=1)
+        jobs, cands = synth.make_fast_search_extras(jobs, sr, seed=sr + mode)
+        ses.set_fast_search_params(el, fastbi)
+        ses.set_mv_candidates(cands)
+        res, preds = ses.search(jobs, want_preds=True)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), width=W, height=H, search_range=sr, sub_dfunc=sub, full_dfunc=full,
+                            search_mode=mode, el_search_range=el, fast_bi_search=fastbi, frame0=f0, frame1=f1,
+                            cb0=c0[0], cr0=c0[1], cb1=c1[0], cr1=c1[1], jobs=jobs, cands=cands, results=res, preds=preds)
+        print(name, len(jobs), "jobs")
+
+
+GROUPS = {"fast": gen_fast, "yuv": gen_yuv, "mc": gen_mc, "search": gen_search, "org": gen_org, "fullpel": gen_fullpel, "table": gen_table}
 
 
 def main():

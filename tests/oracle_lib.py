@@ -53,6 +53,15 @@ class CpuSession:
     def map_cost_factor(self, factor_full_pel, factor_sub_pel):
         assert self.be.map_cost_factor(self.ctx, int(factor_full_pel), int(factor_sub_pel)) == 0
 
+    def set_fast_search_params(self, el_search_range=0, fast_bi_search=0):
+        assert self.be.set_fast_search_params(self.ctx, int(el_search_range), int(fast_bi_search)) == 0
+
+    def set_mv_candidates(self, abc):
+        """(n_jobs, 3, 2) int16: MVs of the neighbours A, B, C per job (FAST / TZ searches); None clears."""
+        self._cands = None if abc is None else np.ascontiguousarray(abc, np.int16).reshape(-1, 3, 2)
+        assert self.be.set_mv_candidates(self.ctx, None if self._cands is None else self._cands.ctypes.data,
+                                         0 if self._cands is None else len(self._cands)) == 0
+
     def compensate(self, mc_jobs, chroma=True):
         jobs = np.ascontiguousarray(mc_jobs, MC_JOB_DTYPE)
         n = len(jobs)
@@ -103,6 +112,8 @@ class CpuBackend:
                   ("set_chroma_u8", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
                   ("set_org_chroma", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
                   ("map_cost_factor", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+                  ("set_fast_search_params", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+                  ("set_mv_candidates", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
                   ("compensate", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
                   ("cost_factor", C.c_uint32, [C.c_double, C.c_int]),
                   ("distortion", C.c_uint32, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int])]
@@ -111,8 +122,8 @@ class CpuBackend:
             fn.restype, fn.argtypes = rt, at
             setattr(self, name, fn)
 
-    def session(self, width, height, n_slots, search_range, sub_dfunc, full_dfunc=0):
-        return CpuSession(self, width, height, n_slots, search_range, sub_dfunc, full_dfunc)
+    def session(self, width, height, n_slots, search_range, sub_dfunc, full_dfunc=0, search_mode=0):
+        return CpuSession(self, width, height, n_slots, search_range, sub_dfunc, full_dfunc, search_mode)
 
 
 # ---- the checker on many host cores: full-frame comparisons (tests) and bench.py's parity sample ----

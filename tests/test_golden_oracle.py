@@ -10,6 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SEARCH_CASES = ["tiny_all41_had", "tiny_9_sad", "qcif_9_had", "qcif_9_zero_sr32", "cif_9_sr64", "org_override_8bit", "org_override_16bit",
                 "fullpel_had_had", "fullpel_had_sad_all41", "fullpel_ssd_ssd", "fullpel_ssd_ssd_16bit", "fullpel_had_had_16bit",
                 "yuvsad_had_all41", "yuvsad_sad_org_chroma", "yuvsad_had_org_lumaonly", "yuvsad_ssd_mixed", "sad_ssd_mixed", "ssd_had_mixed"]
+FAST_CASES = ["fast_spiral_sr8", "fast_log_sr16", "fast_log_sr64_had", "fast_fme_sr32", "fast_tz_sr32", "fast_tz_sr64_fastbi", "fast_tz_sr16_yuv",
+              "block_fastbi_sr16"]
 MC_KINDS = ["uni", "bi", "uni_w", "bi_w", "bi_implicit"]
 
 
@@ -23,6 +25,9 @@ def prepare_session(ses, g):
     if "factor_pair" in g.files:
         ses.map_cost_factor(int(g["factor_pair"][0]), int(g["factor_pair"][1]))
     ses.set_org_chroma(g["org_chroma"] if "org_chroma" in g.files else None)
+    if "search_mode" in g.files:
+        ses.set_fast_search_params(int(g["el_search_range"]), int(g["fast_bi_search"]))
+        ses.set_mv_candidates(g["cands"])
 
 
 def load(name):
@@ -30,14 +35,15 @@ def load(name):
 
 
 def test_fixtures_present():
-    assert len(glob.glob(os.path.join(HERE, "golden", "*.npz"))) >= 19
+    assert len(glob.glob(os.path.join(HERE, "golden", "*.npz"))) >= 27
 
 
-@pytest.mark.parametrize("name", SEARCH_CASES)
+@pytest.mark.parametrize("name", SEARCH_CASES + FAST_CASES)
 def test_oracle_search_matches_reference_golden(oracle, name):
     g = load(name)
     W, H = int(g["width"]), int(g["height"])
-    ses = oracle.session(W, H, 2, int(g["search_range"]), int(g["sub_dfunc"]), int(g["full_dfunc"]) if "full_dfunc" in g.files else 0)
+    ses = oracle.session(W, H, 2, int(g["search_range"]), int(g["sub_dfunc"]), int(g["full_dfunc"]) if "full_dfunc" in g.files else 0,
+                         int(g["search_mode"]) if "search_mode" in g.files else 0)
     prepare_session(ses, g)
     org = g["org_mbs"] if "org_mbs" in g.files else None
     res, preds = ses.search(g["jobs"], org_mbs=org, want_preds=True)

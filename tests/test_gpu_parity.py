@@ -37,6 +37,7 @@ def _setup(me, oracle, synth, cfg, seed, n_frames=2, sub_dfunc=None):
     frames = [seq.frame(n) for n in range(n_frames)]
     me.configure(W, H, n_frames)
     me.set_params(cfg["search_range"], sub)
+    me.set_fast_search_params(0, 0)
     ses = oracle.session(W, H, n_frames, cfg["search_range"], sub)
     for s, f in enumerate(frames):
         me.upload_plane(s, f)
@@ -89,12 +90,21 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
                                   "org_override_16bit", "fullpel_had_had", "fullpel_had_sad_all41", "fullpel_ssd_ssd",
                                   "fullpel_ssd_ssd_16bit", "fullpel_had_had_16bit",
                                   "yuvsad_had_all41", "yuvsad_sad_org_chroma", "yuvsad_had_org_lumaonly", "yuvsad_ssd_mixed",
-                                  "sad_ssd_mixed", "ssd_had_mixed"])
+                                  "sad_ssd_mixed", "ssd_had_mixed",
+                                  "fast_spiral_sr8", "fast_log_sr16", "fast_log_sr64_had", "fast_fme_sr32", "fast_tz_sr32",
+                                  "fast_tz_sr64_fastbi", "fast_tz_sr16_yuv", "block_fastbi_sr16"])
 def test_cuda_matches_reference_golden(me, name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     W, H = int(g["width"]), int(g["height"])
     me.configure(W, H, 2)
-    me.set_params(int(g["search_range"]), int(g["sub_dfunc"]), int(g["full_dfunc"]) if "full_dfunc" in g.files else 0)
+    me.set_params(int(g["search_range"]), int(g["sub_dfunc"]), int(g["full_dfunc"]) if "full_dfunc" in g.files else 0,
+                  int(g["search_mode"]) if "search_mode" in g.files else 0)
+    if "search_mode" in g.files:                          # SPIRAL / LOG / FAST / TZ: neighbour-MV candidates, EL range, FastBiSearch
+        me.set_fast_search_params(int(g["el_search_range"]), int(g["fast_bi_search"]))
+        me.set_mv_candidates(g["cands"])
+    else:
+        me.set_fast_search_params(0, 0)
+        me.set_mv_candidates(None)
     me.upload_plane(0, g["frame0"]); me.upload_plane(1, g["frame1"])
     me.interp_halfpel([0, 1])
     if "cb0" in g.files:                                  # YUV_SAD: chroma planes (+ chroma originals of prepared macroblocks)
@@ -108,6 +118,8 @@ def test_cuda_matches_reference_golden(me, name):
     assert np.array_equal(preds, g["preds"])
     if "halfpel0" in g.files:
         assert np.array_equal(me.halfpel_plane(0), g["halfpel0"])
+    me.set_fast_search_params(0, 0)
+    me.set_mv_candidates(None)
 
 
 @pytest.mark.parametrize("sub_dfunc", [0, 2])

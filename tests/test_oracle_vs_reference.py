@@ -94,3 +94,36 @@ def test_compensate_identical(oracle, reference, synth, kind):
     a, b = [s.compensate(jobs) for s in sessions]
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("search_mode", [1, 2, 3, 4])
+@pytest.mark.parametrize("sr,fast_bi,full", [(16, 0, 0), (32, 1, 0), (8, 0, 3), (16, 1, 2)])
+def test_fast_searches_identical(oracle, reference, synth, search_mode, sr, fast_bi, full):
+    """f2: SPIRAL / LOG / FAST / TZ searches of the C port against the reference's, with neighbour-MV candidates, EL ranges,
+    bi-predictive calls and per-call ranges; windows clipped by the picture on every side."""
+    import oracle_lib
+    W, H = 176, 144
+    if search_mode == 1:
+        W, H = 352, 288                              # the spiral search needs room for its un-clipped window
+        if sr > 16:
+            pytest.skip("spiral window larger than the clamp interval of a CIF macroblock row")
+    if search_mode in (2, 3) and full == 3:
+        pytest.skip("xPelLogSearch never sets pUSearch / pVSearch (ENC/MotionEstimation.cpp:472-709): YUV_SAD crashes the reference there")
+    seq = synth.Sequence(W, H, 600 + sr)
+    sessions = [oracle_lib.CpuSession(be, W, H, 2, sr, 2, full, search_mode) for be in (oracle, reference)]
+    jobs = synth.make_jobs(W, H, synth.PARTS_41, 1, 0, qp=32, field="split", seed=search_mode, bits_in=1,
+                           mb_subset=None if W == 176 else [(0, 0), (0, 21), (17, 0), (17, 21), (8, 10), (3, 15), (12, 4)])
+    jobs, cands = synth.make_fast_search_extras(jobs, sr // 2, seed=sr + search_mode)
+    outs = []
+    for s in sessions:
+        for slot in range(2):
+            s.set_plane(slot, seq.frame(2 * slot))
+            s.set_chroma(slot, *synth.chroma_planes(W, H, 90 + slot))
+        s.set_fast_search_params(sr // 2, fast_bi)
+        s.set_mv_candidates(cands)
+        outs.append(s.search(jobs, want_preds=True))
+    (ra, pa), (rb, pb) = outs
+    for f in ra.dtype.names:
+        bad = np.nonzero(ra[f] != rb[f])[0]
+        assert len(bad) == 0, (f, len(bad), jobs[bad[0]], ra[bad[0]], rb[bad[0]])
+    assert np.array_equal(pa, pb)
