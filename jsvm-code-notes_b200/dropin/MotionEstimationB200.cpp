@@ -47,7 +47,7 @@ struct LayerStore {
 
 struct B200State {
   std::map<std::pair<int, int>, LayerStore*> layers;
-  int search_range, sub_dfunc, full_dfunc;
+  int search_range, sub_dfunc, full_dfunc, search_mode, el_search_range, fast_bi_search;
   bool params_valid;
   int device;
   // the buffers compensateBlock serves from (the reference keeps m_aXHPelSearch / m_aXQPelSearch)
@@ -55,7 +55,7 @@ struct B200State {
   bool last_valid;
   unsigned long long n_calls, n_calls_16bit, n_calls_bipred, n_frames;
   unsigned long long n_wp_uni, n_wp_bi_explicit, n_wp_bi_implicit;     // calls whose original went through weightInverseLumaSamples
-  B200State() : search_range(0), sub_dfunc(0), full_dfunc(0), params_valid(false), device(0), last_valid(false), n_calls(0), n_calls_16bit(0),
+  B200State() : search_range(0), sub_dfunc(0), full_dfunc(0), search_mode(0), el_search_range(0), fast_bi_search(0), params_valid(false), device(0), last_valid(false), n_calls(0), n_calls_16bit(0),
                 n_calls_bipred(0), n_frames(0), n_wp_uni(0), n_wp_bi_explicit(0), n_wp_bi_implicit(0) {
     const char* d = getenv("JSVM_ME_DEVICE");
     if (d) device = atoi(d);
@@ -131,6 +131,11 @@ ErrVal QuarterPelFilter::filterFrame( YuvPicBuffer* pcPelBuffer, YuvPicBuffer* p
     return reportFailure( "jsvm_me_upload_plane_xpel" );
   if( jsvm_me_interp_halfpel( ls->ctx, slot ) != JSVM_ME_OK )
     return reportFailure( "jsvm_me_interp_halfpel" );
+  if( state().full_dfunc == JSVM_DF_YUV_SAD )              // the YUV-SAD search also reads Cb / Cr (margins were filled by extendFrame)
+  {
+    if( jsvm_me_upload_chroma_xpel( ls->ctx, slot, pcPelBuffer->getMbCbAddr(), pcPelBuffer->getMbCrAddr(), pcPelBuffer->getCStride() ) != JSVM_ME_OK )
+      return reportFailure( "jsvm_me_upload_chroma_xpel" );
+  }
   return Err::m_nOK;
 }
 
@@ -178,15 +183,20 @@ ErrVal MotionEstimation::init( XDistortion*      pcXDistortion,
   st.params_valid = false;
   // only what the device path implements; anything else is an error, not a silent CPU search
   const UInt uiFull = m_cParams.getFullPelDFunc(), uiSub = m_cParams.getSubPelDFunc();
-  const Bool bSadClass = ( uiFull == DF_SAD || uiFull == DF_HADAMARD ) && ( uiSub == DF_SAD || uiSub == DF_HADAMARD );
-  const Bool bSseClass = ( uiFull == DF_SSD && uiSub == DF_SSD );      // one cost factor per job: no mixing of the two classes
-  if( m_cParams.getSearchMode() != BLOCK_SEARCH || !( bSadClass || bSseClass ) ||
-      m_cParams.getSearchRange() < 1 || m_cParams.getSearchRange() > 64 || m_cParams.getFastBiSearch() )
+  if( m_cParams.getSearchRange() < 1 || m_cParams.getSearchRange() > 64 || m_cParams.getELSearchRange() > 64 )
   {
-    fprintf( stderr, "jsvm_me_b200: unsupported MotionVectorSearchParams (need SearchMode 0, SearchFuncFullPel / SearchFuncSubPel "
-                     "both in {0, 2} or both 1, SearchRange 1..64, FastBiSearch 0)\n" );
+    fprintf( stderr, "jsvm_me_b200: unsupported MotionVectorSearchParams (SearchRange / ELSearchRange must be in 1..64)\n" );
     return Err::m_nERR;
   }
+  if( ( m_cParams.getSearchMode() == LOG_SEARCH || m_cParams.getSearchMode() == FAST_SEARCH ) && uiFull == DF_YUV_SAD )
+  {
+    fprintf( stderr, "jsvm_me_b200: SearchMode %u with SearchFuncFullPel 3 is undefined in the reference (xPelLogSearch leaves the chroma pointers unset)\n",
+             m_cParams.getSearchMode() );
+    return Err::m_nERR;
+  }
+  st.search_mode     = (int)m_cParams.getSearchMode();
+  st.el_search_range = (int)m_cParams.getELSearchRange();
+  st.fast_bi_search  = (int)m_cParams.getFastBiSearch();
   st.search_range = (int)m_cParams.getSearchRange();
   st.sub_dfunc    = (int)uiSub;
   st.full_dfunc   = (int)uiFull;
@@ -233,6 +243,8 @@ MotionEstimation::estimateBlockWithStart( const MbDataAccess&          rcMbDataA
   YuvMbBuffer  cPrepared;
   YuvMbBuffer* pcOrg   = m_pcXDistortion->getYuvMbBuffer();
   Double       fWeight = 1.0;
+  Double       afCW[2] = { 1.0, 1.0 };
+  const Bool   bYuvSad = ( st.full_dfunc == JSVM_DF_YUV_SAD );
   if( pcBSP )
   {
     ROF( pcBSP->pcAltRefPelData && pcBSP->pcAltRefFrame && pcBSP->apcWeight[LIST_0] && pcBSP->apcWeight[LIST_1] );
@@ -273,15 +285,19 @@ MotionEstimation::estimateBlockWithStart( const MbDataAccess&          rcMbDataA
   else
   {
     ROF( pcPW );
-    if( pcPW->getLumaWeightFlag() )
+    if( pcPW->getLumaWeightFlag() || ( bYuvSad && pcPW->getChromaWeightFlag() ) )
     {
       cPrepared.set4x4Block( cIdx );
       m_pcXDistortion->set4x4Block( cIdx );
       st.n_wp_uni++;
       m_pcSampleWeighting->weightInverseLumaSamples( &cPrepared, pcOrg, pcPW, fWeight, iYSize, iXSize );
+      if( bYuvSad )
+        m_pcSampleWeighting->weightInverseChromaSamples( &cPrepared, pcOrg, pcPW, afCW, iYSize, iXSize );
       pcOrg = &cPrepared;
     }
   }
+  // ENC/MotionEstimation.cpp:250-253: YUV-SAD only for uni-directional searches with equal component weights
+  const Bool bChromaInSearch = bYuvSad && !pcBSP && fWeight == afCW[0] && fWeight == afCW[1];
 
   // ---- the job ----
   YuvPicBuffer* pcHalf = const_cast<Frame&>( rcRefFrame ).getHalfPelYuvBuffer();
@@ -296,8 +312,10 @@ MotionEstimation::estimateBlockWithStart( const MbDataAccess&          rcMbDataA
   }
   if( st.n_calls == 0 || st.search_range != 0 )
   {
-    if( jsvm_me_set_params( ls->ctx, JSVM_SEARCH_BLOCK, st.full_dfunc, st.sub_dfunc, st.search_range ) != JSVM_ME_OK )
+    if( jsvm_me_set_params( ls->ctx, st.search_mode, st.full_dfunc, st.sub_dfunc, st.search_range ) != JSVM_ME_OK )
       return reportFailure( "jsvm_me_set_params" );
+    if( jsvm_me_set_fast_search_params( ls->ctx, st.el_search_range, st.fast_bi_search ) != JSVM_ME_OK )
+      return reportFailure( "jsvm_me_set_fast_search_params" );
   }
   st.n_calls++;
 
@@ -305,19 +323,26 @@ MotionEstimation::estimateBlockWithStart( const MbDataAccess&          rcMbDataA
   const Int iMbX = ( -( m_cMin.getHor() >> 2 ) - 24 ) >> 4;
   const Int iMbY = ( -( m_cMin.getVer() >> 2 ) - 24 ) >> 4;
 
-  xSetMEPars( 0, st.sub_dfunc != JSVM_DF_SSD );            // SAD factor for SAD and HADAMARD (N7), SSE factor for SSD (both stages then);
-                                                           // also used below for the final cost
+  // cost factors of the two stages (ENC/MotionEstimation.cpp:255, 325): SSE class iff the stage's function is SSD (N7)
+  xSetMEPars( 2, st.full_dfunc != JSVM_DF_SSD );
+  const UInt uiFactorFull = m_uiCostFactor;
+  xSetMEPars( 0, st.sub_dfunc != JSVM_DF_SSD );            // stays set: also used below for the final cost
+  if( ( st.full_dfunc == JSVM_DF_SSD ) != ( st.sub_dfunc == JSVM_DF_SSD ) )
+  {
+    if( jsvm_me_map_cost_factor( ls->ctx, uiFactorFull, m_uiCostFactor ) != JSVM_ME_OK )
+      return reportFailure( "jsvm_me_map_cost_factor" );
+  }
   jsvm_me_job cJob;
   cJob.cur_slot     = (int16_t)it->second;                 // unused: the original comes from org_mbs
   cJob.ref_slot     = (int16_t)it->second;
   cJob.mb_x         = (int16_t)iMbX;
   cJob.mb_y         = (int16_t)iMbY;
   cJob.blk          = (uint8_t)uiBlk;
-  cJob.mode         = (uint8_t)uiMode;
+  cJob.mode         = (uint8_t)( uiMode | ( pcBSP ? JSVM_JOB_BIPRED : 0 ) | ( m_bELWithBLMv ? JSVM_JOB_EL : 0 ) );
   cJob.search_range = (int16_t)uiSearchRange;
   cJob.start.hor    = rcMv.getHor();      cJob.start.ver = rcMv.getVer();
   cJob.pred.hor     = rcMvPred.getHor();  cJob.pred.ver  = rcMvPred.getVer();
-  cJob.cost_factor  = m_uiCostFactor;
+  cJob.cost_factor  = uiFactorFull;
   cJob.bits_in      = ruiBits;
   cJob.org_index    = 0;
 
@@ -342,6 +367,29 @@ MotionEstimation::estimateBlockWithStart( const MbDataAccess&          rcMbDataA
     for( Int y = 0; y < 16; y++ )
       for( Int x = 0; x < 16; x++ )
         if( x < bx || x >= bx + iXSize || y < by || y >= by + iYSize ) asOrg[y * 16 + x] = 0;
+  }
+
+  // chroma original of the macroblock for the YUV-SAD search (pUOrg / pVOrg, :259-260); without it the library searches luma only
+  int16_t asOrgChroma[128];
+  if( bChromaInSearch )
+  {
+    const XPel* pU = pcOrg->getMbCbAddr();
+    const XPel* pV = pcOrg->getMbCrAddr();
+    const Int   iCS = pcOrg->getCStride();
+    for( Int y = 0; y < 8; y++ )
+      for( Int x = 0; x < 8; x++ ) { asOrgChroma[y * 8 + x] = pU[y * iCS + x]; asOrgChroma[64 + y * 8 + x] = pV[y * iCS + x]; }
+  }
+  if( bYuvSad && jsvm_me_set_org_chroma( ls->ctx, bChromaInSearch ? asOrgChroma : 0, bChromaInSearch ? 1 : 0 ) != JSVM_ME_OK )
+    return reportFailure( "jsvm_me_set_org_chroma" );
+  // the neighbours' MVs for FAST_SEARCH / TZ_SEARCH (MbDataAccess::addMvPredictors, :293-305)
+  jsvm_mv acCand[3] = { { 0, 0 }, { 0, 0 }, { 0, 0 } };
+  if( !uiSearchRange && ( st.search_mode == JSVM_SEARCH_FAST || st.search_mode == JSVM_SEARCH_TZ ) )
+  {
+    std::vector<Mv> cList;
+    rcMbDataAccess.addMvPredictors( cList );
+    for( size_t n = 0; n < 3 && n < cList.size(); n++ ) { acCand[n].hor = cList[n].getHor(); acCand[n].ver = cList[n].getVer(); }
+    if( jsvm_me_set_mv_candidates( ls->ctx, acCand, 1 ) != JSVM_ME_OK )
+      return reportFailure( "jsvm_me_set_mv_candidates" );
   }
 
   jsvm_me_result cRes;

@@ -27,8 +27,22 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
     # implicit bi-prediction weights (hierarchical B with unequal temporal distances needs refs > 1)
     ["--frames", "9", "--gop", "4", "--sr", "8", "--subpel", "2", "--wp", "1", "--wbp", "1", "--fade", "0.04"],
     ["--frames", "9", "--gop", "4", "--sr", "8", "--subpel", "2", "--wp", "1", "--wbp", "2", "--fade", "0.04", "--refs", "2"],
+    # the fast searches: the shipped encoder.cfg defaults (TZ, EL range 4, FastBiSearch, 4 bi-pred iterations over +-8) on two
+    # spatial layers; FAST (log search seeded with the neighbours' MVs); LOG; SPIRAL; and BLOCK_SEARCH with the FastBiSearch refinement
+    ["--width", "352", "--height", "288", "--layers", "2", "--frames", "5", "--gop", "4", "--sr", "32", "--subpel", "2",
+     "--searchmode", "4", "--elsr", "4", "--fastbi", "1", "--bipreditr", "4", "--itersr", "8"],
+    ["--frames", "9", "--gop", "8", "--sr", "16", "--subpel", "2", "--searchmode", "3", "--all-partitions"],
+    ["--frames", "5", "--gop", "4", "--sr", "32", "--subpel", "0", "--searchmode", "2", "--refs", "2"],
+    ["--width", "352", "--height", "288", "--frames", "3", "--gop", "2", "--sr", "8", "--subpel", "2", "--searchmode", "1"],
+    ["--frames", "5", "--gop", "4", "--sr", "16", "--subpel", "2", "--fastbi", "1", "--itersr", "8"],
+    # YUV-SAD full-pel search on textured chroma (block search and TZ), and the mixed cost-factor classes
+    ["--frames", "5", "--gop", "4", "--sr", "8", "--subpel", "2", "--fullpel", "3", "--chroma"],
+    ["--frames", "5", "--gop", "4", "--sr", "16", "--subpel", "2", "--fullpel", "3", "--chroma", "--searchmode", "4", "--wp", "1", "--wbp", "1", "--fade", "0.04"],
+    ["--frames", "5", "--gop", "4", "--sr", "8", "--subpel", "1", "--fullpel", "0"],
+    ["--frames", "5", "--gop", "4", "--sr", "8", "--subpel", "2", "--fullpel", "1"],
 ], ids=["C1-qcif-hierB-satd", "all41-2refs-sad", "C2-two-spatial-layers", "C5-spatial+quality-2refs", "fullpel-hadamard", "ssd-ssd",
-        "weighted-explicit", "weighted-implicit"])
+        "weighted-explicit", "weighted-implicit", "tz-shipped-defaults-2-layers", "fast-all41", "log-2refs", "spiral-cif", "block-fastbi",
+        "yuvsad-block", "yuvsad-tz-weighted", "sad-then-ssd", "ssd-then-satd"])
 def test_encoder_with_dropin_is_bit_identical(args):
     import system_parity
     if not (os.path.exists(system_parity.STOCK) and os.path.exists(system_parity.B200)):

@@ -35,14 +35,14 @@ IntraPeriod -1
 NumberReferenceFrames {refs}
 BaseLayerMode 2
 ConstrainedIntraUps 1
-SearchMode 0
+SearchMode {searchmode}
 SearchFuncFullPel {fullpel}
 SearchFuncSubPel {subpel}
 SearchRange {sr}
-ELSearchRange 0
-FastBiSearch 0
-BiPredIter 2
-IterSearchRange 4
+ELSearchRange {elsr}
+FastBiSearch {fastbi}
+BiPredIter {bipreditr}
+IterSearchRange {itersr}
 LoopFilterDisable 0
 LoopFilterAlphaC0Offset 0
 LoopFilterBetaOffset 0
@@ -104,13 +104,17 @@ def md5(path):
     return h.hexdigest()
 
 
-def write_yuv(path, frames_u8):
+def write_yuv(path, frames_u8, textured_chroma=False):
     h, w = frames_u8[0].shape
     chroma = np.full((h // 2) * (w // 2) * 2, 128, np.uint8).tobytes()
     with open(path, "wb") as f:
         for fr in frames_u8:
             f.write(np.ascontiguousarray(fr).tobytes())
-            f.write(chroma)
+            if textured_chroma:                       # chroma that follows the luma motion: 2x2 means of the luma, Cr inverted
+                c = ((fr[0::2, 0::2].astype(np.uint16) + fr[0::2, 1::2] + fr[1::2, 0::2] + fr[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+                f.write(c.tobytes()); f.write((255 - c).tobytes())
+            else:
+                f.write(chroma)
 
 
 def layer_plan(a):
@@ -144,7 +148,7 @@ def write_inputs(workdir, a):
         cur = [((f[0::2, 0::2].astype(np.uint16) + f[0::2, 1::2] + f[1::2, 0::2] + f[1::2, 1::2] + 2) >> 2).astype(np.uint8) for f in cur]
         by_spatial[s] = cur
     for s, frs in by_spatial.items():
-        write_yuv(os.path.join(workdir, f"in_s{s}.yuv"), frs)
+        write_yuv(os.path.join(workdir, f"in_s{s}.yuv"), frs, a.chroma)
 
 
 def run(exe, workdir, tag, a):
@@ -161,7 +165,8 @@ def run(exe, workdir, tag, a):
                                                 profile=100 if i == 0 else 86))
         lines += f"LayerCfg {layer}\n"
     open(main_cfg, "w").write(MAIN_CFG.format(out=out, frames=a.frames, gop=a.gop, refs=a.refs, sr=a.sr, subpel=a.subpel, fullpel=a.fullpel,
-                                              nlayers=len(plan), layercfgs=lines, wp=a.wp, wbp=a.wbp))
+                                              nlayers=len(plan), layercfgs=lines, wp=a.wp, wbp=a.wbp,
+                                              searchmode=a.searchmode, elsr=a.elsr, fastbi=a.fastbi, bipreditr=a.bipreditr, itersr=a.itersr))
     t0 = time.perf_counter()
     p = subprocess.run([exe, "-pf", main_cfg], cwd=workdir, capture_output=True, text=True, timeout=a.timeout,
                        env=dict(os.environ, JSVM_ME_STATS="1"))
@@ -186,7 +191,13 @@ def compare(argv=None):
     ap.add_argument("--refs", type=int, default=1)
     ap.add_argument("--sr", type=int, default=16)
     ap.add_argument("--subpel", type=int, default=2)
-    ap.add_argument("--fullpel", type=int, default=0, help="SearchFuncFullPel: 0 SAD, 1 SSD, 2 HADAMARD")
+    ap.add_argument("--fullpel", type=int, default=0, help="SearchFuncFullPel: 0 SAD, 1 SSD, 2 HADAMARD, 3 YUV-SAD")
+    ap.add_argument("--searchmode", type=int, default=0, help="SearchMode: 0 block, 1 spiral, 2 log, 3 fast, 4 TZ (the shipped default)")
+    ap.add_argument("--elsr", type=int, default=0, help="ELSearchRange")
+    ap.add_argument("--fastbi", type=int, default=0, help="FastBiSearch")
+    ap.add_argument("--bipreditr", type=int, default=2, help="BiPredIter")
+    ap.add_argument("--itersr", type=int, default=4, help="IterSearchRange")
+    ap.add_argument("--chroma", action="store_true", help="textured chroma planes instead of flat 128 (YUV-SAD)")
     ap.add_argument("--qp", type=float, default=32.0)
     ap.add_argument("--all-partitions", action="store_true")
     ap.add_argument("--seed", type=int, default=1235)
