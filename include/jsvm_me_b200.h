@@ -122,7 +122,10 @@ int jsvm_me_configure(jsvm_me_ctx* ctx, int width, int height, int n_slots);
 /* MotionEstimation::init reading MotionVectorSearchParams (ENC/MotionEstimation.cpp:38-66,
  * include/CodingParameter.h:41-89; value ranges checked as MotionVectorSearchParams::check, ENC/CodingParameter.cpp:17-36).
  * SearchMode: BLOCK_SEARCH (0, the measured hot path), SPIRAL (1), LOG (2), FAST (3), TZ (4; one warp per job, see
- * jsvm_me_set_fast_search_params / jsvm_me_set_mv_candidates; LOG and FAST refuse YUV_SAD as the reference is undefined there).
+ * jsvm_me_set_fast_search_params / jsvm_me_set_mv_candidates; LOG and FAST refuse YUV_SAD as MotionVectorSearchParams::check does).
+ * SearchRange: 1..4096; the packed-byte full-search kernels stage windows of up to 129 x 129 positions, so BLOCK_SEARCH with a range
+ * above 64 runs unstaged on the one-warp-per-job kernel (correct, not tuned; the reference has no limit either: its bit table is sized
+ * from the range, ENC/MotionEstimationCost.cpp:27-45).
  * SearchFuncFullPel: SAD (0), SSD (1), HADAMARD (2), YUV_SAD (3); SearchFuncSubPel: SAD (0),
  * SSD (1), HADAMARD (2) -- every combination.  Full-pel SAD is the measured hot path (packed-byte kernels); the other full-pel
  * functions run a plain one-CTA-per-job kernel.  YUV_SAD needs the chroma planes of the slots (jsvm_me_upload_chroma_*).
@@ -253,6 +256,38 @@ typedef struct jsvm_mc_job {
 int jsvm_me_compensate(jsvm_me_ctx* ctx, const jsvm_mc_job* jobs, int n_jobs, uint8_t* pred_y, uint8_t* pred_cb, uint8_t* pred_cr);
 /* The same with every buffer in device memory, asynchronous on the ctx stream. */
 int jsvm_me_compensate_device(jsvm_me_ctx* ctx, const jsvm_mc_job* d_jobs, int n_jobs, uint8_t* d_pred_y, uint8_t* d_pred_cb, uint8_t* d_pred_cr);
+
+/* ---- picture-level motion search: MV prediction and per-macroblock scheduling on the device ----
+ * For every macroblock of a P picture, in the dependency order of the encoder (left, above, above-right / above-left neighbours
+ * first), the list-0 loops of MbEncoder::xEstimateMb16x16 / 16x8 / 8x16 / 8x8 (ENC/MbEncoder.cpp:4449-4560, 4830-4935, 5234-5330,
+ * 5637-5700, 5950-6040): for every partition and every reference frame the MV predictor of MbDataAccess::getMvPredictor
+ * (INCC/MbDataAccess.h:289-296, 485-513, COM/MbDataAccess.cpp:137-187), estimateBlockWithStart with start = predictor and the mode /
+ * reference-index bits of those loops, the reference with the smallest cost per partition, and -- instead of the rate-distortion
+ * decision of xSetRdCostInterMb, which is outside this library -- the macroblock mode with the smallest SUM of motion costs
+ * (strict '<' in the order 16x16, 16x8, 8x16, 8x8).  Needs SearchMode BLOCK_SEARCH, SearchFuncFullPel SAD, SearchRange <= 64.
+ * All pictures of one call are independent of each other (a temporal level of hierarchical B pictures) and advance
+ * together, wavefront by wavefront; they must use the same number of reference frames. */
+#define JSVM_PIC_MAX_REFS 8
+typedef struct jsvm_pic_task {
+  int16_t  cur_slot;                       /* original picture */
+  int16_t  n_refs;                         /* active entries of reference list 0 (1..8) */
+  int16_t  ref_slot[JSVM_PIC_MAX_REFS];    /* RefFrameList0[ 1 .. n_refs ] */
+  uint32_t cost_factor;                    /* SAD-class motion cost factor of the picture (see jsvm_me_job) */
+} jsvm_pic_task;
+typedef struct jsvm_pic_mb {
+  uint8_t  mode;                           /* MbMode: 1 16x16, 2 16x8, 3 8x16, 4 8x8 (four BLK_8x8) */
+  uint8_t  pad[3];
+  int8_t   ref_idx[4];                     /* per 8x8 block (MbMotionData::m_ascRefIdx), 1-based */
+  jsvm_mv  mv[16];                         /* per 4x4 block, raster order (MbMvData::m_acMv) */
+  uint32_t cost;                           /* sum of the chosen mode's partition costs */
+  jsvm_mv  part_mv[9];                     /* every partition that was estimated: 16x16 | 16x8 upper, lower | 8x16 left, right | 8x8 #0..#3 */
+  int8_t   part_ref[9];
+  int8_t   pad2[3];
+  uint32_t part_cost[9];                   /* ruiCost of the winning reference (bits: mode + reference index + MV) */
+} jsvm_pic_mb;
+/* out: n_pics x (height/16 * width/16) records in raster order, HOST memory; NULL keeps them on the device (jsvm_me_download_pictures). */
+int jsvm_me_estimate_pictures(jsvm_me_ctx* ctx, const jsvm_pic_task* tasks, int n_pics, jsvm_pic_mb* out);
+int jsvm_me_download_pictures(jsvm_me_ctx* ctx, jsvm_pic_mb* out, int n_pics);
 
 int jsvm_me_sync(jsvm_me_ctx* ctx);
 

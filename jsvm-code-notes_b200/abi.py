@@ -62,6 +62,13 @@ MC_JOB_DTYPE = np.dtype([("ref_slot", "<i2", (2,)), ("mb_x", "<i2"), ("mb_y", "<
                          ("log_denom", "u1", (2,)), ("weight_flag", "u1", (2,))])
 assert MC_JOB_DTYPE.itemsize == 48
 
+# jsvm_pic_task / jsvm_pic_mb (picture-level motion search)
+PIC_MAX_REFS = 8
+PIC_TASK_DTYPE = np.dtype([("cur_slot", "<i2"), ("n_refs", "<i2"), ("ref_slot", "<i2", (PIC_MAX_REFS,)), ("cost_factor", "<u4")])
+PIC_MB_DTYPE = np.dtype([("mode", "u1"), ("pad", "u1", (3,)), ("ref_idx", "i1", (4,)), ("mv", "<i2", (16, 2)), ("cost", "<u4"),
+                         ("part_mv", "<i2", (9, 2)), ("part_ref", "i1", (9,)), ("pad2", "i1", (3,)), ("part_cost", "<u4", (9,))])
+assert PIC_TASK_DTYPE.itemsize == 24 and PIC_MB_DTYPE.itemsize == 160
+
 # every symbol the header declares: (name, restype, argtypes)
 PROTOTYPES = [
     ("jsvm_me_create", C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
@@ -93,6 +100,8 @@ PROTOTYPES = [
     ("jsvm_me_plan_host", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(PlanInfo)]),
     ("jsvm_me_search_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(PlanInfo),
                                         C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    ("jsvm_me_estimate_pictures", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    ("jsvm_me_download_pictures", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     ("jsvm_me_fetch_pred", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     ("jsvm_me_sync", C.c_int, [C.c_void_p]),
     ("jsvm_me_launch_count", C.c_uint64, [C.c_void_p]),

@@ -28,6 +28,7 @@
 #include "k3_subpel.cuh"
 #include "k4_mc.cuh"
 #include "k5_fastsearch.cuh"
+#include "k6_picture.cuh"
 
 using namespace jsvm;
 
@@ -48,7 +49,8 @@ int fail(const char* fmt, ...) {
 constexpr int kV8 = 8;        // strip height of the 8x8-granular search kernel
 constexpr int kV4 = 4;        // strip height of the 4x4-granular search kernel
 constexpr int kMaxUH = 176;   // tallest union window one CTA handles (by-table rows, shared memory)
-constexpr int kMaxSearchRange = 64;   // windows of at most 129 x 129 positions per job (k2_generic.cuh stages 129 + 15 columns)
+constexpr int kMaxSearchRange = 64;   // staged windows of at most 129 x 129 positions per job (packed-byte kernels, k2_generic.cuh)
+constexpr int kMaxWideRange = 4096;   // beyond 64 the searches run unstaged, one warp per job (K5); windows stay clipped to the padded picture
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -143,6 +145,14 @@ struct jsvm_me_ctx {
   struct Timed { cudaEvent_t e0, e1; int kind; };
   std::vector<Timed> timed;
   double last_mc_ms = 0; uint64_t last_mc_n = 0;
+  // picture-level search (jsvm_me_estimate_pictures)
+  std::vector<int2> wave_mbs; std::vector<int> wave_off;     // macroblocks sorted by wavefront x + 2y, offsets per wave
+  DevBuf<int2> d_wave_mbs;
+  DevBuf<jsvm_pic_task> d_pic_tasks;
+  DevBuf<jsvm_pic_mb> d_pic_field;
+  DevBuf<PicTemp> d_pic_temp;
+  DevBuf<jsvm_me_result> d_pic_results[2];
+  int pic_n_last = 0;
 };
 
 namespace {
@@ -389,7 +399,8 @@ int run_search(jsvm_me_ctx* c, const jsvm_me_job* d_jobs, int job_begin, int job
                const int16_t* d_org, uint32_t* d_keys, JobAux* d_aux, jsvm_me_result* d_results, uint8_t* d_preds,
                const int16_t* d_org_chroma = nullptr, const jsvm_mv* d_cands = nullptr) {
   if (!c->params_set) return fail("jsvm_me_set_params has not been called");
-  const bool fast = c->search_mode != JSVM_SEARCH_BLOCK;     // SPIRAL / LOG / FAST / TZ: one warp per job (K5), no plan
+  // SPIRAL / LOG / FAST / TZ, and the full search with SearchRange > 64 (windows too large to stage): one warp per job (K5), no plan
+  const bool fast = c->search_mode != JSVM_SEARCH_BLOCK || c->search_range > kMaxSearchRange;
   const bool refine = !fast && c->fast_bi_search;            // BLOCK_SEARCH + FastBiSearch: the jobs with a per-call range are redone by K5
   if (!fast && (info->max_uh_8x8 > kMaxUH || info->max_uh_4x4 > kMaxUH)) return fail("plan: union window taller than %d", kMaxUH);
   const int n = job_end - job_begin;
@@ -413,7 +424,7 @@ int run_search(jsvm_me_ctx* c, const jsvm_me_job* d_jobs, int job_begin, int job
   };
   if (fast) {
     if (launch_k5(0)) return JSVM_ME_ERR;
-    static const char* const names[5] = {"", "fast_search_kernel(SPIRAL)", "fast_search_kernel(LOG)", "fast_search_kernel(FAST)", "fast_search_kernel(TZ)"};
+    static const char* const names[5] = {"fast_search_kernel(BLOCK, SearchRange > 64)", "fast_search_kernel(SPIRAL)", "fast_search_kernel(LOG)", "fast_search_kernel(FAST)", "fast_search_kernel(TZ)"};
     c->last_k2 = names[c->search_mode];
   }
   const bool generic = !fast && c->full_dfunc != JSVM_DF_SAD;         // SSD / Hadamard / YUV-SAD full search: one CTA per job, no grouping
@@ -507,7 +518,7 @@ int search_fast_host(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const 
     if (j.blk > 15 || partition_slot(j.mode, j.blk) < 0) return fail("job %d: blk %d is not a legal origin for mode %d", i, (int)j.blk, (int)(j.mode & JSVM_JOB_MODE_MASK));
     if (j.cur_slot < 0 || j.cur_slot >= c->n_slots || j.ref_slot < 0 || j.ref_slot >= c->n_slots) return fail("job %d: plane slot out of range", i);
     if (j.mb_x < 0 || j.mb_x >= mbw || j.mb_y < 0 || j.mb_y >= mbh) return fail("job %d: macroblock (%d,%d) outside the picture", i, j.mb_x, j.mb_y);
-    if (j.search_range < 0 || j.search_range > kMaxSearchRange) return fail("job %d: per-job search range %d outside [0,%d]", i, (int)j.search_range, kMaxSearchRange);
+    if (j.search_range < 0 || j.search_range > kMaxWideRange) return fail("job %d: per-job search range %d outside [0,%d]", i, (int)j.search_range, kMaxWideRange);
     if (j.org_index >= n_org_mbs) return fail("job %d: org_index %d >= n_org_mbs %d", i, j.org_index, n_org_mbs);
     if (j.org_index < 0 && !c->slot_full[j.cur_slot]) return fail("job %d: cur_slot %d is empty", i, (int)j.cur_slot);
     if (!c->slot_half[j.ref_slot]) return fail("job %d: ref_slot %d has no half-pel plane", i, (int)j.ref_slot);
@@ -622,6 +633,7 @@ int jsvm_me_destroy(jsvm_me_ctx* c) {
   if (c->d_chroma) cudaFree(c->d_chroma);
   if (c->d_slot_ids) cudaFree(c->d_slot_ids);
   if (c->d_bad) cudaFree(c->d_bad);
+  c->d_wave_mbs.release(); c->d_pic_tasks.release(); c->d_pic_field.release(); c->d_pic_temp.release(); c->d_pic_results[0].release(); c->d_pic_results[1].release();
   c->d_cands.release(); c->d_factor_map.release(); c->d_org_chroma.release(); c->d_mc_jobs.release(); c->d_mc_pred.release();
   c->d_jobs.release(); c->d_groups.release(); c->d_keys.release(); c->d_full_costs.release(); c->d_aux.release();
   c->d_results.release(); c->d_preds.release(); c->d_org.release(); c->d_stage.release();
@@ -647,6 +659,7 @@ int jsvm_me_configure(jsvm_me_ctx* c, int width, int height, int n_slots) {
   if (c->d_chroma) { cudaFree(c->d_chroma); c->d_chroma = nullptr; }
   if (c->d_slot_ids) { cudaFree(c->d_slot_ids); c->d_slot_ids = nullptr; }
   c->W = width; c->H = height; c->n_slots = n_slots;
+  c->wave_mbs.clear(); c->wave_off.clear(); c->pic_n_last = 0;
   c->cands = nullptr; c->n_cands = 0; c->d_cands_user = nullptr; c->org_chroma = nullptr; c->n_org_chroma = 0;   // per-call inputs of the old geometry
   c->plane_stride = width + 2 * kMargin; c->plane_rows = height + 2 * kMargin;
   c->plane_bytes = (size_t)c->plane_stride * c->plane_rows;
@@ -669,18 +682,18 @@ int jsvm_me_set_params(jsvm_me_ctx* c, int search_mode, int full_pel_dfunc, int 
   // MotionVectorSearchParams::check (ENC/CodingParameter.cpp:17-36)
   if (search_mode < JSVM_SEARCH_BLOCK || search_mode > JSVM_SEARCH_TZ) return fail("No Such Search Mode %d: 0==Block, 1==Spiral, 2==Log, 3==Fast, 4==TZ", search_mode);
   if ((search_mode == JSVM_SEARCH_LOG || search_mode == JSVM_SEARCH_FAST) && full_pel_dfunc == JSVM_DF_YUV_SAD)
-    return fail("SearchMode %d with SearchFuncFullPel 3: xPelLogSearch never sets the chroma search pointers (ENC/MotionEstimation.cpp:472-709), "
-                "the reference's result is undefined there", search_mode);
+    return fail("Log and Fast search not possible in comb. with distortion measure 3 (ENC/CodingParameter.cpp:21; xPelLogSearch never sets the "
+                "chroma search pointers, ENC/MotionEstimation.cpp:472-709)");
   if (full_pel_dfunc < 0 || full_pel_dfunc > 3) return fail("No Such Search Func (Full Pel) %d: 0==SAD, 1==SSE, 2==Hadamard, 3==YUV-SAD", full_pel_dfunc);
   if (sub_pel_dfunc < 0 || sub_pel_dfunc > 2) return fail("No Such Search Func (Sub Pel) %d: 0==SAD, 1==SSE, 2==Hadamard", sub_pel_dfunc);
-  if (search_range < 1 || search_range > kMaxSearchRange) return fail("SearchRange %d outside [1,%d]", search_range, kMaxSearchRange);
+  if (search_range < 1 || search_range > kMaxWideRange) return fail("SearchRange %d outside [1,%d]", search_range, kMaxWideRange);
   c->search_range = search_range; c->sub_dfunc = sub_pel_dfunc; c->full_dfunc = full_pel_dfunc; c->search_mode = search_mode; c->params_set = true;
   return JSVM_ME_OK;
 }
 
 int jsvm_me_set_fast_search_params(jsvm_me_ctx* c, int el_search_range, int fast_bi_search) {
   if (!c) return fail("null context");
-  if (el_search_range < 0 || el_search_range > kMaxSearchRange) return fail("ELSearchRange %d outside [0,%d]", el_search_range, kMaxSearchRange);
+  if (el_search_range < 0 || el_search_range > kMaxWideRange) return fail("ELSearchRange %d outside [0,%d]", el_search_range, kMaxWideRange);
   c->el_search_range = el_search_range; c->fast_bi_search = fast_bi_search != 0;
   return JSVM_ME_OK;
 }
@@ -962,7 +975,7 @@ int jsvm_me_search_device(jsvm_me_ctx* c, const jsvm_me_job* d_jobs, int n_jobs,
                           const int16_t* d_org_mbs, int n_org_mbs, jsvm_me_result* d_results, uint8_t* d_preds) {
   (void)n_org_mbs;
   if (!c || !d_jobs || !d_results) return fail("null argument");
-  const bool fast = c->search_mode != JSVM_SEARCH_BLOCK;     // the fast searches need no plan
+  const bool fast = c->search_mode != JSVM_SEARCH_BLOCK || c->search_range > kMaxSearchRange;     // these searches need no plan
   if (!fast && (!d_groups || !info)) return fail("null argument");
   if (n_jobs <= 0) return JSVM_ME_OK;
   CU_OK(cudaSetDevice(c->device));
@@ -985,7 +998,7 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
       if (org_mbs[i] < -1024 || org_mbs[i] > 1023)      // residual-prediction originals span [-255, 510] (N3); the key widths assume |v| < 1024
         return fail("org_mbs sample %zu = %d outside [-1024,1023]", i, (int)org_mbs[i]);
   }
-  if (c->search_mode != JSVM_SEARCH_BLOCK) return search_fast_host(c, jobs, n_jobs, org_mbs, n_org_mbs, results, preds);
+  if (c->search_mode != JSVM_SEARCH_BLOCK || c->search_range > kMaxSearchRange) return search_fast_host(c, jobs, n_jobs, org_mbs, n_org_mbs, results, preds);
   if (n_jobs <= 64 && n_org_mbs <= 64) return search_small(c, jobs, n_jobs, org_mbs, n_org_mbs, results, preds);
   c->last_small = false;
   CU_OK(cudaSetDevice(c->device));
@@ -1131,6 +1144,94 @@ int jsvm_me_fetch_pred(jsvm_me_ctx* c, int job_idx, int16_t* dst, int dst_stride
   }
   for (int y = 0; y < h; ++y)
     for (int x = 0; x < w; ++x) dst[y * dst_stride + x] = blk[y * 16 + x];
+  return JSVM_ME_OK;
+}
+
+// ---- K6: whole pictures, MV prediction and macroblock scheduling on the device ----
+int jsvm_me_estimate_pictures(jsvm_me_ctx* c, const jsvm_pic_task* tasks, int n_pics, jsvm_pic_mb* out) {
+  if (!c || !tasks) return fail("null argument");
+  if (!c->d_planes) return fail("jsvm_me_configure has not been called");
+  if (!c->params_set) return fail("jsvm_me_set_params has not been called");
+  if (c->search_mode != JSVM_SEARCH_BLOCK || c->full_dfunc != JSVM_DF_SAD || c->search_range > kMaxSearchRange || c->fast_bi_search)
+    return fail("jsvm_me_estimate_pictures needs SearchMode 0, SearchFuncFullPel 0, SearchRange <= %d, FastBiSearch 0", kMaxSearchRange);
+  if (mixed_factor_classes(c)) return fail("jsvm_me_estimate_pictures: one cost factor per picture (SearchFuncSubPel 1 needs the SSE factor)");
+  if (n_pics <= 0) return JSVM_ME_OK;
+  const int R = tasks[0].n_refs;
+  if (R < 1 || R > JSVM_PIC_MAX_REFS) return fail("n_refs %d outside [1,%d]", R, JSVM_PIC_MAX_REFS);
+  for (int p = 0; p < n_pics; ++p) {
+    const jsvm_pic_task& t = tasks[p];
+    if (t.n_refs != R) return fail("picture %d: n_refs %d differs from picture 0 (%d)", p, (int)t.n_refs, R);
+    if (t.cur_slot < 0 || t.cur_slot >= c->n_slots || !c->slot_full[t.cur_slot]) return fail("picture %d: cur_slot %d is empty or out of range", p, (int)t.cur_slot);
+    for (int r = 0; r < R; ++r)
+      if (t.ref_slot[r] < 0 || t.ref_slot[r] >= c->n_slots || !c->slot_half[t.ref_slot[r]])
+        return fail("picture %d: ref_slot %d has no half-pel plane or is out of range", p, (int)t.ref_slot[r]);
+  }
+  CU_OK(cudaSetDevice(c->device));
+  const int mbw = c->W >> 4, mbh = c->H >> 4, n_mb = mbw * mbh;
+  if (c->wave_mbs.empty()) {
+    const int n_waves = mbw + 2 * (mbh - 1);
+    c->wave_off.assign(n_waves + 1, 0);
+    for (int y = 0; y < mbh; ++y) for (int x = 0; x < mbw; ++x) c->wave_off[x + 2 * y + 1]++;
+    for (int w = 0; w < n_waves; ++w) c->wave_off[w + 1] += c->wave_off[w];
+    c->wave_mbs.resize(n_mb);
+    std::vector<int> fill(c->wave_off.begin(), c->wave_off.end() - 1);
+    for (int y = 0; y < mbh; ++y) for (int x = 0; x < mbw; ++x) c->wave_mbs[fill[x + 2 * y]++] = make_int2(x, y);
+    if (c->d_wave_mbs.reserve(n_mb)) return JSVM_ME_ERR;
+    CU_OK(cudaMemcpyAsync(c->d_wave_mbs.p, c->wave_mbs.data(), sizeof(int2) * n_mb, cudaMemcpyHostToDevice, c->stream));
+    CU_OK(cudaStreamSynchronize(c->stream));
+  }
+  const int n_waves = (int)c->wave_off.size() - 1;
+  int max_wave = 0;
+  for (int w = 0; w < n_waves; ++w) max_wave = std::max(max_wave, c->wave_off[w + 1] - c->wave_off[w]);
+  const size_t max_jobs = (size_t)n_pics * max_wave * R * 4;
+  if (c->d_pic_tasks.reserve(n_pics) || c->d_pic_field.reserve((size_t)n_pics * n_mb) || c->d_pic_temp.reserve((size_t)n_pics * n_mb) ||
+      c->d_pic_results[0].reserve(max_jobs) || c->d_pic_results[1].reserve(max_jobs) || c->d_jobs.reserve(max_jobs) || c->d_groups.reserve(max_jobs) ||
+      c->d_keys.reserve(max_jobs) || c->d_aux.reserve(max_jobs)) return JSVM_ME_ERR;
+  CU_OK(cudaMemcpyAsync(c->d_pic_tasks.p, tasks, sizeof(jsvm_pic_task) * n_pics, cudaMemcpyHostToDevice, c->stream));
+  if (sync_factor_map(c)) return JSVM_ME_ERR;
+  // union windows of a step: at most the window of one job plus 32 rows of spread between the partitions' predictors
+  const int cap_uh = std::min(kMaxUH, 2 * c->search_range + 1 + 32);
+  const size_t smem = k2_smem_bytes<kV8, false>(cap_uh);
+  if (raise_dyn_smem(c->device, 0, full_search_kernel<kV8, false>, smem)) return JSVM_ME_ERR;
+  auto k3 = c->sub_dfunc == JSVM_DF_HADAMARD ? subpel_kernel<JSVM_DF_HADAMARD>
+          : c->sub_dfunc == JSVM_DF_SSD ? subpel_kernel<JSVM_DF_SSD> : subpel_kernel<JSVM_DF_SAD>;
+  int flip = 0;
+  for (int w = 0; w < n_waves; ++w) {
+    const int n_wave = c->wave_off[w + 1] - c->wave_off[w];
+    const int n_thr = n_pics * n_wave;
+    for (int step = 0; step <= 4; ++step) {
+      picture_step_kernel<<<(n_thr + 127) / 128, 128, 0, c->stream>>>(
+          c->d_pic_tasks.p, n_pics, mbw, mbh, c->d_wave_mbs.p + c->wave_off[w], n_wave, step, R, c->search_range, cap_uh,
+          c->d_pic_field.p, c->d_pic_temp.p, c->d_pic_results[flip ^ 1].p, c->d_jobs.p, c->d_groups.p);
+      c->launches++;
+      if (step == 4) break;
+      const int n_jobs = n_thr * R * pic_step_jobs(step);
+      begin_timed(c, 1);
+      full_search_kernel<kV8, false><<<n_jobs, kK2Threads, smem, c->stream>>>(
+          c->d_planes, c->plane_bytes, c->plane_stride, c->d_groups.p, c->d_jobs.p, nullptr, mbw, mbh, c->search_range, c->d_keys.p, c->d_aux.p);
+      end_timed(c);
+      begin_timed(c, 2);
+      k3<<<(n_jobs + kK3WarpsPerCta - 1) / kK3WarpsPerCta, 32 * kK3WarpsPerCta, 0, c->stream>>>(
+          c->d_planes, c->plane_bytes, c->plane_stride, c->d_half, c->half_bytes, c->half_stride,
+          c->d_jobs.p, c->d_aux.p, n_jobs, nullptr, c->d_keys.p, nullptr, c->d_pic_results[flip].p, nullptr, c->d_factor_map.p, 0);
+      end_timed(c);
+      c->launches += 2;
+      flip ^= 1;
+    }
+    CU_OK(cudaGetLastError());
+  }
+  c->last_k2 = "full_search_kernel<8,false>";
+  c->pic_n_last = n_pics;
+  if (out) return jsvm_me_download_pictures(c, out, n_pics);
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_download_pictures(jsvm_me_ctx* c, jsvm_pic_mb* out, int n_pics) {
+  if (!c || !out) return fail("null argument");
+  if (n_pics <= 0 || n_pics > c->pic_n_last) return fail("n_pics %d: the last jsvm_me_estimate_pictures call covered %d pictures", n_pics, c->pic_n_last);
+  CU_OK(cudaSetDevice(c->device));
+  CU_OK(cudaMemcpyAsync(out, c->d_pic_field.p, sizeof(jsvm_pic_mb) * (size_t)n_pics * (c->W >> 4) * (c->H >> 4), cudaMemcpyDeviceToHost, c->stream));
+  CU_OK(cudaStreamSynchronize(c->stream));
   return JSVM_ME_OK;
 }
 

@@ -625,6 +625,7 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
   using SM = K2Smem<V, GRAN4>;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const Group& g = groups[blockIdx.x];
+  if (g.n_jobs == 0) return;      // empty slot of a device-planned launch (k6_picture.cuh)
   const int tid = threadIdx.x, lane = tid & 31;
   const K2Geo<V> geo((kMargin + 16 * g.mb_x + g.ux0) & 3, g.uw, g.uh);
   const K2Stage<V, GRAN4> st(smem_raw, geo);

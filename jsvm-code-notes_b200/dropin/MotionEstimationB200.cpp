@@ -183,9 +183,9 @@ ErrVal MotionEstimation::init( XDistortion*      pcXDistortion,
   st.params_valid = false;
   // only what the device path implements; anything else is an error, not a silent CPU search
   const UInt uiFull = m_cParams.getFullPelDFunc(), uiSub = m_cParams.getSubPelDFunc();
-  if( m_cParams.getSearchRange() < 1 || m_cParams.getSearchRange() > 64 || m_cParams.getELSearchRange() > 64 )
+  if( m_cParams.getSearchRange() < 1 || m_cParams.getSearchRange() > 4096 || m_cParams.getELSearchRange() > 4096 )
   {
-    fprintf( stderr, "jsvm_me_b200: unsupported MotionVectorSearchParams (SearchRange / ELSearchRange must be in 1..64)\n" );
+    fprintf( stderr, "jsvm_me_b200: unsupported MotionVectorSearchParams (SearchRange / ELSearchRange must be in 1..4096)\n" );
     return Err::m_nERR;
   }
   if( ( m_cParams.getSearchMode() == LOG_SEARCH || m_cParams.getSearchMode() == FAST_SEARCH ) && uiFull == DF_YUV_SAD )

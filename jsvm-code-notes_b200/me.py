@@ -17,7 +17,7 @@ import ctypes as C
 import numpy as np
 
 from . import abi
-from .abi import JOB_DTYPE, RESULT_DTYPE, MC_JOB_DTYPE, PlanInfo
+from .abi import JOB_DTYPE, RESULT_DTYPE, MC_JOB_DTYPE, PIC_TASK_DTYPE, PIC_MB_DTYPE, PlanInfo
 
 
 class MotionEstimationError(RuntimeError):
@@ -200,6 +200,19 @@ class MotionEstimator:
             n_org = len(org_mbs)
         self._check(self._lib.jsvm_me_search(self._ctx, _ptr(jobs), n, _ptr(org_mbs), n_org, _ptr(res), _ptr(preds)))
         return (res, preds) if want_preds else res
+
+    def estimate_pictures(self, tasks, download=True):
+        """Picture-level motion search (MV prediction and macroblock scheduling on the device) for every PIC_TASK_DTYPE record.
+        Returns (n_pics, H/16, W/16) PIC_MB_DTYPE records, or None with download=False (results stay on the device)."""
+        tasks = np.ascontiguousarray(tasks, dtype=PIC_TASK_DTYPE)
+        out = np.zeros((len(tasks), self.height // 16, self.width // 16), PIC_MB_DTYPE) if download else None
+        self._check(self._lib.jsvm_me_estimate_pictures(self._ctx, _ptr(tasks), len(tasks), _ptr(out)))
+        return out
+
+    def download_pictures(self, n_pics):
+        out = np.zeros((n_pics, self.height // 16, self.width // 16), PIC_MB_DTYPE)
+        self._check(self._lib.jsvm_me_download_pictures(self._ctx, _ptr(out), n_pics))
+        return out
 
     def plan(self, jobs):
         jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)

@@ -12,7 +12,7 @@ import math
 
 import numpy as np
 
-from .abi import (MC_JOB_DTYPE, MC_WEIGHT_UNI, MC_WEIGHT_BI, JOB_DTYPE, MODE_16x16, MODE_16x8, MODE_8x16, BLK_8x8, BLK_8x4, BLK_4x8, BLK_4x4, DF_SAD, DF_HADAMARD)
+from .abi import (PIC_TASK_DTYPE, MC_JOB_DTYPE, MC_WEIGHT_UNI, MC_WEIGHT_BI, JOB_DTYPE, MODE_16x16, MODE_16x8, MODE_8x16, BLK_8x8, BLK_8x4, BLK_4x8, BLK_4x4, DF_SAD, DF_HADAMARD)
 
 # (mode, blk) of the 9-partition set {16x16, 2 x 16x8, 2 x 8x16, 4 x 8x8} and of all 41 partitions
 PARTS_9 = [(MODE_16x16, 0), (MODE_16x8, 0), (MODE_16x8, 8), (MODE_8x16, 0), (MODE_8x16, 2),
@@ -78,6 +78,21 @@ class Sequence:
         rng = np.random.default_rng(self.seed * 1000003 + n)
         f = f + rng.normal(0.0, 2.0, f.shape)
         return np.clip(np.rint(f), 0, 255).astype(np.uint8)
+
+
+class LocalMotionSequence:
+    """Two textures moving differently, stitched along a grid of `tile`-sized squares that is NOT aligned with the macroblock
+    grid: macroblocks straddling a seam prefer split partitions, neighbouring macroblocks get different MVs (so that the MV
+    predictors of the picture-level search are non-trivial)."""
+
+    def __init__(self, width, height, seed, tile=20):
+        self.a = Sequence(width, height, seed, motion_qpel=(9, 5))
+        self.b = Sequence(width, height, seed + 1, motion_qpel=(-14, 11))
+        yy, xx = np.mgrid[0:height, 0:width]
+        self.mask = (((xx + 7) // tile + (yy + 3) // tile) & 1).astype(bool)
+
+    def frame(self, n):
+        return np.where(self.mask, self.a.frame(n), self.b.frame(n)).astype(np.uint8)
 
 
 def chroma_planes(width, height, seed):
@@ -205,6 +220,16 @@ def make_fast_search_extras(jobs, search_range, seed=0, p_el=0.2, p_bipred=0.25,
     span = min(600, (4 * search_range + 4) * 16 - 48)
     cands[wild] = (np.broadcast_to(base, cands.shape)[wild] + rng.integers(-span, span + 1, (int(wild.sum()), 2)))
     return out, np.clip(cands, -32768, 32767).astype(np.int16)
+
+
+def make_pic_tasks(cur_slots, ref_slots, qp=30):
+    """Picture-level search tasks: cur_slots[i] is searched in ref_slots[i] (a list of 1..8 reference slots, list-0 order)."""
+    tasks = np.zeros(len(cur_slots), PIC_TASK_DTYPE)
+    for i, (c, refs) in enumerate(zip(cur_slots, ref_slots)):
+        tasks["cur_slot"][i], tasks["n_refs"][i] = c, len(refs)
+        tasks["ref_slot"][i, :len(refs)] = refs
+    tasks["cost_factor"] = cost_factor_for_qp(qp)
+    return tasks
 
 
 def hierarchical_b_pairs(gop, refs=1):

@@ -869,3 +869,98 @@ int jsvm_ora_compensate(jsvm_ora_ctx* c, const jsvm_mc_job* jobs, int n_jobs, ui
   }
   return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * f1  Picture-level motion search: MV prediction (MbDataAccess::xGetMvPredictor, COM/MbDataAccess.cpp:137-187; neighbour lookup
+ *     INCC/MbDataAccess.h:1193-1348) + the list-0 loops of MbEncoder::xEstimateMb16x16 / 16x8 / 8x16 / 8x8
+ *     (ENC/MbEncoder.cpp:4449-4560, 4830-4935, 5234-5330, 5637-5700, 5950-6040), macroblocks in raster order, the macroblock mode
+ *     by the smallest sum of motion costs.  Sequential, as the encoder runs it.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { int hor, ver, ref; } mv3d;                 /* ref 0 = BLOCK_NOT_AVAILABLE (INCC/Mv.h:131-135) */
+
+static mv3d field_block(const jsvm_pic_mb* f, int mbw, int mbh, int mx, int my, int b4) {
+  mv3d r = { 0, 0, 0 };
+  if (mx < 0 || my < 0 || mx >= mbw || my >= mbh) return r;          /* m_rcMbUnavailable */
+  const jsvm_pic_mb* m = &f[my * mbw + mx];
+  r.hor = m->mv[b4].hor; r.ver = m->mv[b4].ver; r.ref = m->ref_idx[((b4 >> 3) << 1) | ((b4 & 3) >> 1)];
+  return r;
+}
+static int med3(int a, int b, int c) { return a > b ? (a > c ? (b > c ? b : c) : a) : (b > c ? (a > c ? a : c) : b); }
+
+/* type: 0 MEDIAN, 1 PRED_A, 2 PRED_B, 3 PRED_C */
+static jsvm_mv mv_predictor(mv3d A, mv3d B, mv3d C, mv3d D, int ref, int type) {
+  jsvm_mv m;
+  if (C.ref == 0) C = D;
+  if ((type == 1 && A.ref == ref) || (A.ref == ref && B.ref != ref && C.ref != ref) || (B.ref == 0 && C.ref == 0)) { m.hor = (int16_t)A.hor; m.ver = (int16_t)A.ver; return m; }
+  if ((type == 2 && B.ref == ref) || (A.ref != ref && B.ref == ref && C.ref != ref)) { m.hor = (int16_t)B.hor; m.ver = (int16_t)B.ver; return m; }
+  if ((type == 3 && C.ref == ref) || (A.ref != ref && B.ref != ref && C.ref == ref)) { m.hor = (int16_t)C.hor; m.ver = (int16_t)C.ver; return m; }
+  m.hor = (int16_t)med3(A.hor, B.hor, C.hor); m.ver = (int16_t)med3(A.ver, B.ver, C.ver);
+  return m;
+}
+
+static uint32_t ref_idx_bits(int r, int n) { return n == 1 ? 0u : n == 2 ? 1u : (r < 2 ? 1u : r < 4 ? 3u : r < 8 ? 5u : 7u); }
+
+int jsvm_ora_estimate_pictures(jsvm_ora_ctx* c, const jsvm_pic_task* tasks, int n_pics, jsvm_pic_mb* out) {
+  if (!c) return -1;
+  const int mbw = c->width >> 4, mbh = c->height >> 4;
+  static const uint8_t part_mode[9] = { JSVM_MODE_16x16, JSVM_MODE_16x8, JSVM_MODE_16x8, JSVM_MODE_8x16, JSVM_MODE_8x16, JSVM_BLK_8x8, JSVM_BLK_8x8, JSVM_BLK_8x8, JSVM_BLK_8x8 };
+  static const uint8_t part_blk[9]  = { 0, 0, 8, 0, 2, 0, 2, 8, 10 };
+  static const uint8_t part_bits[9] = { 1, 3, 3, 3, 3, 6, 1, 1, 1 };
+  for (int p = 0; p < n_pics; ++p) {
+    const jsvm_pic_task* t = &tasks[p];
+    const int R = t->n_refs;
+    jsvm_pic_mb* f = out + (size_t)p * mbw * mbh;
+    memset(f, 0, sizeof(jsvm_pic_mb) * (size_t)mbw * mbh);
+    for (int my = 0; my < mbh; ++my)
+      for (int mx = 0; mx < mbw; ++mx) {
+        jsvm_pic_mb* o = &f[my * mbw + mx];
+        mv3d cur[9];                                       /* partitions of this macroblock estimated so far */
+        for (int part = 0; part < 9; ++part) {
+          /* neighbours of the partition's corner blocks: A left of the first 4x4, B above it, C above-right of the LAST 4x4 of
+           * the top row, D above-left of the first (used when C is not available) */
+          mv3d A, B, C, D = { 0, 0, 0 };
+          int type = 0;
+          switch (part) {
+            case 0: case 1: case 3: case 5:
+              A = field_block(f, mbw, mbh, mx - 1, my, 3); B = field_block(f, mbw, mbh, mx, my - 1, 12);
+              C = part <= 1 ? field_block(f, mbw, mbh, mx + 1, my - 1, 12) : field_block(f, mbw, mbh, mx, my - 1, 14);
+              D = field_block(f, mbw, mbh, mx - 1, my - 1, 15);
+              type = part == 1 ? 2 : part == 3 ? 1 : 0;
+              break;
+            case 2: A = field_block(f, mbw, mbh, mx - 1, my, 11); B = cur[1]; C.hor = C.ver = C.ref = 0; D = field_block(f, mbw, mbh, mx - 1, my, 7); type = 1; break;
+            case 4: case 6:
+              A = cur[part == 4 ? 3 : 5]; B = field_block(f, mbw, mbh, mx, my - 1, 14);
+              C = field_block(f, mbw, mbh, mx + 1, my - 1, 12); D = field_block(f, mbw, mbh, mx, my - 1, 13);
+              type = part == 4 ? 3 : 0;
+              break;
+            case 7: A = field_block(f, mbw, mbh, mx - 1, my, 11); B = cur[5]; C = cur[6]; break;
+            default: A = cur[7]; B = cur[6]; C.hor = C.ver = C.ref = 0; D = cur[5]; break;
+          }
+          uint32_t best = 0xffffffffu; int best_r = 0; jsvm_mv best_mv = { 0, 0 };
+          for (int r = 1; r <= R; ++r) {
+            jsvm_me_job j; jsvm_me_result res;
+            memset(&j, 0, sizeof(j));
+            j.cur_slot = t->cur_slot; j.ref_slot = t->ref_slot[r - 1]; j.mb_x = (int16_t)mx; j.mb_y = (int16_t)my;
+            j.blk = part_blk[part]; j.mode = part_mode[part];
+            j.pred = mv_predictor(A, B, C, D, r, type); j.start = j.pred;
+            j.cost_factor = t->cost_factor; j.bits_in = part_bits[part] + ref_idx_bits(r, R); j.org_index = -1;
+            if (jsvm_ora_search(c, &j, 1, NULL, 0, &res, NULL)) return -1;
+            if (res.cost < best) { best = res.cost; best_r = r; best_mv = res.mv; }
+          }
+          cur[part].hor = best_mv.hor; cur[part].ver = best_mv.ver; cur[part].ref = best_r;
+          o->part_mv[part] = best_mv; o->part_ref[part] = (int8_t)best_r; o->part_cost[part] = best;
+        }
+        const uint32_t cost[4] = { o->part_cost[0], o->part_cost[1] + o->part_cost[2], o->part_cost[3] + o->part_cost[4],
+                                   o->part_cost[5] + o->part_cost[6] + o->part_cost[7] + o->part_cost[8] };
+        int mode = 1; uint32_t best = cost[0];
+        for (int m = 1; m < 4; ++m) if (cost[m] < best) { best = cost[m]; mode = m + 1; }
+        o->mode = (uint8_t)mode; o->cost = best;
+        for (int b8 = 0; b8 < 4; ++b8) {
+          const int part = mode == 1 ? 0 : mode == 2 ? 1 + (b8 >> 1) : mode == 3 ? 3 + (b8 & 1) : 5 + b8;
+          o->ref_idx[b8] = o->part_ref[part];
+          for (int k = 0; k < 4; ++k) o->mv[((b8 >> 1) * 2 + (k >> 1)) * 4 + (b8 & 1) * 2 + (k & 1)] = o->part_mv[part];
+        }
+      }
+  }
+  return 0;
+}

@@ -50,6 +50,9 @@ int jsvm_ora_compensate(jsvm_ora_ctx* ctx, const jsvm_mc_job* jobs, int n_jobs, 
 int jsvm_ora_set_fast_search_params(jsvm_ora_ctx* ctx, int el_search_range, int fast_bi_search);
 int jsvm_ora_set_mv_candidates(jsvm_ora_ctx* ctx, const jsvm_mv* abc, int n_jobs);
 
+/* picture-level motion search (MV prediction + per-macroblock loops), see jsvm_me_estimate_pictures */
+int jsvm_ora_estimate_pictures(jsvm_ora_ctx* ctx, const jsvm_pic_task* tasks, int n_pics, jsvm_pic_mb* out);
+
 #ifdef __cplusplus
 }
 #endif

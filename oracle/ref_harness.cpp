@@ -506,3 +506,83 @@ extern "C" int jsvm_ref_set_mv_candidates(jsvm_ref_ctx* c, const jsvm_mv* abc, i
   c->cands = abc; c->n_cands = abc ? n_jobs : 0;
   return 0;
 }
+
+// Picture-level motion search (see jsvm_me_estimate_pictures): the reference's own MV prediction (MbDataAccess::getMvPredictor on a
+// real MbDataCtrl, neighbours resolved by MbDataCtrl::initMb) and estimateBlockWithStart, composed as the list-0 loops of
+// MbEncoder::xEstimateMb16x16 / 16x8 / 8x16 / 8x8 compose them (ENC/MbEncoder.cpp:4449-4560, 4830-4935, 5234-5330, 5637-5700,
+// 5950-6040), with the macroblock mode chosen by the sum of the motion costs.
+namespace {
+UInt refIdxBits(int r, int n) { return n == 1 ? 0 : n == 2 ? 1 : (r < 2 ? 1 : r < 4 ? 3 : r < 8 ? 5 : 7); }   // getRefIdxBits / g_aucFrameBits
+}
+
+extern "C" int jsvm_ref_estimate_pictures(jsvm_ref_ctx* c, const jsvm_pic_task* tasks, int n_pics, jsvm_pic_mb* out) {
+  if (!c) return -1;
+  static const ParIdx16x8 k16x8[2] = { PART_16x8_0, PART_16x8_1 };
+  static const ParIdx8x16 k8x16[2] = { PART_8x16_0, PART_8x16_1 };
+  static const ParIdx8x8  k8x8 [4] = { PART_8x8_0, PART_8x8_1, PART_8x8_2, PART_8x8_3 };
+  for (int p = 0; p < n_pics; ++p) {
+    const jsvm_pic_task& t = tasks[p];
+    const int R = t.n_refs;
+    MbDataCtrl ctrl;
+    CHKI(ctrl.init(*c->sps));
+    CHKI(ctrl.initSlice(*c->sh, PRE_PROCESS, false, NULL));
+    c->rd->m_uiFactor = t.cost_factor; c->rd->m_uiFactorSse = t.cost_factor;
+    for (UInt mby = 0; mby < c->mbh; ++mby)
+      for (UInt mbx = 0; mbx < c->mbw; ++mbx) {
+        MbDataAccess* mba = 0;
+        CHKI(ctrl.initMb(mba, mby, mbx));
+        CHKI(c->full_ctrl->initMb(mby, mbx, false));
+        CHKI(c->half_ctrl->initMb(mby, mbx, false));
+        CHKI(c->me->initMb(mby, mbx, *mba));
+        YuvMbBuffer* org = 0;
+        c->dist->loadOrgMbPelData(c->frames[t.cur_slot]->getFullPelYuvBuffer(), org);
+        MbMotionData& mot = mba->getMbMotionData(LIST_0);
+        jsvm_pic_mb& o = out[(size_t)p * c->mbw * c->mbh + mby * c->mbw + mbx];
+        memset(&o, 0, sizeof(o));
+        // one partition: every reference, keep the cheapest ( uiCostTest < uiCost[0] )
+        struct Est { Mv mv; int ref; UInt cost; };
+        #define ESTIMATE(GETPRED, BLK, MODE, MODEBITS, RESULT)                                             \
+          do { (RESULT).cost = MSYS_UINT_MAX; (RESULT).ref = 0;                                            \
+            for (int r = 1; r <= R; ++r) {                                                                 \
+              Mv pred; GETPRED;                                                                            \
+              Mv mv = pred; UInt bits = (MODEBITS) + refIdxBits(r, R), cost = 0;                           \
+              CHKI(c->me->estimateBlockWithStart(*mba, *c->frames[t.ref_slot[r - 1]], mv, pred, bits, cost, BLK, MODE, 0, &c->pw, 0)); \
+              if (cost < (RESULT).cost) { (RESULT).cost = cost; (RESULT).ref = r; (RESULT).mv = mv; }      \
+            } } while (0)
+        Est e[9];
+        mot.clear(BLOCK_NOT_AVAILABLE); mot.setAllMv(Mv::ZeroMv());
+        ESTIMATE(mba->getMvPredictor(pred, r, LIST_0), 0, MODE_16x16, 1, e[0]);
+        mot.clear(BLOCK_NOT_AVAILABLE); mot.setAllMv(Mv::ZeroMv());
+        for (int k = 0; k < 2; ++k) {
+          ESTIMATE(mba->getMvPredictor(pred, r, LIST_0, k16x8[k]), k16x8[k], MODE_16x8, 3, e[1 + k]);
+          mot.setRefIdx(e[1 + k].ref, k16x8[k]); mot.setAllMv(e[1 + k].mv, k16x8[k]);
+        }
+        mot.clear(BLOCK_NOT_AVAILABLE); mot.setAllMv(Mv::ZeroMv());
+        for (int k = 0; k < 2; ++k) {
+          ESTIMATE(mba->getMvPredictor(pred, r, LIST_0, k8x16[k]), k8x16[k], MODE_8x16, 3, e[3 + k]);
+          mot.setRefIdx(e[3 + k].ref, k8x16[k]); mot.setAllMv(e[3 + k].mv, k8x16[k]);
+        }
+        mot.clear(BLOCK_NOT_AVAILABLE); mot.setAllMv(Mv::ZeroMv());
+        for (int k = 0; k < 4; ++k) {
+          ESTIMATE(mba->getMvPredictor(pred, r, LIST_0, k8x8[k]), k8x8[k] + SPART_8x8, BLK_8x8, 1 + (k == 0 ? 5 : 0), e[5 + k]);
+          mot.setRefIdx(e[5 + k].ref, k8x8[k]); mot.setAllMv(e[5 + k].mv, k8x8[k]);
+        }
+        #undef ESTIMATE
+        const UInt cost[4] = { e[0].cost, e[1].cost + e[2].cost, e[3].cost + e[4].cost, e[5].cost + e[6].cost + e[7].cost + e[8].cost };
+        int mode = 1; UInt best = cost[0];
+        for (int m = 1; m < 4; ++m) if (cost[m] < best) { best = cost[m]; mode = m + 1; }
+        // final motion of the macroblock: what the next macroblocks predict from
+        mot.clear(BLOCK_NOT_AVAILABLE);
+        for (int b8 = 0; b8 < 4; ++b8) {
+          const int part = mode == 1 ? 0 : mode == 2 ? 1 + (b8 >> 1) : mode == 3 ? 3 + (b8 & 1) : 5 + b8;
+          mot.setRefIdx(e[part].ref, k8x8[b8]); mot.setAllMv(e[part].mv, k8x8[b8]);
+          o.ref_idx[b8] = (int8_t)e[part].ref;
+        }
+        o.mode = (uint8_t)mode; o.cost = best;
+        for (int b = 0; b < 16; ++b) { const Mv& m = mot.getMv(B4x4Idx(b)); o.mv[b].hor = m.getHor(); o.mv[b].ver = m.getVer(); }
+        for (int k = 0; k < 9; ++k) { o.part_mv[k].hor = e[k].mv.getHor(); o.part_mv[k].ver = e[k].mv.getVer(); o.part_ref[k] = (int8_t)e[k].ref; o.part_cost[k] = e[k].cost; }
+      }
+    ctrl.uninit();
+  }
+  return 0;
+}

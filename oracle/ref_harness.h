@@ -62,6 +62,9 @@ int jsvm_ref_compensate(jsvm_ref_ctx* ctx, const jsvm_mc_job* jobs, int n_jobs, 
 int jsvm_ref_set_fast_search_params(jsvm_ref_ctx* ctx, int el_search_range, int fast_bi_search);
 int jsvm_ref_set_mv_candidates(jsvm_ref_ctx* ctx, const jsvm_mv* abc, int n_jobs);
 
+/* Picture-level motion search with the reference's MV prediction (see jsvm_me_estimate_pictures). */
+int jsvm_ref_estimate_pictures(jsvm_ref_ctx* ctx, const jsvm_pic_task* tasks, int n_pics, jsvm_pic_mb* out);
+
 #ifdef __cplusplus
 }
 #endif

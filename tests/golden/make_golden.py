@@ -3,7 +3,7 @@
 /root/reference by `make -C oracle ref`).  Run in the build container only; the fixtures are committed so
 that the GPU box (which has no /root/reference) can pin the oracle and the CUDA path against them.
 
-    python tests/golden/make_golden.py [group ...]      groups: search, org, fullpel, table, yuv, mc, fast (default: all)
+    python tests/golden/make_golden.py [group ...]      groups: search, org, fullpel, table, yuv, mc, fast, pic (default: all)
 """
 import importlib
 import os
@@ -200,7 +200,22 @@ def gen_fast(ref):
         print(name, len(jobs), "jobs")
 
 
-GROUPS = {"fast": gen_fast, "yuv": gen_yuv, "mc": gen_mc, "search": gen_search, "org": gen_org, "fullpel": gen_fullpel, "table": gen_table}
+def gen_pic(ref):
+    # picture-level search: the reference's getMvPredictor on a real MbDataCtrl + estimateBlockWithStart per partition and reference
+    W, H, sr = 176, 144, 16
+    seq = synth.LocalMotionSequence(W, H, 51)
+    frames = [seq.frame(i) for i in range(4)]
+    ses = ref.session(W, H, 4, sr, 2)
+    for s, f in enumerate(frames):
+        ses.set_plane(s, f)
+    tasks = synth.make_pic_tasks([2, 3, 3], [[1, 0], [2, 1], [0, 2]], qp=31)
+    out = ses.estimate_pictures(tasks)
+    np.savez_compressed(os.path.join(HERE, "picture_search_qcif.npz"), width=W, height=H, search_range=sr, sub_dfunc=2,
+                        frames=np.stack(frames), tasks=tasks, field=out)
+    print("picture_search_qcif", out.shape, "modes", np.bincount(out["mode"].ravel()))
+
+
+GROUPS = {"pic": gen_pic, "fast": gen_fast, "yuv": gen_yuv, "mc": gen_mc, "search": gen_search, "org": gen_org, "fullpel": gen_fullpel, "table": gen_table}
 
 
 def main():

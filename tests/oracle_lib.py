@@ -17,6 +17,7 @@ _spec = importlib.util.spec_from_file_location(
 abi = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(abi)
 JOB_DTYPE, RESULT_DTYPE, MC_JOB_DTYPE = abi.JOB_DTYPE, abi.RESULT_DTYPE, abi.MC_JOB_DTYPE
+PIC_TASK_DTYPE, PIC_MB_DTYPE = abi.PIC_TASK_DTYPE, abi.PIC_MB_DTYPE
 
 
 class CpuSession:
@@ -61,6 +62,12 @@ class CpuSession:
         self._cands = None if abc is None else np.ascontiguousarray(abc, np.int16).reshape(-1, 3, 2)
         assert self.be.set_mv_candidates(self.ctx, None if self._cands is None else self._cands.ctypes.data,
                                          0 if self._cands is None else len(self._cands)) == 0
+
+    def estimate_pictures(self, tasks):
+        tasks = np.ascontiguousarray(tasks, PIC_TASK_DTYPE)
+        out = np.zeros((len(tasks), self.height // 16, self.width // 16), PIC_MB_DTYPE)
+        assert self.be.estimate_pictures(self.ctx, tasks.ctypes.data, len(tasks), out.ctypes.data) == 0, "checker estimate_pictures() failed"
+        return out
 
     def compensate(self, mc_jobs, chroma=True):
         jobs = np.ascontiguousarray(mc_jobs, MC_JOB_DTYPE)
@@ -114,6 +121,7 @@ class CpuBackend:
                   ("map_cost_factor", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
                   ("set_fast_search_params", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
                   ("set_mv_candidates", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+                  ("estimate_pictures", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
                   ("compensate", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
                   ("cost_factor", C.c_uint32, [C.c_double, C.c_int]),
                   ("distortion", C.c_uint32, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int])]

@@ -35,7 +35,7 @@ def load(name):
 
 
 def test_fixtures_present():
-    assert len(glob.glob(os.path.join(HERE, "golden", "*.npz"))) >= 27
+    assert len(glob.glob(os.path.join(HERE, "golden", "*.npz"))) >= 28
 
 
 @pytest.mark.parametrize("name", SEARCH_CASES + FAST_CASES)
@@ -66,6 +66,19 @@ def test_oracle_compensate_matches_reference_golden(oracle, kind):
         ses.set_chroma(s, g["cb"][s], g["cr"][s])
     py, pcb, pcr = ses.compensate(g["jobs_" + kind])
     assert np.array_equal(py, g["y_" + kind]) and np.array_equal(pcb, g["cb_" + kind]) and np.array_equal(pcr, g["cr_" + kind])
+
+
+def test_oracle_picture_search_matches_reference_golden(oracle):
+    """f1: MV prediction + per-macroblock loops of the C port against the reference's getMvPredictor / estimateBlockWithStart."""
+    g = load("picture_search_qcif")
+    W, H = int(g["width"]), int(g["height"])
+    ses = oracle.session(W, H, 4, int(g["search_range"]), int(g["sub_dfunc"]))
+    for s in range(4):
+        ses.set_plane(s, g["frames"][s])
+    out = ses.estimate_pictures(g["tasks"])
+    for f in out.dtype.names:
+        assert np.array_equal(out[f], g["field"][f]), f
+    assert len(np.unique(g["field"]["mode"])) == 4 and len(np.unique(g["field"]["part_ref"])) == 2
 
 
 def test_mc_golden_covers_all_phases_and_clamps():

@@ -127,3 +127,20 @@ def test_fast_searches_identical(oracle, reference, synth, search_mode, sr, fast
         bad = np.nonzero(ra[f] != rb[f])[0]
         assert len(bad) == 0, (f, len(bad), jobs[bad[0]], ra[bad[0]], rb[bad[0]])
     assert np.array_equal(pa, pb)
+
+
+@pytest.mark.parametrize("W,H,sr,n_refs,sub", [(96, 80, 12, 1, 2), (176, 144, 16, 3, 0), (64, 48, 8, 2, 2)])
+def test_picture_level_search_identical(oracle, reference, synth, W, H, sr, n_refs, sub):
+    """f1: the C port's MV prediction + per-macroblock loops against the reference's MbDataAccess::getMvPredictor driven on a real
+    MbDataCtrl (every partition's MV, reference index and cost, the macroblock mode and the final 4x4 motion field)."""
+    seq = synth.LocalMotionSequence(W, H, 700 + W)
+    sessions = [be.session(W, H, n_refs + 2, sr, sub) for be in (oracle, reference)]
+    for s in sessions:
+        for slot in range(n_refs + 2):
+            s.set_plane(slot, seq.frame(slot))
+    tasks = synth.make_pic_tasks([n_refs, n_refs + 1], [list(range(n_refs)), list(range(1, n_refs + 1))[::-1]], qp=33)
+    a, b = [s.estimate_pictures(tasks) for s in sessions]
+    for f in a.dtype.names:
+        bad = np.argwhere(a[f] != b[f])
+        assert len(bad) == 0, (f, len(bad), bad[0], a[tuple(bad[0][:3])], b[tuple(bad[0][:3])])
+    assert len(np.unique(a["mode"])) >= 3 and (a["part_mv"] != 0).any()
