@@ -289,6 +289,56 @@ typedef struct jsvm_pic_mb {
 int jsvm_me_estimate_pictures(jsvm_me_ctx* ctx, const jsvm_pic_task* tasks, int n_pics, jsvm_pic_mb* out);
 int jsvm_me_download_pictures(jsvm_me_ctx* ctx, jsvm_pic_mb* out, int n_pics);
 
+/* ---- inter-layer resampling for the enhancement-layer motion search ----
+ * The fields of ResizeParameters the progressive resampling reads (include/ResizeParameters.h:70-101; both layers frame_mbs_only,
+ * no field pictures, no MBAFF -- the five configurations are progressive). */
+typedef struct jsvm_resize_params {
+  int32_t level_idc;                             /* m_iLevelIdc: <= 30 selects 16-bit position arithmetic */
+  int32_t frame_width, frame_height;             /* current (enhancement) layer: m_iFrameWidth / m_iFrameHeight */
+  int32_t ref_frame_width, ref_frame_height;     /* reference (base) layer: m_iRefLayerFrmWidth / m_iRefLayerFrmHeight */
+  int32_t scaled_ref_width, scaled_ref_height;   /* m_iScaledRefFrmWidth / m_iScaledRefFrmHeight */
+  int32_t left_offset, top_offset;               /* m_iLeftFrmOffset / m_iTopFrmOffset */
+  int32_t chroma_phase_x, chroma_phase_y;        /* m_iChromaPhaseX / Y */
+  int32_t ref_chroma_phase_x, ref_chroma_phase_y;/* m_iRefLayerChromaPhaseX / Y */
+} jsvm_resize_params;
+/* Frame::residualUpsampling -> DownConvert::xResidualUpsampling (COM/Frame.cpp:398-406, COM/DownConvert.cpp:2476-2958): the
+ * base-layer residual, upsampled to the enhancement-layer grid, that the residual-prediction passes subtract from the original
+ * before the motion search (N3).  Dense int16 planes in HOST memory: base luma ref_w x ref_h, base chroma (ref_w/2) x (ref_h/2);
+ * outputs frame_w x frame_h and (frame_w/2) x (frame_h/2).  base_transform8x8: one byte per base-layer macroblock, raster order
+ * (MbData::isTransformSize8x8).  Chroma pointers may all be NULL (luma only). */
+int jsvm_me_upsample_residual(jsvm_me_ctx* ctx, const jsvm_resize_params* params,
+                              const int16_t* base_y, const int16_t* base_cb, const int16_t* base_cr, const uint8_t* base_transform8x8,
+                              int16_t* out_y, int16_t* out_cb, int16_t* out_cr);
+
+/* MbDataCtrl::upsampleMotion / MotionUpsampling::resample (COM/MbDataCtrl.cpp:85-1110, 1115-1140; subclauses G.6.1, G.6.2, G.8.6.1 of
+ * the SVC specification): the inter-layer motion prediction -- for every enhancement-layer macroblock the partitioning, reference
+ * indices and motion vectors derived from the base layer, which the enhancement-layer passes use as search start and MV
+ * predictor (cBLMvPred / iBLRefIdx, ENC/MbEncoder.cpp:4483-4497, 4516-4560; estimateBlockWithStart with JSVM_JOB_EL).
+ * Progressive layers, no per-picture cropping change (ESS_PICT), no coefficient prediction (SCoeff / TCoeff).
+ * One record per macroblock, raster order; the same record describes the base layer (input) and the prediction (output). */
+typedef struct jsvm_mb_motion {
+  uint8_t  mb_mode;          /* MbMode (INCC/CommonDefs.h:169-180): 0 SKIP, 1 16x16, 2 16x8, 3 8x16, 4 8x8, 5 8x8ref0, >= 6 intra, 36 INTRA_BL */
+  uint8_t  slice_type;       /* input: SliceType of the macroblock's slice (0 P, 1 B, 2 I); output: 0 */
+  uint8_t  blk_mode[4];      /* BlkMode per 8x8: 8 8x8, 9 8x4, 10 4x8, 11 4x4, 0 BLK_SKIP */
+  uint8_t  in_crop_window;   /* output: MbData::getInCropWindowFlag */
+  uint8_t  res_pred_safe;    /* output: MbData::getSafeResPred */
+  uint16_t fwd_bwd;          /* output: MbData::getFwdBwd */
+  uint8_t  base_intra;       /* output: bit ( x + 2 y ) = m_aabBaseIntra[x][y] */
+  uint8_t  pad;
+  int8_t   ref_idx[2][4];    /* per list and 8x8 block; -1 = BLOCK_NOT_PREDICTED, 0 = BLOCK_NOT_AVAILABLE */
+  jsvm_mv  mv[2][16];        /* per list and 4x4 block (raster) */
+} jsvm_mb_motion;
+typedef struct jsvm_motion_upsample_params {
+  jsvm_resize_params resize;
+  int32_t slice_type;            /* of the enhancement-layer slice: 0 P (list 0 only), 1 B, 2 I (no motion) */
+  int32_t ref_layer_dq_id;       /* SliceHeader::getRefLayerDQId (B_Skip / direct partitions are only split when it is 0) */
+  int32_t direct_8x8_inference;  /* SPS direct_8x8_inference_flag */
+  int32_t check_residual_pred;   /* bCheckResidualPred (m_uiEssRPChkEnable) and its MV threshold (m_uiMVThres) */
+  int32_t mv_threshold;
+} jsvm_motion_upsample_params;
+/* base: (ref_h/16) x (ref_w/16) records, out: (frame_h/16) x (frame_w/16) records, HOST memory. */
+int jsvm_me_upsample_motion(jsvm_me_ctx* ctx, const jsvm_motion_upsample_params* params, const jsvm_mb_motion* base, jsvm_mb_motion* out);
+
 int jsvm_me_sync(jsvm_me_ctx* ctx);
 
 /* Measurement helpers (bench.py): kernel launches issued so far, and CUDA-event timing of the

@@ -69,6 +69,25 @@ PIC_MB_DTYPE = np.dtype([("mode", "u1"), ("pad", "u1", (3,)), ("ref_idx", "i1", 
                          ("part_mv", "<i2", (9, 2)), ("part_ref", "i1", (9,)), ("pad2", "i1", (3,)), ("part_cost", "<u4", (9,))])
 assert PIC_TASK_DTYPE.itemsize == 24 and PIC_MB_DTYPE.itemsize == 160
 
+
+MB_MOTION_DTYPE = np.dtype([("mb_mode", "u1"), ("slice_type", "u1"), ("blk_mode", "u1", (4,)), ("in_crop_window", "u1"), ("res_pred_safe", "u1"),
+                            ("fwd_bwd", "<u2"), ("base_intra", "u1"), ("pad", "u1"), ("ref_idx", "i1", (2, 4)), ("mv", "<i2", (2, 16, 2))])
+assert MB_MOTION_DTYPE.itemsize == 148
+
+
+class ResizeParams(C.Structure):
+    """jsvm_resize_params: the fields of ResizeParameters the progressive inter-layer resampling reads."""
+    _fields_ = [(n, C.c_int32) for n in ("level_idc", "frame_width", "frame_height", "ref_frame_width", "ref_frame_height",
+                                         "scaled_ref_width", "scaled_ref_height", "left_offset", "top_offset",
+                                         "chroma_phase_x", "chroma_phase_y", "ref_chroma_phase_x", "ref_chroma_phase_y")]
+
+
+class MotionUpsampleParams(C.Structure):
+    """jsvm_motion_upsample_params"""
+    _fields_ = [("resize", ResizeParams)] + [(n, C.c_int32) for n in ("slice_type", "ref_layer_dq_id", "direct_8x8_inference",
+                                                                      "check_residual_pred", "mv_threshold")]
+
+
 # every symbol the header declares: (name, restype, argtypes)
 PROTOTYPES = [
     ("jsvm_me_create", C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
@@ -102,6 +121,8 @@ PROTOTYPES = [
                                         C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     ("jsvm_me_estimate_pictures", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     ("jsvm_me_download_pictures", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    ("jsvm_me_upsample_motion", C.c_int, [C.c_void_p, C.POINTER(MotionUpsampleParams), C.c_void_p, C.c_void_p]),
+    ("jsvm_me_upsample_residual", C.c_int, [C.c_void_p, C.POINTER(ResizeParams)] + [C.c_void_p] * 7),
     ("jsvm_me_fetch_pred", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     ("jsvm_me_sync", C.c_int, [C.c_void_p]),
     ("jsvm_me_launch_count", C.c_uint64, [C.c_void_p]),

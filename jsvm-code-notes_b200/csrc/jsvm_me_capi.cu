@@ -29,6 +29,7 @@
 #include "k4_mc.cuh"
 #include "k5_fastsearch.cuh"
 #include "k6_picture.cuh"
+#include "k7_interlayer.cuh"
 
 using namespace jsvm;
 
@@ -153,6 +154,10 @@ struct jsvm_me_ctx {
   DevBuf<PicTemp> d_pic_temp;
   DevBuf<jsvm_me_result> d_pic_results[2];
   int pic_n_last = 0;
+  // inter-layer resampling scratch
+  DevBuf<int16_t> d_rs_src, d_rs_dst;
+  DevBuf<uint8_t> d_rs_t8x8;
+  DevBuf<jsvm_mb_motion> d_mu_base, d_mu_out;
 };
 
 namespace {
@@ -633,7 +638,7 @@ int jsvm_me_destroy(jsvm_me_ctx* c) {
   if (c->d_chroma) cudaFree(c->d_chroma);
   if (c->d_slot_ids) cudaFree(c->d_slot_ids);
   if (c->d_bad) cudaFree(c->d_bad);
-  c->d_wave_mbs.release(); c->d_pic_tasks.release(); c->d_pic_field.release(); c->d_pic_temp.release(); c->d_pic_results[0].release(); c->d_pic_results[1].release();
+  c->d_mu_base.release(); c->d_mu_out.release(); c->d_rs_src.release(); c->d_rs_dst.release(); c->d_rs_t8x8.release(); c->d_wave_mbs.release(); c->d_pic_tasks.release(); c->d_pic_field.release(); c->d_pic_temp.release(); c->d_pic_results[0].release(); c->d_pic_results[1].release();
   c->d_cands.release(); c->d_factor_map.release(); c->d_org_chroma.release(); c->d_mc_jobs.release(); c->d_mc_pred.release();
   c->d_jobs.release(); c->d_groups.release(); c->d_keys.release(); c->d_full_costs.release(); c->d_aux.release();
   c->d_results.release(); c->d_preds.release(); c->d_org.release(); c->d_stage.release();
@@ -1231,6 +1236,123 @@ int jsvm_me_download_pictures(jsvm_me_ctx* c, jsvm_pic_mb* out, int n_pics) {
   if (n_pics <= 0 || n_pics > c->pic_n_last) return fail("n_pics %d: the last jsvm_me_estimate_pictures call covered %d pictures", n_pics, c->pic_n_last);
   CU_OK(cudaSetDevice(c->device));
   CU_OK(cudaMemcpyAsync(out, c->d_pic_field.p, sizeof(jsvm_pic_mb) * (size_t)n_pics * (c->W >> 4) * (c->H >> 4), cudaMemcpyDeviceToHost, c->stream));
+  CU_OK(cudaStreamSynchronize(c->stream));
+  return JSVM_ME_OK;
+}
+
+// ---- K7: inter-layer resampling ----
+namespace {
+int ceil_log2(int i) { int s = 0; --i; while (i > 0) { ++s; i >>= 1; } return s; }          // include/ResizeParameters.h:30-39
+
+// xCompResidualUpsampling (COM/DownConvert.cpp:2733-2817) for progressive layers: the arguments of xBasicResidualUpsampling
+ResamplePlane residual_plane(const jsvm_resize_params& rp, bool chroma) {
+  const int f = chroma ? 2 : 1;
+  const int ref_phase_x = chroma ? rp.ref_chroma_phase_x : 0, ref_phase_y = chroma ? rp.ref_chroma_phase_y : 0;
+  const int phase_x = chroma ? rp.chroma_phase_x : 0, phase_y = chroma ? rp.chroma_phase_y : 0;
+  const int ref_w = rp.ref_frame_width / f, ref_h = rp.ref_frame_height / f;
+  const int out_w = rp.scaled_ref_width / f, out_h = rp.scaled_ref_height / f;
+  ResamplePlane P;
+  P.base_w = ref_w; P.base_h = ref_h; P.cur_w = rp.frame_width / f; P.cur_h = rp.frame_height / f;
+  P.l_off = rp.left_offset / f; P.t_off = rp.top_offset / f;
+  P.r_off = P.cur_w - P.l_off - out_w; P.b_off = P.cur_h - P.t_off - out_h;
+  const int shift_x = rp.level_idc <= 30 ? 16 : 31 - ceil_log2(ref_w), shift_y = rp.level_idc <= 30 ? 16 : 31 - ceil_log2(ref_h);
+  P.shift_x_m4 = shift_x - 4; P.shift_y_m4 = shift_y - 4;
+  P.scale_x = (int)((((uint32_t)ref_w << shift_x) + (uint32_t)(out_w >> 1)) / (uint32_t)out_w);
+  P.scale_y = (int)((((uint32_t)ref_h << shift_y) + (uint32_t)(out_h >> 1)) / (uint32_t)out_h);
+  P.offset_x = P.l_off; P.offset_y = P.t_off;
+  P.add_x = (((ref_w * (2 + phase_x)) << (shift_x - 2)) + (out_w >> 1)) / out_w + (1 << (shift_x - 5));
+  P.add_y = (((ref_h * (2 + phase_y)) << (shift_y - 2)) + (out_h >> 1)) / out_h + (1 << (shift_y - 5));
+  P.delta_x = 4 * (2 + ref_phase_x); P.delta_y = 4 * (2 + ref_phase_y);
+  P.mb_size = chroma ? 8 : 16; P.mbs_per_row = rp.ref_frame_width / 16; P.chroma = chroma ? 1 : 0;
+  return P;
+}
+}  // namespace
+
+int jsvm_me_upsample_residual(jsvm_me_ctx* c, const jsvm_resize_params* rp, const int16_t* base_y, const int16_t* base_cb, const int16_t* base_cr,
+                              const uint8_t* base_transform8x8, int16_t* out_y, int16_t* out_cb, int16_t* out_cr) {
+  if (!c || !rp || !base_y || !base_transform8x8 || !out_y) return fail("null argument");
+  const bool chroma = base_cb || base_cr || out_cb || out_cr;
+  if (chroma && !(base_cb && base_cr && out_cb && out_cr)) return fail("chroma planes: all four pointers or none");
+  if (rp->frame_width <= 0 || rp->frame_height <= 0 || (rp->frame_width & 15) || (rp->frame_height & 15) ||
+      rp->ref_frame_width <= 0 || rp->ref_frame_height <= 0 || (rp->ref_frame_width & 15) || (rp->ref_frame_height & 15))
+    return fail("layer sizes must be positive multiples of 16");
+  if (rp->scaled_ref_width <= 0 || rp->scaled_ref_height <= 0 || rp->left_offset < 0 || rp->top_offset < 0 ||
+      rp->left_offset + rp->scaled_ref_width > rp->frame_width || rp->top_offset + rp->scaled_ref_height > rp->frame_height ||
+      (rp->scaled_ref_width & 1) || (rp->scaled_ref_height & 1) || (rp->left_offset & 1) || (rp->top_offset & 1))
+    return fail("scaled reference window %dx%d at (%d,%d) does not fit the %dx%d frame (even sizes and offsets)", rp->scaled_ref_width,
+                rp->scaled_ref_height, rp->left_offset, rp->top_offset, rp->frame_width, rp->frame_height);
+  CU_OK(cudaSetDevice(c->device));
+  const size_t n_src = (size_t)rp->ref_frame_width * rp->ref_frame_height, n_dst = (size_t)rp->frame_width * rp->frame_height;
+  const size_t n_mb = n_src / 256;
+  if (c->d_rs_src.reserve(n_src * 3 / 2) || c->d_rs_dst.reserve(n_dst * 3 / 2) || c->d_rs_t8x8.reserve(n_mb)) return JSVM_ME_ERR;
+  CU_OK(cudaMemcpyAsync(c->d_rs_t8x8.p, base_transform8x8, n_mb, cudaMemcpyHostToDevice, c->stream));
+  const int16_t* srcs[3] = { base_y, base_cb, base_cr };
+  int16_t* dsts[3] = { out_y, out_cb, out_cr };
+  size_t so = 0, dof = 0;
+  for (int k = 0; k < (chroma ? 3 : 1); ++k) {
+    const ResamplePlane P = residual_plane(*rp, k > 0);
+    const size_t ns = (size_t)P.base_w * P.base_h, nd = (size_t)P.cur_w * P.cur_h;
+    CU_OK(cudaMemcpyAsync(c->d_rs_src.p + so, srcs[k], ns * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream));
+    dim3 grid((P.cur_w + 255) / 256, P.cur_h), block(256);
+    begin_timed(c, 3);
+    residual_upsample_kernel<<<grid, block, 0, c->stream>>>(P, c->d_rs_src.p + so, c->d_rs_t8x8.p, c->d_rs_dst.p + dof);
+    end_timed(c);
+    c->launches++;
+    CU_OK(cudaGetLastError());
+    CU_OK(cudaMemcpyAsync(dsts[k], c->d_rs_dst.p + dof, nd * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream));
+    so += ns; dof += nd;
+  }
+  CU_OK(cudaStreamSynchronize(c->stream));
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_upsample_motion(jsvm_me_ctx* c, const jsvm_motion_upsample_params* p, const jsvm_mb_motion* base, jsvm_mb_motion* out) {
+  if (!c || !p || !base || !out) return fail("null argument");
+  const jsvm_resize_params& r = p->resize;
+  if (r.frame_width <= 0 || r.frame_height <= 0 || (r.frame_width & 15) || (r.frame_height & 15) ||
+      r.ref_frame_width <= 0 || r.ref_frame_height <= 0 || (r.ref_frame_width & 15) || (r.ref_frame_height & 15))
+    return fail("layer sizes must be positive multiples of 16");
+  if (r.scaled_ref_width <= 0 || r.scaled_ref_height <= 0 || r.left_offset < 0 || r.top_offset < 0 ||
+      r.left_offset + r.scaled_ref_width > r.frame_width || r.top_offset + r.scaled_ref_height > r.frame_height)
+    return fail("scaled reference window %dx%d at (%d,%d) does not fit the %dx%d frame", r.scaled_ref_width, r.scaled_ref_height, r.left_offset,
+                r.top_offset, r.frame_width, r.frame_height);
+  if (p->slice_type < 0 || p->slice_type > 2) return fail("slice_type %d: 0 P, 1 B, 2 I", p->slice_type);
+  const int nb = (r.ref_frame_width >> 4) * (r.ref_frame_height >> 4), nc = (r.frame_width >> 4) * (r.frame_height >> 4);
+  for (int i = 0; i < nb; ++i) {
+    const jsvm_mb_motion& b = base[i];
+    if (b.mb_mode >= 6) continue;
+    bool ok = b.slice_type <= 2;
+    for (int k = 0; k < 4; ++k) ok = ok && (b.blk_mode[k] == 0 || (b.blk_mode[k] >= 8 && b.blk_mode[k] <= 11));
+    if (!ok) return fail("base macroblock %d: illegal slice type or sub-macroblock mode", i);
+  }
+  MotionUpsample M;
+  // getSpatialResolutionChangeFlag / getRestrictedSpatialResolutionChangeFlag (include/ResizeParameters.h:130-153), progressive layers
+  const bool change = (r.left_offset % 16) || (r.top_offset % 16) || r.ref_frame_width != r.scaled_ref_width || r.ref_frame_height != r.scaled_ref_height ||
+                      r.ref_chroma_phase_x != r.chroma_phase_x || r.ref_chroma_phase_y != r.chroma_phase_y;
+  M.rs_change = !change || (!(r.left_offset % 16) && !(r.top_offset % 16) &&
+                            (r.ref_frame_height == r.scaled_ref_height || 2 * r.ref_frame_height == r.scaled_ref_height) &&
+                            (r.ref_frame_width == r.scaled_ref_width || 2 * r.ref_frame_width == r.scaled_ref_width));
+  M.frame_mbw = r.frame_width >> 4; M.frame_mbh = r.frame_height >> 4; M.ref_w = r.ref_frame_width; M.ref_h = r.ref_frame_height;
+  M.crop_x0 = (r.left_offset + 15) / 16; M.crop_y0 = (r.top_offset + 15) / 16;
+  M.crop_x1 = (r.left_offset + r.scaled_ref_width) / 16; M.crop_y1 = (r.top_offset + r.scaled_ref_height) / 16;
+  M.shift_x = r.level_idc <= 30 ? 16 : 31 - ceil_log2(M.ref_w); M.shift_y = r.level_idc <= 30 ? 16 : 31 - ceil_log2(M.ref_h);
+  M.scale_x = (int)((((uint32_t)M.ref_w << M.shift_x) + (uint32_t)(r.scaled_ref_width >> 1)) / (uint32_t)r.scaled_ref_width);
+  M.scale_y = (int)((((uint32_t)M.ref_h << M.shift_y) + (uint32_t)(r.scaled_ref_height >> 1)) / (uint32_t)r.scaled_ref_height);
+  M.add_x = (1 << (M.shift_x - 1)) - r.left_offset * M.scale_x; M.add_y = (1 << (M.shift_y - 1)) - r.top_offset * M.scale_y;
+  M.mv_scale_x = (int)((((uint64_t)r.scaled_ref_width << 16) + (uint64_t)(M.ref_w >> 1)) / (uint64_t)M.ref_w);
+  M.mv_scale_y = (int)((((uint64_t)r.scaled_ref_height << 16) + (uint64_t)(M.ref_h >> 1)) / (uint64_t)M.ref_h);
+  M.max_list = p->slice_type == 1 ? 2 : (p->slice_type == 2 ? 0 : 1);
+  M.slice_type = p->slice_type; M.ref_layer_dq_id = p->ref_layer_dq_id; M.direct_8x8_inference = p->direct_8x8_inference;
+  M.check_residual_pred = p->check_residual_pred; M.mv_threshold = p->mv_threshold;
+  CU_OK(cudaSetDevice(c->device));
+  if (c->d_mu_base.reserve(nb) || c->d_mu_out.reserve(nc)) return JSVM_ME_ERR;
+  CU_OK(cudaMemcpyAsync(c->d_mu_base.p, base, sizeof(jsvm_mb_motion) * nb, cudaMemcpyHostToDevice, c->stream));
+  begin_timed(c, 3);
+  motion_upsample_kernel<<<(nc + 63) / 64, 64, 0, c->stream>>>(M, c->d_mu_base.p, c->d_mu_out.p);
+  end_timed(c);
+  c->launches++;
+  CU_OK(cudaGetLastError());
+  CU_OK(cudaMemcpyAsync(out, c->d_mu_out.p, sizeof(jsvm_mb_motion) * nc, cudaMemcpyDeviceToHost, c->stream));
   CU_OK(cudaStreamSynchronize(c->stream));
   return JSVM_ME_OK;
 }

@@ -214,6 +214,28 @@ class MotionEstimator:
         self._check(self._lib.jsvm_me_download_pictures(self._ctx, _ptr(out), n_pics))
         return out
 
+    def upsample_residual(self, params, base_y, base_cb=None, base_cr=None, base_transform8x8=None):
+        """Frame::residualUpsampling for progressive layers.  params: abi.ResizeParams; base planes int16 (ref_h, ref_w) and
+        (ref_h/2, ref_w/2); base_transform8x8: (ref_h/16, ref_w/16) flags.  Returns (y, cb, cr) int16 at the enhancement size."""
+        by = np.ascontiguousarray(base_y, np.int16)
+        chroma = base_cb is not None
+        bcb = np.ascontiguousarray(base_cb, np.int16) if chroma else None
+        bcr = np.ascontiguousarray(base_cr, np.int16) if chroma else None
+        t8 = np.ascontiguousarray(base_transform8x8 if base_transform8x8 is not None else np.zeros((by.shape[0] // 16, by.shape[1] // 16)), np.uint8)
+        oy = np.zeros((params.frame_height, params.frame_width), np.int16)
+        ocb = np.zeros((params.frame_height // 2, params.frame_width // 2), np.int16) if chroma else None
+        ocr = np.zeros((params.frame_height // 2, params.frame_width // 2), np.int16) if chroma else None
+        self._check(self._lib.jsvm_me_upsample_residual(self._ctx, C.byref(params), _ptr(by), _ptr(bcb), _ptr(bcr), _ptr(t8), _ptr(oy), _ptr(ocb), _ptr(ocr)))
+        return oy, ocb, ocr
+
+    def upsample_motion(self, params, base):
+        """MbDataCtrl::upsampleMotion for progressive layers.  params: abi.MotionUpsampleParams; base: (ref_h/16, ref_w/16)
+        MB_MOTION_DTYPE records.  Returns the (frame_h/16, frame_w/16) prediction records."""
+        base = np.ascontiguousarray(base, dtype=abi.MB_MOTION_DTYPE)
+        out = np.zeros((params.resize.frame_height // 16, params.resize.frame_width // 16), abi.MB_MOTION_DTYPE)
+        self._check(self._lib.jsvm_me_upsample_motion(self._ctx, C.byref(params), _ptr(base), _ptr(out)))
+        return out
+
     def plan(self, jobs):
         jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
         gsz = self._lib.jsvm_me_group_size()

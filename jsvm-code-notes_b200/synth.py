@@ -232,6 +232,87 @@ def make_pic_tasks(cur_slots, ref_slots, qp=30):
     return tasks
 
 
+def make_resize_case(ref_w, ref_h, cur_w, cur_h, scaled_w=None, scaled_h=None, left=0, top=0, level_idc=40, seed=0, phases=(-1, 0, -1, 0)):
+    """Inter-layer resampling inputs: ResizeParams + a seeded base-layer residual (luma, Cb, Cr: smooth signal with sharp steps and
+    many zeros, range about +-255) + per-macroblock transform-size flags.  phases = (chroma_phase_x, chroma_phase_y,
+    ref_chroma_phase_x, ref_chroma_phase_y), JSVM defaults -1 / 0."""
+    from .abi import ResizeParams
+    p = ResizeParams()
+    p.level_idc = level_idc
+    p.frame_width, p.frame_height, p.ref_frame_width, p.ref_frame_height = cur_w, cur_h, ref_w, ref_h
+    p.scaled_ref_width, p.scaled_ref_height = scaled_w or cur_w, scaled_h or cur_h
+    p.left_offset, p.top_offset = left, top
+    p.chroma_phase_x, p.chroma_phase_y, p.ref_chroma_phase_x, p.ref_chroma_phase_y = phases
+    rng = np.random.default_rng(seed)
+
+    def plane(h, w):
+        a = _box_blur(rng.normal(0, 90, (h, w)), 3)
+        a[rng.random((h, w)) < 0.3] = 0
+        a += (rng.random((h, w)) < 0.02) * rng.integers(-255, 256, (h, w))
+        return np.clip(np.rint(a), -255, 255).astype(np.int16)
+    t8 = (rng.random((ref_h // 16, ref_w // 16)) < 0.5).astype(np.uint8)
+    return p, plane(ref_h, ref_w), plane(ref_h // 2, ref_w // 2), plane(ref_h // 2, ref_w // 2), t8
+
+
+def make_motion_params(resize, slice_type, ref_layer_dq_id=0, direct_8x8_inference=1, check_residual_pred=1, mv_threshold=1):
+    from .abi import MotionUpsampleParams
+    p = MotionUpsampleParams()
+    p.resize = resize
+    p.slice_type, p.ref_layer_dq_id, p.direct_8x8_inference = slice_type, ref_layer_dq_id, direct_8x8_inference
+    p.check_residual_pred, p.mv_threshold = check_residual_pred, mv_threshold
+    return p
+
+
+def make_base_motion(ref_w, ref_h, seed=0, slice_type=0, p_intra=0.15):
+    """A seeded base-layer motion field (MB_MOTION_DTYPE, (ref_h/16, ref_w/16)): every macroblock mode and sub-macroblock mode,
+    intra macroblocks (alone and in clusters), one or two lists (B: blocks predicted from one list only, B_Skip / direct), reference
+    indices 1..2, MVs that are equal, 1 quarter-pel apart (merged by the G.8.6.1.2 threshold) or far apart between partitions."""
+    from .abi import MB_MOTION_DTYPE
+    rng = np.random.default_rng(seed)
+    mbh, mbw = ref_h // 16, ref_w // 16
+    f = np.zeros((mbh, mbw), MB_MOTION_DTYPE)
+    f["slice_type"] = slice_type
+    f["blk_mode"] = 8
+    f["ref_idx"] = -1
+    lists = 2 if slice_type == 1 else 1
+    part8 = {1: [0, 0, 0, 0], 2: [0, 0, 1, 1], 3: [0, 1, 0, 1], 4: [0, 1, 2, 3], 5: [0, 1, 2, 3]}
+    part4 = {8: [0, 0, 0, 0], 9: [0, 0, 1, 1], 10: [0, 1, 0, 1], 11: [0, 1, 2, 3], 0: [0, 0, 0, 0]}
+    base_mv = rng.integers(-40, 41, 2)
+    for y in range(mbh):
+        for x in range(mbw):
+            m = f[y, x]
+            if rng.random() < p_intra or (x > 0 and f[y, x - 1]["mb_mode"] >= 6 and rng.random() < 0.4):
+                m["mb_mode"] = rng.choice([6, 7, 31])
+                continue
+            mode = int(rng.choice([0, 1, 2, 3, 4, 4, 5]))
+            if mode == 5 and slice_type == 1:
+                mode = 4
+            m["mb_mode"] = mode
+            if mode in (4, 5):
+                m["blk_mode"] = rng.choice([8, 9, 10, 11] + ([0] if slice_type == 1 else []), 4)
+            if rng.random() < 0.3:
+                base_mv = base_mv + rng.integers(-30, 31, 2)
+            for l in range(lists):
+                p8 = part8.get(mode, [0, 0, 0, 0])
+                n8 = max(p8) + 1
+                refs = rng.integers(1, 3, n8)
+                if lists == 2:                              # some partitions use one list only
+                    refs = np.where(rng.random(n8) < 0.25, -1, refs)
+                if mode == 5:
+                    refs[:] = 1
+                mvs8 = base_mv + rng.choice([0, 0, 1, -1, 12], (n8, 2))
+                for b8 in range(4):
+                    m["ref_idx"][l][b8] = refs[p8[b8]]
+                    p4 = part4[int(m["blk_mode"][b8])] if mode in (4, 5) else [0, 0, 0, 0]
+                    sub = mvs8[p8[b8]] + rng.choice([0, 0, 1, -1, 9], (max(p4) + 1, 2))
+                    for b4 in range(4):
+                        blk = ((b8 >> 1) * 2 + (b4 >> 1)) * 4 + (b8 & 1) * 2 + (b4 & 1)
+                        m["mv"][l][blk] = sub[p4[b4]] if refs[p8[b8]] > 0 else 0
+            if lists == 2 and (m["ref_idx"] < 1).all():     # a B macroblock predicts from at least one list
+                m["ref_idx"][0] = 1
+    return f
+
+
 def hierarchical_b_pairs(gop, refs=1):
     """(current, reference) picture pairs of one GOP, grouped by temporal level (coarsest first).
 

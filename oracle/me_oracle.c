@@ -964,3 +964,313 @@ int jsvm_ora_estimate_pictures(jsvm_ora_ctx* c, const jsvm_pic_task* tasks, int 
   }
   return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * f4  Residual upsampling for progressive layers: DownConvert::xCompResidualUpsampling, xDetermineTransBlkIdcs,
+ *     xBasicResidualUpsampling (COM/DownConvert.cpp:2733-2817, 2604-2650, 2867-2958).  Two full passes over an int image buffer,
+ *     as the reference does it (the product fuses them per output sample).
+ * ------------------------------------------------------------------------------------------- */
+static int ceil_log2(int i) { int s = 0; --i; while (i > 0) { ++s; i >>= 1; } return s; }
+static int xclip(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+static void upsample_residual_plane(const jsvm_resize_params* rp, int chroma, const int16_t* src, const uint8_t* t8x8, int16_t* dst) {
+  const int f = chroma ? 2 : 1;
+  const int ref_phase_x = chroma ? rp->ref_chroma_phase_x : 0, ref_phase_y = chroma ? rp->ref_chroma_phase_y : 0;
+  const int phase_x = chroma ? rp->chroma_phase_x : 0, phase_y = chroma ? rp->chroma_phase_y : 0;
+  const int base_w = rp->ref_frame_width / f, base_h = rp->ref_frame_height / f;
+  const int out_w = rp->scaled_ref_width / f, out_h = rp->scaled_ref_height / f;
+  const int cur_w = rp->frame_width / f, cur_h = rp->frame_height / f;
+  const int l_off = rp->left_offset / f, t_off = rp->top_offset / f, r_off = cur_w - l_off - out_w, b_off = cur_h - t_off - out_h;
+  const int shift_x = rp->level_idc <= 30 ? 16 : 31 - ceil_log2(base_w), shift_y = rp->level_idc <= 30 ? 16 : 31 - ceil_log2(base_h);
+  const int scale_x = (int)((((unsigned)base_w << shift_x) + (unsigned)(out_w >> 1)) / (unsigned)out_w);
+  const int scale_y = (int)((((unsigned)base_h << shift_y) + (unsigned)(out_h >> 1)) / (unsigned)out_h);
+  const int add_x = (((base_w * (2 + phase_x)) << (shift_x - 2)) + (out_w >> 1)) / out_w + (1 << (shift_x - 5));
+  const int add_y = (((base_h * (2 + phase_y)) << (shift_y - 2)) + (out_h >> 1)) / out_h + (1 << (shift_y - 5));
+  const int delta_x = 4 * (2 + ref_phase_x), delta_y = 4 * (2 + ref_phase_y);
+  const int mbs = chroma ? 8 : 16, mbw = rp->ref_frame_width / 16;
+  const int stride = cur_w > base_w ? cur_w : base_w, rows = cur_h > base_h ? cur_h : base_h;
+  int* img = (int*)calloc((size_t)stride * rows, sizeof(int));
+  int* idc = (int*)calloc((size_t)stride * rows, sizeof(int));
+  int* tmp = (int*)calloc((size_t)(stride > rows ? stride : rows), sizeof(int));
+  for (int y = 0; y < base_h; ++y)
+    for (int x = 0; x < base_w; ++x) {
+      img[y * stride + x] = src[(size_t)y * base_w + x];
+      const int mb = (y / mbs) * mbw + x / mbs, ix = x % mbs, iy = y % mbs;
+      idc[y * stride + x] = (!chroma && t8x8[mb]) ? ((((iy >> 3) << 1) + (ix >> 3) + (mb << 2)) << 1) + 1 : (((iy >> 2) << 2) + (ix >> 2) + (mb << 4)) << 1;
+    }
+  for (int j = 0; j < base_h; ++j) {                        /* horizontal pass */
+    int* ps = img + j * stride;
+    for (int i = 0; i < cur_w; ++i) {
+      if (i < l_off || i >= cur_w - r_off) { tmp[i] = 0; continue; }
+      const int p16 = (int)((unsigned)((i - l_off) * scale_x + add_x) >> (shift_x - 4)) - delta_x;
+      const int ph = p16 & 15, x0 = xclip(p16 >> 4, 0, base_w - 1), x1 = xclip((p16 >> 4) + 1, 0, base_w - 1);
+      tmp[i] = idc[j * stride + x0] == idc[j * stride + x1] ? (16 - ph) * ps[x0] + ph * ps[x1] : ps[ph < 8 ? x0 : x1] << 4;
+    }
+    memcpy(ps, tmp, (size_t)cur_w * sizeof(int));
+  }
+  for (int i = 0; i < cur_w; ++i) {                         /* vertical pass */
+    const int p16x = (int)((unsigned)((i - l_off) * scale_x + add_x) >> (shift_x - 4)) - delta_x;
+    const int xr = xclip((p16x >> 4) + ((p16x & 15) >> 3), 0, base_w - 1);
+    for (int j = 0; j < cur_h; ++j) {
+      if (i < l_off || i >= cur_w - r_off || j < t_off || j >= cur_h - b_off) { tmp[j] = 0; continue; }
+      const int pre = (j - t_off) * scale_y + add_y;
+      const int post = j >= t_off ? (int)((unsigned)pre >> (shift_y - 4)) : (pre >> (shift_y - 4));
+      const int p16 = post - delta_y, ph = p16 & 15, y0 = xclip(p16 >> 4, 0, base_h - 1), y1 = xclip((p16 >> 4) + 1, 0, base_h - 1);
+      tmp[j] = idc[y0 * stride + xr] == idc[y1 * stride + xr] ? ((16 - ph) * img[y0 * stride + i] + ph * img[y1 * stride + i] + 128) >> 8
+                                                              : (img[(ph < 8 ? y0 : y1) * stride + i] + 8) >> 4;
+    }
+    for (int j = 0; j < cur_h; ++j) dst[(size_t)j * cur_w + i] = (int16_t)tmp[j];
+  }
+  free(img); free(idc); free(tmp);
+}
+
+int jsvm_ora_upsample_residual(const jsvm_resize_params* rp, const int16_t* base_y, const int16_t* base_cb, const int16_t* base_cr,
+                               const uint8_t* base_transform8x8, int16_t* out_y, int16_t* out_cb, int16_t* out_cr) {
+  if (!rp || !base_y || !out_y || !base_transform8x8) return -1;
+  upsample_residual_plane(rp, 0, base_y, base_transform8x8, out_y);
+  if (base_cb && base_cr && out_cb && out_cr) {
+    upsample_residual_plane(rp, 1, base_cb, base_transform8x8, out_cb);
+    upsample_residual_plane(rp, 1, base_cr, base_transform8x8, out_cr);
+  }
+  return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * f4  Inter-layer motion prediction for progressive layers: MbDataCtrl::upsampleMotion -> MotionUpsampling::resample
+ *     (COM/MbDataCtrl.cpp:1115-1140, 122-150) with xInitMb :152-195, xIsInCropWindow :197-208, xGetRefLayerMb :211-288 (G.6.1),
+ *     xGetRefLayerPartIdc :290-365 (G.6.2), xSetPartIdcArray :368-473 (G.8.6.1.1), xGetInitialBaseRefIdxAndMv :476-548,
+ *     xGetRefIdxAndInitialMvPred :561-625, xDeriveBlockModeAndUpdateMv :636-723 (G.8.6.1.2), xDeriveMbMode :737-759,
+ *     xDeriveFwdBwd :762-773, xSetInterIntraIdc :776-798, xSetResPredSafeFlag :801-859, xSetPredMbData :862-945;
+ *     PosCalcParam / MvScaleParam :14-84.  Frame macroblocks only, no cropping change per picture, no coefficient prediction.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const jsvm_motion_upsample_params* p; const jsvm_mb_motion* base;
+  int rs_change, ref_w, ref_h, shift_x, shift_y, scale_x, scale_y, add_x, add_y;       /* PosCalcParam */
+  int mv_scale_x, mv_scale_y;                                                          /* MvScaleParam */
+  int max_list;
+  int mbx, mby;
+} mu_ctx;
+
+static int mu_spatial_change(const jsvm_resize_params* r) {          /* getSpatialResolutionChangeFlag, progressive */
+  if (r->left_offset % 16 || r->top_offset % 16) return 1;
+  if (r->ref_frame_width != r->scaled_ref_width || r->ref_frame_height != r->scaled_ref_height) return 1;
+  if (r->ref_chroma_phase_x != r->chroma_phase_x || r->ref_chroma_phase_y != r->chroma_phase_y) return 1;
+  return 0;
+}
+static int mu_restricted_change(const jsvm_resize_params* r) {       /* getRestrictedSpatialResolutionChangeFlag */
+  if (!mu_spatial_change(r)) return 1;
+  if (r->left_offset % 16 || r->top_offset % 16) return 0;
+  if (!(r->ref_frame_height == r->scaled_ref_height || 2 * r->ref_frame_height == r->scaled_ref_height)) return 0;
+  if (!(r->ref_frame_width == r->scaled_ref_width || 2 * r->ref_frame_width == r->scaled_ref_width)) return 0;
+  return 1;
+}
+
+/* G.6.1 + G.6.2: partition indication ( base macroblock index << 4 | 4x4 block of the partition's first block ), -1 = intra */
+static int mu_part_idc(const mu_ctx* m, int x_in_mb, int y_in_mb) {
+  const int cx = (m->mbx << 4) + x_in_mb, cy = (m->mby << 4) + y_in_mb;
+  int bx = (int)((unsigned)(cx * m->scale_x + m->add_x) >> m->shift_x), by = (int)((unsigned)(cy * m->scale_y + m->add_y) >> m->shift_y);
+  bx = imin(bx, m->ref_w - 1); by = imin(by, m->ref_h - 1);
+  const int mb_idx = (by >> 4) * (m->ref_w >> 4) + (bx >> 4), xi = bx & 15, yi = by & 15;
+  const jsvm_mb_motion* b = &m->base[mb_idx];
+  if (b->mb_mode >= 6) return -1;
+  const int b8 = ((yi >> 3) << 1) + (xi >> 3), b4 = (((yi & 7) >> 2) << 1) + ((xi & 7) >> 2);
+  static const uint8_t nxn[6][4] = { {0,0,0,0}, {0,0,0,0}, {0,0,2,2}, {0,1,0,1}, {0,1,2,3}, {0,1,2,3} };
+  int part8 = 0, part4 = 0;
+  if (b->mb_mode == 0 && b->slice_type == 1) {                          /* B_Skip / B_Direct_16x16 */
+    if (m->p->ref_layer_dq_id == 0) { part8 = b8; part4 = b4; }
+  } else {
+    part8 = nxn[b->mb_mode][b8];
+    if (b->mb_mode == 4 || b->mb_mode == 5) {
+      const int bm = b->blk_mode[b8];
+      if (bm == 0) { if (m->p->ref_layer_dq_id == 0) part4 = b4; }
+      else part4 = nxn[bm - 8 + 1][b4];
+    }
+  }
+  const int x4 = ((part8 & 1) << 1) + (part4 & 1), y4 = ((part8 >> 1) << 1) + (part4 >> 1);
+  return (mb_idx << 4) + (y4 << 2) + x4;
+}
+
+static int mu_min_ref(int a, int b) { return a < 1 ? b : (b < 1 ? a : imin(a, b)); }
+static int mu_mv_diff(jsvm_mv a, jsvm_mv b) { return abs(a.hor - b.hor) + abs(a.ver - b.ver); }
+static jsvm_mv mu_avg(const jsvm_mv* v, int n) {          /* ( a + b [+ c + d] + Mv( n/2, n/2 ) ) >> log2 n on Shorts */
+  int h = n / 2, w = n / 2;
+  for (int i = 0; i < n; ++i) { h = (int16_t)(h + v[i].hor); w = (int16_t)(w + v[i].ver); }
+  jsvm_mv r; r.hor = (int16_t)(h >> (n == 4 ? 2 : 1)); r.ver = (int16_t)(w >> (n == 4 ? 2 : 1));
+  return r;
+}
+
+static void mu_resample_mb(mu_ctx* m, jsvm_mb_motion* o) {
+  const jsvm_resize_params* r = &m->p->resize;
+  memset(o, 0, sizeof(*o));
+  for (int k = 0; k < 4; ++k) o->blk_mode[k] = 8;
+  memset(o->ref_idx, -1, sizeof(o->ref_idx));
+  /* xIsInCropWindow */
+  const int x0 = (r->left_offset + 15) / 16, y0 = (r->top_offset + 15) / 16;
+  const int x1 = (r->left_offset + r->scaled_ref_width) / 16, y1 = (r->top_offset + r->scaled_ref_height) / 16;
+  const int in_crop = m->mbx >= x0 && m->mbx < x1 && m->mby >= y0 && m->mby < y1;
+  o->in_crop_window = (uint8_t)in_crop;
+  o->res_pred_safe = (uint8_t)in_crop;
+  if (!in_crop) return;
+  int idc[4][4];                                                /* [x][y] */
+  int intra_bl = 1;
+  for (int y = 0; y < 4; ++y)
+    for (int x = 0; x < 4; ++x) { idc[x][y] = mu_part_idc(m, (x << 2) + 1, (y << 2) + 1); intra_bl = intra_bl && idc[x][y] == -1; }
+  if (intra_bl) { o->mb_mode = 36; }
+  else {
+    if (!m->rs_change) {
+      for (int yp = 0; yp < 2; ++yp)                            /* replace -1 on a 4x4 basis */
+        for (int xp = 0; xp < 2; ++xp) {
+          int proc[2][2] = { {0, 0}, {0, 0} };
+          for (int ys = 0; ys < 2; ++ys)
+            for (int xs = 0; xs < 2; ++xs) {
+              const int yc = (yp << 1) + ys, xc = (xp << 1) + xs;
+              if (idc[xc][yc] != -1) continue;
+              const int yi = 1 - ys, xi = 1 - xs, yci = (yp << 1) + yi, xci = (xp << 1) + xi;
+              proc[xs][ys] = 1;
+              if (!proc[xi][ys] && idc[xci][yc] != -1) idc[xc][yc] = idc[xci][yc];
+              else if (!proc[xs][yi] && idc[xc][yci] != -1) idc[xc][yc] = idc[xc][yci];
+              else if (!proc[xi][yi] && idc[xci][yci] != -1) idc[xc][yc] = idc[xci][yci];
+            }
+        }
+      int proc8[2][2] = { {0, 0}, {0, 0} };                     /* replace -1 on an 8x8 basis */
+      for (int yp = 0; yp < 2; ++yp)
+        for (int xp = 0; xp < 2; ++xp) {
+          const int ypi = 1 - yp, xpi = 1 - xp, yo = yp << 1, xo = xp << 1, yoi = 2 - yp, xoi = 2 - xp;
+          if (idc[xo][yo] != -1) continue;
+          proc8[xp][yp] = 1;
+          if (!proc8[xpi][yp] && idc[xoi][yo] != -1) {
+            idc[xo][yo] = idc[xoi][yo]; idc[xo + 1][yo] = idc[xoi][yo]; idc[xo][yo + 1] = idc[xoi][yo + 1]; idc[xo + 1][yo + 1] = idc[xoi][yo + 1];
+          } else if (!proc8[xp][ypi] && idc[xo][yoi] != -1) {
+            idc[xo][yo] = idc[xo][yoi]; idc[xo + 1][yo] = idc[xo + 1][yoi]; idc[xo][yo + 1] = idc[xo][yoi]; idc[xo + 1][yo + 1] = idc[xo + 1][yoi];
+          } else if (!proc8[xpi][ypi] && idc[xoi][yoi] != -1) {
+            idc[xo][yo] = idc[xo + 1][yo] = idc[xo][yo + 1] = idc[xo + 1][yo + 1] = idc[xoi][yoi];
+          }
+        }
+    }
+    int ref8[2][2][2];                                          /* [list][x][y] */
+    jsvm_mv mv[2][4][4];                                        /* [list][x][y] */
+    memset(mv, 0, sizeof(mv));
+    for (int l = 0; l < 2; ++l) for (int x = 0; x < 2; ++x) for (int y = 0; y < 2; ++y) ref8[l][x][y] = -1;
+    for (int l = 0; l < m->max_list; ++l) {
+      int rtmp[4][4];
+      for (int y = 0; y < 4; ++y)
+        for (int x = 0; x < 4; ++x) {
+          const jsvm_mb_motion* b = &m->base[idc[x][y] >> 4];
+          const int b4 = idc[x][y] & 15, rb = b->ref_idx[l][((b4 >> 3) << 1) | ((b4 & 3) >> 1)];
+          if (rb < 1) { rtmp[x][y] = -1; mv[l][x][y].hor = mv[l][x][y].ver = 0; continue; }
+          rtmp[x][y] = rb;
+          mv[l][x][y].hor = (int16_t)((b->mv[l][b4].hor * m->mv_scale_x + 32768) >> 16);
+          mv[l][x][y].ver = (int16_t)((b->mv[l][b4].ver * m->mv_scale_y + 32768) >> 16);
+        }
+      ref8[l][0][0] = rtmp[0][0]; ref8[l][0][1] = rtmp[0][2]; ref8[l][1][0] = rtmp[2][0]; ref8[l][1][1] = rtmp[2][2];
+      if (m->rs_change) continue;
+      for (int y8 = 0; y8 < 2; ++y8)
+        for (int x8 = 0; x8 < 2; ++x8) {
+          for (int y4 = 0; y4 < 2; ++y4)
+            for (int x4 = 0; x4 < 2; ++x4) ref8[l][x8][y8] = mu_min_ref(ref8[l][x8][y8], rtmp[(x8 << 1) + x4][(y8 << 1) + y4]);
+          for (int ys = 0; ys < 2; ++ys)
+            for (int xs = 0; xs < 2; ++xs) {
+              const int y = (y8 << 1) + ys, x = (x8 << 1) + xs;
+              if (ref8[l][x8][y8] == rtmp[x][y]) continue;
+              const int yi = (y8 << 1) + 1 - ys, xi = (x8 << 1) + 1 - xs;
+              if (ref8[l][x8][y8] == rtmp[xi][y]) mv[l][x][y] = mv[l][xi][y];
+              else if (ref8[l][x8][y8] == rtmp[x][yi]) mv[l][x][y] = mv[l][x][yi];
+              else mv[l][x][y] = mv[l][xi][yi];
+            }
+        }
+    }
+    for (int b8 = 0; b8 < 4; ++b8) {                            /* xDeriveBlockModeAndUpdateMv */
+      const int thr = m->rs_change ? 0 : 1, xo = (b8 & 1) << 1, yo = (b8 >> 1) << 1;
+      int hor = 1, ver = 1, all = 1;
+      if (m->p->direct_8x8_inference && !m->rs_change && m->p->slice_type == 1) {
+        const int xc = (xo >> 1) * 3, yc = (yo >> 1) * 3;
+        for (int l = 0; l < m->max_list; ++l) {
+          const jsvm_mv t = mv[l][xc][yc];
+          mv[l][xo][yo] = mv[l][xo + 1][yo] = mv[l][xo][yo + 1] = mv[l][xo + 1][yo + 1] = t;
+        }
+      }
+      for (int l = 0; l < m->max_list; ++l) {
+        const int h1 = mu_mv_diff(mv[l][xo][yo], mv[l][xo + 1][yo]) <= thr, h2 = mu_mv_diff(mv[l][xo][yo + 1], mv[l][xo + 1][yo + 1]) <= thr;
+        const int v1 = mu_mv_diff(mv[l][xo][yo], mv[l][xo][yo + 1]) <= thr, v2 = mu_mv_diff(mv[l][xo + 1][yo], mv[l][xo + 1][yo + 1]) <= thr;
+        const int dg = mu_mv_diff(mv[l][xo][yo], mv[l][xo + 1][yo + 1]) <= thr;
+        all = all && h1 && v1 && dg; hor = hor && h1 && h2; ver = ver && v1 && v2;
+      }
+      const int bm = all ? 8 : hor ? 9 : ver ? 10 : 11;
+      o->blk_mode[b8] = (uint8_t)bm;
+      if (m->rs_change || bm == 11) continue;
+      for (int l = 0; l < m->max_list; ++l) {
+        if (bm == 8) {
+          jsvm_mv v[4] = { mv[l][xo][yo], mv[l][xo + 1][yo], mv[l][xo][yo + 1], mv[l][xo + 1][yo + 1] };
+          mv[l][xo][yo] = mv[l][xo + 1][yo] = mv[l][xo][yo + 1] = mv[l][xo + 1][yo + 1] = mu_avg(v, 4);
+        } else if (bm == 9) {
+          jsvm_mv a[2] = { mv[l][xo][yo], mv[l][xo + 1][yo] }, b[2] = { mv[l][xo][yo + 1], mv[l][xo + 1][yo + 1] };
+          mv[l][xo][yo] = mv[l][xo + 1][yo] = mu_avg(a, 2); mv[l][xo][yo + 1] = mv[l][xo + 1][yo + 1] = mu_avg(b, 2);
+        } else {
+          jsvm_mv a[2] = { mv[l][xo][yo], mv[l][xo][yo + 1] }, b[2] = { mv[l][xo + 1][yo], mv[l][xo + 1][yo + 1] };
+          mv[l][xo][yo] = mv[l][xo][yo + 1] = mu_avg(a, 2); mv[l][xo + 1][yo] = mv[l][xo + 1][yo + 1] = mu_avg(b, 2);
+        }
+      }
+    }
+    int mode = 4;                                               /* xDeriveMbMode */
+    if (o->blk_mode[0] == 8 && o->blk_mode[1] == 8 && o->blk_mode[2] == 8 && o->blk_mode[3] == 8) {
+      int hm = 1, vm = 1;
+#define SAME8(l, a, b) (ref8[l][(a) & 1][(a) >> 1] == ref8[l][(b) & 1][(b) >> 1] && \
+                        mv[l][((a) & 1) << 1][((a) >> 1) << 1].hor == mv[l][((b) & 1) << 1][((b) >> 1) << 1].hor && \
+                        mv[l][((a) & 1) << 1][((a) >> 1) << 1].ver == mv[l][((b) & 1) << 1][((b) >> 1) << 1].ver)
+      for (int l = 0; l < m->max_list; ++l) { hm = hm && SAME8(l, 0, 1) && SAME8(l, 2, 3); vm = vm && SAME8(l, 0, 2) && SAME8(l, 1, 3); }
+#undef SAME8
+      static const uint8_t modes[4] = { 4, 2, 3, 1 };
+      mode = modes[(vm ? 2 : 0) + (hm ? 1 : 0)];
+    }
+    o->mb_mode = (uint8_t)mode;
+    unsigned fb = 0;                                            /* xDeriveFwdBwd */
+    for (int n = 3; n >= 0; --n) { fb <<= 4; fb += ref8[0][n & 1][n >> 1] > 0 ? 1 : 0; fb += ref8[1][n & 1][n >> 1] > 0 ? 2 : 0; }
+    o->fwd_bwd = (uint16_t)fb;
+    if (!m->rs_change)                                          /* xSetInterIntraIdc */
+      for (int y = 0; y < 2; ++y) for (int x = 0; x < 2; ++x) if (mu_part_idc(m, x * 15, y * 15) == -1) o->base_intra |= (uint8_t)(1 << (x + 2 * y));
+    for (int l = 0; l < m->max_list; ++l) {                     /* xSetPredMbData */
+      for (int b8 = 0; b8 < 4; ++b8) o->ref_idx[l][b8] = (int8_t)ref8[l][b8 & 1][b8 >> 1];
+      for (int b4 = 0; b4 < 16; ++b4) o->mv[l][b4] = mv[l][b4 & 3][b4 >> 2];
+    }
+  }
+  /* xSetResPredSafeFlag */
+  if (m->p->check_residual_pred && !m->rs_change) {
+    int safe = 1;
+    for (int y = 0; y < 4 && safe; ++y)
+      for (int x = 0; x < 4 && safe; ++x) {
+        int pi[4], same = 1, nointer = 0;
+        for (int k = 0; k < 4; ++k) { pi[k] = mu_part_idc(m, (x << 2) + 3 * (k & 1), (y << 2) + 3 * (k >> 1)); same = same && pi[k] == pi[0]; nointer = nointer || pi[k] < 0; }
+        if (same || nointer) { safe = nointer; continue; }
+        for (int l = 0; l < 2 && safe; ++l) {
+          int rf[4]; jsvm_mv v[4];
+          for (int k = 0; k < 4; ++k) {
+            const jsvm_mb_motion* b = &m->base[pi[k] >> 4]; const int b4 = pi[k] & 15;
+            rf[k] = b->ref_idx[l][((b4 >> 3) << 1) | ((b4 & 3) >> 1)]; v[k] = b->mv[l][b4];
+          }
+          for (int k = 0; k < 4 && safe; ++k) safe = rf[k] == rf[0];
+          if (safe) { const jsvm_mv avg = mu_avg(v, 4); for (int k = 0; k < 4 && safe; ++k) safe = mu_mv_diff(v[k], avg) <= m->p->mv_threshold; }
+        }
+      }
+    o->res_pred_safe = (uint8_t)safe;
+  }
+}
+
+int jsvm_ora_upsample_motion(const jsvm_motion_upsample_params* p, const jsvm_mb_motion* base, jsvm_mb_motion* out) {
+  if (!p || !base || !out) return -1;
+  const jsvm_resize_params* r = &p->resize;
+  mu_ctx m;
+  m.p = p; m.base = base;
+  m.rs_change = mu_restricted_change(r);
+  m.ref_w = r->ref_frame_width; m.ref_h = r->ref_frame_height;
+  m.shift_x = r->level_idc <= 30 ? 16 : 31 - ceil_log2(m.ref_w); m.shift_y = r->level_idc <= 30 ? 16 : 31 - ceil_log2(m.ref_h);
+  m.scale_x = (int)((((unsigned)m.ref_w << m.shift_x) + (unsigned)(r->scaled_ref_width >> 1)) / (unsigned)r->scaled_ref_width);
+  m.scale_y = (int)((((unsigned)m.ref_h << m.shift_y) + (unsigned)(r->scaled_ref_height >> 1)) / (unsigned)r->scaled_ref_height);
+  m.add_x = (1 << (m.shift_x - 1)) - r->left_offset * m.scale_x; m.add_y = (1 << (m.shift_y - 1)) - r->top_offset * m.scale_y;
+  m.mv_scale_x = (int)((((uint64_t)r->scaled_ref_width << 16) + (uint64_t)(m.ref_w >> 1)) / (uint64_t)m.ref_w);
+  m.mv_scale_y = (int)((((uint64_t)r->scaled_ref_height << 16) + (uint64_t)(m.ref_h >> 1)) / (uint64_t)m.ref_h);
+  m.max_list = p->slice_type == 1 ? 2 : (p->slice_type == 2 ? 0 : 1);
+  const int mbw = r->frame_width >> 4, mbh = r->frame_height >> 4;
+  for (m.mby = 0; m.mby < mbh; ++m.mby)
+    for (m.mbx = 0; m.mbx < mbw; ++m.mbx) mu_resample_mb(&m, &out[m.mby * mbw + m.mbx]);
+  return 0;
+}

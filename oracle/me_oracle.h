@@ -53,6 +53,13 @@ int jsvm_ora_set_mv_candidates(jsvm_ora_ctx* ctx, const jsvm_mv* abc, int n_jobs
 /* picture-level motion search (MV prediction + per-macroblock loops), see jsvm_me_estimate_pictures */
 int jsvm_ora_estimate_pictures(jsvm_ora_ctx* ctx, const jsvm_pic_task* tasks, int n_pics, jsvm_pic_mb* out);
 
+/* residual upsampling of progressive layers (DownConvert::xResidualUpsampling), see jsvm_me_upsample_residual */
+int jsvm_ora_upsample_residual(const jsvm_resize_params* params, const int16_t* base_y, const int16_t* base_cb, const int16_t* base_cr,
+                               const uint8_t* base_transform8x8, int16_t* out_y, int16_t* out_cb, int16_t* out_cr);
+
+/* inter-layer motion prediction of progressive layers (MbDataCtrl::upsampleMotion), see jsvm_me_upsample_motion */
+int jsvm_ora_upsample_motion(const jsvm_motion_upsample_params* params, const jsvm_mb_motion* base, jsvm_mb_motion* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,8 @@
 #include "H264AVCCommonLib/SliceHeader.h"
 #include "H264AVCCommonLib/SequenceParameterSet.h"
 #include "H264AVCCommonLib/PictureParameterSet.h"
+#include "DownConvert.h"
+#include "ResizeParameters.h"
 #include "MotionEstimation.h"
 #include "MotionEstimationQuarterPel.h"
 #include "RateDistortion.h"
@@ -585,4 +587,127 @@ extern "C" int jsvm_ref_estimate_pictures(jsvm_ref_ctx* c, const jsvm_pic_task* 
     ctrl.uninit();
   }
   return 0;
+}
+
+// Frame::residualUpsampling (DownConvert::xResidualUpsampling) on caller-supplied dense planes, progressive layers.
+namespace {
+void fillResizeParameters(ResizeParameters& rp, const jsvm_resize_params& p) {
+  rp.m_iExtendedSpatialScalability = ESS_SEQ;
+  rp.m_iLevelIdc = p.level_idc;
+  rp.m_bFrameMbsOnlyFlag = true; rp.m_bFieldPicFlag = false; rp.m_bBotFieldFlag = false; rp.m_bIsMbAffFrame = false;
+  rp.m_iFrameWidth = p.frame_width; rp.m_iFrameHeight = p.frame_height;
+  rp.m_iWidthInSamples = p.frame_width; rp.m_iHeightInSamples = p.frame_height;
+  rp.m_iChromaPhaseX = p.chroma_phase_x; rp.m_iChromaPhaseY = p.chroma_phase_y;
+  rp.m_iScaledRefFrmWidth = p.scaled_ref_width; rp.m_iScaledRefFrmHeight = p.scaled_ref_height;
+  rp.m_iLeftFrmOffset = p.left_offset; rp.m_iTopFrmOffset = p.top_offset;
+  rp.m_iRefLayerChromaPhaseX = p.ref_chroma_phase_x; rp.m_iRefLayerChromaPhaseY = p.ref_chroma_phase_y;
+  rp.m_bRefLayerFrameMbsOnlyFlag = true; rp.m_bRefLayerFieldPicFlag = false; rp.m_bRefLayerBotFieldFlag = false; rp.m_bRefLayerIsMbAffFrame = false;
+  rp.m_iRefLayerFrmWidth = p.ref_frame_width; rp.m_iRefLayerFrmHeight = p.ref_frame_height;
+  rp.m_iRefLayerWidthInSamples = p.ref_frame_width; rp.m_iRefLayerHeightInSamples = p.ref_frame_height;
+}
+struct LayerBuffers {          // a Frame of one layer size with its own buffer control
+  YuvBufferCtrl* ctrl; Frame* frame;
+  LayerBuffers() : ctrl(0), frame(0) {}
+  int init(int w, int h) {
+    if (YuvBufferCtrl::create(ctrl) != Err::m_nOK || ctrl->initSPS(h, w, YUV_Y_MARGIN, YUV_X_MARGIN) != Err::m_nOK) return -1;
+    frame = new Frame(*ctrl, *ctrl, FRAME, 0);
+    return frame->init() == Err::m_nOK ? 0 : -1;
+  }
+  ~LayerBuffers() { if (frame) { frame->uninit(); delete frame; } if (ctrl) { ctrl->uninit(); ctrl->destroy(); } }
+};
+}  // namespace
+
+extern "C" int jsvm_ref_upsample_residual(const jsvm_resize_params* p, const int16_t* base_y, const int16_t* base_cb, const int16_t* base_cr,
+                                          const uint8_t* base_transform8x8, int16_t* out_y, int16_t* out_cb, int16_t* out_cr) {
+  ResizeParameters rp;
+  fillResizeParameters(rp, *p);
+  LayerBuffers base, cur;
+  if (base.init(p->ref_frame_width, p->ref_frame_height) || cur.init(p->frame_width, p->frame_height)) return -1;
+  // base-layer macroblock data: only the transform size is read (xDetermineTransBlkIdcs)
+  SequenceParameterSet* sps = 0;
+  CHKI(SequenceParameterSet::create(sps));
+  sps->setFrameWidthInMbs(p->ref_frame_width >> 4); sps->setFrameHeightInMbs(p->ref_frame_height >> 4);
+  MbDataCtrl ctrl;
+  CHKI(ctrl.init(*sps));
+  const int n_mb = (p->ref_frame_width >> 4) * (p->ref_frame_height >> 4);
+  for (int i = 0; i < n_mb; ++i) ctrl.getMbDataByIndex(i).setTransformSize8x8(base_transform8x8[i] != 0);
+  base.ctrl->initMb(); cur.ctrl->initMb();
+  YuvPicBuffer* bb = base.frame->getFullPelYuvBuffer();
+  const bool chroma = base_cb && base_cr && out_cb && out_cr;
+  for (int y = 0; y < p->ref_frame_height; ++y)
+    for (int x = 0; x < p->ref_frame_width; ++x) bb->getMbLumAddr()[y * bb->getLStride() + x] = base_y[(size_t)y * p->ref_frame_width + x];
+  for (int y = 0; y < p->ref_frame_height / 2; ++y)
+    for (int x = 0; x < p->ref_frame_width / 2; ++x) {
+      bb->getMbCbAddr()[y * bb->getCStride() + x] = chroma ? base_cb[(size_t)y * (p->ref_frame_width / 2) + x] : 0;
+      bb->getMbCrAddr()[y * bb->getCStride() + x] = chroma ? base_cr[(size_t)y * (p->ref_frame_width / 2) + x] : 0;
+    }
+  DownConvert dc;
+  dc.init(p->frame_width > p->ref_frame_width ? p->frame_width : p->ref_frame_width, p->frame_height > p->ref_frame_height ? p->frame_height : p->ref_frame_height, 16);
+  CHKI(cur.frame->residualUpsampling(base.frame, dc, &rp, &ctrl));
+  cur.ctrl->initMb();
+  YuvPicBuffer* cb = cur.frame->getFullPelYuvBuffer();
+  for (int y = 0; y < p->frame_height; ++y)
+    for (int x = 0; x < p->frame_width; ++x) out_y[(size_t)y * p->frame_width + x] = cb->getMbLumAddr()[y * cb->getLStride() + x];
+  if (chroma)
+    for (int y = 0; y < p->frame_height / 2; ++y)
+      for (int x = 0; x < p->frame_width / 2; ++x) {
+        out_cb[(size_t)y * (p->frame_width / 2) + x] = cb->getMbCbAddr()[y * cb->getCStride() + x];
+        out_cr[(size_t)y * (p->frame_width / 2) + x] = cb->getMbCrAddr()[y * cb->getCStride() + x];
+      }
+  ctrl.uninit();
+  return 0;
+}
+
+// MbDataCtrl::upsampleMotion on caller-supplied base-layer motion, progressive layers.
+extern "C" int jsvm_ref_upsample_motion(const jsvm_motion_upsample_params* p, const jsvm_mb_motion* base, jsvm_mb_motion* out) {
+  ResizeParameters rp;
+  fillResizeParameters(rp, p->resize);
+  SequenceParameterSet* spsB = 0; SequenceParameterSet* spsC = 0; PictureParameterSet* pps = 0;
+  CHKI(SequenceParameterSet::create(spsB)); CHKI(SequenceParameterSet::create(spsC)); CHKI(PictureParameterSet::create(pps));
+  spsB->setFrameWidthInMbs(p->resize.ref_frame_width >> 4); spsB->setFrameHeightInMbs(p->resize.ref_frame_height >> 4);
+  spsC->setFrameWidthInMbs(p->resize.frame_width >> 4);     spsC->setFrameHeightInMbs(p->resize.frame_height >> 4);
+  spsC->setDirect8x8InferenceFlag(p->direct_8x8_inference != 0);
+  pps->setNumSliceGroupsMinus1(0);
+  int rc = 0;
+  {
+    SliceHeader sh(*spsC, *pps);
+    sh.setSliceType(SliceType(p->slice_type));
+    sh.setRefLayerDQId(p->ref_layer_dq_id);
+    sh.setSCoeffResidualPredFlag((ResizeParameters*)0);
+    sh.setTCoeffLevelPredictionFlag(false);
+    MbDataCtrl baseCtrl, curCtrl;
+    CHKI(baseCtrl.init(*spsB)); CHKI(curCtrl.init(*spsC));
+    const int nb = (p->resize.ref_frame_width >> 4) * (p->resize.ref_frame_height >> 4);
+    const int nc = (p->resize.frame_width >> 4) * (p->resize.frame_height >> 4);
+    static const ParIdx8x8 k8x8[4] = { PART_8x8_0, PART_8x8_1, PART_8x8_2, PART_8x8_3 };
+    for (int i = 0; i < nb; ++i) {
+      MbData& d = baseCtrl.getMbDataByIndex(i);
+      const jsvm_mb_motion& b = base[i];
+      d.initMbData(0, 0, 1, i, i, SliceType(b.slice_type));
+      d.setMbMode(MbMode(b.mb_mode));
+      for (int k = 0; k < 4; ++k) d.setBlkMode(Par8x8(k), BlkMode(b.blk_mode[k]));
+      for (int l = 0; l < 2; ++l) {
+        MbMotionData& mot = d.getMbMotionData(ListIdx(l));
+        for (int k = 0; k < 4; ++k) mot.setRefIdx(b.ref_idx[l][k], k8x8[k]);
+        for (int k = 0; k < 16; ++k) mot.setMv(Mv(b.mv[l][k].hor, b.mv[l][k].ver), B4x4Idx(k));
+      }
+    }
+    if (curCtrl.upsampleMotion(&sh, &rp, &baseCtrl, NULL, NULL, false, p->check_residual_pred != 0, p->mv_threshold) != Err::m_nOK) rc = -1;
+    for (int i = 0; i < nc && rc == 0; ++i) {
+      MbData& d = curCtrl.getMbDataByIndex(i);
+      jsvm_mb_motion& o = out[i];
+      memset(&o, 0, sizeof(o));
+      o.mb_mode = (uint8_t)d.getMbMode();
+      for (int k = 0; k < 4; ++k) o.blk_mode[k] = (uint8_t)d.getBlkMode(Par8x8(k));
+      o.in_crop_window = d.getInCropWindowFlag(); o.res_pred_safe = d.getSafeResPred(); o.fwd_bwd = d.getFwdBwd();
+      for (int k = 0; k < 4; ++k) if (d.isBaseIntra(k & 1, k >> 1)) o.base_intra |= (uint8_t)(1 << k);
+      for (int l = 0; l < 2; ++l) {
+        MbMotionData& mot = d.getMbMotionData(ListIdx(l));
+        for (int k = 0; k < 4; ++k) o.ref_idx[l][k] = mot.getRefIdx(k8x8[k]);
+        for (int k = 0; k < 16; ++k) { const Mv& m = mot.getMv(B4x4Idx(k)); o.mv[l][k].hor = m.getHor(); o.mv[l][k].ver = m.getVer(); }
+      }
+    }
+    baseCtrl.uninit(); curCtrl.uninit();
+  }
+  return rc;      // the parameter sets are leaked on purpose, see jsvm_ref_destroy
 }

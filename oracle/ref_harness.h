@@ -65,6 +65,13 @@ int jsvm_ref_set_mv_candidates(jsvm_ref_ctx* ctx, const jsvm_mv* abc, int n_jobs
 /* Picture-level motion search with the reference's MV prediction (see jsvm_me_estimate_pictures). */
 int jsvm_ref_estimate_pictures(jsvm_ref_ctx* ctx, const jsvm_pic_task* tasks, int n_pics, jsvm_pic_mb* out);
 
+/* Frame::residualUpsampling (DownConvert::xResidualUpsampling) on dense int16 planes; see jsvm_me_upsample_residual. */
+int jsvm_ref_upsample_residual(const jsvm_resize_params* params, const int16_t* base_y, const int16_t* base_cb, const int16_t* base_cr,
+                               const uint8_t* base_transform8x8, int16_t* out_y, int16_t* out_cb, int16_t* out_cr);
+
+/* MbDataCtrl::upsampleMotion on caller-supplied base-layer motion; see jsvm_me_upsample_motion. */
+int jsvm_ref_upsample_motion(const jsvm_motion_upsample_params* params, const jsvm_mb_motion* base, jsvm_mb_motion* out);
+
 #ifdef __cplusplus
 }
 #endif

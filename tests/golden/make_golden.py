@@ -215,7 +215,45 @@ def gen_pic(ref):
     print("picture_search_qcif", out.shape, "modes", np.bincount(out["mode"].ravel()))
 
 
-GROUPS = {"pic": gen_pic, "fast": gen_fast, "yuv": gen_yuv, "mc": gen_mc, "search": gen_search, "org": gen_org, "fullpel": gen_fullpel, "table": gen_table}
+def gen_resample(ref):
+    # residual upsampling (DownConvert::xResidualUpsampling): dyadic, level <= 30 arithmetic, ESS with cropping window, other phases
+    cases = [dict(ref_w=176, ref_h=144, cur_w=352, cur_h=288), dict(ref_w=176, ref_h=144, cur_w=352, cur_h=288, level_idc=30),
+             dict(ref_w=176, ref_h=144, cur_w=272, cur_h=224, scaled_w=264, scaled_h=216, left=4, top=6),
+             dict(ref_w=160, ref_h=128, cur_w=352, cur_h=288, scaled_w=300, scaled_h=250, left=32, top=16, phases=(0, 1, -1, -1))]
+    out = {}
+    for i, case in enumerate(cases):
+        p, y, cb, cr, t8 = synth.make_resize_case(seed=60 + i, **case)
+        oy, ocb, ocr = ref.upsample_residual(p, y, cb, cr, t8)
+        out.update({f"params{i}": np.array([getattr(p, n) for n, _ in p._fields_], np.int32), f"y{i}": y, f"cb{i}": cb, f"cr{i}": cr, f"t8_{i}": t8,
+                    f"oy{i}": oy, f"ocb{i}": ocb, f"ocr{i}": ocr})
+        print("residual upsampling", case, int(np.abs(oy).sum()))
+    np.savez_compressed(os.path.join(HERE, "residual_upsampling.npz"), n=len(cases), **out)
+
+
+MOTION_GOLDEN = [
+    (dict(ref_w=176, ref_h=144, cur_w=352, cur_h=288), 0, 0, 1), (dict(ref_w=176, ref_h=144, cur_w=352, cur_h=288), 1, 0, 1),
+    (dict(ref_w=176, ref_h=144, cur_w=352, cur_h=288), 1, 16, 0),
+    (dict(ref_w=176, ref_h=144, cur_w=272, cur_h=224, scaled_w=264, scaled_h=216, left=4, top=6), 1, 0, 1),
+    (dict(ref_w=160, ref_h=128, cur_w=352, cur_h=288, scaled_w=300, scaled_h=250, left=32, top=16, level_idc=30), 0, 0, 0),
+    (dict(ref_w=176, ref_h=144, cur_w=176, cur_h=144), 1, 0, 1),
+]
+
+
+def gen_motion(ref):
+    # inter-layer motion prediction (MbDataCtrl::upsampleMotion): dyadic P / B, ESS, arbitrary ratio, same resolution
+    out = {}
+    for i, (case, st, dq, d8) in enumerate(MOTION_GOLDEN):
+        resize = synth.make_resize_case(seed=1, **case)[0]
+        base = synth.make_base_motion(case["ref_w"], case["ref_h"], seed=70 + i, slice_type=st)
+        p = synth.make_motion_params(resize, st, dq, d8)
+        pred = ref.upsample_motion(p, base)
+        out.update({f"resize{i}": np.array([getattr(resize, n) for n, _ in resize._fields_], np.int32), f"switches{i}": np.array([st, dq, d8, 1, 1], np.int32),
+                    f"base{i}": base, f"pred{i}": pred})
+        print("motion upsampling", case, "modes", np.bincount(pred["mb_mode"].ravel()))
+    np.savez_compressed(os.path.join(HERE, "motion_upsampling.npz"), n=len(MOTION_GOLDEN), **out)
+
+
+GROUPS = {"motion": gen_motion, "resample": gen_resample, "pic": gen_pic, "fast": gen_fast, "yuv": gen_yuv, "mc": gen_mc, "search": gen_search, "org": gen_org, "fullpel": gen_fullpel, "table": gen_table}
 
 
 def main():

@@ -130,6 +130,25 @@ class CpuBackend:
             fn.restype, fn.argtypes = rt, at
             setattr(self, name, fn)
 
+    def upsample_residual(self, params, base_y, base_cb, base_cr, base_transform8x8):
+        by, bcb, bcr = [np.ascontiguousarray(a, np.int16) for a in (base_y, base_cb, base_cr)]
+        t8 = np.ascontiguousarray(base_transform8x8, np.uint8)
+        oy = np.zeros((params.frame_height, params.frame_width), np.int16)
+        ocb = np.zeros((params.frame_height // 2, params.frame_width // 2), np.int16)
+        ocr = np.zeros_like(ocb)
+        fn = getattr(self.lib, self.prefix + "upsample_residual")
+        fn.restype, fn.argtypes = C.c_int, [C.c_void_p] * 8
+        assert fn(C.addressof(params), by.ctypes.data, bcb.ctypes.data, bcr.ctypes.data, t8.ctypes.data, oy.ctypes.data, ocb.ctypes.data, ocr.ctypes.data) == 0
+        return oy, ocb, ocr
+
+    def upsample_motion(self, params, base):
+        base = np.ascontiguousarray(base, abi.MB_MOTION_DTYPE)
+        out = np.zeros((params.resize.frame_height // 16, params.resize.frame_width // 16), abi.MB_MOTION_DTYPE)
+        fn = getattr(self.lib, self.prefix + "upsample_motion")
+        fn.restype, fn.argtypes = C.c_int, [C.c_void_p] * 3
+        assert fn(C.addressof(params), base.ctypes.data, out.ctypes.data) == 0
+        return out
+
     def session(self, width, height, n_slots, search_range, sub_dfunc, full_dfunc=0, search_mode=0):
         return CpuSession(self, width, height, n_slots, search_range, sub_dfunc, full_dfunc, search_mode)
 

@@ -35,7 +35,7 @@ def load(name):
 
 
 def test_fixtures_present():
-    assert len(glob.glob(os.path.join(HERE, "golden", "*.npz"))) >= 28
+    assert len(glob.glob(os.path.join(HERE, "golden", "*.npz"))) >= 30
 
 
 @pytest.mark.parametrize("name", SEARCH_CASES + FAST_CASES)
@@ -79,6 +79,41 @@ def test_oracle_picture_search_matches_reference_golden(oracle):
     for f in out.dtype.names:
         assert np.array_equal(out[f], g["field"][f]), f
     assert len(np.unique(g["field"]["mode"])) == 4 and len(np.unique(g["field"]["part_ref"])) == 2
+
+
+def resize_params_from(abi, arr):
+    p = abi.ResizeParams()
+    for (n, _), v in zip(p._fields_, arr):
+        setattr(p, n, int(v))
+    return p
+
+
+def test_oracle_residual_upsampling_matches_reference_golden(oracle):
+    import oracle_lib
+    g = load("residual_upsampling")
+    for i in range(int(g["n"])):
+        p = resize_params_from(oracle_lib.abi, g[f"params{i}"])
+        oy, ocb, ocr = oracle.upsample_residual(p, g[f"y{i}"], g[f"cb{i}"], g[f"cr{i}"], g[f"t8_{i}"])
+        assert np.array_equal(oy, g[f"oy{i}"]) and np.array_equal(ocb, g[f"ocb{i}"]) and np.array_equal(ocr, g[f"ocr{i}"]), i
+
+
+def motion_case(synth, abi, g, i):
+    resize = resize_params_from(abi, g[f"resize{i}"])
+    st, dq, d8, chk, thr = [int(v) for v in g[f"switches{i}"]]
+    p = abi.MotionUpsampleParams()
+    import ctypes
+    ctypes.memmove(ctypes.addressof(p.resize), ctypes.addressof(resize), ctypes.sizeof(resize))
+    p.slice_type, p.ref_layer_dq_id, p.direct_8x8_inference, p.check_residual_pred, p.mv_threshold = st, dq, d8, chk, thr
+    return p
+
+
+def test_oracle_motion_upsampling_matches_reference_golden(oracle, synth):
+    import oracle_lib
+    g = load("motion_upsampling")
+    for i in range(int(g["n"])):
+        pred = oracle.upsample_motion(motion_case(synth, oracle_lib.abi, g, i), g[f"base{i}"])
+        for f in pred.dtype.names:
+            assert np.array_equal(pred[f], g[f"pred{i}"][f]), (i, f)
 
 
 def test_mc_golden_covers_all_phases_and_clamps():

@@ -144,3 +144,54 @@ def test_picture_level_search_identical(oracle, reference, synth, W, H, sr, n_re
         bad = np.argwhere(a[f] != b[f])
         assert len(bad) == 0, (f, len(bad), bad[0], a[tuple(bad[0][:3])], b[tuple(bad[0][:3])])
     assert len(np.unique(a["mode"])) >= 3 and (a["part_mv"] != 0).any()
+
+
+RESIZE_CASES = [
+    dict(ref_w=176, ref_h=144, cur_w=352, cur_h=288),                                               # dyadic QCIF -> CIF (C2)
+    dict(ref_w=176, ref_h=144, cur_w=352, cur_h=288, level_idc=30),                                 # 16-bit position arithmetic
+    dict(ref_w=176, ref_h=144, cur_w=272, cur_h=224, scaled_w=264, scaled_h=216, left=4, top=6),    # ESS ratio 3:2 with cropping window
+    dict(ref_w=160, ref_h=128, cur_w=352, cur_h=288, scaled_w=300, scaled_h=250, left=32, top=16, phases=(0, 1, -1, -1)),   # arbitrary ratio, other chroma phases
+    dict(ref_w=96, ref_h=80, cur_w=96, cur_h=80),                                                   # same resolution: identity
+]
+
+
+@pytest.mark.parametrize("case", RESIZE_CASES, ids=[str(i) for i in range(len(RESIZE_CASES))])
+def test_residual_upsampling_identical(oracle, reference, synth, case):
+    """f4: DownConvert::xResidualUpsampling of the C port against the reference's (luma with 4x4 / 8x8 transform blocks, chroma)."""
+    p, y, cb, cr, t8 = synth.make_resize_case(seed=len(str(case)), **case)
+    a = oracle.upsample_residual(p, y, cb, cr, t8)
+    if case["cur_w"] == case["ref_w"]:
+        # no resolution change and no cropping: DownConvert::residualUpsampling does nothing (COM/DownConvert.cpp:623-631, the caller
+        # uses the base residual as it is); the resampling arithmetic degenerates to the identity
+        assert np.array_equal(a[0], y) and np.array_equal(a[1], cb) and np.array_equal(a[2], cr)
+        return
+    b = reference.upsample_residual(p, y, cb, cr, t8)
+    for k, (u, v) in enumerate(zip(a, b)):
+        assert np.array_equal(u, v), (k, np.argwhere(u != v)[:3])
+    assert (a[0] != 0).any()
+
+
+MOTION_CASES = [
+    (dict(ref_w=176, ref_h=144, cur_w=352, cur_h=288), 0, 0, 1),                                             # dyadic, P
+    (dict(ref_w=176, ref_h=144, cur_w=352, cur_h=288), 1, 0, 1),                                             # dyadic, B
+    (dict(ref_w=176, ref_h=144, cur_w=352, cur_h=288), 1, 16, 0),                                            # B, ref layer DQId != 0, no 8x8 inference
+    (dict(ref_w=176, ref_h=144, cur_w=272, cur_h=224, scaled_w=264, scaled_h=216, left=4, top=6), 0, 0, 1),   # ESS 3:2 with cropping window
+    (dict(ref_w=176, ref_h=144, cur_w=272, cur_h=224, scaled_w=264, scaled_h=216, left=4, top=6), 1, 0, 1),
+    (dict(ref_w=160, ref_h=128, cur_w=352, cur_h=288, scaled_w=300, scaled_h=250, left=32, top=16, level_idc=30), 1, 0, 0),
+    (dict(ref_w=176, ref_h=144, cur_w=176, cur_h=144), 1, 0, 1),                                             # same resolution (quality layer)
+    (dict(ref_w=176, ref_h=144, cur_w=352, cur_h=288, scaled_w=352, scaled_h=288), 2, 0, 1),                 # I slice: no lists
+]
+
+
+@pytest.mark.parametrize("case,slice_type,dq,d8", MOTION_CASES, ids=[str(i) for i in range(len(MOTION_CASES))])
+def test_motion_upsampling_identical(oracle, reference, synth, case, slice_type, dq, d8):
+    """f4: MotionUpsampling::resample of the C port against MbDataCtrl::upsampleMotion (every output field of every macroblock)."""
+    resize = synth.make_resize_case(seed=1, **case)[0]
+    base = synth.make_base_motion(case["ref_w"], case["ref_h"], seed=len(str(case)) + slice_type, slice_type=min(slice_type, 1))
+    p = synth.make_motion_params(resize, slice_type, dq, d8)
+    a, b = oracle.upsample_motion(p, base), reference.upsample_motion(p, base)
+    for f in a.dtype.names:
+        bad = np.argwhere(a[f] != b[f])
+        assert len(bad) == 0, (f, len(bad), bad[0], a[tuple(bad[0][:2])], b[tuple(bad[0][:2])])
+    if slice_type < 2:
+        assert len(np.unique(a["mb_mode"])) >= 4 and (a["mv"] != 0).any()
