@@ -5,8 +5,9 @@ One "step" = one pass of the hot path over one batch: the top temporal level of 
 sequence at 1920x1088 (BASELINE.json configs[3]): 8 B pictures x 2 lists = 16 independent (current,
 reference) pairs per GPU -- K1 half-pel planes of the 9 reference pictures, K2 full search (SR +-64) and
 K3 quarter-pel refinement for all 8160 macroblocks x 9 partitions of every pair (1.17 M
-estimateBlockWithStart results per step per GPU).  Pairs shard across ranks (weak scaling, no data-path
-collective); for N > 1 the result field is gathered to rank 0 over NCCL inside the timed region.
+estimateBlockWithStart results per step per GPU).  The batch is ONE global list of pairs (N x 16 pairs = N GOPs for weak scaling,
+16 pairs in total with --scaling strong) dealt round-robin to the ranks by sharding.shard_pairs: no data-path collective; for N > 1
+the result field is gathered to rank 0 over NCCL by the library itself (jsvm_me_gather_results_device) inside the timed region.
 
 `value`   : pairs/s with planes, jobs and search groups already resident in HBM (CUDA events, max over ranks).
 `e2e`     : pairs/s through the host-buffer C ABI (jsvm_me_upload_plane_u8 / jsvm_me_search): pinned host
@@ -62,6 +63,8 @@ def parse_args():
     ap.add_argument("--field", default="random", choices=["zero", "random", "split"])
     ap.add_argument("--pairs", type=int, default=16, help="(current, reference) pairs per GPU per step")
     ap.add_argument("--cpu-sample-mbs", type=int, default=0, help="macroblocks in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --pairs per GPU (N GOPs); strong: --pairs in total")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short measurements of the other kernels (TZ, picture-level, MC, resampling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--parity-fraction", type=float, default=0.05, help="fraction of the macroblocks of a step that is re-computed by "
@@ -72,24 +75,33 @@ def parse_args():
 # ------------------------------------------------------------------------------------------------
 # workload
 # ------------------------------------------------------------------------------------------------
-def build_workload(synth, cfg, n_pairs, field, rank):
-    """Planes and jobs of the top temporal level: pictures 1,3,5,.. reference their even neighbours."""
+def global_pairs(n_pairs):
+    """The batch: pair g = (gop, current, reference).  Every GOP contributes the 16 pairs of its top temporal level: pictures
+    1, 3, .. 15 each referencing their two even neighbours."""
+    out = []
+    for g in range(n_pairs):
+        gop, k = divmod(g, 16)
+        c = 2 * (k // 2) + 1
+        out.append((gop, c, c - 1 if k % 2 == 0 else c + 1))
+    return out
+
+
+def pair_jobs(synth, cfg, g, cur_slot, ref_slot, field):
+    return synth.make_jobs(cfg["width"], cfg["height"], cfg["parts"], cur_slot, ref_slot, qp=35, field=field, seed=100 + g)   # QP of the top level (DQP4TLevel)
+
+
+def build_workload(synth, sharding, cfg, n_pairs_global, field, rank, world):
+    """Planes and jobs of this rank's share of the batch (round-robin whole pairs, sharding.shard_pairs)."""
     W, H = cfg["width"], cfg["height"]
-    seq = synth.Sequence(W, H, 1234 + 4 + 1000 * rank)
-    n_cur = (n_pairs + 1) // 2
-    pics = list(range(0, 2 * n_cur + 1))                      # 0 .. 2*n_cur ; even = references, odd = current
-    frames = {p: seq.frame(p) for p in pics}
-    slot_of = {p: i for i, p in enumerate(pics)}
-    pairs = []
-    for c in range(1, 2 * n_cur, 2):
-        pairs += [(c, c - 1), (c, c + 1)]
-    pairs = pairs[:n_pairs]
-    qp = 35                                                   # top temporal level (DQP4TLevel), SURVEY 8d
-    jobs = [synth.make_jobs(W, H, cfg["parts"], slot_of[c], slot_of[r], qp=qp, field=field, seed=100 * rank + i)
-            for i, (c, r) in enumerate(pairs)]
-    jobs = np.concatenate(jobs)
-    ref_slots = sorted({slot_of[r] for _, r in pairs})
-    return frames, slot_of, pairs, jobs, ref_slots
+    seq = synth.Sequence(W, H, 1234 + 4)
+    mine = sharding.shard_pairs(global_pairs(n_pairs_global), rank, world)
+    pics = sorted({(gop, p) for _, (gop, c, r) in mine for p in (c, r)})
+    frames = {k: seq.frame(k[1], gop=k[0]) for k in pics}
+    slot_of = {k: i for i, k in enumerate(pics)}
+    jobs = [pair_jobs(synth, cfg, g, slot_of[(gop, c)], slot_of[(gop, r)], field) for g, (gop, c, r) in mine]
+    jobs = np.concatenate(jobs) if jobs else np.zeros(0, synth.JOB_DTYPE)
+    ref_slots = sorted({slot_of[(gop, r)] for _, (gop, c, r) in mine})
+    return seq, frames, slot_of, mine, jobs, ref_slots
 
 
 # ------------------------------------------------------------------------------------------------
@@ -153,29 +165,43 @@ def cpu_baseline(synth, cfg, field, sample_mbs, steps=1):
                       f"{len(chunks)} processes x 1 thread, search time only"}, values, walls
 
 
-def parity_check(cfg, frames, slot_of, jobs, legs, fraction, seed=4242):
-    """Re-computes a seeded sample of the step's macroblocks (all their partitions) with the CPU checker -- the compiled unmodified
+def parity_check(synth, cfg, seq, field, legs, fraction, seed=4242):
+    """Re-computes a seeded sample of the batch's macroblocks (all their partitions) with the CPU checker -- the compiled unmodified
     reference when oracle/_ref is present, else the C restatement -- and compares every result field of every timed leg with it.
+    legs: {name: (global pair indices the leg covers, results in that pair order)} -- for N > 1 the gathered field of ALL ranks.
     Runs after the timed regions; the checker is never the thing measured."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     W, H = cfg["width"], cfg["height"]
     per_mb = len(cfg["parts"])
-    n_units = len(jobs) // per_mb                                  # (pair, macroblock) units, jobs are MB-major inside a pair
-    rng = np.random.default_rng(seed)
-    pick = np.sort(rng.choice(n_units, size=max(1, int(round(fraction * n_units))), replace=False))
-    idx = (pick[:, None] * per_mb + np.arange(per_mb)[None, :]).reshape(-1)
+    n_mb = (W // 16) * (H // 16)
+    per_pair = n_mb * per_mb
     path, prefix, kind = oracle_lib.best_checker(ROOT)
-    planes = {slot_of[p]: f for p, f in frames.items()}
-    want = oracle_lib.parallel_search(path, prefix, W, H, len(frames), cfg["search_range"], cfg["sub_dfunc"], planes, jobs[idx])
-    bad = {}
-    for name, got in legs.items():
-        g = got[idx]
-        n_bad = int(sum(np.count_nonzero(g[f] != want[f]) for f in want.dtype.names))
+    rng = np.random.default_rng(seed)
+    bad, n_jobs_checked, n_units = {}, 0, 0
+    for name, (pair_ids, got) in legs.items():
+        pairs = global_pairs(max(pair_ids) + 1)
+        units = len(pair_ids) * n_mb
+        pick = np.sort(rng.choice(units, size=max(1, int(round(fraction * units))), replace=False))
+        pics = sorted({(pairs[pair_ids[u // n_mb]][0], p) for u in pick for p in pairs[pair_ids[u // n_mb]][1:]})
+        slot = {k: i for i, k in enumerate(pics)}
+        planes = {slot[k]: seq.frame(k[1], gop=k[0]) for k in pics}
+        want_jobs, got_rows = [], []
+        for li in np.unique(pick // n_mb):
+            g = pair_ids[li]
+            gop, c, r = pairs[g]
+            jb = pair_jobs(synth, cfg, g, slot[(gop, c)], slot[(gop, r)], field)
+            mbs = pick[pick // n_mb == li] % n_mb
+            idx = (mbs[:, None] * per_mb + np.arange(per_mb)[None, :]).reshape(-1)
+            want_jobs.append(jb[idx]); got_rows.append(got[li * per_pair + idx])
+        want = oracle_lib.parallel_search(path, prefix, W, H, len(pics), cfg["search_range"], cfg["sub_dfunc"], planes, np.concatenate(want_jobs))
+        g_all = np.concatenate(got_rows)
+        n_bad = int(sum(np.count_nonzero(g_all[f] != want[f]) for f in want.dtype.names))
         if n_bad:
             bad[name] = n_bad
-    return {"jobs": int(len(idx)), "macroblocks": int(len(pick)), "fraction": float(len(pick) / n_units), "checker": kind,
-            "legs": sorted(legs), "fields": list(want.dtype.names), "mismatches": bad}
+        n_jobs_checked += len(g_all); n_units += len(pick)
+    return {"jobs": int(n_jobs_checked), "macroblocks": int(n_units), "fraction": float(fraction), "checker": kind,
+            "legs": sorted(legs), "fields": list(oracle_lib.RESULT_DTYPE.names), "mismatches": bad}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -240,6 +266,76 @@ def int32_peak():
     return INT32_PEAK_FALLBACK, "recorded (profiles/int32_peak_r01.json)"
 
 
+def measure_extras(pkg, synth, me, cfg, torch, dev, hbm_peak, peak):
+    """Short device-timed measurements of the kernels beside the headline path (K4 motion compensation, K5 TZ search, K6
+    picture-level search, K7 inter-layer resampling) at the same picture size; reported under `extras`, not part of `value`."""
+    W, H, sr = cfg["width"], cfg["height"], cfg["search_range"]
+    n_mb = (W // 16) * (H // 16)
+    out = {}
+    seq = synth.LocalMotionSequence(W, H, 99, tile=52)
+    n_slots = 10
+    me.configure(W, H, n_slots)
+    for s_ in range(n_slots):
+        me.upload_plane(s_, seq.frame(s_ % 5))
+        me.upload_chroma(s_, *synth.chroma_planes(W, H, 200 + s_ % 3))
+    me.interp_halfpel(list(range(n_slots)))
+
+    def timed(fn, reps=3):
+        fn(); me.sync()
+        me.timing_begin()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        me.sync()
+        dt = (time.perf_counter() - t0) / reps
+        kt = me.timing_end()
+        return dt, {k: v / reps for k, v in kt.items()}
+
+    # K6: picture-level search, 8 independent P pictures (a temporal level), one reference each
+    me.set_params(sr, cfg["sub_dfunc"])
+    tasks = synth.make_pic_tasks(list(range(1, 9)), [[p - 1] for p in range(1, 9)], qp=35)
+    dt, kt = timed(lambda: me.estimate_pictures(tasks, download=False), reps=2)
+    out["picture_level_search"] = {"pictures_per_s": len(tasks) / dt, "pictures_per_call": len(tasks), "refs": 1, "ms_per_call": dt * 1e3,
+                                   "k2_ms": kt["search_ms"], "k3_ms": kt["subpel_ms"],
+                                   "what": "jsvm_me_estimate_pictures: MV prediction + wavefront scheduling + planning on the device, 9 partitions x 8160 MBs per picture"}
+    # K5: TZ search with the shipped encoder.cfg switches (ELSearchRange 8, FastBiSearch 1) on 4 pairs
+    jobs = np.concatenate([synth.make_jobs(W, H, cfg["parts"], 2 * i + 1, 2 * i, qp=35, field="random", seed=300 + i) for i in range(4)])
+    jobs, cands = synth.make_fast_search_extras(jobs, sr, seed=5, p_el=0.0, p_bipred=0.0, p_iter=0.0)
+    d_jobs = torch.from_numpy(jobs.view(np.uint8)).to(dev)
+    d_cands = torch.from_numpy(cands.view(np.uint8).reshape(-1)).to(dev)
+    d_res = torch.zeros(len(jobs) * 32, dtype=torch.uint8, device=dev)
+    me.set_params(sr, cfg["sub_dfunc"], 0, 4)
+    me.set_fast_search_params(8, 1)
+    me._check(me._lib.jsvm_me_set_mv_candidates_device(me._ctx, d_cands.data_ptr()))
+    info = pkg.PlanInfo()
+    dt, kt = timed(lambda: me.search_device(d_jobs.data_ptr(), len(jobs), 0, info, d_res.data_ptr()))
+    out["tz_search"] = {"pairs_per_s": 4 / dt, "ms_per_pair": dt * 1e3 / 4, "k5_ms_per_pair": kt["search_ms"] / 4, "k3_ms_per_pair": kt["subpel_ms"] / 4,
+                        "kernel": me.last_search_kernel(), "what": "SearchMode 4 (xTZSearch), one warp per job, neighbour-MV candidates, resident inputs"}
+    me._check(me._lib.jsvm_me_set_mv_candidates_device(me._ctx, None))
+    me.set_fast_search_params(0, 0)
+    me.set_params(sr, cfg["sub_dfunc"])
+    # K4: bi-predictive 16x16 blocks with chroma, one job per macroblock of 8 pictures
+    mc = synth.make_mc_jobs(W, H, 8 * n_mb, n_slots, seed=3, kind="bi", sizes=((16, 16),))
+    dt, kt = timed(lambda: me.compensate(mc))
+    mc_bytes = len(mc) * (2 * (256 + 128) + 384 + 48)
+    out["motion_compensation"] = {"blocks_per_s": len(mc) / (kt["other_ms"] * 1e-3), "kernel_ms": kt["other_ms"], "call_ms": dt * 1e3,
+                                  "roofline": {"bound": "hbm", "achieved": mc_bytes / (kt["other_ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                               "frac": mc_bytes / (kt["other_ms"] * 1e-3) / 1e9 / hbm_peak, "alg_bytes_per_launch": mc_bytes},
+                                  "what": "jsvm_me_compensate: 16x16 bi-predictive luma + chroma blocks (predBlk / xPredChroma / xMixB)"}
+    # K7: residual upsampling half size -> full size (C5: 540p -> 1080p), luma + chroma; inter-layer motion prediction
+    rp, y, cb, cr, t8 = synth.make_resize_case(W // 2 // 16 * 16, H // 2 // 16 * 16, W, H, seed=2)
+    dt, kt = timed(lambda: me.upsample_residual(rp, y, cb, cr, t8))
+    rs_bytes = 2 * (y.size + cb.size + cr.size) + 2 * (W * H * 3 // 2)
+    out["residual_upsampling"] = {"frames_per_s_kernel": 1.0 / (kt["other_ms"] * 1e-3), "kernel_ms": kt["other_ms"], "call_ms_with_copies": dt * 1e3,
+                                  "roofline": {"bound": "hbm", "achieved": rs_bytes / (kt["other_ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                               "frac": rs_bytes / (kt["other_ms"] * 1e-3) / 1e9 / hbm_peak, "alg_bytes_per_launch": rs_bytes}}
+    base = synth.make_base_motion(rp.ref_frame_width, rp.ref_frame_height, seed=4, slice_type=1)
+    mp_ = synth.make_motion_params(rp, 1)
+    dt, kt = timed(lambda: me.upsample_motion(mp_, base))
+    out["motion_upsampling"] = {"frames_per_s_kernel": 1.0 / (kt["other_ms"] * 1e-3), "kernel_ms": kt["other_ms"], "call_ms_with_copies": dt * 1e3}
+    return out
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -248,7 +344,8 @@ def main():
     # (the reference arm never imports the package itself: its __init__ dlopens the CUDA library)
     synth = light_module("synth") if args.impl == "reference" else importlib.import_module(PKG + ".synth")
     cfg = synth.CONFIGS[args.config]
-    workload = f"{args.config}: {cfg['name']}, top temporal level of GOP 16, {args.pairs} (cur,ref) pairs/GPU/step, " \
+    per = "GPU" if args.scaling == "weak" else "step in total"
+    workload = f"{args.config}: {cfg['name']}, top temporal level of GOP 16, {args.pairs} (cur,ref) pairs/{per}/step, " \
                f"{len(cfg['parts'])} partitions/MB, start=pred field '{args.field}'"
     n_mb = (cfg["width"] // 16) * (cfg["height"] // 16)
     config = {"workload": workload, "jobs_per_step_per_gpu": args.pairs * n_mb * len(cfg["parts"])}      # the same dict in both arms
@@ -281,10 +378,15 @@ def main():
     stream = torch.cuda.current_stream()
 
     W, H = cfg["width"], cfg["height"]
-    frames, slot_of, pairs, jobs, ref_slots = build_workload(synth, cfg, args.pairs, args.field, rank)
+    sharding = importlib.import_module(PKG + ".sharding")
+    n_pairs_global = args.pairs * world if args.scaling == "weak" else args.pairs
+    seq, frames, slot_of, mine, jobs, ref_slots = build_workload(synth, sharding, cfg, n_pairs_global, args.field, rank, world)
     n_jobs = len(jobs)
+    per_pair = n_mb * len(cfg["parts"])
+    n_per_rank = np.array([sharding.pairs_of_rank(n_pairs_global, r, world) * per_pair for r in range(world)], np.int32)
+    n_max = int(n_per_rank.max())
     me = pkg.MotionEstimator(local_rank)
-    me.configure(W, H, len(frames))
+    me.configure(W, H, max(1, len(frames)))
     me.set_params(cfg["search_range"], cfg["sub_dfunc"])
     me.set_stream(stream.cuda_stream)
 
@@ -295,15 +397,22 @@ def main():
     groups, info = me.plan(jobs)
     d_jobs = torch.from_numpy(jobs.view(np.uint8)).to(dev)
     d_groups = torch.from_numpy(groups).to(dev)
-    d_results = torch.zeros(n_jobs * 32, dtype=torch.uint8, device=dev)
-    gathered = [torch.zeros_like(d_results) for _ in range(world)] if (world > 1 and rank == 0) else None
+    d_results = torch.zeros(max(1, n_jobs) * 32, dtype=torch.uint8, device=dev)
+    d_all = torch.zeros(world * n_max * 32, dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
+    if world > 1:
+        # the gather runs inside the library (NCCL behind the C ABI); torch.distributed only carries the 128-byte unique id
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(me.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, src=0)
+        me.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     def step_resident():
         me.interp_halfpel(ref_slots)
         me.search_device(d_jobs.data_ptr(), n_jobs, d_groups.data_ptr(), info, d_results.data_ptr())
         if world > 1:
-            dist.gather(d_results, gathered, dst=0)
+            me.gather_results_device(d_results.data_ptr(), n_jobs, n_per_rank, d_all.data_ptr() if d_all is not None else 0, n_max, 0)
 
     def barrier():
         if world > 1:
@@ -334,11 +443,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    value = args.pairs * world / (ms_per_step * 1e-3)
+    value = n_pairs_global / (ms_per_step * 1e-3)
 
     legs = {}
     if rank == 0 and args.parity_fraction > 0:
-        legs["value (jsvm_me_search_device)"] = d_results.cpu().numpy().view(pkg.RESULT_DTYPE).copy()
+        if world > 1:
+            # the gathered field of ALL ranks, put back into global pair order (rank r holds pairs r, r + N, ..)
+            allr = d_all.cpu().numpy().view(pkg.RESULT_DTYPE).reshape(world, n_max)
+            order = [(g % world, g // world) for g in range(n_pairs_global)]
+            glob = np.concatenate([allr[r, k * per_pair:(k + 1) * per_pair] for r, k in order])
+            legs["value (jsvm_me_search_device + jsvm_me_gather_results_device, all ranks)"] = (list(range(n_pairs_global)), glob)
+        else:
+            legs["value (jsvm_me_search_device)"] = ([g for g, _ in mine], d_results.cpu().numpy().view(pkg.RESULT_DTYPE)[:n_jobs].copy())
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
     e2e = None
@@ -367,12 +483,14 @@ def main():
         dt = float(tt.item())
         h2d = sum(int(tns.numel()) for tns in host_planes.values()) + n_jobs * 32 + len(groups)
         if rank == 0 and args.parity_fraction > 0:
-            legs["e2e (jsvm_me_search)"] = hr.copy()
-        e2e = {"value": args.pairs * world * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+            legs["e2e (jsvm_me_search), rank 0"] = ([g for g, _ in mine], hr.copy())
+        e2e = {"value": n_pairs_global * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": n_jobs * 32, "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3}
 
     if rank != 0:
         if world > 1:
+            dist.barrier()                       # rank 0 still reads the gathered buffer
+            me.comm_destroy()
             dist.destroy_process_group()
         return
 
@@ -382,7 +500,7 @@ def main():
     alg_ops_per_launch = info.n_positions / len(cfg["parts"]) * per_pos
     k2_ms = kt["search_ms"] / max(1, kt["search_launches"])
     achieved = alg_ops_per_launch / (k2_ms * 1e-3)
-    traffic = ncu_traffic(args.pairs) if args.config == "C4" else {}
+    traffic = ncu_traffic(len(mine)) if args.config == "C4" else {}
     roofline = {"bound": "int32", "kernel": me.last_search_kernel(), "achieved": achieved / 1e12, "peak": peak / 1e12,
                 "unit": "Tlane-op/s", "frac": achieved / peak, "traffic": traffic.get("k2_full_search"),
                 "alg_ops_per_launch": alg_ops_per_launch, "ms_per_launch": k2_ms, "peak_source": peak_how,
@@ -405,7 +523,7 @@ def main():
     # ---- what was timed is what the reference computes: a seeded sample of the step against the CPU checker ----
     parity = None
     if legs:
-        parity = parity_check(cfg, frames, slot_of, jobs, legs, args.parity_fraction)
+        parity = parity_check(synth, cfg, seq, args.field, legs, args.parity_fraction / (world if args.scaling == "weak" else 1))
 
     # K3 (sub-pel refinement): algorithmic INT32 lane-ops per job = 17 candidates x (4x4 blocks of the partition) x OPS_4x4, plus
     # the 8 quarter-pel candidates' byte-wise averages (one lane-op per 4 samples) -- DESIGN.md section 3
@@ -419,12 +537,19 @@ def main():
                    "alg_ops_per_launch": k3_ops, "alg_ops_per_4x4_candidate": ops_4x4, "ms_per_launch": k3_ms, "peak_source": peak_how,
                    "share_of_step": kt["subpel_ms"] / total_ms}
 
+    extras = None
+    if world == 1 and not args.no_extras:
+        try:
+            extras = measure_extras(pkg, synth, me, cfg, torch, dev, hbm_peak, peak)
+        except Exception as e:                          # the headline line must not depend on the side measurements
+            extras = {"error": repr(e)}
+
     base = None
     if not args.no_cpu_baseline and world == 1:
         base, _, _ = cpu_baseline(synth, cfg, args.field, args.cpu_sample_mbs)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": config,
             "method": {"l2": "256 MiB L2 flush between timed iterations",
@@ -432,10 +557,15 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roofline, "roofline_k1": roofline_k1, "roofline_k3": roofline_k3, "cpu_baseline": base,
             "parity_checked": parity["jobs"] if parity else 0, "parity": parity,
+            "multi_gpu": {"pairs_global": n_pairs_global, "sharding": "sharding.shard_pairs (round-robin whole pairs)",
+                          "collective": "jsvm_me_gather_results_device (NCCL send/recv inside the library)" if world > 1 else None},
+            "extras": extras,
             "kernel_ms_per_step": {"k1_halfpel": kt["interp_ms"] / args.steps, "k2_full_search": kt["search_ms"] / args.steps,
                                    "k3_subpel": kt["subpel_ms"] / args.steps}}
     print(json.dumps(line))
     if world > 1:
+        dist.barrier()
+        me.comm_destroy()
         dist.destroy_process_group()
     if parity and parity["mismatches"]:
         sys.stderr.write(f"PARITY FAILURE: {parity['mismatches']} result fields differ from the {parity['checker']} checker\n")

@@ -339,6 +339,18 @@ typedef struct jsvm_motion_upsample_params {
 /* base: (ref_h/16) x (ref_w/16) records, out: (frame_h/16) x (frame_w/16) records, HOST memory. */
 int jsvm_me_upsample_motion(jsvm_me_ctx* ctx, const jsvm_motion_upsample_params* params, const jsvm_mb_motion* base, jsvm_mb_motion* out);
 
+/* ---- multi-GPU: one process per GPU, whole (current, reference) pairs per rank, ONE exchange: the gather of the result field to
+ * the rank that owns mode decision.  NCCL over NVLink / NVSwitch, issued on the ctx stream; the library is resolved at run
+ * time (libnccl.so.2), single-GPU use never touches it.  The 128-byte unique id travels by whatever the launcher offers
+ * (bench.py: a torch.distributed broadcast). */
+int jsvm_me_comm_unique_id(uint8_t id[128]);                                        /* ncclGetUniqueId, on the root rank */
+int jsvm_me_comm_init(jsvm_me_ctx* ctx, int rank, int world, const uint8_t id[128]);
+/* Every rank sends n_local records; the root receives rank r's records at d_all + r * n_max (n_max >= every rank's n_local; ranks
+ * may hold different numbers of pairs).  d_all is only read on the root.  Asynchronous on the ctx stream. */
+int jsvm_me_gather_results_device(jsvm_me_ctx* ctx, const jsvm_me_result* d_local, int n_local, const int* n_per_rank,
+                                  jsvm_me_result* d_all, int n_max, int root);
+int jsvm_me_comm_destroy(jsvm_me_ctx* ctx);
+
 int jsvm_me_sync(jsvm_me_ctx* ctx);
 
 /* Measurement helpers (bench.py): kernel launches issued so far, and CUDA-event timing of the

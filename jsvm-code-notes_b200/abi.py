@@ -123,6 +123,10 @@ PROTOTYPES = [
     ("jsvm_me_download_pictures", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     ("jsvm_me_upsample_motion", C.c_int, [C.c_void_p, C.POINTER(MotionUpsampleParams), C.c_void_p, C.c_void_p]),
     ("jsvm_me_upsample_residual", C.c_int, [C.c_void_p, C.POINTER(ResizeParams)] + [C.c_void_p] * 7),
+    ("jsvm_me_comm_unique_id", C.c_int, [C.c_void_p]),
+    ("jsvm_me_comm_init", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    ("jsvm_me_gather_results_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    ("jsvm_me_comm_destroy", C.c_int, [C.c_void_p]),
     ("jsvm_me_fetch_pred", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     ("jsvm_me_sync", C.c_int, [C.c_void_p]),
     ("jsvm_me_launch_count", C.c_uint64, [C.c_void_p]),

@@ -7,6 +7,8 @@
 // There is no CPU implementation behind any compute entry point: without a usable sm_100 device
 // jsvm_me_create fails and everything else refuses to run.
 #include <cuda.h>
+#include <dlfcn.h>
+#include <nccl.h>
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdarg>
@@ -158,6 +160,8 @@ struct jsvm_me_ctx {
   DevBuf<int16_t> d_rs_src, d_rs_dst;
   DevBuf<uint8_t> d_rs_t8x8;
   DevBuf<jsvm_mb_motion> d_mu_base, d_mu_out;
+  // multi-GPU gather
+  ncclComm_t comm = nullptr; int comm_rank = 0, comm_world = 1;
 };
 
 namespace {
@@ -633,6 +637,7 @@ int jsvm_me_destroy(jsvm_me_ctx* c) {
   if (!c) return JSVM_ME_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  jsvm_me_comm_destroy(c);
   if (c->d_planes) cudaFree(c->d_planes);
   if (c->d_half) cudaFree(c->d_half);
   if (c->d_chroma) cudaFree(c->d_chroma);
@@ -1354,6 +1359,86 @@ int jsvm_me_upsample_motion(jsvm_me_ctx* c, const jsvm_motion_upsample_params* p
   CU_OK(cudaGetLastError());
   CU_OK(cudaMemcpyAsync(out, c->d_mu_out.p, sizeof(jsvm_mb_motion) * nc, cudaMemcpyDeviceToHost, c->stream));
   CU_OK(cudaStreamSynchronize(c->stream));
+  return JSVM_ME_OK;
+}
+
+// ---- multi-GPU gather over NCCL (resolved at run time: no link-time dependency, single-GPU use never loads it) ----
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+int load_nccl() {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  if (g_nccl.lib) return JSVM_ME_OK;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);      // the copy the process already mapped (torch's), else the system one
+  if (!lib) return fail("libnccl.so.2 not found (%s): the multi-GPU gather needs NCCL", dlerror());
+  #define SYM(field, name) do { *(void**)(&g_nccl.field) = dlsym(lib, name); if (!g_nccl.field) return fail("NCCL symbol %s missing", name); } while (0)
+  SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
+  SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd"); SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv");
+  SYM(GetErrorString, "ncclGetErrorString");
+  #undef SYM
+  g_nccl.lib = lib;
+  return JSVM_ME_OK;
+}
+#define NCCL_OK(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) return fail("%s failed: %s", #call, g_nccl.GetErrorString(r_)); } while (0)
+}  // namespace
+
+int jsvm_me_comm_unique_id(uint8_t id[128]) {
+  if (!id) return fail("null argument");
+  if (load_nccl()) return JSVM_ME_ERR;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId u;
+  NCCL_OK(g_nccl.GetUniqueId(&u));
+  memcpy(id, &u, 128);
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_comm_init(jsvm_me_ctx* c, int rank, int world, const uint8_t id[128]) {
+  if (!c || !id) return fail("null argument");
+  if (world < 1 || rank < 0 || rank >= world) return fail("rank %d / world %d", rank, world);
+  if (c->comm) return fail("communicator already initialised");
+  if (load_nccl()) return JSVM_ME_ERR;
+  CU_OK(cudaSetDevice(c->device));
+  ncclUniqueId u;
+  memcpy(&u, id, 128);
+  NCCL_OK(g_nccl.CommInitRank(&c->comm, world, u, rank));
+  c->comm_rank = rank; c->comm_world = world;
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_gather_results_device(jsvm_me_ctx* c, const jsvm_me_result* d_local, int n_local, const int* n_per_rank,
+                                  jsvm_me_result* d_all, int n_max, int root) {
+  if (!c || !c->comm) return fail("jsvm_me_comm_init has not been called");
+  if (!n_per_rank || root < 0 || root >= c->comm_world) return fail("bad argument");
+  if (n_per_rank[c->comm_rank] != n_local || n_local > n_max) return fail("rank %d: n_local %d does not match n_per_rank / n_max", c->comm_rank, n_local);
+  if (c->comm_rank == root && !d_all) return fail("null receive buffer on the root");
+  CU_OK(cudaSetDevice(c->device));
+  NCCL_OK(g_nccl.GroupStart());
+  if (n_local > 0 && c->comm_rank != root) NCCL_OK(g_nccl.Send(d_local, (size_t)n_local * sizeof(jsvm_me_result), ncclUint8, root, c->comm, c->stream));
+  if (c->comm_rank == root)
+    for (int r = 0; r < c->comm_world; ++r) {
+      if (r == root || n_per_rank[r] <= 0) continue;
+      NCCL_OK(g_nccl.Recv(d_all + (size_t)r * n_max, (size_t)n_per_rank[r] * sizeof(jsvm_me_result), ncclUint8, r, c->comm, c->stream));
+    }
+  NCCL_OK(g_nccl.GroupEnd());
+  if (c->comm_rank == root && n_local > 0 && d_local != d_all + (size_t)root * n_max)
+    CU_OK(cudaMemcpyAsync(d_all + (size_t)root * n_max, d_local, (size_t)n_local * sizeof(jsvm_me_result), cudaMemcpyDeviceToDevice, c->stream));
+  return JSVM_ME_OK;
+}
+
+int jsvm_me_comm_destroy(jsvm_me_ctx* c) {
+  if (!c) return fail("null context");
+  if (c->comm) { cudaStreamSynchronize(c->stream); g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
   return JSVM_ME_OK;
 }
 

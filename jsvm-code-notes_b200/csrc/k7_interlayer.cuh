@@ -29,8 +29,9 @@ __device__ __forceinline__ int clip_int(int v, int lo, int hi) { return v < lo ?
 // m_paiTransBlkIdc (xDetermineTransBlkIdcs, progressive branch): an id that is equal for two samples iff they lie in the same
 // transform block of the base layer
 __device__ __forceinline__ int trans_blk_idc(const ResamplePlane& P, const uint8_t* __restrict__ t8x8, int x, int y) {
-  const int mb = (y / P.mb_size) * P.mbs_per_row + x / P.mb_size;
-  const int ix = x % P.mb_size, iy = y % P.mb_size;
+  const int sh = P.chroma ? 3 : 4;                           // macroblock size 8 (chroma) or 16
+  const int mb = (y >> sh) * P.mbs_per_row + (x >> sh);
+  const int ix = x & (P.mb_size - 1), iy = y & (P.mb_size - 1);
   if (!P.chroma && t8x8[mb]) return ((((iy >> 3) << 1) + (ix >> 3) + (mb << 2)) << 1) + 1;
   return (((iy >> 2) << 2) + (ix >> 2) + (mb << 4)) << 1;
 }

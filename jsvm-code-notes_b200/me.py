@@ -236,6 +236,24 @@ class MotionEstimator:
         self._check(self._lib.jsvm_me_upsample_motion(self._ctx, C.byref(params), _ptr(base), _ptr(out)))
         return out
 
+    # ---- multi-GPU gather (NCCL inside the library) --------------------------------------------
+    def comm_unique_id(self):
+        buf = (C.c_uint8 * 128)()
+        self._check(self._lib.jsvm_me_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, rank, world, unique_id):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self._lib.jsvm_me_comm_init(self._ctx, rank, world, buf))
+
+    def gather_results_device(self, d_local, n_local, n_per_rank, d_all, n_max, root=0):
+        npr = np.ascontiguousarray(n_per_rank, dtype=np.int32)
+        self._check(self._lib.jsvm_me_gather_results_device(self._ctx, C.c_void_p(int(d_local)), n_local, _ptr(npr),
+                                                           C.c_void_p(int(d_all)) if d_all else None, n_max, root))
+
+    def comm_destroy(self):
+        self._check(self._lib.jsvm_me_comm_destroy(self._ctx))
+
     def plan(self, jobs):
         jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
         gsz = self._lib.jsvm_me_group_size()
@@ -273,8 +291,11 @@ class MotionEstimator:
         ms = [C.c_double() for _ in range(3)]
         n = [C.c_uint64() for _ in range(3)]
         self._check(self._lib.jsvm_me_timing_end(self._ctx, *[C.byref(x) for x in ms], *[C.byref(x) for x in n]))
+        mc_ms, mc_n = C.c_double(), C.c_uint64()
+        self._check(self._lib.jsvm_me_timing_compensate(self._ctx, C.byref(mc_ms), C.byref(mc_n)))
         return {"interp_ms": ms[0].value, "search_ms": ms[1].value, "subpel_ms": ms[2].value,
-                "interp_launches": n[0].value, "search_launches": n[1].value, "subpel_launches": n[2].value}
+                "interp_launches": n[0].value, "search_launches": n[1].value, "subpel_launches": n[2].value,
+                "other_ms": mc_ms.value, "other_launches": mc_n.value}      # K4 (compensate) / K7 (inter-layer resampling)
 
 
 # ---------------------------------------------------------------------------------------------

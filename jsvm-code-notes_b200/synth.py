@@ -67,15 +67,16 @@ class Sequence:
         lo, hi = fine.min(), fine.max()
         self.tex = ((fine - lo) / (hi - lo) * 255.0).astype(np.float32)
 
-    def frame(self, n):
-        """8-bit luma of picture n: texture translated by n * motion quarter-pels, + N(0,2)."""
+    def frame(self, n, gop=0):
+        """8-bit luma of picture n: texture translated by n * motion quarter-pels, + N(0,2).  `gop` selects another noise
+        realisation of the same motion (picture n of GOP `gop`: independent pictures for multi-GOP batches)."""
         g = 4 * self.guard
         dx, dy = n * self.motion[0], n * self.motion[1]
         if abs(dx) > g or abs(dy) > g:
             raise ValueError("picture index outside the guard band of the synthetic texture")
         y0, x0 = g + dy, g + dx
         f = self.tex[y0:y0 + 4 * self.height:4, x0:x0 + 4 * self.width:4].astype(np.float64)
-        rng = np.random.default_rng(self.seed * 1000003 + n)
+        rng = np.random.default_rng(self.seed * 1000003 + n + 4099 * gop)
         f = f + rng.normal(0.0, 2.0, f.shape)
         return np.clip(np.rint(f), 0, 255).astype(np.uint8)
 
