@@ -33,7 +33,9 @@ struct K5Job {
   const uint8_t* ref0;          // reference luma sample under the block's top-left corner at displacement (0,0)
   const uint8_t* cref0[2];      // the same for Cb / Cr (YUV_SAD)
   const int16_t* org;           // shared: block-relative original, stride 16
+  const uint32_t* orgp;         // shared: the same clipped to [0,255] and packed, 4 words per row (SAD / YUV_SAD)
   const int16_t* corg;          // shared: chroma originals [2][64], stride 8
+  int w, h;
   int plane_stride, chroma_stride;
   int nbx, nb;                  // 4x4 sub-blocks per row / in the block
   int pred_h, pred_v;
@@ -71,11 +73,47 @@ __device__ __forceinline__ uint32_t had4x4_from_diffs(const int (&d)[16]) {     
   return sum >> 1;
 }
 
-// this lane's share (sub-blocks sub, sub + 4, ...) of the distortion at displacement (x, y)
+// this lane's share of the distortion at displacement (x, y).
+// SAD (and the luma part of YUV_SAD): rows sub, sub + 4, ... of the block on packed bytes -- the reference row is assembled from
+// aligned words with funnel shifts and meets the clipped, packed original in VABSDIFF4 (4 abs-diffs + add per instruction).
+// Originals outside [0,255] (residual-prediction passes, N3) are searched as their clip: |o - p| = |clip(o) - p| + |o - clip(o)|
+// for p in [0,255], and the second term does not depend on the displacement (the kernel adds it to the cost it reports).
+// SSD / HADAMARD: sub-blocks sub, sub + 4, ... on the true 16-bit differences.
 template <int DFUNC>
-__device__ __forceinline__ uint32_t k5_partial(const K5Job& J, int x, int y, int sub) {
+__device__ __forceinline__ uint32_t k5_partial(const K5Job& J, int x, int y, int sub, int nsub) {
   uint32_t dist = 0;
-  for (int b = sub; b < J.nb; b += 4) {
+  if (DFUNC == JSVM_DF_SAD || DFUNC == JSVM_DF_YUV_SAD) {
+    const int nw = J.w >> 2;
+    for (int r = sub; r < J.h; r += nsub) {
+      const uint8_t* rp = J.ref0 + (ptrdiff_t)(y + r) * J.plane_stride + x;
+      const uintptr_t a = reinterpret_cast<uintptr_t>(rp);
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+      const uint32_t sh = (uint32_t)(a & 3) * 8;
+      const uint32_t* op = J.orgp + r * 4;
+      uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1);
+      dist = sad4(op[0], __funnelshift_r(w0, w1, sh), dist);
+      if (nw >= 2) {
+        w0 = __ldg(wp + 2);
+        dist = sad4(op[1], __funnelshift_r(w1, w0, sh), dist);
+        if (nw == 4) {
+          w1 = __ldg(wp + 3);
+          dist = sad4(op[2], __funnelshift_r(w0, w1, sh), dist);
+          w0 = __ldg(wp + 4);
+          dist = sad4(op[3], __funnelshift_r(w1, w0, sh), dist);
+        }
+      }
+    }
+    if (DFUNC == JSVM_DF_YUV_SAD && J.yuv) {
+      // chroma: (w/2) x (h/2) samples of Cb and Cr displaced by ( x>>1, y>>1 ) (ENC/MotionEstimation.cpp:743-744); rows sub, sub + 4, ..
+      for (int comp = 0; comp < 2; ++comp)
+        for (int r = sub; r < (J.h >> 1); r += nsub) {
+          const uint8_t* cp = J.cref0[comp] + (ptrdiff_t)((y >> 1) + r) * J.chroma_stride + (x >> 1);
+          const int16_t* co = J.corg + comp * 64 + r * 8;
+          for (int c = 0; c < (J.w >> 1); ++c) dist += (uint32_t)abs((int)co[c] - (int)__ldg(cp + c));
+        }
+    }
+  } else {
+  for (int b = sub; b < J.nb; b += nsub) {
     const int bx = (b % J.nbx) * 4, by = (b / J.nbx) * 4;
     const uint8_t* rp = J.ref0 + (ptrdiff_t)(y + by) * J.plane_stride + x + bx;
     int d[16];
@@ -93,16 +131,7 @@ __device__ __forceinline__ uint32_t k5_partial(const K5Job& J, int x, int y, int
 #pragma unroll
       for (int i = 0; i < 16; ++i) dist += DFUNC == JSVM_DF_SSD ? (uint32_t)(d[i] * d[i]) : (uint32_t)abs(d[i]);
     }
-    if (DFUNC == JSVM_DF_YUV_SAD && J.yuv) {
-      // the 2x2 chroma samples under this 4x4, displaced by ( x>>1, y>>1 ) (ENC/MotionEstimation.cpp:743-744)
-#pragma unroll
-      for (int comp = 0; comp < 2; ++comp) {
-        const uint8_t* cp = J.cref0[comp] + (ptrdiff_t)((y >> 1) + (by >> 1)) * J.chroma_stride + (x >> 1) + (bx >> 1);
-        const int16_t* co = J.corg + comp * 64 + (by >> 1) * 8 + (bx >> 1);
-        dist += (uint32_t)abs((int)co[0] - (int)__ldg(cp)) + (uint32_t)abs((int)co[1] - (int)__ldg(cp + 1)) +
-                (uint32_t)abs((int)co[8] - (int)__ldg(cp + J.chroma_stride)) + (uint32_t)abs((int)co[9] - (int)__ldg(cp + J.chroma_stride + 1));
-      }
-    }
+  }
   }
   return dist;
 }
@@ -114,12 +143,29 @@ template <int DFUNC, typename Gen>
 __device__ __forceinline__ int k5_round(const K5Job& J, K5Best& st, int count, Gen gen) {
   const int lane = threadIdx.x & 31, g = lane >> 2, sub = lane & 3;
   int winner = -1;                                            // list index of the point that replaced the incumbent, if any
-  for (int k0 = 0; k0 < count; k0 += 8) {
+  int k0 = 0;
+  // long lists (raster, spiral, block search): 32 points at a time, one lane per point -- no partial sums to combine
+  for (; k0 + 32 <= count; k0 += 32) {
+    const int k = k0 + lane;
+    const K5Point p = gen(k);
+    uint32_t cost = 0xffffffffu;
+    if (p.valid)
+      cost = k5_partial<DFUNC>(J, p.x, p.y, 0, 1) + rate_cost(J.f, mv_component_bits((p.x << 2) - J.pred_h) + mv_component_bits((p.y << 2) - J.pred_v));
+    const uint32_t m = __reduce_min_sync(0xffffffffu, cost);
+    if (m < st.cost) {
+      const int src = __ffs(__ballot_sync(0xffffffffu, p.valid && cost == m)) - 1;
+      st.cost = m;
+      st.x = __shfl_sync(0xffffffffu, p.x, src); st.y = __shfl_sync(0xffffffffu, p.y, src);
+      st.dist = __shfl_sync(0xffffffffu, p.dist, src); st.nr = __shfl_sync(0xffffffffu, p.nr, src);
+      winner = k0 + src;
+    }
+  }
+  for (; k0 < count; k0 += 8) {
     const int k = k0 + g;
     K5Point p = gen(k);
     p.valid = p.valid && k < count;
     uint32_t cost = 0xffffffffu;
-    uint32_t part = p.valid ? k5_partial<DFUNC>(J, p.x, p.y, sub) : 0u;
+    uint32_t part = p.valid ? k5_partial<DFUNC>(J, p.x, p.y, sub, 4) : 0u;
     part += __shfl_xor_sync(0xffffffffu, part, 1);
     part += __shfl_xor_sync(0xffffffffu, part, 2);
     if (p.valid)    // xGetCost( x, y ) with m_uiMvScaleShift = 2 (N6), 32-bit wrap-around (N5)
@@ -220,6 +266,7 @@ fast_search_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int p
                    uint32_t* __restrict__ keys, uint32_t* __restrict__ full_costs, JobAux* __restrict__ aux)
 {
   __shared__ __align__(16) int16_t s_org[kK5WarpsPerCta][256];
+  __shared__ __align__(16) uint32_t s_orgp[kK5WarpsPerCta][64];
   __shared__ __align__(16) int16_t s_corg[kK5WarpsPerCta][128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int job_idx = blockIdx.x * kK5WarpsPerCta + warp;
@@ -234,7 +281,8 @@ fast_search_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int p
   K5Job J;
   J.plane_stride = plane_stride; J.chroma_stride = chroma_stride;
   J.ref0 = planes + (size_t)j.ref_slot * plane_bytes + (size_t)(kMargin + by0) * plane_stride + kMargin + bx0;
-  J.org = s_org[warp]; J.corg = s_corg[warp];
+  J.org = s_org[warp]; J.orgp = s_orgp[warp]; J.corg = s_corg[warp];
+  J.w = w; J.h = h;
   J.nbx = w >> 2; J.nb = (w >> 2) * (h >> 2);
   J.pred_h = j.pred.hor; J.pred_v = j.pred.ver;
   J.f = j.cost_factor;
@@ -249,6 +297,20 @@ fast_search_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int p
           ? __ldg(org_mbs + (size_t)j.org_index * 256 + (4 * (j.blk >> 2) + y) * 16 + 4 * (j.blk & 3) + x)
           : (int16_t)__ldg(planes + (size_t)j.cur_slot * plane_bytes + (size_t)(kMargin + by0 + y) * plane_stride + kMargin + bx0 + x);
     s_org[warp][i] = v;
+  }
+  // clipped, packed copy for the byte-wise SAD and the displacement-independent excess of originals outside [0,255]
+  uint32_t excess = 0;
+  if (DFUNC == JSVM_DF_SAD || DFUNC == JSVM_DF_YUV_SAD) {
+    __syncwarp();
+    for (int i = lane; i < 64; i += 32) {
+      const short4 q = *reinterpret_cast<const short4*>(&s_org[warp][4 * i]);
+      s_orgp[warp][i] = pack_clip8(q);
+      const int o[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) excess += (uint32_t)abs(o[k] - min(max(o[k], 0), 255));
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) excess += __shfl_xor_sync(0xffffffffu, excess, off);
   }
   if (DFUNC == JSVM_DF_YUV_SAD && J.yuv) {
     for (int comp = 0; comp < 2; ++comp)
@@ -397,7 +459,7 @@ fast_search_kernel(const uint8_t* __restrict__ planes, size_t plane_bytes, int p
 
   if (lane == 0) {
     keys[job_idx] = 0;                                        // K3: winner = (ux0, uy0) + index 0 of a 1-wide window
-    full_costs[job_idx] = st.cost;
+    full_costs[job_idx] = st.cost + excess;
     JobAux a; a.ux0 = (int16_t)st.x; a.uy0 = (int16_t)st.y; a.uw = 1; a.pad = 1;
     aux[job_idx] = a;
   }
