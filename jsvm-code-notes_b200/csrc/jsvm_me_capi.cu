@@ -156,6 +156,10 @@ struct jsvm_me_ctx {
   DevBuf<PicTemp> d_pic_temp;
   DevBuf<jsvm_me_result> d_pic_results[2];
   int pic_n_last = 0;
+  // the wave loop of jsvm_me_estimate_pictures as a CUDA graph (3302 dependent launches at 1080p), re-captured when its key changes
+  cudaGraphExec_t pic_graph = nullptr; cudaStream_t pic_stream = nullptr; cudaEvent_t pic_ev[2] = {nullptr, nullptr};
+  struct PicKey { int n_pics, refs, sub, sr; const void* p[8]; } pic_key{};
+  const void* pic_aux = nullptr; uint64_t pic_launches = 0;
   // inter-layer resampling scratch
   DevBuf<int16_t> d_rs_src, d_rs_dst;
   DevBuf<uint8_t> d_rs_t8x8;
@@ -638,6 +642,9 @@ int jsvm_me_destroy(jsvm_me_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   jsvm_me_comm_destroy(c);
+  if (c->pic_graph) cudaGraphExecDestroy(c->pic_graph);
+  if (c->pic_stream) cudaStreamDestroy(c->pic_stream);
+  for (auto& e : c->pic_ev) if (e) cudaEventDestroy(e);
   if (c->d_planes) cudaFree(c->d_planes);
   if (c->d_half) cudaFree(c->d_half);
   if (c->d_chroma) cudaFree(c->d_chroma);
@@ -670,6 +677,7 @@ int jsvm_me_configure(jsvm_me_ctx* c, int width, int height, int n_slots) {
   if (c->d_slot_ids) { cudaFree(c->d_slot_ids); c->d_slot_ids = nullptr; }
   c->W = width; c->H = height; c->n_slots = n_slots;
   c->wave_mbs.clear(); c->wave_off.clear(); c->pic_n_last = 0;
+  if (c->pic_graph) { cudaGraphExecDestroy(c->pic_graph); c->pic_graph = nullptr; }
   c->cands = nullptr; c->n_cands = 0; c->d_cands_user = nullptr; c->org_chroma = nullptr; c->n_org_chroma = 0;   // per-call inputs of the old geometry
   c->plane_stride = width + 2 * kMargin; c->plane_rows = height + 2 * kMargin;
   c->plane_bytes = (size_t)c->plane_stride * c->plane_rows;
@@ -1203,32 +1211,82 @@ int jsvm_me_estimate_pictures(jsvm_me_ctx* c, const jsvm_pic_task* tasks, int n_
   const int cap_uh = std::min(kMaxUH, 2 * c->search_range + 1 + 32);
   const size_t smem = k2_smem_bytes<kV8, false>(cap_uh);
   if (raise_dyn_smem(c->device, 0, full_search_kernel<kV8, false>, smem)) return JSVM_ME_ERR;
+  {
+    // the single-8x8 variant for steps 3 and 4 (its own function, hence its own shared-memory attribute)
+    static std::mutex mu; static size_t configured[kMaxDevices] = {};
+    std::lock_guard<std::mutex> lk(mu);
+    if (smem > configured[c->device % kMaxDevices]) {
+      CU_OK(cudaFuncSetAttribute(full_search_kernel<kV8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured[c->device % kMaxDevices] = smem;
+    }
+  }
   auto k3 = c->sub_dfunc == JSVM_DF_HADAMARD ? subpel_kernel<JSVM_DF_HADAMARD>
           : c->sub_dfunc == JSVM_DF_SSD ? subpel_kernel<JSVM_DF_SSD> : subpel_kernel<JSVM_DF_SAD>;
-  int flip = 0;
-  for (int w = 0; w < n_waves; ++w) {
-    const int n_wave = c->wave_off[w + 1] - c->wave_off[w];
-    const int n_thr = n_pics * n_wave;
-    for (int step = 0; step <= 4; ++step) {
-      picture_step_kernel<<<(n_thr + 127) / 128, 128, 0, c->stream>>>(
-          c->d_pic_tasks.p, n_pics, mbw, mbh, c->d_wave_mbs.p + c->wave_off[w], n_wave, step, R, c->search_range, cap_uh,
-          c->d_pic_field.p, c->d_pic_temp.p, c->d_pic_results[flip ^ 1].p, c->d_jobs.p, c->d_groups.p);
-      c->launches++;
-      if (step == 4) break;
-      const int n_jobs = n_thr * R * pic_step_jobs(step);
-      begin_timed(c, 1);
-      full_search_kernel<kV8, false><<<n_jobs, kK2Threads, smem, c->stream>>>(
-          c->d_planes, c->plane_bytes, c->plane_stride, c->d_groups.p, c->d_jobs.p, nullptr, mbw, mbh, c->search_range, c->d_keys.p, c->d_aux.p);
-      end_timed(c);
-      begin_timed(c, 2);
-      k3<<<(n_jobs + kK3WarpsPerCta - 1) / kK3WarpsPerCta, 32 * kK3WarpsPerCta, 0, c->stream>>>(
-          c->d_planes, c->plane_bytes, c->plane_stride, c->d_half, c->half_bytes, c->half_stride,
-          c->d_jobs.p, c->d_aux.p, n_jobs, nullptr, c->d_keys.p, nullptr, c->d_pic_results[flip].p, nullptr, c->d_factor_map.p, 0);
-      end_timed(c);
-      c->launches += 2;
-      flip ^= 1;
+  // The wave loop: 13 small dependent launches per wave.  Issued directly when kernel timing is on (events cannot be timed inside a
+  // graph); otherwise captured ONCE into a CUDA graph on a private stream and replayed -- the launch sequence is a pure function of
+  // the picture size, the batch size and the buffer addresses (PicKey).
+  auto issue = [&](cudaStream_t stream) -> int {
+    int flip = 0;
+    for (int w = 0; w < n_waves; ++w) {
+      const int n_wave = c->wave_off[w + 1] - c->wave_off[w];
+      const int n_thr = n_pics * n_wave;
+      for (int step = 0; step <= 4; ++step) {
+        picture_step_kernel<<<(n_thr + 127) / 128, 128, 0, stream>>>(
+            c->d_pic_tasks.p, n_pics, mbw, mbh, c->d_wave_mbs.p + c->wave_off[w], n_wave, step, R, c->search_range, cap_uh,
+            c->d_pic_field.p, c->d_pic_temp.p, c->d_pic_results[flip ^ 1].p, c->d_jobs.p, c->d_groups.p);
+        c->launches++;
+        if (step == 4) break;
+        const int n_jobs = n_thr * R * pic_step_jobs(step);
+        begin_timed(c, 1);
+        if (step < 2)
+          full_search_kernel<kV8, false><<<n_jobs, kK2Threads, smem, stream>>>(
+              c->d_planes, c->plane_bytes, c->plane_stride, c->d_groups.p, c->d_jobs.p, nullptr, mbw, mbh, c->search_range, c->d_keys.p, c->d_aux.p);
+        else          // steps 3 and 4: one 8x8 job per group
+          full_search_kernel<kV8, false, true><<<n_jobs, kK2Threads, smem, stream>>>(
+              c->d_planes, c->plane_bytes, c->plane_stride, c->d_groups.p, c->d_jobs.p, nullptr, mbw, mbh, c->search_range, c->d_keys.p, c->d_aux.p);
+        end_timed(c);
+        begin_timed(c, 2);
+        k3<<<(n_jobs + kK3WarpsPerCta - 1) / kK3WarpsPerCta, 32 * kK3WarpsPerCta, 0, stream>>>(
+            c->d_planes, c->plane_bytes, c->plane_stride, c->d_half, c->half_bytes, c->half_stride,
+            c->d_jobs.p, c->d_aux.p, n_jobs, nullptr, c->d_keys.p, nullptr, c->d_pic_results[flip].p, nullptr, c->d_factor_map.p, 0);
+        end_timed(c);
+        c->launches += 2;
+        flip ^= 1;
+      }
     }
     CU_OK(cudaGetLastError());
+    return JSVM_ME_OK;
+  };
+  if (c->timing || getenv("JSVM_ME_NO_GRAPH")) {
+    if (issue(c->stream)) return JSVM_ME_ERR;
+  } else {
+    jsvm_me_ctx::PicKey key{n_pics, R, c->sub_dfunc, c->search_range,
+                            {c->d_pic_tasks.p, c->d_pic_field.p, c->d_pic_temp.p, c->d_pic_results[0].p, c->d_pic_results[1].p, c->d_jobs.p, c->d_groups.p, c->d_keys.p}};
+    if (!c->pic_stream) {
+      CU_OK(cudaStreamCreateWithFlags(&c->pic_stream, cudaStreamNonBlocking));
+      for (auto& e : c->pic_ev) CU_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    if (!c->pic_graph || memcmp(&key, &c->pic_key, sizeof(key)) != 0 || c->d_aux.p != c->pic_aux) {
+      if (c->pic_graph) { cudaGraphExecDestroy(c->pic_graph); c->pic_graph = nullptr; }
+      const uint64_t launches_before = c->launches;
+      cudaGraph_t graph = nullptr;
+      CU_OK(cudaStreamBeginCapture(c->pic_stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = issue(c->pic_stream);
+      const cudaError_t e = cudaStreamEndCapture(c->pic_stream, &graph);
+      if (rc || e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return rc ? JSVM_ME_ERR : fail("cudaStreamEndCapture failed: %s", cudaGetErrorString(e)); }
+      const cudaError_t ei = cudaGraphInstantiate(&c->pic_graph, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ei != cudaSuccess) { c->pic_graph = nullptr; return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(ei)); }
+      c->pic_key = key; c->pic_aux = c->d_aux.p;
+      c->pic_launches = c->launches - launches_before;
+      c->launches = launches_before;                         // capturing launched nothing
+    }
+    CU_OK(cudaEventRecord(c->pic_ev[0], c->stream));
+    CU_OK(cudaStreamWaitEvent(c->pic_stream, c->pic_ev[0], 0));
+    CU_OK(cudaGraphLaunch(c->pic_graph, c->pic_stream));
+    CU_OK(cudaEventRecord(c->pic_ev[1], c->pic_stream));
+    CU_OK(cudaStreamWaitEvent(c->stream, c->pic_ev[1], 0));
+    c->launches += c->pic_launches;                          // kernels the graph runs
   }
   c->last_k2 = "full_search_kernel<8,false>";
   c->pic_n_last = n_pics;

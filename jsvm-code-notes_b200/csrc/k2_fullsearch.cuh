@@ -244,6 +244,10 @@ __device__ __forceinline__ void k2_build_stage(const Group& g, const K2Geo<V>& g
   if (ptid == 0) {
     sm.next_unit = first_unit;
     sm.ux0 = g.ux0; sm.uy0 = g.uy0; sm.uw = g.uw; sm.uh = g.uh; sm.xa = (int16_t)xa;
+    // groups that hold a single 8x8 job (the picture-level search, k6_picture.cuh): which quadrant (read by the QUAD search loop)
+    int quad = 0;
+    if (!GRAN4) for (int q = 0; q < 4; ++q) if (g.slot_job[5 + q] >= 0) quad = q;
+    sm.pad = (int16_t)quad;
   }
 
   // ---- 2: the four byte-shifted copies of the reference window ----
@@ -376,7 +380,9 @@ __device__ __forceinline__ void k2_build_stage(const Group& g, const K2Geo<V>& g
 
 // ---- the search loop of one warp over one staged group: batches of 32 units (unit = column x strip of V displacements)
 //      pulled from the stage's counter, always one batch ahead of the one being worked on ----
-template <int V, bool GRAN4>
+// QUAD: the group holds ONE job, an 8x8 block (slot 5 + quadrant): the SAD pass covers only the 8 rows x 2 words of that quadrant
+// and the rate / argmin pass only that slot -- a quarter of the SAD work and a ninth of the slot work of the general loop.
+template <int V, bool GRAN4, bool QUAD = false>
 __device__ __forceinline__ void k2_search_units(const K2Geo<V>& geo, const K2Stage<V, GRAN4>& st, const int lane, const int first_u0,
                                                 uint32_t (&best)[K2Smem<V, GRAN4>::NBEST])
 {
@@ -413,6 +419,53 @@ __device__ __forceinline__ void k2_search_units(const K2Geo<V>& geo, const K2Sta
     const int x = 4 * m + s - xa;                                 // column inside the union window (negative: alignment columns)
     const int ys = strip * V;
     const int cidx = s * kMaxM + m;
+
+    if constexpr (QUAD && !GRAN4) {
+      const int quad = sm.pad, sl = 5 + quad;
+      const Mask mxq = live ? sm.xmask[cidx] : (Mask)0;
+      const bool fullq = ((mxq & sm.yfull[strip]) >> sl) & 1, anyq = ((mxq & sm.yany[strip]) >> sl) & 1;
+      if (__all_sync(0xffffffffu, !anyq)) continue;
+      uint32_t accq[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) accq[v] = 0;
+      const int r0 = (quad >> 1) * 8, k0 = (quad & 1) * 2;
+      const uint32_t* rq = winw + s * copy_words + (ys + r0) * kWinRowWords + m + k0;
+      {
+        uint32_t ref[V][2];
+#pragma unroll
+        for (int r = 0; r < V - 1; ++r) { ref[r][0] = rq[r * kWinRowWords]; ref[r][1] = rq[r * kWinRowWords + 1]; }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          ref[(c + V - 1) % V][0] = rq[(c + V - 1) * kWinRowWords]; ref[(c + V - 1) % V][1] = rq[(c + V - 1) * kWinRowWords + 1];
+          const uint2 cq = *reinterpret_cast<const uint2*>(&sm.cur[r0 + c][k0]);
+#pragma unroll
+          for (int v = 0; v < V; ++v) accq[v] = sad4(cq.x, ref[(c + v) % V][0], accq[v]);
+#pragma unroll
+          for (int v = 0; v < V; ++v) accq[v] = sad4(cq.y, ref[(c + v) % V][1], accq[v]);
+        }
+      }
+      const uint32_t f = sm.factor[sl];
+      const uint32_t fbx = f * (uint32_t)sm.bx[sl][cidx];
+      uint32_t kv[V];
+#pragma unroll
+      for (int v4 = 0; v4 < V; v4 += 4) {
+        const uint4 q = *reinterpret_cast<const uint4*>(&by_tab[sl * by_stride + ys + v4]);
+        const uint32_t byv[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+        for (int v = 0; v < 4; ++v) kv[v4 + v] = rate_key(f, byv[v], fbx, accq[v4 + v], (uint32_t)((ys + v4 + v) * uw + x));
+      }
+      uint32_t b = best[0];                                         // QUAD keeps its single running minimum in best[0]
+      if (fullq) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) b = min(b, kv[v]);
+      } else if (anyq) {
+        const int lo = sm.ylo[sl] - ys, hi = sm.yhi[sl] - ys;
+#pragma unroll
+        for (int v = 0; v < V; ++v) if (v >= lo && v <= hi) b = min(b, kv[v]);
+      }
+      best[0] = b;
+      continue;
+    }
 
     // ---- SAD pass over the strip ----
     // Row c of the current macroblock (one broadcast LDS.128) meets the V reference rows c .. c+V-1, which sit in a sliding
@@ -611,7 +664,7 @@ __device__ __forceinline__ void k2_flush(const K2Smem<V, GRAN4>& sm, const int p
 }
 
 // ---- kernel A: one CTA per search group (small launches, 4x4-granular groups, very tall union windows) ----
-template <int V, bool GRAN4>
+template <int V, bool GRAN4, bool QUAD = false>
 __global__ void __launch_bounds__(kK2Threads, 2)
 full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel plane pool [slot][H+64][W+64]
                    size_t plane_bytes, int plane_stride,
@@ -637,8 +690,13 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
   uint32_t best[SM::NBEST];
 #pragma unroll
   for (int sl = 0; sl < SM::NBEST; ++sl) best[sl] = kKeyInvalid;
-  k2_search_units<V, GRAN4>(geo, st, lane, (tid >> 5) * 32, best);
-  k2_warp_reduce<V, GRAN4>(*st.sm, lane, best);
+  k2_search_units<V, GRAN4, QUAD>(geo, st, lane, (tid >> 5) * 32, best);
+  if constexpr (QUAD) {
+    const uint32_t w = __reduce_min_sync(0xffffffffu, best[0]);
+    if (lane == 0 && w != kKeyInvalid) smem_min(&st.sm->best[5 + st.sm->pad], w);
+  } else {
+    k2_warp_reduce<V, GRAN4>(*st.sm, lane, best);
+  }
   __syncthreads();
   k2_flush<V, GRAN4>(*st.sm, tid, kK2Threads, keys, aux);
 }
