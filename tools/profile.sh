@@ -3,7 +3,7 @@
 # Writes gpurun_out/{launches.csv, prof_k*.ncu-rep, ncu_k*.json, traffic.json}; copy the summaries to profiles/ afterwards.
 set -x
 PAIRS=${PAIRS:-16}
-ARGS="--steps 2 --warmup 1 --no-cpu-baseline --no-e2e --pairs $PAIRS"
+ARGS="--steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-extras --parity-fraction 0 --pairs $PAIRS"
 python bench.py $ARGS > gpurun_out/plain.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py $ARGS > gpurun_out/ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:full_search -s 1 -c 1 -f -o gpurun_out/prof_k2 python bench.py $ARGS > gpurun_out/ncu_k2.log 2>&1
