@@ -20,6 +20,7 @@
 #include <functional>
 #include <mutex>
 #include <condition_variable>
+#include <chrono>
 #include <string>
 
 #include "../../include/jsvm_me_b200.h"
@@ -135,6 +136,7 @@ struct jsvm_me_ctx {
   struct SmallArena {
     jsvm_me_job job[64]; Group group[64]; jsvm_me_result result[64];
     int16_t org[64 * 256]; uint8_t pred[64 * 256];
+    jsvm_mv cands[64 * 3];
   };
   SmallArena* small = nullptr;
   bool last_small = false;
@@ -520,9 +522,7 @@ int prepare_search_extras(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, i
 }
 
 // jsvm_me_search for SPIRAL / LOG / FAST / TZ: no plan, one batch (these searches touch a few hundred points per job).
-int search_fast_host(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const int16_t* org_mbs, int n_org_mbs,
-                     jsvm_me_result* results, uint8_t* preds) {
-  CU_OK(cudaSetDevice(c->device));
+int check_fast_jobs(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, int n_org_mbs) {
   const int mbw = c->W >> 4, mbh = c->H >> 4;
   for (int i = 0; i < n_jobs; ++i) {
     const jsvm_me_job& j = jobs[i];
@@ -546,6 +546,14 @@ int search_fast_host(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const 
   }
   const bool need_cands = c->search_mode == JSVM_SEARCH_FAST || c->search_mode == JSVM_SEARCH_TZ;
   if (need_cands && c->cands && c->n_cands < n_jobs) return fail("jsvm_me_set_mv_candidates registered %d jobs, the call passes %d", c->n_cands, n_jobs);
+  return JSVM_ME_OK;
+}
+
+int search_fast_host(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const int16_t* org_mbs, int n_org_mbs,
+                     jsvm_me_result* results, uint8_t* preds) {
+  CU_OK(cudaSetDevice(c->device));
+  if (check_fast_jobs(c, jobs, n_jobs, n_org_mbs)) return JSVM_ME_ERR;
+  const bool need_cands = c->search_mode == JSVM_SEARCH_FAST || c->search_mode == JSVM_SEARCH_TZ;
   const bool want_preds = preds != nullptr || n_jobs <= 4096;
   if (c->d_jobs.reserve(n_jobs) || c->d_keys.reserve(n_jobs) || c->d_full_costs.reserve(n_jobs) || c->d_aux.reserve(n_jobs) ||
       c->d_results.reserve(n_jobs) || (want_preds && c->d_preds.reserve((size_t)n_jobs * 256)) ||
@@ -577,9 +585,19 @@ int search_small(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const int1
   CU_OK(cudaSetDevice(c->device));
   if (!c->small) CU_OK(cudaHostAlloc((void**)&c->small, sizeof(jsvm_me_ctx::SmallArena), cudaHostAllocMapped));
   jsvm_me_ctx::SmallArena* a = c->small;                     // unified addressing: the same pointer is valid on the device
+  const bool fast = c->search_mode != JSVM_SEARCH_BLOCK || c->search_range > kMaxSearchRange;
   PlanChunk pc;
-  plan_range(c->W, c->H, c->n_slots, c->search_range, jobs, 0, n_jobs, pc);
-  if (pc.err_job >= 0) return fail("job %d: %s", pc.err_job, pc.err);
+  const jsvm_mv* d_cands = nullptr;
+  if (fast) {                                                // SPIRAL / LOG / FAST / TZ: no plan; the neighbours' MVs travel in the arena
+    if (check_fast_jobs(c, jobs, n_jobs, n_org_mbs)) return JSVM_ME_ERR;
+    if ((c->search_mode == JSVM_SEARCH_FAST || c->search_mode == JSVM_SEARCH_TZ) && c->cands) {
+      memcpy(a->cands, c->cands, sizeof(jsvm_mv) * 3 * n_jobs);
+      d_cands = a->cands;
+    }
+  } else {
+    plan_range(c->W, c->H, c->n_slots, c->search_range, jobs, 0, n_jobs, pc);
+    if (pc.err_job >= 0) return fail("job %d: %s", pc.err_job, pc.err);
+  }
   jsvm_me_plan_info info{};
   info.n_groups_8x8 = (int32_t)pc.g8.size(); info.n_groups = (int32_t)(pc.g8.size() + pc.g4.size()); info.n_positions = pc.npos;
   int ng = 0;
@@ -597,7 +615,7 @@ int search_small(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const int1
   if (c->d_keys.reserve(64) || c->d_full_costs.reserve(64) || c->d_aux.reserve(64)) return JSVM_ME_ERR;
   const int16_t* d_org_chroma = nullptr;
   if (prepare_search_extras(c, jobs, n_jobs, n_org_mbs, &d_org_chroma)) return JSVM_ME_ERR;
-  if (run_search(c, a->job, 0, n_jobs, a->group, &info, a->org, c->d_keys.p, c->d_aux.p, a->result, a->pred, d_org_chroma)) return JSVM_ME_ERR;
+  if (run_search(c, a->job, 0, n_jobs, a->group, &info, a->org, c->d_keys.p, c->d_aux.p, a->result, a->pred, d_org_chroma, d_cands)) return JSVM_ME_ERR;
   CU_OK(cudaStreamSynchronize(c->stream));
   memcpy(results, a->result, sizeof(jsvm_me_result) * n_jobs);
   if (preds) memcpy(preds, a->pred, (size_t)n_jobs * 256);
@@ -1016,8 +1034,8 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
       if (org_mbs[i] < -1024 || org_mbs[i] > 1023)      // residual-prediction originals span [-255, 510] (N3); the key widths assume |v| < 1024
         return fail("org_mbs sample %zu = %d outside [-1024,1023]", i, (int)org_mbs[i]);
   }
-  if (c->search_mode != JSVM_SEARCH_BLOCK || c->search_range > kMaxSearchRange) return search_fast_host(c, jobs, n_jobs, org_mbs, n_org_mbs, results, preds);
   if (n_jobs <= 64 && n_org_mbs <= 64) return search_small(c, jobs, n_jobs, org_mbs, n_org_mbs, results, preds);
+  if (c->search_mode != JSVM_SEARCH_BLOCK || c->search_range > kMaxSearchRange) return search_fast_host(c, jobs, n_jobs, org_mbs, n_org_mbs, results, preds);
   c->last_small = false;
   CU_OK(cudaSetDevice(c->device));
   // every error exit below: nothing may still be copying into the caller's buffers, and no prediction of an earlier call may be served
@@ -1055,6 +1073,7 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
   int kUnit = 16384;
   if (const char* e = getenv("JSVM_ME_CHUNK")) kUnit = std::max(1024, std::min(1 << 17, atoi(e)));     // tuning knob (jobs per planning unit)
   constexpr int kMaxUnits = 8;
+  const bool merge_launches = getenv("JSVM_ME_NO_MERGE") == nullptr;       // A/B knob
   std::vector<int> cut(1, 0);
   while (cut.back() < n_jobs) {
     // the first units are small (2 K, 4 K, 8 K jobs): the GPU has nothing to do until unit 0 is planned and uploaded
@@ -1094,10 +1113,25 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
       std::unique_lock<std::mutex> lk(mu);
       cv.wait(lk, [&] { return status[k] != 0; });
       // 4x4-granular groups sit behind the 8x8-granular ones of their unit: such a unit is launched on its own
-      while (m < n_units && m - k < kMaxUnits && status[m] != 0 && (m == k || (plans[m].g4.empty() && plans[k].g4.empty()))) {
-        if (status[m] < 0) break;
-        ++m;
-      }
+      auto take_ready = [&] {
+        while (m < n_units && m - k < kMaxUnits && status[m] != 0 && (m == k || (plans[m].g4.empty() && plans[k].g4.empty()))) {
+          if (status[m] < 0) break;
+          ++m;
+        }
+      };
+      take_ready();
+      // While the GPU still has work queued on the ctx stream (the plane uploads and K1 in front of the first launch, the previous
+      // launch later) there is no hurry: keep collecting planned units, so that the launch is larger (every persistent K2 launch pays
+      // its pipeline fill and its last-wave imbalance once).
+      if (merge_launches && n_workers > 0)
+        while (m > k && m < n_units && m - k < kMaxUnits && status[m] == 0 && plans[k].g4.empty()) {
+          lk.unlock();
+          const bool busy = cudaStreamQuery(c->stream) == cudaErrorNotReady;
+          lk.lock();
+          if (!busy) break;
+          cv.wait_for(lk, std::chrono::microseconds(30), [&] { return status[m] != 0; });
+          take_ready();
+        }
       if (m == k) m = k + 1;                                // unit k failed: reported below
     }
     for (int u = k; u < m; ++u)
