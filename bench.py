@@ -6,7 +6,7 @@ sequence at 1920x1088 (BASELINE.json configs[3]): 8 B pictures x 2 lists = 16 in
 reference) pairs per GPU -- K1 half-pel planes of the 9 reference pictures, K2 full search (SR +-64) and
 K3 quarter-pel refinement for all 8160 macroblocks x 9 partitions of every pair (1.17 M
 estimateBlockWithStart results per step per GPU).  The batch is ONE global list of pairs (N x 16 pairs = N GOPs for weak scaling,
-16 pairs in total with --scaling strong) dealt round-robin to the ranks by sharding.shard_pairs: no data-path collective; for N > 1
+16 pairs in total with --scaling strong) dealt in contiguous blocks to the ranks by sharding.shard_pairs: no data-path collective; for N > 1
 the result field is gathered to rank 0 over NCCL by the library itself (jsvm_me_gather_results_device) inside the timed region.
 
 `value`   : pairs/s with planes, jobs and search groups already resident in HBM (CUDA events, max over ranks).
@@ -91,7 +91,7 @@ def pair_jobs(synth, cfg, g, cur_slot, ref_slot, field):
 
 
 def build_workload(synth, sharding, cfg, n_pairs_global, field, rank, world):
-    """Planes and jobs of this rank's share of the batch (round-robin whole pairs, sharding.shard_pairs)."""
+    """Planes and jobs of this rank's share of the batch (contiguous blocks of whole pairs, sharding.shard_pairs)."""
     W, H = cfg["width"], cfg["height"]
     seq = synth.Sequence(W, H, 1234 + 4)
     mine = sharding.shard_pairs(global_pairs(n_pairs_global), rank, world)
@@ -462,10 +462,9 @@ def main():
     legs = {}
     if rank == 0 and args.parity_fraction > 0:
         if world > 1:
-            # the gathered field of ALL ranks, put back into global pair order (rank r holds pairs r, r + N, ..)
+            # the gathered field of ALL ranks in global pair order: rank r holds the contiguous block sharding.rank_range( r )
             allr = d_all.cpu().numpy().view(pkg.RESULT_DTYPE).reshape(world, n_max)
-            order = [(g % world, g // world) for g in range(n_pairs_global)]
-            glob = np.concatenate([allr[r, k * per_pair:(k + 1) * per_pair] for r, k in order])
+            glob = np.concatenate([allr[r, :n_per_rank[r]] for r in range(world)])
             legs["value (jsvm_me_search_device + jsvm_me_gather_results_device, all ranks)"] = (list(range(n_pairs_global)), glob)
         else:
             legs["value (jsvm_me_search_device)"] = ([g for g, _ in mine], d_results.cpu().numpy().view(pkg.RESULT_DTYPE)[:n_jobs].copy())
@@ -571,7 +570,7 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roofline, "roofline_k1": roofline_k1, "roofline_k3": roofline_k3, "cpu_baseline": base,
             "parity_checked": parity["jobs"] if parity else 0, "parity": parity,
-            "multi_gpu": {"pairs_global": n_pairs_global, "sharding": "sharding.shard_pairs (round-robin whole pairs)",
+            "multi_gpu": {"pairs_global": n_pairs_global, "sharding": "sharding.shard_pairs (contiguous blocks of whole pairs: neighbouring pairs share planes)",
                           "collective": "jsvm_me_gather_results_device (NCCL send/recv inside the library)" if world > 1 else None},
             "extras": extras,
             "kernel_ms_per_step": {"k1_halfpel": kt["interp_ms"] / args.steps, "k2_full_search": kt["search_ms"] / args.steps,

@@ -1,4 +1,4 @@
-"""world_size-2 gloo test of the multi-GPU layout: round-robin pair sharding + final result gather (CPU)."""
+"""world_size-2 gloo test of the multi-GPU layout: pair sharding in contiguous blocks + final result gather (CPU)."""
 import importlib
 import os
 import sys
@@ -48,9 +48,13 @@ def test_shard_and_gather_two_ranks(tmp_path, n_pairs, port):
     assert np.array_equal(full[:, 1], np.tile(np.arange(jobs_per_pair), n_pairs))
 
 
-def test_round_robin_owner():
+def test_block_owner():
     sharding = importlib.import_module("jsvm-code-notes_b200.sharding")
     pairs = list(range(10))
     got = [sharding.shard_pairs(pairs, r, 4) for r in range(4)]
-    assert sorted(i for g in got for i, _ in g) == list(range(10))
-    assert all(sharding.pair_owner(i, 4) == r for r, g in enumerate(got) for i, _ in g)
+    assert [i for g in got for i, _ in g] == list(range(10))                      # contiguous blocks in rank order
+    assert [len(g) for g in got] == [3, 3, 2, 2]
+    assert all(sharding.pair_owner(i, 4, 10) == r for r, g in enumerate(got) for i, _ in g)
+    # the two pairs of a current picture (2k, 2k + 1) stay on one rank whenever the blocks are even
+    got = [sharding.shard_pairs(list(range(16)), r, 8) for r in range(8)]
+    assert all([i for i, _ in g] == [2 * r, 2 * r + 1] for r, g in enumerate(got))
