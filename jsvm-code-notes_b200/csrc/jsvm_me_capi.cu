@@ -53,6 +53,8 @@ int fail(const char* fmt, ...) {
 constexpr int kV8 = 8;        // strip height of the 8x8-granular search kernel
 constexpr int kV4 = 4;        // strip height of the 4x4-granular search kernel
 constexpr int kMaxUH = 176;   // tallest union window one CTA handles (by-table rows, shared memory)
+constexpr int kSmallUH = 56;  // union windows up to this height (search range <= ~20) use the 128-thread form of the one-CTA-per-group kernel
+constexpr size_t kMaxDynSmemTotal = 228 * 1024 - 4 * 1024;   // shared memory of an SM available to resident CTAs (1 KB reserved per CTA)
 constexpr int kMaxSearchRange = 64;   // staged windows of at most 129 x 129 positions per job (packed-byte kernels, k2_generic.cuh)
 constexpr int kMaxWideRange = 4096;   // beyond 64 the searches run unstaged, one warp per job (K5); windows stay clipped to the padded picture
 
@@ -176,7 +178,7 @@ namespace {
 // drop-in keeps one per spatial layer) share it, so the configured maximum is process-wide state per device and is only ever raised.
 constexpr int kMaxDevices = 64;
 std::mutex g_smem_mu;
-size_t g_smem_configured[kMaxDevices][4] = {};      // {group, persistent} x {8x8, 4x4}
+size_t g_smem_configured[kMaxDevices][5] = {};      // {group, persistent} x {8x8, 4x4}, group 8x8 with 128 threads
 template <typename Fn>
 int raise_dyn_smem(int device, int which, Fn* fn, size_t smem) {
   std::lock_guard<std::mutex> lk(g_smem_mu);
@@ -347,8 +349,18 @@ int launch_search(jsvm_me_ctx* c, const Group* d_groups, int first_group, int n_
                   const jsvm_me_job* d_jobs, const int16_t* d_org, uint32_t* d_keys, JobAux* d_aux) {
   if (n_groups <= 0) return JSVM_ME_OK;
   const size_t smem = k2_smem_bytes<V, GRAN4>(max_uh);
-  if (raise_dyn_smem(c->device, GRAN4 ? 1 : 0, full_search_kernel<V, GRAN4>, smem)) return JSVM_ME_ERR;
+  // small windows (8x8-granular groups, union windows of at most kSmallUH rows): 128-thread CTAs, four per SM
+  static const int small_uh = getenv("JSVM_ME_SMALL_UH") ? atoi(getenv("JSVM_ME_SMALL_UH")) : kSmallUH;
+  const bool small = !GRAN4 && max_uh <= small_uh && 4 * smem <= kMaxDynSmemTotal;
+  if (small) {
+    if (raise_dyn_smem(c->device, 4, full_search_kernel<V, false, false, 128>, smem)) return JSVM_ME_ERR;
+  } else if (raise_dyn_smem(c->device, GRAN4 ? 1 : 0, full_search_kernel<V, GRAN4>, smem)) return JSVM_ME_ERR;
   begin_timed(c, 1);
+  if (small)
+    full_search_kernel<V, false, false, 128><<<n_groups, 128, smem, c->stream>>>(
+        c->d_planes, c->plane_bytes, c->plane_stride, d_groups + first_group, d_jobs, d_org,
+        c->W >> 4, c->H >> 4, c->search_range, d_keys, d_aux);
+  else
   full_search_kernel<V, GRAN4><<<n_groups, kK2Threads, smem, c->stream>>>(
       c->d_planes, c->plane_bytes, c->plane_stride, d_groups + first_group, d_jobs, d_org,
       c->W >> 4, c->H >> 4, c->search_range, d_keys, d_aux);

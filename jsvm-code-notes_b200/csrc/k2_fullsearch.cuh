@@ -664,8 +664,10 @@ __device__ __forceinline__ void k2_flush(const K2Smem<V, GRAN4>& sm, const int p
 }
 
 // ---- kernel A: one CTA per search group (small launches, 4x4-granular groups, very tall union windows) ----
-template <int V, bool GRAN4, bool QUAD = false>
-__global__ void __launch_bounds__(kK2Threads, 2)
+// THREADS: 256 (2 CTAs per SM), or 128 with 4 CTAs per SM for small windows (search range <= ~24: a group is only ~6 batches of 32
+// units, too little for 8 warps, and twice as many groups in flight hide each other's staging)
+template <int V, bool GRAN4, bool QUAD = false, int THREADS = kK2Threads>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS)
 full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel plane pool [slot][H+64][W+64]
                    size_t plane_bytes, int plane_stride,
                    const Group* __restrict__ groups,
@@ -684,7 +686,7 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
   const K2Stage<V, GRAN4> st(smem_raw, geo);
 
   // the first batch of every warp is static (u0 = 32 * warp), the counter starts behind them
-  k2_build_stage<V, GRAN4, kK2Threads>(g, geo, st, planes, plane_bytes, plane_stride, jobs, org_mbs, mb_w, mb_h, default_range, tid, kK2Threads);
+  k2_build_stage<V, GRAN4, THREADS>(g, geo, st, planes, plane_bytes, plane_stride, jobs, org_mbs, mb_w, mb_h, default_range, tid, THREADS);
   __syncthreads();            // window copies and tables visible
 
   uint32_t best[SM::NBEST];
@@ -698,7 +700,7 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
     k2_warp_reduce<V, GRAN4>(*st.sm, lane, best);
   }
   __syncthreads();
-  k2_flush<V, GRAN4>(*st.sm, tid, kK2Threads, keys, aux);
+  k2_flush<V, GRAN4>(*st.sm, tid, THREADS, keys, aux);
 }
 
 // ---- kernel B: persistent, one CTA per SM, producer / consumer warps over two shared-memory stages ----
