@@ -17,6 +17,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
 
+@pytest.hookimpl(hookwrapper=True)
+def pytest_runtest_makereport(item, call):
+    """Keep the full text of every failure in gpurun_out/test_failures.log (the -q summary line is cut at the terminal width)."""
+    outcome = yield
+    rep = outcome.get_result()
+    if rep.failed:
+        try:
+            d = os.path.join(ROOT, "gpurun_out")
+            os.makedirs(d, exist_ok=True)
+            with open(os.path.join(d, "test_failures.log"), "a") as f:
+                f.write(f"==== {rep.nodeid} [{rep.when}]\n{rep.longreprtext}\n")
+        except OSError:
+            pass
+
+
 @pytest.fixture(scope="session")
 def pkg():
     """The product package (its directory name has a hyphen, so it is imported by string)."""

@@ -23,6 +23,22 @@ CASES = [
 ]
 
 
+def _explain_disagreement(got, got_dev, want, jobs, planes, path, prefix, W, H, n_refs, cfg):
+    """On a mismatch, say which side moved: the macroblocks that differ are searched again by the checker in THIS process (no fork
+    pool), and the report names the jobs for which the checker's second answer differs from its first."""
+    raw = lambda a: np.ascontiguousarray(a).view(np.uint8).reshape(len(jobs), -1)
+    bad = np.flatnonzero((raw(got) != raw(want)).any(axis=1) | (raw(got_dev) != raw(want)).any(axis=1))
+    if not len(bad):
+        return
+    sel = np.flatnonzero(np.isin(jobs["mb_y"].astype(np.int64) * 4096 + jobs["mb_x"], np.unique(jobs["mb_y"][bad].astype(np.int64) * 4096 + jobs["mb_x"][bad]))
+                         & np.isin(jobs["ref_slot"], np.unique(jobs["ref_slot"][bad])))[:4096]
+    again = oracle_lib.parallel_search(path, prefix, W, H, n_refs + 1, cfg["search_range"], cfg["sub_dfunc"], planes, jobs[sel], n_proc=1)
+    moved = int((raw(want)[sel] != np.ascontiguousarray(again).view(np.uint8).reshape(len(sel), -1)).any(axis=1).sum())
+    print(f"{len(bad)} jobs differ (host-buffer path {int((raw(got) != raw(want)).any(axis=1).sum())}, resident path "
+          f"{int((raw(got_dev) != raw(want)).any(axis=1).sum())}); the checker changed its own answer on {moved} of the {len(sel)} jobs re-run in-process; "
+          f"host-buffer vs resident results differ on {int((raw(got) != raw(got_dev)).any(axis=1).sum())} jobs")
+
+
 @pytest.mark.parametrize("cfg_name,field,n_refs,kernel", CASES, ids=[f"{c[0]}-{c[1]}-{c[2]}ref" for c in CASES])
 def test_every_macroblock_of_a_pair_bit_exact(pkg, synth, cfg_name, field, n_refs, kernel):
     import torch
@@ -61,6 +77,7 @@ def test_every_macroblock_of_a_pair_bit_exact(pkg, synth, cfg_name, field, n_ref
 
     path, prefix, kind = oracle_lib.best_checker(ROOT)
     want, wp = oracle_lib.parallel_search(path, prefix, W, H, n_refs + 1, cfg["search_range"], cfg["sub_dfunc"], planes, jobs, want_preds=True)
+    _explain_disagreement(got, got_dev, want, jobs, planes, path, prefix, W, H, n_refs, cfg)
     assert_results_equal(got, want, jobs)
     assert np.array_equal(gp, wp)
     assert_results_equal(got_dev, want, jobs)
