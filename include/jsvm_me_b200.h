@@ -359,7 +359,7 @@ uint64_t jsvm_me_launch_count(jsvm_me_ctx* ctx);
 /* Name of the full-search kernel the last search launched (for the 8x8-granular groups if there were any, else for the
  * 4x4-granular ones): "full_search_persistent_kernel<V,GRAN4>" (one CTA per SM over two shared-memory stages) or
  * "full_search_kernel<V,GRAN4>" (one CTA per group: small launches, union windows too tall for two stages);
- * "" before the first search. */
+ * a host-buffer call that was served by several launches names the kernel of its largest launch; "" before the first search. */
 const char* jsvm_me_last_search_kernel(jsvm_me_ctx* ctx);
 int jsvm_me_timing_begin(jsvm_me_ctx* ctx);                  /* start accumulating per-kernel event times */
 int jsvm_me_timing_end(jsvm_me_ctx* ctx, double* ms_interp, double* ms_search, double* ms_subpel,

@@ -148,6 +148,7 @@ struct jsvm_me_ctx {
   // measurement
   uint64_t launches = 0;
   const char* last_k2 = "";
+  int last_k2_units = 0;                 // groups / jobs served by last_k2 in the current call (a call of several launches reports its largest one)
   bool timing = false;
   struct Timed { cudaEvent_t e0, e1; int kind; };
   std::vector<Timed> timed;
@@ -473,8 +474,13 @@ int run_search(jsvm_me_ctx* c, const jsvm_me_job* d_jobs, int job_begin, int job
   const int n8 = generic || fast ? 0 : info->n_groups_8x8, n4 = generic || fast ? 0 : info->n_groups - info->n_groups_8x8;
   bool p8 = false, p4 = false;
   if (choose_persistent<kV8, false>(c, n8, info->max_uh_8x8, &p8) || choose_persistent<kV4, true>(c, n4, info->max_uh_4x4, &p4)) return JSVM_ME_ERR;
-  if (n8 > 0) c->last_k2 = p8 ? "full_search_persistent_kernel<8,false>" : "full_search_kernel<8,false>";
-  else if (n4 > 0) c->last_k2 = p4 ? "full_search_persistent_kernel<4,true>" : "full_search_kernel<4,true>";
+  // a host-buffer call is served by several launches (the first and the last of them can be small): report the largest one
+  if (job_begin == 0) c->last_k2_units = 0;
+  if (std::max(n8, n4) >= c->last_k2_units) {
+    c->last_k2_units = std::max(n8, n4);
+    if (n8 > 0) c->last_k2 = p8 ? "full_search_persistent_kernel<8,false>" : "full_search_kernel<8,false>";
+    else if (n4 > 0) c->last_k2 = p4 ? "full_search_persistent_kernel<4,true>" : "full_search_kernel<4,true>";
+  }
   if (n8 > 0 && (p8 ? launch_search_persistent<kV8, false>(c, d_groups, n8, info->max_uh_8x8, d_jobs, d_org, d_keys, d_aux)
                     : launch_search<kV8, false>(c, d_groups, 0, n8, info->max_uh_8x8, d_jobs, d_org, d_keys, d_aux))) return JSVM_ME_ERR;
   if (n4 > 0 && (p4 ? launch_search_persistent<kV4, true>(c, d_groups + n8, n4, info->max_uh_4x4, d_jobs, d_org, d_keys, d_aux)
