@@ -1067,6 +1067,7 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
       c->last_jobs.clear(); c->last_has_preds = false;
     }
   } guard{c};
+  const auto t_entry = std::chrono::steady_clock::now();
   const bool want_preds = preds != nullptr || n_jobs <= 4096;
   if (c->d_jobs.reserve(n_jobs) || c->d_keys.reserve(n_jobs) || c->d_full_costs.reserve(n_jobs) || c->d_aux.reserve(n_jobs) ||
       c->d_results.reserve(n_jobs) || (want_preds && c->d_preds.reserve((size_t)n_jobs * 256)) ||
@@ -1111,9 +1112,15 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
   std::vector<PlanChunk> plans(n_units);
   std::vector<int> status(n_units, 0);                      // 0 = pending, 1 = planned, -1 = failed
   std::mutex mu; std::condition_variable cv;
-  const int n_workers = n_units <= 1 ? 0 : (int)std::min<unsigned>((unsigned)n_units, std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
+  // Planner threads: one thread plans 2.2x faster than the GPU searches (150 vs 67 jobs/us on C4), so a few are enough; a thread per
+  // core (16 on the measured box) starves this thread and the driver's copy threads: 19.4 instead of 19.0 ms per 16-pair call.
+  unsigned max_workers = 4;
+  if (const char* e = getenv("JSVM_ME_PLAN_THREADS")) max_workers = (unsigned)std::max(1, std::min(64, atoi(e)));      // tuning knob
+  const int n_workers = n_units <= 1 ? 0 : (int)std::min<unsigned>((unsigned)n_units, std::min(max_workers, std::max(1u, std::thread::hardware_concurrency())));
   auto plan_unit = [&](int k) {
     plan_range(c->W, c->H, c->n_slots, c->search_range, jobs, cut[k], cut[k + 1], plans[k]);
+    if (getenv("JSVM_ME_TRACE") && (k < 12 || k % 8 == 0))
+      fprintf(stderr, "[jsvm_me trace] host %8.3f ms: unit %d planned\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count(), k);
     { std::lock_guard<std::mutex> lk(mu); status[k] = plans[k].err_job >= 0 ? -1 : 1; }
     cv.notify_all();
   };
@@ -1155,6 +1162,9 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
     for (int u = k; u < m; ++u)
       if (status[u] < 0) return fail("job %d: %s", plans[u].err_job, plans[u].err);
     const int begin = cut[k], end = cut[m];
+    if (getenv("JSVM_ME_TRACE"))
+      fprintf(stderr, "[jsvm_me trace] host %8.3f ms: launch %d takes units %d..%d (jobs %d..%d)\n",
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count(), launch, k, m - 1, begin, end);
     Group* pg = c->pinned_groups[launch & 3];
     if (launch >= 4) CU_OK(cudaEventSynchronize(c->chunk_done[launch & 3]));        // the slot's previous upload has been consumed
     jsvm_me_plan_info info{};
@@ -1191,8 +1201,12 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
     k = m;
   }
   if (preds) CU_OK(cudaMemcpyAsync(preds, c->d_preds.p, (size_t)n_jobs * 256, cudaMemcpyDeviceToHost, c->stream));
+  if (getenv("JSVM_ME_TRACE"))
+    fprintf(stderr, "[jsvm_me trace] host %8.3f ms: all launches queued\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count());
   CU_OK(cudaStreamSynchronize(c->stream));
   CU_OK(cudaStreamSynchronize(c->down_stream));
+  if (getenv("JSVM_ME_TRACE"))
+    fprintf(stderr, "[jsvm_me trace] host %8.3f ms: results on the host\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count());
   if (want_preds && n_jobs <= 4096) c->last_jobs.assign(jobs, jobs + n_jobs); else c->last_jobs.clear();
   c->last_has_preds = want_preds && n_jobs <= 4096;
   guard.ok = true;
@@ -1576,12 +1590,18 @@ int jsvm_me_timing_end(jsvm_me_ctx* c, double* ms_interp, double* ms_search, dou
   CU_OK(cudaSetDevice(c->device));
   CU_OK(cudaStreamSynchronize(c->stream));
   double ms[4] = {0, 0, 0, 0}; uint64_t n[4] = {0, 0, 0, 0};
+  const bool trace = getenv("JSVM_ME_TRACE") != nullptr;      // debugging aid: the timeline of the timed launches on stderr
   for (auto& t : c->timed) {
     float f = 0;
     CU_OK(cudaEventElapsedTime(&f, t.e0, t.e1));
+    if (trace) {
+      float a = 0;
+      cudaEventElapsedTime(&a, c->timed.front().e0, t.e0);
+      fprintf(stderr, "[jsvm_me trace] kind %d  start %8.3f ms  end %8.3f ms  (%.3f ms)\n", t.kind, a, a + f, f);
+    }
     ms[t.kind] += f; n[t.kind]++;
-    cudaEventDestroy(t.e0); cudaEventDestroy(t.e1);
   }
+  for (auto& t : c->timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
   c->timed.clear();
   c->timing = false;
   if (ms_interp) *ms_interp = ms[0]; if (ms_search) *ms_search = ms[1]; if (ms_subpel) *ms_subpel = ms[2];
