@@ -295,6 +295,35 @@ def test_large_configs_subset_bit_exact(me, oracle, synth, cfg_name, n_inner, fi
     assert np.array_equal(me.halfpel_plane(0), ses.halfpel(0))
 
 
+def test_reuploaded_slots_get_fresh_margins(me, oracle, synth):
+    """Plane uploads only queue their copy; YuvPicBuffer::fillMargin runs in front of the first reader.  Slots that are uploaded
+    again (new pictures in the same slots, then the two pictures swapped, with and without a new half-pel plane in between) must
+    be searched with the margins of what they hold NOW: start vectors point across every picture edge."""
+    cfg = synth.CONFIGS["C1"]
+    W, H = cfg["width"], cfg["height"]
+    seq = synth.Sequence(W, H, 77)
+    me.configure(W, H, 2)
+    me.set_params(cfg["search_range"], cfg["sub_dfunc"])
+    me.set_fast_search_params(0, 0)
+    for rnd, (a, b) in enumerate([(0, 1), (2, 3), (3, 2), (5, 2)]):
+        fa, fb = seq.frame(a), seq.frame(b)
+        me.upload_plane(0, fa)
+        if rnd != 3:
+            me.upload_plane(1, fb)                                           # round 3 keeps slot 1 and its half-pel plane
+            me.interp_halfpel([1])
+        me.upload_plane(0, fa)                                               # twice in a row: still one entry in the list
+        ses = oracle.session(W, H, 2, cfg["search_range"], cfg["sub_dfunc"])
+        ses.set_plane(0, fa)
+        ses.set_plane(1, fb)
+        jobs = synth.make_jobs(W, H, cfg["parts"], cur_slot=0, ref_slot=1, qp=30, field="random", seed=900 + rnd)
+        edge = (jobs["mb_x"] == 0) | (jobs["mb_y"] == 0) | (jobs["mb_x"] == W // 16 - 1) | (jobs["mb_y"] == H // 16 - 1)
+        jobs["start_hor"][edge] = np.where(jobs["mb_x"][edge] == 0, -200, 200).astype(np.int16)      # far outside: clamped to the MV limits
+        jobs["start_ver"][edge] = np.where(jobs["mb_y"][edge] == 0, -200, 200).astype(np.int16)
+        got = me.search(jobs)
+        assert_results_equal(got, ses.search(jobs), jobs)
+        assert np.array_equal(me.halfpel_plane(1), ses.halfpel(1))
+
+
 def test_persistent_and_per_group_kernels_agree(me, oracle, synth, monkeypatch):
     """The same whole-picture job list through full_search_persistent_kernel (one CTA per SM, producer / consumer warps over two
     shared-memory stages) and through full_search_kernel (one CTA per group): identical bytes, and both equal to the checker."""
