@@ -1155,9 +1155,10 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
     {
       std::unique_lock<std::mutex> lk(mu);
       cv.wait(lk, [&] { return status[k] != 0; });
-      // 4x4-granular groups sit behind the 8x8-granular ones of their unit: such a unit is launched on its own
+      // (the launch list below holds the 8x8-granular groups of all its units first, then the 4x4-granular ones)
+      const bool merge_g4 = getenv("JSVM_ME_NO_MERGE_G4") == nullptr;       // A/B knob
       auto take_ready = [&] {
-        while (m < n_units && m - k < kMaxUnits && status[m] != 0 && (m == k || (plans[m].g4.empty() && plans[k].g4.empty()))) {
+        while (m < n_units && m - k < kMaxUnits && status[m] != 0 && (m == k || merge_g4 || (plans[m].g4.empty() && plans[k].g4.empty()))) {
           if (status[m] < 0) break;
           ++m;
         }
@@ -1167,7 +1168,7 @@ int jsvm_me_search(jsvm_me_ctx* c, const jsvm_me_job* jobs, int n_jobs, const in
       // launch later) there is no hurry: keep collecting planned units, so that the launch is larger (every persistent K2 launch pays
       // its pipeline fill and its last-wave imbalance once).
       if (merge_launches && n_workers > 0)
-        while (m > k && m < n_units && m - k < kMaxUnits && status[m] == 0 && plans[k].g4.empty()) {
+        while (m > k && m < n_units && m - k < kMaxUnits && status[m] == 0 && (merge_g4 || plans[k].g4.empty())) {
           lk.unlock();
           const bool busy = cudaStreamQuery(c->stream) == cudaErrorNotReady;
           lk.lock();
