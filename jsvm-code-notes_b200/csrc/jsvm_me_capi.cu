@@ -1637,4 +1637,13 @@ int jsvm_me_timing_compensate(jsvm_me_ctx* c, double* ms_compensate, uint64_t* n
   return JSVM_ME_OK;
 }
 
+#ifdef K2_PRUNE_STATS
+int jsvm_me_debug_prune_stats(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, jsvm::g_prune_stats, 32);
+  if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(jsvm::g_prune_stats, z, 32); }
+  return 0;
+}
+#endif
+
 }  // extern "C"

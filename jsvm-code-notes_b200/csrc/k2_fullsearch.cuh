@@ -37,6 +37,12 @@ namespace jsvm {
 #define K2_COPY_UNROLL 4            // window-copy items a staging thread keeps in flight
 #endif
 constexpr int kK2Threads   = K2_THREADS;
+#ifndef K2_PRUNE
+#define K2_PRUNE 1
+#endif
+#ifdef K2_PRUNE_STATS
+__device__ unsigned long long g_prune_stats[4];     // batches, batches with no live slot, live slots, slots inside the window
+#endif
 constexpr int kWinRowBytes = 160;                 // bytes per staged window row (max 145 positions + 15)
 constexpr int kWinRowWords = kWinRowBytes / 4;    // 40 words: 40 mod 32 = 8 keeps successive rows on different banks
 constexpr int kMaxUW       = 145;                 // widest union window handled by one CTA
@@ -382,7 +388,10 @@ __device__ __forceinline__ void k2_build_stage(const Group& g, const K2Geo<V>& g
 //      pulled from the stage's counter, always one batch ahead of the one being worked on ----
 // QUAD: the group holds ONE job, an 8x8 block (slot 5 + quadrant): the SAD pass covers only the 8 rows x 2 words of that quadrant
 // and the rate / argmin pass only that slot -- a quarter of the SAD work and a ninth of the slot work of the general loop.
-template <int V, bool GRAN4, bool QUAD = false>
+// PRUNE: skip a slot's rate / key code when no SAD of the batch can beat the stage's incumbent (see live_slots).  Off for the
+// 4x4-granular groups (small partitions have SADs below their rate-dominated incumbents almost everywhere: 36 % slower on C3)
+// and for the small-window form (every displacement is near the winner).
+template <int V, bool GRAN4, bool QUAD = false, bool PRUNE = (K2_PRUNE != 0) && !GRAN4>
 __device__ __forceinline__ void k2_search_units(const K2Geo<V>& geo, const K2Stage<V, GRAN4>& st, const int lane, const int first_u0,
                                                 uint32_t (&best)[K2Smem<V, GRAN4>::NBEST])
 {
@@ -413,8 +422,11 @@ __device__ __forceinline__ void k2_search_units(const K2Geo<V>& geo, const K2Sta
     const bool live = u0 + lane < nunits;
     const int u = live ? u0 + lane : nunits - 1;                  // idle lanes redo the last unit with every slot masked off
     u0 = fetched;
-    const int strip = (int)__umulhi((uint32_t)u, inv_ups);
-    const int rem = u - strip * units_per_strip;
+    const int strip_k = (int)__umulhi((uint32_t)u, inv_ups);
+    const int rem = u - strip_k * units_per_strip;
+    // PRUNE: strips are visited from the middle of the union window outwards (k = 0, 1, 2, .. -> mid, mid + 1, mid - 1, ..): the
+    // winners sit near the start vectors, so the bounds below are tight after the first round of batches
+    const int strip = PRUNE ? ((geo.nstrips - 1) >> 1) + ((strip_k & 1) ? ((strip_k + 1) >> 1) : -(strip_k >> 1)) : strip_k;
     const int s = (int)__umulhi((uint32_t)rem, inv_m), m = rem - s * M;
     const int x = 4 * m + s - xa;                                 // column inside the union window (negative: alignment columns)
     const int ys = strip * V;
@@ -509,6 +521,43 @@ __device__ __forceinline__ void k2_search_units(const K2Geo<V>& geo, const K2Sta
     const Mask mfull = mx & sm.yfull[strip], many = mx & sm.yany[strip];
     if (__all_sync(0xffffffffu, many == 0)) continue;               // outside every job's window (alignment columns, x >= uw)
     const Mask part = many & ~mfull;                                // slots with only SOME valid rows in this strip
+    // cost = SAD + rate >= SAD, and a key replaces the incumbent only with cost <= the incumbent's: a slot whose SADs over the
+    // strip all exceed the cost of the stage's incumbent (a candidate some warp of the CTA has evaluated) cannot win -- exact,
+    // independent of the order in which warps see the displacements.  Lower bounds of the partition SADs
+    // come from the minima of the four quadrant SADs over the strip (min(a + b) >= min a + min b); each lane sets a bit per slot
+    // that can still change, one warp-wide OR makes them uniform, and pass 1 runs only for those slots -- on textured content
+    // for few of them.
+    uint32_t live_slots = 0xffffffffu;
+    if constexpr (PRUNE && !GRAN4) {
+      uint32_t q[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        q[a] = acc[0][a];
+#pragma unroll
+        for (int v = 1; v < V; ++v) q[a] = min(q[a], acc[v][a]);
+      }
+      const uint32_t lb[9] = { q[0] + q[1] + q[2] + q[3], q[0] + q[1], q[2] + q[3], q[0] + q[2], q[1] + q[3], q[0], q[1], q[2], q[3] };
+      uint32_t bits = 0;
+#pragma unroll
+      for (int sl = 0; sl < 9; ++sl) {
+        // the stage's running minimum of the slot: all warps of the CTA fold their improvements in (below); a stale value is
+        // only a looser bound
+        const uint32_t bound = *reinterpret_cast<const volatile uint32_t*>(&sm.best[sl]) >> kIdxBits;
+        bits |= lb[sl] <= bound ? (1u << sl) : 0u;
+      }
+      live_slots = __reduce_or_sync(0xffffffffu, bits & (uint32_t)mfull);
+#ifdef K2_PRUNE_STATS
+      {
+        const uint32_t inside = __reduce_or_sync(0xffffffffu, (uint32_t)mfull) & 0x1ffu;
+        if (lane == 0) {
+          atomicAdd(&g_prune_stats[0], 1ull);
+          atomicAdd(&g_prune_stats[1], (unsigned long long)(live_slots == 0));
+          atomicAdd(&g_prune_stats[2], (unsigned long long)__popc(live_slots));
+          atomicAdd(&g_prune_stats[3], (unsigned long long)__popc(inside));
+        }
+      }
+#endif
+    }
     uint32_t idxv[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) idxv[v] = (uint32_t)((ys + v) * uw + x);
@@ -526,6 +575,7 @@ __device__ __forceinline__ void k2_search_units(const K2Geo<V>& geo, const K2Sta
       for (int v = 0; v < V; ++v) kv[v] = rate_key(f, byv[v], fbx, sadv[v], idxv[v]);
     };
     auto update_full = [&](const int sl, const uint32_t (&sadv)[V]) {
+      if constexpr (PRUNE && !GRAN4) { if (!((live_slots >> sl) & 1u)) return; }     // warp-uniform: see live_slots
       uint32_t kv[V];
       slot_keys(sl, sadv, kv);
       // two levels of three-input minima (VIMNMX3) instead of a serial chain through best[sl].  (A 4-instruction tree that
@@ -537,6 +587,10 @@ __device__ __forceinline__ void k2_search_units(const K2Geo<V>& geo, const K2Sta
       else        m = min(min(kv[0], kv[3]), kv[V - 1]);
       if (!GRAN4) {
         if ((mfull >> sl) & 1) best[sl] = min(best[sl], m);
+        if constexpr (PRUNE) {                                    // every warp's bound: fold the improvement into the stage now
+          const uint32_t w = __reduce_min_sync(0xffffffffu, best[sl]);
+          if (lane == 0 && w != kKeyInvalid) smem_min(&sm.best[sl], w);
+        }
       } else {
         const uint32_t w = __reduce_min_sync(0xffffffffu, ((mfull >> sl) & 1) ? m : kKeyInvalid);
         if (lane == (sl & 31)) best[sl >> 5] = min(best[sl >> 5], w);
@@ -613,7 +667,7 @@ __device__ __forceinline__ void k2_search_units(const K2Geo<V>& geo, const K2Sta
       }
     };
 
-    for_each_slot(update_full);
+    if (!PRUNE || live_slots != 0) for_each_slot(update_full);
     if (__any_sync(0xffffffffu, part != 0)) {
       // the keys are recomputed from an opaque copy of the column: keeping the 8 x NS keys of pass 1 alive for this rare
       // pass would spill them in the hot path
@@ -692,7 +746,7 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
   uint32_t best[SM::NBEST];
 #pragma unroll
   for (int sl = 0; sl < SM::NBEST; ++sl) best[sl] = kKeyInvalid;
-  k2_search_units<V, GRAN4, QUAD>(geo, st, lane, (tid >> 5) * 32, best);
+  k2_search_units<V, GRAN4, QUAD, (K2_PRUNE != 0) && !GRAN4 && THREADS == kK2Threads>(geo, st, lane, (tid >> 5) * 32, best);
   if constexpr (QUAD) {
     const uint32_t w = __reduce_min_sync(0xffffffffu, best[0]);
     if (lane == 0 && w != kKeyInvalid) smem_min(&st.sm->best[5 + st.sm->pad], w);
