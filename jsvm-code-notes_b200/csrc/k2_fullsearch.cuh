@@ -536,14 +536,16 @@ __device__ __forceinline__ void k2_search_units(const K2Geo<V>& geo, const K2Sta
 #pragma unroll
         for (int v = 1; v < V; ++v) q[a] = min(q[a], acc[v][a]);
       }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) q[a] <<= kIdxBits;              // in key units (SAD <= 65280: no overflow); lb <= key >> 15  <=>  lb << 15 <= key
       const uint32_t lb[9] = { q[0] + q[1] + q[2] + q[3], q[0] + q[1], q[2] + q[3], q[0] + q[2], q[1] + q[3], q[0], q[1], q[2], q[3] };
       uint32_t bits = 0;
 #pragma unroll
       for (int sl = 0; sl < 9; ++sl) {
         // the stage's running minimum of the slot: all warps of the CTA fold their improvements in (below); a stale value is
         // only a looser bound
-        const uint32_t bound = *reinterpret_cast<const volatile uint32_t*>(&sm.best[sl]) >> kIdxBits;
-        bits |= lb[sl] <= bound ? (1u << sl) : 0u;
+        const uint32_t incumbent = *reinterpret_cast<const volatile uint32_t*>(&sm.best[sl]);
+        bits |= lb[sl] <= incumbent ? (1u << sl) : 0u;
       }
       live_slots = __reduce_or_sync(0xffffffffu, bits & (uint32_t)mfull);
 #ifdef K2_PRUNE_STATS
