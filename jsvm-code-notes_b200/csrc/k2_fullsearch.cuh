@@ -764,10 +764,10 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
 // (and write the finished group's keys to HBM), handing stages over with mbarriers.  The search warps never execute
 // staging code and never wait at a CTA-wide barrier, so the ALU pipe always has SAD work queued.
 #ifndef K2P_CONSUMERS
-#define K2P_CONSUMERS 13
+#define K2P_CONSUMERS 12
 #endif
 #ifndef K2P_PRODUCERS
-#define K2P_PRODUCERS 3
+#define K2P_PRODUCERS 4
 #endif
 // (8x8-granular groups: 13 + 3; 4x4-granular groups stage 41 rate tables per group and search a smaller window: K2P_PRODUCERS_G4)
 #ifndef K2P_PRODUCERS_G4
@@ -807,19 +807,24 @@ full_search_persistent_kernel(const uint8_t* __restrict__ planes, size_t plane_b
   const int n_mine = ((int)blockIdx.x < n_groups) ? (n_groups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // groups b, b + G, ...
   if (tid == 0) {
     mbar_init(&full[0], 32 * kK2PProducers); mbar_init(&full[1], 32 * kK2PProducers);
-    mbar_init(&done[0], kK2PConsumers);      mbar_init(&done[1], kK2PConsumers);
+    mbar_init(&done[0], kK2PConsumers + kK2PProducers); mbar_init(&done[1], kK2PConsumers + kK2PProducers);   // one arrival per warp
     fence_barrier_init();
   }
   __syncthreads();
 
-  if (warp >= kK2PConsumers) {
-    // ================= producers =================
-    const int ptid = tid - 32 * kK2PConsumers;
-    constexpr int pthreads = 32 * kK2PProducers;
-    for (int k = 0; k < n_mine + 2; ++k) {
+  // Every warp runs the same loop.  Iteration k: the staging warps first retire group k - 2 (wait until all sixteen warps have
+  // folded their minima in, write its keys) and build the stage of group k; then EVERY warp searches -- the search warps group k,
+  // the staging warps group k - 1, whose stage they finished an iteration ago and which the search warps are still working on:
+  // staging takes a third of a group's search time, and for the rest of it the three staging warps pull batches from the same
+  // counter instead of idling (13 search warps leave three of the four sub-cores with three warps: their ALU pipes were 78 % busy).
+  const bool producer = warp >= kK2PConsumers;
+  const int ptid = tid - 32 * kK2PConsumers;
+  constexpr int pthreads = 32 * kK2PProducers;
+  for (int k = 0; k < n_mine + 2; ++k) {
+    if (producer) {
       const int s = k & 1, use = k >> 1;
       if (k >= 2) {
-        // stage s was used by group k - 2: wait until every search warp has folded its minima in, then write the keys out
+        // stage s was used by group k - 2: wait until every warp has folded its minima in, then write the keys out
         mbar_wait_relaxed(&done[s], (uint32_t)((use - 1) & 1));
         const Group& gp = groups[blockIdx.x + (size_t)(k - 2) * gridDim.x];
         const K2Geo<V> geop((kMargin + 16 * gp.mb_x + gp.ux0) & 3, gp.uw, gp.uh);
@@ -837,13 +842,12 @@ full_search_persistent_kernel(const uint8_t* __restrict__ planes, size_t plane_b
         mbar_arrive(&full[s]);                                // release: this thread's stage writes are visible to waiters
       }
     }
-  } else {
-    // ================= search warps =================
-    for (int k = 0; k < n_mine; ++k) {
-      const int s = k & 1, use = k >> 1;
+    const int kk = producer ? k - 1 : k;                      // the group this warp searches in this iteration
+    if (kk >= 0 && kk < n_mine) {
+      const int s = kk & 1, use = kk >> 1;
       mbar_wait(&full[s], (uint32_t)(use & 1));
       // the stage record sits behind the group's window copies: recover the geometry from the group itself
-      const Group& g = groups[blockIdx.x + (size_t)k * gridDim.x];
+      const Group& g = groups[blockIdx.x + (size_t)kk * gridDim.x];
       const K2Geo<V> geo((kMargin + 16 * g.mb_x + g.ux0) & 3, g.uw, g.uh);
       const K2Stage<V, GRAN4> st(K2P_STAGE(s), geo);
       uint32_t best[SM::NBEST];
@@ -852,7 +856,7 @@ full_search_persistent_kernel(const uint8_t* __restrict__ planes, size_t plane_b
       k2_search_units<V, GRAN4>(geo, st, lane, -1, best);
       k2_warp_reduce<V, GRAN4>(*st.sm, lane, best);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&done[s]);                   // release: the atomicMin results are visible to the producer
+      if (lane == 0) mbar_arrive(&done[s]);                   // release: the atomicMin results are visible to the staging warps
     }
   }
 #undef K2P_STAGE
