@@ -343,6 +343,41 @@ def test_persistent_and_per_group_kernels_agree(me, oracle, synth, monkeypatch):
     assert_results_equal(out["persistent"][sub], want, jobs[sub])
 
 
+@pytest.mark.parametrize("content", ["flat", "periodic", "steps"])
+def test_tie_heavy_content_bit_exact(me, oracle, synth, monkeypatch, content):
+    """Content on which many displacements have EXACTLY the same cost: flat pictures (every SAD is 0, the rate decides, then the
+    raster order), an 8-pixel periodic pattern (zero-SAD ties one period apart), flat halves with one edge.  The full search
+    visits strips centre-out and skips the rate / compare code of batches that cannot beat the incumbent; the winner must still
+    be the reference's first strict minimum in raster order, through both kernels."""
+    cfg = synth.CONFIGS["C2"]
+    W, H = cfg["width"], cfg["height"]
+    yy, xx = np.mgrid[0:H, 0:W]
+    if content == "flat":
+        frames = [np.full((H, W), 117, np.uint8), np.full((H, W), 117, np.uint8)]
+    elif content == "periodic":
+        base = (((xx // 4) + (yy // 4)) & 1) * 160 + 40
+        frames = [base.astype(np.uint8), np.roll(base, (4, 8), axis=(0, 1)).astype(np.uint8)]
+    else:
+        frames = [np.where(xx < W // 2, 60, 190).astype(np.uint8), np.where(xx < W // 2 + 3, 60, 190).astype(np.uint8)]
+    me.configure(W, H, 2)
+    me.set_params(cfg["search_range"], cfg["sub_dfunc"])
+    me.set_fast_search_params(0, 0)
+    ses = oracle.session(W, H, 2, cfg["search_range"], cfg["sub_dfunc"])
+    for s_, f in enumerate(frames):
+        me.upload_plane(s_, f)
+        ses.set_plane(s_, f)
+    me.interp_halfpel([0, 1])
+    jobs = np.concatenate([synth.make_jobs(W, H, cfg["parts"], cur_slot=1, ref_slot=0, qp=q, field=f, seed=5) for q, f in ((30, "random"), (44, "zero"))])
+    out = {}
+    for mode in ("persistent", "group"):
+        monkeypatch.setenv("JSVM_ME_K2", mode)
+        out[mode] = me.search(jobs)
+    monkeypatch.delenv("JSVM_ME_K2")
+    assert out["persistent"].tobytes() == out["group"].tobytes()
+    sub = np.arange(0, len(jobs), 3)
+    assert_results_equal(out["persistent"][sub], ses.search(jobs[sub]), jobs[sub])
+
+
 # ---- full-size (1080p, SR 64, every macroblock) size-independent properties, no oracle needed ----
 @pytest.fixture(scope="module")
 def full_1080p(me, synth):
