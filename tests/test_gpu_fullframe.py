@@ -18,6 +18,7 @@ CASES = [
     # config, start/pred field, reference pictures, expected full-search kernel
     ("C4", "random", 1, "full_search_persistent_kernel<8,false>"),
     ("C4", "split", 1, "full_search_persistent_kernel<8,false>"),
+    ("C2", "random", 2, "full_search_kernel<8,false>"),
     ("C3", "split", 1, "full_search_kernel<4,true>"),
     ("C5", "random", 4, "full_search_persistent_kernel<8,false>"),
 ]
