@@ -787,6 +787,10 @@ int jsvm_me_set_mv_candidates_device(jsvm_me_ctx* c, const jsvm_mv* d_abc) {
 
 int jsvm_me_set_stream(jsvm_me_ctx* c, void* s) {
   if (!c) return fail("null context");
+  if (c->stream != (cudaStream_t)s && !c->margin_dirty.empty()) {      // pending fillMargin launches stay behind their uploads, on the old stream
+    CU_OK(cudaSetDevice(c->device));
+    if (flush_margins(c)) return JSVM_ME_ERR;
+  }
   c->stream = (cudaStream_t)s;
   return JSVM_ME_OK;
 }
