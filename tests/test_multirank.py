@@ -58,3 +58,66 @@ def test_block_owner():
     # the two pairs of a current picture (2k, 2k + 1) stay on one rank whenever the blocks are even
     got = [sharding.shard_pairs(list(range(16)), r, 8) for r in range(8)]
     assert all([i for i, _ in g] == [2 * r, 2 * r + 1] for r, g in enumerate(got))
+
+
+# ---- the same layout carrying real motion-estimation records (the CPU checker stands in for the GPU search) ----
+def _level(synth, n_pairs):
+    """Pictures and job lists of one temporal level on a 64x48 picture: pair g = (2g + 1, 2g)."""
+    W, H = 64, 48
+    seq = synth.Sequence(W, H, 321)
+    pairs = [(2 * g + 1, 2 * g) for g in range(n_pairs)]
+    return W, H, seq, pairs
+
+
+def _search_pairs(ROOT_, synth, oracle_lib, W, H, seq, mine):
+    """Results of the given [(global index, (cur, ref)), ...] pairs, concatenated in that order (int32 view of the 32-byte records)."""
+    import subprocess
+    lib = os.path.join(ROOT_, "oracle", "libme_oracle.so")
+    if not os.path.exists(lib):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT_, "oracle"), "libme_oracle.so"])
+    be = oracle_lib.CpuBackend(lib, "jsvm_ora_")
+    out = []
+    for g, (c, r) in mine:
+        ses = be.session(W, H, 2, 8, 2)
+        ses.set_plane(0, seq.frame(r))
+        ses.set_plane(1, seq.frame(c))
+        jobs = synth.make_jobs(W, H, synth.PARTS_9, cur_slot=1, ref_slot=0, qp=33, field="random", seed=700 + g)
+        out.append(np.ascontiguousarray(ses.search(jobs)).view(np.int32).reshape(len(jobs), 8))
+    return np.concatenate(out) if out else np.zeros((0, 8), np.int32)
+
+
+def _me_worker(rank, world, port, n_pairs, out_path):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    sharding = importlib.import_module("jsvm-code-notes_b200.sharding")
+    synth = importlib.import_module("jsvm-code-notes_b200.synth")
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    W, H, seq, pairs = _level(synth, n_pairs)
+    mine = sharding.shard_pairs(pairs, rank, world)
+    jobs_per_pair = (W // 16) * (H // 16) * len(synth.PARTS_9)
+    local = torch.from_numpy(_search_pairs(ROOT, synth, oracle_lib, W, H, seq, mine))
+    gathered = sharding.gather_results(local, dst=0, n_pairs=n_pairs, jobs_per_pair=jobs_per_pair)
+    if rank == 0:
+        np.save(out_path, sharding.assemble_level(gathered, len(mine), jobs_per_pair, world, n_pairs).numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_pairs,port", [(4, 29541), (5, 29543)])
+def test_sharded_search_results_match_the_unsharded_level(tmp_path, n_pairs, port):
+    """Every rank searches its block of pairs, the result RECORDS (MVs, SADs, costs, modes) are gathered and re-assembled on rank 0:
+    byte-identical to one process searching the whole level."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    synth = importlib.import_module("jsvm-code-notes_b200.synth")
+    out = str(tmp_path / "level.npy")
+    mp.spawn(_me_worker, args=(2, port, n_pairs, out), nprocs=2, join=True)
+    W, H, seq, pairs = _level(synth, n_pairs)
+    want = _search_pairs(ROOT, synth, oracle_lib, W, H, seq, list(enumerate(pairs)))
+    got = np.load(out)
+    assert got.shape == want.shape and got.dtype == want.dtype
+    assert np.array_equal(got, want)
+    assert np.any(got[:, 0] != 0)                                             # real motion vectors, not padding
