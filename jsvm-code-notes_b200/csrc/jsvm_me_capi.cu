@@ -411,7 +411,7 @@ int choose_persistent(jsvm_me_ctx* c, int n_groups, int max_uh, bool* persistent
   // JSVM_ME_K2 = group | persistent forces one of the two kernels (A/B measurements)
   const char* force = getenv("JSVM_ME_K2");
   const bool fits = k2p_smem_bytes<V, GRAN4>(max_uh) <= kMaxDynSmem;
-  // 4x4-granular groups (41 slots): staging 41 rate tables keeps 3 producer warps busier than 13 search warps; measured
+  // 4x4-granular groups (41 slots): staging 41 rate tables keeps the staging warps busier than the search warps; measured
   // 19 % slower than one CTA per group on C3, so the persistent kernel is only chosen for them when forced
   // Small windows (search range <= ~40: union windows of at most 96 rows) leave a group too little work to hide the hand-over
   // between stages: one CTA per group measured 8 % (CIF, SR 32) to 17 % (QCIF, SR 16) faster there.

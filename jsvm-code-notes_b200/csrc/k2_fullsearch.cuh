@@ -759,17 +759,17 @@ full_search_kernel(const uint8_t* __restrict__ planes,            // full-pel pl
   k2_flush<V, GRAN4>(*st.sm, tid, THREADS, keys, aux);
 }
 
-// ---- kernel B: persistent, one CTA per SM, producer / consumer warps over two shared-memory stages ----
+// ---- kernel B: persistent, one CTA per SM, staging / search warps over two shared-memory stages ----
 // kK2PConsumers warps run the search loop on stage s while kK2PProducers warps stage the next group into stage s ^ 1
-// (and write the finished group's keys to HBM), handing stages over with mbarriers.  The search warps never execute
-// staging code and never wait at a CTA-wide barrier, so the ALU pipe always has SAD work queued.
+// (and write the finished group's keys to HBM), then join the search of the current group; stages are handed over with
+// mbarriers.  No warp waits at a CTA-wide barrier, so the ALU pipe always has SAD work queued.
 #ifndef K2P_CONSUMERS
 #define K2P_CONSUMERS 12
 #endif
 #ifndef K2P_PRODUCERS
 #define K2P_PRODUCERS 4
 #endif
-// (8x8-granular groups: 13 + 3; 4x4-granular groups stage 41 rate tables per group and search a smaller window: K2P_PRODUCERS_G4)
+// (8x8-granular groups: 12 + 4; 4x4-granular groups stage 41 rate tables per group and search a smaller window: K2P_PRODUCERS_G4)
 #ifndef K2P_PRODUCERS_G4
 #define K2P_PRODUCERS_G4 5
 #endif
@@ -816,7 +816,7 @@ full_search_persistent_kernel(const uint8_t* __restrict__ planes, size_t plane_b
   // folded their minima in, write its keys) and build the stage of group k; then EVERY warp searches -- the search warps group k,
   // the staging warps group k - 1, whose stage they finished an iteration ago and which the search warps are still working on:
   // staging takes a third of a group's search time, and for the rest of it the three staging warps pull batches from the same
-  // counter instead of idling (13 search warps leave three of the four sub-cores with three warps: their ALU pipes were 78 % busy).
+  // counter instead of idling (with 13 + 3 and idle staging warps the ALU pipes of three of the four sub-cores were 78 % busy).
   const bool producer = warp >= kK2PConsumers;
   const int ptid = tid - 32 * kK2PConsumers;
   constexpr int pthreads = 32 * kK2PProducers;
